@@ -1,0 +1,199 @@
+/*
+ * morl_b200.h -- C-ABI of libmorl_b200.so: the B200 (sm_100a) update engine for the batched
+ * multi-objective value-update hot path of LucasAlegre/morl-baselines (reference @ a8acdbb).
+ *
+ * The reference has NO plugin / FFI layer: its boundary is the Python class API.
+ * Each entry point below therefore replaces an *inline tensor-op sequence* of the reference; the
+ * file:line it replaces is cited per function (paths relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never allocates,
+ *     frees or retains device memory; tensors are contiguous row-major, base pointers 16-byte aligned;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it; no host sync, no
+ *     allocation => safe under CUDA-graph capture; re-entrant (no mutable global state);
+ *   - return value: 0 = success; negative = MORL_ERR_* argument error; positive = cudaError_t of
+ *     the launch.  morl_last_error() returns a thread-local message for the last non-zero return;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ *
+ * Row-index maps.  Several per-row inputs of the reference are broadcast by `Tensor.repeat` (tile) or
+ * `repeat_interleave` (block).  Instead of materialising them, an input X with x_rows < N rows is
+ * addressed as
+ *      MORL_MAP_TILE  : X[k % x_rows]            (reference: b_rewards.repeat(num_sample_w, 1), envelope.py:285-291)
+ *      MORL_MAP_BLOCK : X[k / (N / x_rows)]      (reference: sampled_w.repeat_interleave(B, 0), envelope.py:284)
+ *   x_rows == N is the identity under both maps.
+ *
+ * Scalarisation arithmetic (`dot_mode`).  s = w . q over D objectives, fp32:
+ *      MORL_DOT_UNFUSED : ((w0*q0 + w1*q1) + w2*q2) + ...   every op rounded (IEEE, no contraction).  This is
+ *                         bit-equal to the reference's th.einsum on CPU for small products (N_cols < 128),
+ *                         e.g. the reference default num_sample_w=4 and every max_action / gpi_action call.
+ *      MORL_DOT_PAIRFMA : fl(fma(w1,q1, fl(w0*q0)) + fl(w2*q2))   (D==3 only) -- bit-equal to what MKL's sgemm
+ *                         produces for th.einsum("br,bwar->bwa") on the build container's AVX-512 CPU once
+ *                         W*A >= 192 (probe in DESIGN.md); offered so golden vectors of the real reference at the
+ *                         north-star shape can be matched bit-for-bit.
+ *      MORL_DOT_FMA     : fma(w2,q2, fma(w1,q1, fl(w0*q0)))   the GPU-native chain (what cuBLAS would do).
+ *   argmax / argmin are always FIRST-occurrence (th.max / th.argmax / th.argmin semantics).
+ */
+#ifndef MORL_B200_H_
+#define MORL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MORL_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define MORL_API __attribute__((visibility("default")))
+#else
+#define MORL_API
+#endif
+
+/* argument errors (negative); positive returns are cudaError_t values */
+#define MORL_OK 0
+#define MORL_ERR_NULL (-1)        /* required pointer is NULL */
+#define MORL_ERR_SHAPE (-2)       /* non-positive / inconsistent dimension */
+#define MORL_ERR_ALIGN (-3)       /* base pointer not 16-byte aligned */
+#define MORL_ERR_UNSUPPORTED (-4) /* dimension outside the compiled range (D > 8, A > 64, ...) */
+#define MORL_ERR_NO_DEVICE (-5)   /* no CUDA device / wrong architecture */
+
+#define MORL_DOT_UNFUSED 0
+#define MORL_DOT_FMA 1
+#define MORL_DOT_PAIRFMA 2
+
+#define MORL_MAP_TILE 0
+#define MORL_MAP_BLOCK 1
+
+#define MORL_ROWS_REFERENCE 0 /* effective-batch row k = i*B + b  (reference order, envelope.py:284-291) */
+#define MORL_ROWS_BMAJOR 1    /* effective-batch row k = b*W + i  (coalesced order used by the fused update)  */
+
+#define MORL_MAX_D 8
+#define MORL_MAX_A 64
+
+MORL_API int morl_version(void);
+MORL_API const char* morl_last_error(void);
+/* number of SMs of the current device (148 on B200), or a negative MORL_ERR_* */
+MORL_API int morl_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused envelope-max TD target.   Replaces Envelope.envelope_target (multi_policy/envelope/envelope.py:404-440)
+ * + the vector Bellman line (envelope.py:298), evaluated on the B*W DISTINCT (s'_b, w_j) rows instead of the
+ * reference's B*W^2 tiled rows (SURVEY.md headline 2).
+ *   q_online, q_target : f32 [B, W, A, D]   Q(s'_b, w_j)[a, :] of the online / target net (row b*W + j)
+ *   wset               : f32 [W, D]         sampled weight vectors
+ *   reward             : f32 [B, D], done : f32 [B]
+ * For every (i, b):  (j*, a*) = first argmax_{j,a} wset[i] . q_online[b, j, a, :]
+ *                    target[k, :] = reward[b, :] + ((1 - done[b]) * gamma) * q_target[b, j*, a*, :]   (unfused)
+ * with k = i*B + b (MORL_ROWS_REFERENCE) or b*W + i (MORL_ROWS_BMAJOR).
+ *   target_out : f32 [W*B, D];  pref_out, act_out : int32 [W*B] or NULL  (reference keeps them as int64, :424-426)
+ */
+MORL_API int morl_envelope_td_f32(const float* q_online, const float* q_target, const float* wset, const float* reward,
+                         const float* done, float gamma, int B, int W, int A, int D, int dot_mode, int row_order,
+                         float* target_out, int32_t* pref_out, int32_t* act_out, void* stream);
+
+/* Double-DQN target with a per-row weight.  Replaces Envelope.ddqn_target (envelope.py:442-463) + :298, and the
+ * non-GPI branch of GPIPD._reset_priorities (multi_policy/gpi_pd/gpi_pd.py:648-656).
+ *   q_select, q_eval : f32 [N, A, D];  w : f32 [w_rows, D];  reward : f32 [r_rows, D] or NULL;  done : f32 [r_rows]
+ *   a* = first argmax_a w_k . q_select[k, a, :];   out[k] = q_eval[k, a*, :]  (then Bellman if reward != NULL)
+ */
+MORL_API int morl_greedy_td_f32(const float* q_select, const float* q_eval, const float* w, int w_rows, int w_map,
+                       const float* reward, const float* done, int r_rows, int r_map, float gamma, int N, int A,
+                       int D, int dot_mode, float* target_out, int32_t* act_out, void* stream);
+
+/* GPI-PD / GPI-LS critic-min target.  Replaces GPIPD.update's target block (gpi_pd.py:445-463):
+ *   q_nets : f32 [n_nets, N, A, D] target nets;  n*(k,a) = first argmin_n w_k . q_nets[n,k,a,:];
+ *   Q~[k,a,:] = q_nets[n*,k,a,:];  a* = first argmax_a w_k . Q~[k,a,:];  out = reward + ((1-done)*gamma) * Q~[k,a*,:]
+ */
+MORL_API int morl_critic_min_td_f32(const float* q_nets, int n_nets, const float* w, int w_rows, int w_map,
+                           const float* reward, const float* done, int r_rows, int r_map, float gamma, int N,
+                           int A, int D, int dot_mode, float* target_out, int32_t* act_out, void* stream);
+
+/* GPI envelope over a policy/weight-support set with per-row weights.  Replaces GPIPD._envelope_target
+ * (gpi_pd.py:662-690), GPIPD.gpi_action (gpi_pd.py:564-582; n_nets = 1, reward = NULL), its batched twin in
+ * _rollout_dynamics (gpi_pd.py:379-387) and the M x M GPI evaluation of GPIPDContinuousAction.eval
+ * (multi_policy/gpi_pd/gpi_pd_continuous_action.py:464-478).
+ *   q_nets : f32 [n_nets, B, P, A, D];  w : f32 [w_rows, D]
+ *   per (b,p,a): critic-min over n as above (scalarised with w_b), then (p*, a*) = first joint argmax_{p,a}
+ *   out[b,:] = Q~[b,p*,a*,:]  (Bellman applied iff reward != NULL);  policy_out / act_out : int32 [B] or NULL
+ */
+MORL_API int morl_gpi_envelope_f32(const float* q_nets, int n_nets, const float* w, int w_rows, int w_map,
+                          const float* reward, const float* done, int r_rows, int r_map, float gamma, int B, int P,
+                          int A, int D, int dot_mode, float* out, int32_t* policy_out, int32_t* act_out,
+                          void* stream);
+
+/* Actor-critic vector targets (continuous-action algorithms), three "min over critics" rules:
+ *   MORL_AC_ELEMENTWISE_MIN : CAPQL  (multi_policy/capql/capql.py:326-331)  min_n per objective, - alpha*logp, vector target
+ *   MORL_AC_SCALAR_MIN      : MOSAC  (single_policy/ser/mosac_continuous_action.py:435-442) scalarise, min, - alpha*logp;
+ *                             out is [N] and the reward is scalarised with w as well
+ *   MORL_AC_ARGMIN_GATHER   : GPI-PD continuous / TD3 (gpi_pd_continuous_action.py:397-403) first argmin_n w.q_n, gather vector
+ *   q_nets : f32 [n_nets, N, D];  logp : f32 [N] or NULL;  w : [w_rows, D] (unused for ELEMENTWISE_MIN)
+ */
+#define MORL_AC_ELEMENTWISE_MIN 0
+#define MORL_AC_SCALAR_MIN 1
+#define MORL_AC_ARGMIN_GATHER 2
+MORL_API int morl_actor_critic_td_f32(const float* q_nets, int n_nets, const float* w, int w_rows, int w_map,
+                             const float* reward, const float* done, const float* logp, float alpha, float gamma,
+                             int N, int D, int variant, float* target_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused TD loss + gradient seed + PER priority for Envelope.  Replaces envelope.py:301-313 (gather taken action,
+ * MSE, homotopy auxiliary loss) and :329-331 (|w . td| priorities of the first B rows, i.e. weight index 0).
+ *   q_values : f32 [W*B, A, D] online net output on the effective batch (row order `row_order`)
+ *   action   : int32 [B];  target_q : f32 [W*B, D];  wset : f32 [W, D]
+ *   loss_out : f32 [1] = (1-lambda)*mean((q-t)^2) + lambda*mean((w.q - w.t)^2)
+ *   grad_q   : f32 [W*B, A, D] = d loss / d q_values (dense; zero off the taken action), or NULL
+ *   q_taken  : f32 [W*B, D] the gathered Q(s,a) (optional, NULL to skip)
+ *   prio_out : f32 [B] = | wset[0] . (q - t) | for rows with i == 0, or NULL
+ *   workspace: device scratch of morl_td_workspace_bytes(W*B) bytes (no initialisation required)
+ */
+MORL_API size_t morl_td_workspace_bytes(int n_rows);
+MORL_API int morl_td_mse_priority_f32(const float* q_values, const int32_t* action, const float* target_q,
+                             const float* wset, float homotopy_lambda, int B, int W, int A, int D, int row_order,
+                             float* loss_out, float* grad_q, float* q_taken, float* prio_out, void* workspace,
+                             void* stream);
+
+/* Huber-style TD loss of GPI-PD.  Replaces gpi_pd.py:469-487 per net and :507-520 (priority = | w . max_n |delta_n| |).
+ *   q_values : f32 [n_nets, N, A, D];  action : int32 [a_rows] (tile map);  target_q : f32 [N, D]
+ *   target_q_gpi : f32 [N, D] or NULL (gpi_pd=True -> priorities from the GPI envelope target)
+ *   loss_out : f32 [1] = (1/n_nets) * sum_n mean( where(|d|<mp, 0.5 d^2, mp |d|) )   (common/networks.py:90-100)
+ *   grad_q   : f32 [n_nets, N, A, D] or NULL;   prio_out : f32 [p_rows] (first p_rows rows), raw |w . err| before clip/pow
+ */
+MORL_API int morl_td_huber_priority_f32(const float* q_values, int n_nets, const int32_t* action, int a_rows,
+                               const float* target_q, const float* target_q_gpi, const float* w, int w_rows,
+                               int w_map, float min_priority, int N, int A, int D, int p_rows, float* loss_out,
+                               float* grad_q, float* prio_out, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident replay: index gather.  Replaces the 5 fancy-index gathers + 6 host->device copies of
+ * ReplayBuffer.sample (common/buffer.py:82-94) / PrioritizedReplayBuffer.sample (common/prioritized_buffer.py:160-166).
+ *   stores: obs/next_obs f32 [cap, obs_dim], action u8|f32 [cap, act_dim], reward f32 [cap, rew_dim], done f32 [cap]
+ *   idx : int64 [B];  outputs are [B, *];  discrete actions (act_is_u8 != 0) are widened to int32.
+ */
+MORL_API int morl_replay_gather(const float* obs_store, const float* next_obs_store, const void* act_store,
+                       const float* rew_store, const float* done_store, const int64_t* idx, int B, int obs_dim,
+                       int act_dim, int rew_dim, int act_is_u8, int64_t capacity, float* obs_out,
+                       float* next_obs_out, void* act_out, float* rew_out, float* done_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pareto non-dominated mask (maximisation).  Replaces get_non_pareto_dominated_inds (common/pareto.py:34-57):
+ *   keep[i] = 1 iff no OTHER value weakly dominates pts[i] (only exact copies are >= in every coordinate) and,
+ *   when remove_duplicates != 0, i is the first index holding its value.  Comparisons are exact in the input dtype;
+ *   a row containing NaN is never kept.  pts : [N, D] row-major; keep : uint8 [N].  D <= MORL_MAX_D.
+ */
+MORL_API int morl_pareto_mask_f32(const float* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream);
+MORL_API int morl_pareto_mask_f64(const double* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-tensor target-network sync.  Replaces polyak_update (common/networks.py:121-139):
+ *   tau == 1 : target <- param;  else target <- fma(tau, param, fl((1 - tau) * target))   (mul_ then ATen's fused add(alpha))
+ *   params / targets : device arrays of n_tensors device pointers; sizes : device int64 [n_tensors]
+ */
+MORL_API int morl_polyak_f32(const float* const* params, float* const* targets, const int64_t* sizes, int n_tensors,
+                    int64_t max_size, double tau, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORL_B200_H_ */

@@ -1,0 +1,106 @@
+// pareto.cu -- warp-ballot Pareto dominance mask.
+//
+// Replaces get_non_pareto_dominated_inds (reference common/pareto.py:34-57), whose all-pairs broadcast builds two
+// N x N x D boolean temporaries plus a lexicographic np.unique.  Rule reproduced:
+//   keep[i] = no row j holds a DIFFERENT value that is >= pts[i] in every coordinate
+//             AND (remove_duplicates == 0 OR no j < i holds exactly the same value)
+//             AND pts[i] contains no NaN.
+// Comparisons are exact in the input dtype (fp32 or fp64); output order = input order.
+//
+// Mapping: grid = (i-tiles, j-splits).  A CTA stages a tile of IT candidate rows i in shared memory; each lane holds
+// one potential dominator row j in registers (coalesced global load), the warp walks the i-tile with broadcast
+// shared-memory reads, and one __ballot_sync per (i, 32 j's) tells the whole warp whether i was just killed.
+#include "common.cuh"
+
+namespace morl {
+
+constexpr int kParetoThreads = 256;
+constexpr int kParetoTile = 256;  // rows i per CTA
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kParetoThreads) pareto_init_kernel(const T* __restrict__ pts, int N, uint8_t* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        const T v = pts[(size_t)i * D + r];
+        ok = ok && (v == v);
+    }
+    keep[i] = ok ? 1 : 0;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kParetoThreads) pareto_mask_kernel(const T* __restrict__ pts, int N, int remove_duplicates,
+                                                                     int j_per_split, uint8_t* __restrict__ keep) {
+    __shared__ T xi_s[kParetoTile * D];
+    __shared__ uint8_t killed[kParetoTile];
+    const int i0 = blockIdx.x * kParetoTile;
+    const int ni = min(kParetoTile, N - i0);
+    for (int t = threadIdx.x; t < ni * D; t += blockDim.x) xi_s[t] = pts[(size_t)i0 * D + t];
+    for (int t = threadIdx.x; t < kParetoTile; t += blockDim.x) killed[t] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int jbeg = blockIdx.y * j_per_split;
+    const int jend = min(N, jbeg + j_per_split);
+
+    for (int jc = jbeg + warp * 32; jc < jend; jc += nwarps * 32) {
+        const int j = jc + lane;
+        const bool jvalid = j < jend;
+        T xj[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) xj[r] = jvalid ? pts[(size_t)j * D + r] : T(0);
+        for (int ii = 0; ii < ni; ++ii) {
+            bool ge = jvalid, eq = jvalid;
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                const T xi = xi_s[ii * D + r];  // warp-wide broadcast
+                ge = ge && (xj[r] >= xi);
+                eq = eq && (xj[r] == xi);
+            }
+            const bool kill = (ge && !eq) || (remove_duplicates && eq && (j < i0 + ii));
+            const unsigned m = __ballot_sync(0xffffffffu, kill);
+            if (m != 0u && lane == 0) killed[ii] = 1;  // benign same-value race between warps
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ni; t += blockDim.x)
+        if (killed[t]) keep[i0 + t] = 0;  // only ever cleared after pareto_init_kernel set it
+}
+
+template <typename T>
+static int pareto_launch(const char* fn, const T* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream) {
+    MORL_REQUIRE(pts && keep, MORL_ERR_NULL, "%s: NULL pointer argument", fn);
+    MORL_REQUIRE(N >= 0 && D > 0, MORL_ERR_SHAPE, "%s: bad shape N=%d D=%d", fn, N, D);
+    MORL_REQUIRE(D <= MORL_MAX_D, MORL_ERR_UNSUPPORTED, "%s: D=%d > %d", fn, D, MORL_MAX_D);
+    if (N == 0) return MORL_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int itiles = (N + kParetoTile - 1) / kParetoTile;
+    // enough CTAs for ~4 waves of 148 SMs, but never split j finer than one pass of the CTA's 8 warps
+    int jsplits = (4 * 148 + itiles - 1) / itiles;
+    const int max_splits = (N + kParetoThreads - 1) / kParetoThreads;
+    if (jsplits > max_splits) jsplits = max_splits;
+    if (jsplits < 1) jsplits = 1;
+    int j_per_split = (N + jsplits - 1) / jsplits;
+    j_per_split = (j_per_split + 31) / 32 * 32;
+    jsplits = (N + j_per_split - 1) / j_per_split;
+    const dim3 grid((unsigned)itiles, (unsigned)jsplits, 1);
+    MORL_DISPATCH_D(D, {
+        pareto_init_kernel<T, kD><<<(N + kParetoThreads - 1) / kParetoThreads, kParetoThreads, 0, st>>>(pts, N, keep);
+        pareto_mask_kernel<T, kD><<<grid, kParetoThreads, 0, st>>>(pts, N, remove_duplicates, j_per_split, keep);
+    });
+    return check_launch(fn);
+}
+
+}  // namespace morl
+
+extern "C" int morl_pareto_mask_f32(const float* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream) {
+    return morl::pareto_launch<float>("morl_pareto_mask_f32", pts, N, D, remove_duplicates, keep, stream);
+}
+
+extern "C" int morl_pareto_mask_f64(const double* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream) {
+    return morl::pareto_launch<double>("morl_pareto_mask_f64", pts, N, D, remove_duplicates, keep, stream);
+}

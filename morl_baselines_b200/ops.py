@@ -1,0 +1,276 @@
+"""Thin PyTorch-facing wrappers over the C-ABI (include/morl_b200.h).
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every operator below is one (or two) launches of a
+hand-written sm_100a kernel from libmorl_b200.so.  All wrappers require CUDA tensors and raise otherwise -- there is
+no CPU / eager fallback (the CPU restatement lives in oracle/ and is test-only).
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch as th
+
+from . import _lib
+from ._lib import (  # noqa: F401  (re-exported constants)
+    AC_ARGMIN_GATHER,
+    AC_ELEMENTWISE_MIN,
+    AC_SCALAR_MIN,
+    DOT_FMA,
+    DOT_PAIRFMA,
+    DOT_UNFUSED,
+    MAP_BLOCK,
+    MAP_TILE,
+    ROWS_BMAJOR,
+    ROWS_REFERENCE,
+)
+
+# number of kernels launched through this module (bench.py reports it as `gpu_launches`)
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _dev(t: th.Tensor, name: str, dtype=th.float32) -> th.Tensor:
+    if not isinstance(t, th.Tensor) or not t.is_cuda:
+        raise _lib.MorlB200Error(f"{name} must be a CUDA tensor (morl_baselines_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.MorlB200Error(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[th.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return th.cuda.current_stream().cuda_stream
+
+
+def envelope_td(q_online, q_target, wset, reward, done, gamma: float, dot_mode: int = DOT_UNFUSED, row_order: int = ROWS_REFERENCE,
+                want_indices: bool = True, out: Optional[th.Tensor] = None, pref_out=None, act_out=None):
+    """Fused envelope-max TD target (reference envelope.py:404-440 + :298).  q_*: [B, W, A, D]; returns
+    (target [W*B, D], pref [W*B] int32, act [W*B] int32)."""
+    q_online, q_target = _dev(q_online, "q_online"), _dev(q_target, "q_target")
+    B, W, A, D = q_online.shape
+    if q_target.shape != q_online.shape:
+        raise _lib.MorlB200Error("q_online / q_target shape mismatch")
+    wset, reward, done = _dev(wset, "wset"), _dev(reward, "reward"), _dev(done, "done")
+    if wset.shape != (W, D) or reward.shape != (B, D) or done.numel() != B:
+        raise _lib.MorlB200Error(f"bad shapes: wset {tuple(wset.shape)}, reward {tuple(reward.shape)}, done {tuple(done.shape)}")
+    if out is None:
+        out = th.empty((W * B, D), device=q_online.device, dtype=th.float32)
+    if want_indices:
+        pref_out = th.empty(W * B, device=q_online.device, dtype=th.int32) if pref_out is None else pref_out
+        act_out = th.empty(W * B, device=q_online.device, dtype=th.int32) if act_out is None else act_out
+    rc = _lib.load().morl_envelope_td_f32(_ptr(q_online), _ptr(q_target), _ptr(wset), _ptr(reward), _ptr(done), float(gamma), B, W, A, D,
+                                          dot_mode, row_order, _ptr(out), _ptr(pref_out), _ptr(act_out), _stream())
+    _lib.check(rc, "morl_envelope_td_f32")
+    _count()
+    return out, pref_out, act_out
+
+
+def _rows(t, D, name):
+    t = _dev(t, name)
+    return t.reshape(-1, D)
+
+
+def greedy_td(q_select, q_eval, w, reward=None, done=None, gamma: float = 0.0, dot_mode: int = DOT_UNFUSED, w_map: int = MAP_BLOCK,
+              r_map: int = MAP_TILE):
+    """Double-DQN target with per-row weights (reference envelope.py:442-463).  q_*: [N, A, D]."""
+    q_select, q_eval = _dev(q_select, "q_select"), _dev(q_eval, "q_eval")
+    N, A, D = q_select.shape
+    w = _rows(w, D, "w")
+    if reward is not None:
+        reward, done = _rows(reward, D, "reward"), _dev(done, "done").reshape(-1)
+    out = th.empty((N, D), device=q_select.device, dtype=th.float32)
+    act = th.empty(N, device=q_select.device, dtype=th.int32)
+    rc = _lib.load().morl_greedy_td_f32(_ptr(q_select), _ptr(q_eval), _ptr(w), w.shape[0], w_map, _ptr(reward), _ptr(done),
+                                        N if reward is None else reward.shape[0], r_map, float(gamma), N, A, D, dot_mode, _ptr(out),
+                                        _ptr(act), _stream())
+    _lib.check(rc, "morl_greedy_td_f32")
+    _count()
+    return out, act
+
+
+def critic_min_td(q_nets, w, reward=None, done=None, gamma: float = 0.0, dot_mode: int = DOT_UNFUSED, w_map: int = MAP_BLOCK,
+                  r_map: int = MAP_TILE):
+    """GPI-PD critic-min greedy target (reference gpi_pd.py:445-463).  q_nets: [n_nets, N, A, D]."""
+    q_nets = _dev(q_nets, "q_nets")
+    n_nets, N, A, D = q_nets.shape
+    w = _rows(w, D, "w")
+    if reward is not None:
+        reward, done = _rows(reward, D, "reward"), _dev(done, "done").reshape(-1)
+    out = th.empty((N, D), device=q_nets.device, dtype=th.float32)
+    act = th.empty(N, device=q_nets.device, dtype=th.int32)
+    rc = _lib.load().morl_critic_min_td_f32(_ptr(q_nets), n_nets, _ptr(w), w.shape[0], w_map, _ptr(reward), _ptr(done),
+                                            N if reward is None else reward.shape[0], r_map, float(gamma), N, A, D, dot_mode, _ptr(out),
+                                            _ptr(act), _stream())
+    _lib.check(rc, "morl_critic_min_td_f32")
+    _count()
+    return out, act
+
+
+def gpi_envelope(q_nets, w, reward=None, done=None, gamma: float = 0.0, dot_mode: int = DOT_UNFUSED, w_map: int = MAP_BLOCK,
+                 r_map: int = MAP_TILE):
+    """GPI envelope / policy-set evaluation (reference gpi_pd.py:662-690, 564-582).  q_nets: [n_nets, B, P, A, D];
+    returns (out [B, D], policy [B] int32, action [B] int32)."""
+    q_nets = _dev(q_nets, "q_nets")
+    n_nets, B, P, A, D = q_nets.shape
+    w = _rows(w, D, "w")
+    if reward is not None:
+        reward, done = _rows(reward, D, "reward"), _dev(done, "done").reshape(-1)
+    out = th.empty((B, D), device=q_nets.device, dtype=th.float32)
+    pol = th.empty(B, device=q_nets.device, dtype=th.int32)
+    act = th.empty(B, device=q_nets.device, dtype=th.int32)
+    rc = _lib.load().morl_gpi_envelope_f32(_ptr(q_nets), n_nets, _ptr(w), w.shape[0], w_map, _ptr(reward), _ptr(done),
+                                           B if reward is None else reward.shape[0], r_map, float(gamma), B, P, A, D, dot_mode, _ptr(out),
+                                           _ptr(pol), _ptr(act), _stream())
+    _lib.check(rc, "morl_gpi_envelope_f32")
+    _count()
+    return out, pol, act
+
+
+def actor_critic_td(q_nets, w, reward, done, logp, alpha: float, gamma: float, variant: int, w_map: int = MAP_BLOCK):
+    """Continuous-action vector targets (CAPQL / MOSAC / TD3-style GPI-PD).  q_nets: [n_nets, N, D]."""
+    q_nets = _dev(q_nets, "q_nets")
+    n_nets, N, D = q_nets.shape
+    reward, done = _dev(reward, "reward").reshape(N, D), _dev(done, "done").reshape(-1)
+    if w is not None:
+        w = _rows(w, D, "w")
+    if logp is not None:
+        logp = _dev(logp, "logp").reshape(-1)
+    out = th.empty((N,) if variant == AC_SCALAR_MIN else (N, D), device=q_nets.device, dtype=th.float32)
+    rc = _lib.load().morl_actor_critic_td_f32(_ptr(q_nets), n_nets, _ptr(w), 0 if w is None else w.shape[0], w_map, _ptr(reward), _ptr(done),
+                                              _ptr(logp), float(alpha), float(gamma), N, D, variant, _ptr(out), _stream())
+    _lib.check(rc, "morl_actor_critic_td_f32")
+    _count()
+    return out
+
+
+def td_workspace(n_rows: int, device) -> th.Tensor:
+    nbytes = _lib.load().morl_td_workspace_bytes(int(n_rows))
+    return th.empty((nbytes + 3) // 4, device=device, dtype=th.float32)
+
+
+def td_mse_priority(q_values, action, target_q, wset, homotopy_lambda: float, B: int, W: int, row_order: int = ROWS_REFERENCE,
+                    want_grad: bool = True, want_prio: bool = True, workspace: Optional[th.Tensor] = None, loss_out=None, grad_out=None,
+                    prio_out=None, q_taken_out=None):
+    """Fused Envelope TD loss + d loss / d q_values + priorities (reference envelope.py:301-313, 329-331)."""
+    q_values = _dev(q_values, "q_values")
+    N, A, D = q_values.shape
+    if N != B * W:
+        raise _lib.MorlB200Error(f"q_values has {N} rows, expected B*W = {B * W}")
+    action = _dev(action, "action", th.int32).reshape(-1)
+    target_q, wset = _dev(target_q, "target_q"), _dev(wset, "wset")
+    dev = q_values.device
+    loss = th.empty(1, device=dev, dtype=th.float32) if loss_out is None else loss_out
+    grad = (th.empty_like(q_values) if grad_out is None else grad_out) if want_grad else None
+    prio = (th.empty(B, device=dev, dtype=th.float32) if prio_out is None else prio_out) if want_prio else None
+    ws = td_workspace(N, dev) if workspace is None else workspace
+    rc = _lib.load().morl_td_mse_priority_f32(_ptr(q_values), _ptr(action), _ptr(target_q), _ptr(wset), float(homotopy_lambda), B, W, A, D,
+                                              row_order, _ptr(loss), _ptr(grad), _ptr(q_taken_out), _ptr(prio), _ptr(ws), _stream())
+    _lib.check(rc, "morl_td_mse_priority_f32")
+    _count(2)
+    return loss, grad, prio
+
+
+def td_huber_priority(q_values, action, target_q, target_q_gpi, w, min_priority: float, p_rows: int, w_map: int = MAP_BLOCK,
+                      want_grad: bool = True, workspace: Optional[th.Tensor] = None):
+    """GPI-PD Huber-style loss, gradient seed and raw priorities (reference gpi_pd.py:469-487, 507-520)."""
+    q_values = _dev(q_values, "q_values")
+    n_nets, N, A, D = q_values.shape
+    action = _dev(action, "action", th.int32).reshape(-1)
+    target_q = _dev(target_q, "target_q")
+    if target_q_gpi is not None:
+        target_q_gpi = _dev(target_q_gpi, "target_q_gpi")
+    w = _rows(w, D, "w")
+    dev = q_values.device
+    loss = th.empty(1, device=dev, dtype=th.float32)
+    grad = th.empty_like(q_values) if want_grad else None
+    prio = th.empty(p_rows, device=dev, dtype=th.float32) if p_rows > 0 else None
+    ws = td_workspace(N, dev) if workspace is None else workspace
+    rc = _lib.load().morl_td_huber_priority_f32(_ptr(q_values), n_nets, _ptr(action), action.shape[0], _ptr(target_q), _ptr(target_q_gpi),
+                                                _ptr(w), w.shape[0], w_map, float(min_priority), N, A, D, p_rows, _ptr(loss), _ptr(grad),
+                                                _ptr(prio), _ptr(ws), _stream())
+    _lib.check(rc, "morl_td_huber_priority_f32")
+    _count(2)
+    return loss, grad, prio
+
+
+def replay_gather(obs_store, next_obs_store, act_store, rew_store, done_store, idx, outs=None):
+    """Gather a minibatch from device-resident stores (reference buffer.py:82-94).  Returns
+    (obs, actions, rewards, next_obs, dones); uint8 actions come back as int32."""
+    obs_store, next_obs_store = _dev(obs_store, "obs_store"), _dev(next_obs_store, "next_obs_store")
+    rew_store, done_store = _dev(rew_store, "rew_store"), _dev(done_store, "done_store")
+    idx = _dev(idx, "idx", th.int64).reshape(-1)
+    cap, obs_dim = obs_store.shape[0], obs_store[0].numel()
+    is_u8 = act_store.dtype == th.uint8
+    act_store = _dev(act_store, "act_store", th.uint8 if is_u8 else th.float32)
+    act_dim, rew_dim = act_store[0].numel(), rew_store[0].numel()
+    B = idx.shape[0]
+    dev = obs_store.device
+    if outs is None:
+        obs = th.empty((B,) + tuple(obs_store.shape[1:]), device=dev, dtype=th.float32)
+        nobs = th.empty_like(obs)
+        act = th.empty((B, act_dim), device=dev, dtype=th.int32 if is_u8 else th.float32)
+        rew = th.empty((B, rew_dim), device=dev, dtype=th.float32)
+        done = th.empty((B, 1), device=dev, dtype=th.float32)
+    else:
+        obs, act, rew, nobs, done = outs
+    rc = _lib.load().morl_replay_gather(_ptr(obs_store), _ptr(next_obs_store), _ptr(act_store), _ptr(rew_store), _ptr(done_store), _ptr(idx),
+                                        B, obs_dim, act_dim, rew_dim, int(is_u8), cap, _ptr(obs), _ptr(nobs), _ptr(act), _ptr(rew), _ptr(done),
+                                        _stream())
+    _lib.check(rc, "morl_replay_gather")
+    _count()
+    return obs, act, rew, nobs, done
+
+
+def pareto_mask(points: th.Tensor, remove_duplicates: bool = True) -> th.Tensor:
+    """Non-dominated mask (reference pareto.py:34-57) of an [N, D] fp32 / fp64 CUDA tensor -> bool [N]."""
+    if not points.is_cuda:
+        raise _lib.MorlB200Error("points must be a CUDA tensor (morl_baselines_b200 has no CPU fallback)")
+    if points.dtype not in (th.float32, th.float64):
+        raise _lib.MorlB200Error(f"points must be float32 or float64, got {points.dtype}")
+    points = points.contiguous()
+    N, D = points.shape
+    keep = th.empty(N, device=points.device, dtype=th.uint8)
+    fn = _lib.load().morl_pareto_mask_f32 if points.dtype == th.float32 else _lib.load().morl_pareto_mask_f64
+    rc = fn(_ptr(points), N, D, int(bool(remove_duplicates)), _ptr(keep), _stream())
+    _lib.check(rc, "morl_pareto_mask")
+    _count(2)
+    return keep.bool()
+
+
+class PolyakPlan:
+    """Device-side (param, target, size) table for morl_polyak_f32; build once per pair of networks."""
+
+    def __init__(self, params, targets):
+        params, targets = list(params), list(targets)
+        assert len(params) == len(targets) and len(params) > 0
+        for p, t in zip(params, targets):
+            if not (p.is_cuda and t.is_cuda and p.dtype == th.float32 and t.dtype == th.float32 and p.is_contiguous() and t.is_contiguous()):
+                raise _lib.MorlB200Error("polyak: parameters must be contiguous float32 CUDA tensors")
+            assert p.numel() == t.numel()
+        dev = params[0].device
+        self.keepalive = (params, targets)
+        self.p_tab = th.tensor([p.data_ptr() for p in params], dtype=th.int64, device=dev)
+        self.t_tab = th.tensor([t.data_ptr() for t in targets], dtype=th.int64, device=dev)
+        self.sizes = th.tensor([p.numel() for p in params], dtype=th.int64, device=dev)
+        self.n = len(params)
+        self.max_size = max(p.numel() for p in params)
+
+    def run(self, tau: float):
+        rc = _lib.load().morl_polyak_f32(_ptr(self.p_tab), _ptr(self.t_tab), _ptr(self.sizes), self.n, self.max_size, float(tau), _stream())
+        _lib.check(rc, "morl_polyak_f32")
+        _count()
+
+
+def sm_count() -> int:
+    n = _lib.load().morl_device_sm_count()
+    if n < 0:
+        _lib.check(n, "morl_device_sm_count")
+    return n
