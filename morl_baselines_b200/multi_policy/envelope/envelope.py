@@ -1,0 +1,537 @@
+"""Envelope Q-Learning on the B200 update engine (drop-in for reference
+morl_baselines/multi_policy/envelope/envelope.py: same constructor, attributes, ``update / eval / act / max_action /
+envelope_target / ddqn_target / train / save / load / get_config``).
+
+What changes under the API:
+  * the envelope target is evaluated on the B*|W| DISTINCT (s'_b, w_j) rows, not on the reference's B*|W|^2 tiled rows
+    (envelope.py:284-291, 416-418) -- bit-identical result, |W| times fewer MLP rows;
+  * the first dense layer is applied separably, h1[b, j] = relu(W1_s s_b + (W1_w w_j + b1)), so the [s || w] concat
+    (envelope.py:75) is never materialised;
+  * einsum -> max -> argmax -> gather x2 -> Bellman (envelope.py:422-440, 298) is ONE kernel (morl_envelope_td_f32);
+    gather -> MSE -> homotopy loss -> d loss/d q -> PER priorities (envelope.py:301-313, 329-331) is ONE kernel
+    (morl_td_mse_priority_f32); the minibatch gather reads a replay store resident in HBM (morl_replay_gather);
+    the target sync is one multi-tensor launch (morl_polyak_f32);
+  * the whole gradient update is captured in a CUDA graph and replayed (no host sync inside).
+Dense layers run through cuBLAS FP32 (TF32 disabled) via torch autograd.  Everything requires a CUDA device.
+"""
+
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Union
+
+import numpy as np
+import torch as th
+import torch.nn as nn
+import torch.optim as optim
+
+from ... import ops
+from ...common.buffer import ReplayBuffer
+from ...common.morl_algorithm import MOAgent, MOPolicy
+from ...common.networks import NatureCNN, get_grad_norm, layer_init, mlp, polyak_update
+from ...common.prioritized_buffer import PrioritizedReplayBuffer
+from ...common.utils import linearly_decaying_value
+from ...common.weights import equally_spaced_weights, random_weights
+
+
+class QNet(nn.Module):
+    """Weight-conditioned vector Q-network; parameter names equal the reference's (envelope.py:33-77)."""
+
+    def __init__(self, obs_shape, action_dim, rew_dim, net_arch):
+        super().__init__()
+        self.obs_shape = obs_shape
+        self.action_dim = action_dim
+        self.rew_dim = rew_dim
+        if len(obs_shape) == 1:
+            self.feature_extractor = None
+            self.feat_dim = obs_shape[0]
+        else:
+            self.feature_extractor = NatureCNN(self.obs_shape, features_dim=512)
+            self.feat_dim = self.feature_extractor.features_dim
+        self.net = mlp(self.feat_dim + rew_dim, action_dim * rew_dim, net_arch)
+        self.apply(layer_init)
+
+    def forward(self, obs, w):
+        """Q(s, w) for paired rows, the reference's calling convention: [N, A, D]."""
+        feats = self.feature_extractor(obs) if self.feature_extractor is not None else obs
+        if w.dim() == 1 and feats.dim() > 1:
+            w = w.unsqueeze(0)
+        x = th.cat((feats, w), dim=w.dim() - 1)
+        return self.net(x).view(-1, self.action_dim, self.rew_dim)
+
+    def forward_pairs(self, obs, wset):
+        """Q(s_b, w_j) for every pair: obs [B, ...], wset [W, D] -> [B, W, A, D] (row b*W + j of the flattened batch).
+        The first Linear is split column-wise: W1 [s || w] + b1 = W1_s s + (W1_w w + b1)."""
+        feats = self.feature_extractor(obs) if self.feature_extractor is not None else obs
+        first = self.net[0]
+        B, W = feats.shape[0], wset.shape[0]
+        u = feats @ first.weight[:, : self.feat_dim].t()  # [B, H]
+        v = th.addmm(first.bias, wset, first.weight[:, self.feat_dim :].t())  # [W, H]
+        h = (u.unsqueeze(1) + v.unsqueeze(0)).view(B * W, -1)
+        h = self.net[1:](h)
+        return h.view(B, W, self.action_dim, self.rew_dim)
+
+
+class _FusedTDLoss(th.autograd.Function):
+    """critic loss of envelope.py:301-313 as one kernel; backward hands the precomputed d loss / d q_values upstream."""
+
+    @staticmethod
+    def forward(ctx, q_values, action, target_q, wset, lam, B, W, workspace, prio_out):
+        loss, grad, _ = ops.td_mse_priority(q_values.detach(), action, target_q, wset, lam, B, W, ops.ROWS_BMAJOR, want_grad=True,
+                                            want_prio=prio_out is not None, workspace=workspace, prio_out=prio_out)
+        ctx.save_for_backward(grad)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None, None, None, None, None, None, None, None
+
+
+class Envelope(MOPolicy, MOAgent):
+    """Envelope Q-Learning (R. Yang, X. Sun, K. Narasimhan, NeurIPS 2019) -- see the module docstring."""
+
+    def __init__(
+        self,
+        env,
+        learning_rate: float = 3e-4,
+        initial_epsilon: float = 0.01,
+        final_epsilon: float = 0.01,
+        epsilon_decay_steps: int = None,
+        tau: float = 1.0,
+        target_net_update_freq: int = 200,
+        buffer_size: int = int(1e6),
+        net_arch: List = [256, 256, 256, 256],
+        batch_size: int = 256,
+        learning_starts: int = 100,
+        gradient_updates: int = 1,
+        gamma: float = 0.99,
+        max_grad_norm: Optional[float] = 1.0,
+        envelope: bool = True,
+        num_sample_w: int = 4,
+        per: bool = True,
+        per_alpha: float = 0.6,
+        initial_homotopy_lambda: float = 0.0,
+        final_homotopy_lambda: float = 1.0,
+        homotopy_decay_steps: int = None,
+        project_name: str = "MORL-Baselines",
+        experiment_name: str = "Envelope",
+        wandb_entity: Optional[str] = None,
+        log: bool = True,
+        seed: Optional[int] = None,
+        device: Union[th.device, str] = "auto",
+        group: Optional[str] = None,
+        use_cuda_graph: bool = True,
+        replay_on_device: bool = True,
+    ):
+        MOAgent.__init__(self, env, device=device, seed=seed)
+        MOPolicy.__init__(self, device=device)
+        if self.device.type != "cuda":
+            raise ops._lib.MorlB200Error("morl_baselines_b200.Envelope needs a CUDA device: the update path is CUDA-only (no CPU fallback)")
+        ops._lib.load()
+        self.learning_rate = learning_rate
+        self.initial_epsilon = initial_epsilon
+        self.epsilon = initial_epsilon
+        self.epsilon_decay_steps = epsilon_decay_steps
+        self.final_epsilon = final_epsilon
+        self.tau = tau
+        self.target_net_update_freq = target_net_update_freq
+        self.gamma = gamma
+        self.max_grad_norm = max_grad_norm
+        self.buffer_size = buffer_size
+        self.net_arch = net_arch
+        self.learning_starts = learning_starts
+        self.batch_size = batch_size
+        self.per = per
+        self.per_alpha = per_alpha
+        self.gradient_updates = gradient_updates
+        self.initial_homotopy_lambda = initial_homotopy_lambda
+        self.final_homotopy_lambda = final_homotopy_lambda
+        self.homotopy_decay_steps = homotopy_decay_steps
+
+        self.q_net = QNet(self.observation_shape, self.action_dim, self.reward_dim, net_arch=net_arch).to(self.device)
+        self.target_q_net = QNet(self.observation_shape, self.action_dim, self.reward_dim, net_arch=net_arch).to(self.device)
+        self.target_q_net.load_state_dict(self.q_net.state_dict())
+        for p in self.target_q_net.parameters():
+            p.requires_grad = False
+        self.q_optim = optim.Adam(self.q_net.parameters(), lr=self.learning_rate, capturable=True)
+
+        self.envelope = envelope
+        self.num_sample_w = num_sample_w
+        self.homotopy_lambda = self.initial_homotopy_lambda
+        buf_cls = PrioritizedReplayBuffer if self.per else ReplayBuffer
+        self.replay_buffer = buf_cls(self.observation_shape, 1, rew_dim=self.reward_dim, max_size=buffer_size, action_dtype=np.uint8,
+                                     device=self.device if replay_on_device else None)
+        self.dot_mode = ops.DOT_UNFUSED
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self._static = None
+        self._last_loss = None
+        self._last_priority = None
+        self.log = log
+        if log:
+            self.setup_wandb(project_name, experiment_name, wandb_entity, group)
+
+    # ------------------------------------------------------------------------------------------ config / io
+    def get_config(self):
+        return {
+            "env_id": self.env.unwrapped.spec.id,
+            "learning_rate": self.learning_rate,
+            "initial_epsilon": self.initial_epsilon,
+            "epsilon_decay_steps": self.epsilon_decay_steps,
+            "batch_size": self.batch_size,
+            "tau": self.tau,
+            "clip_grand_norm": self.max_grad_norm,
+            "target_net_update_freq": self.target_net_update_freq,
+            "gamma": self.gamma,
+            "use_envelope": self.envelope,
+            "num_sample_w": self.num_sample_w,
+            "net_arch": self.net_arch,
+            "per": self.per,
+            "gradient_updates": self.gradient_updates,
+            "buffer_size": self.buffer_size,
+            "initial_homotopy_lambda": self.initial_homotopy_lambda,
+            "final_homotopy_lambda": self.final_homotopy_lambda,
+            "homotopy_decay_steps": self.homotopy_decay_steps,
+            "learning_starts": self.learning_starts,
+            "seed": self.seed,
+        }
+
+    def save(self, save_replay_buffer: bool = True, save_dir: str = "weights/", filename: Optional[str] = None):
+        """Checkpoint with the reference's keys (envelope.py:230-247)."""
+        os.makedirs(save_dir, exist_ok=True)
+        params = {"q_net_state_dict": self.q_net.state_dict(), "q_net_optimizer_state_dict": self.q_optim.state_dict()}
+        if save_replay_buffer:
+            params["replay_buffer"] = self.replay_buffer
+        filename = getattr(self, "experiment_name", "Envelope") if filename is None else filename
+        th.save(params, save_dir + "/" + filename + ".tar")
+
+    def load(self, path: str, load_replay_buffer: bool = True):
+        """Load a checkpoint written by this class or by the reference (envelope.py:249-261).  Tensors are overwritten in
+        place so a captured CUDA graph stays valid."""
+        params = th.load(path, weights_only=False, map_location=self.device)
+        with th.no_grad():
+            for net in (self.q_net, self.target_q_net):
+                sd = net.state_dict()
+                for k, v in params["q_net_state_dict"].items():
+                    sd[k].copy_(v)
+        self._load_optimizer_inplace(params["q_net_optimizer_state_dict"])
+        if load_replay_buffer and "replay_buffer" in params:
+            self.replay_buffer = params["replay_buffer"]
+            if hasattr(self.replay_buffer, "to"):
+                self.replay_buffer.to(self.device)
+
+    def _load_optimizer_inplace(self, sd):
+        cur = self.q_optim.state_dict()
+        if len(cur["state"]) == 0 or not self._graphs:
+            self.q_optim.load_state_dict(sd)
+            self._graphs = {}  # state tensors were re-created: re-capture lazily
+            return
+        for gi, g in enumerate(sd["param_groups"]):
+            for k, v in g.items():
+                if k != "params":
+                    self.q_optim.param_groups[gi][k] = v
+        params = [p for g in self.q_optim.param_groups for p in g["params"]]
+        for pid, st in sd["state"].items():
+            dst = self.q_optim.state[params[pid]]
+            for k, v in st.items():
+                if th.is_tensor(v):
+                    dst[k].copy_(v)
+                else:
+                    dst[k] = v
+
+    # ------------------------------------------------------------------------------------------ the update
+    def _ensure_static(self):
+        if self._static is not None:
+            return self._static
+        dev, B, W, D = self.device, self.batch_size, self.num_sample_w, self.reward_dim
+        s = {
+            "idx": th.zeros(B, dtype=th.int64, device=dev),
+            "wset": th.full((W, D), 1.0 / D, dtype=th.float32, device=dev),
+            "loss": th.zeros((), dtype=th.float32, device=dev),
+            "prio": th.zeros(B, dtype=th.float32, device=dev),
+            "ws": ops.td_workspace(B * W, dev),
+            "idx_pin": th.zeros(B, dtype=th.int64).pin_memory(),
+            "wset_pin": th.zeros((W, D), dtype=th.float32).pin_memory(),
+            "prio_pin": th.zeros(B, dtype=th.float32).pin_memory(),
+            "h2d_done": th.cuda.Event(),  # guards the pinned staging buffers against being overwritten while a copy is pending
+        }
+        self._static = s
+        return s
+
+    def _gradient_step(self, obs, act, rew, nobs, done, wset):
+        """One gradient update on device tensors (everything between sampling and the priority write-back)."""
+        s = self._static
+        B, W, A, D = obs.shape[0], wset.shape[0], self.action_dim, self.reward_dim
+        with th.no_grad():
+            q_on = self.q_net.forward_pairs(nobs, wset)  # online net selects   (envelope.py:420)
+            q_tg = self.target_q_net.forward_pairs(nobs, wset)  # target net evaluates (envelope.py:429)
+            done1 = done.reshape(-1)
+            if self.envelope:
+                target_q, _, _ = ops.envelope_td(q_on, q_tg, wset, rew, done1, self.gamma, self.dot_mode, ops.ROWS_BMAJOR, want_indices=False)
+            else:
+                target_q, _ = ops.greedy_td(q_on.view(B * W, A, D), q_tg.view(B * W, A, D), wset, rew, done1, self.gamma, self.dot_mode,
+                                            ops.MAP_TILE, ops.MAP_BLOCK)
+        q_values = self.q_net.forward_pairs(obs, wset).view(B * W, A, D)
+        loss = _FusedTDLoss.apply(q_values, act.reshape(-1), target_q, wset, float(self.homotopy_lambda), B, W, s["ws"],
+                                  s["prio"] if self.per else None)
+        self.q_optim.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.max_grad_norm is not None:
+            th.nn.utils.clip_grad_norm_(self.q_net.parameters(), self.max_grad_norm)
+        self.q_optim.step()
+        s["loss"].copy_(loss.detach())
+
+    def _step(self, mode: str):
+        """What one CUDA graph captures.  mode "device": gather from the HBM-resident store by the static index buffer, then
+        the gradient step; mode "host": the gradient step on the static staging tensors the host minibatch was copied into."""
+        s = self._static
+        if mode == "device":
+            obs_s, nobs_s, act_s, rew_s, done_s = self.replay_buffer.device_stores()
+            obs, act, rew, nobs, done = ops.replay_gather(obs_s, nobs_s, act_s, rew_s, done_s, s["idx"])
+        else:
+            st = s["stage"]
+            obs, act, rew, nobs, done = st["obs"][1], st["act"][1], st["rew"][1], st["nobs"][1], st["done"][1]
+        self._gradient_step(obs, act, rew, nobs, done, s["wset"])
+
+    def _snapshot(self):
+        snap = {"p": [p.detach().clone() for p in self.q_net.parameters()], "o": []}
+        for p in self.q_net.parameters():
+            st = self.q_optim.state.get(p, None)
+            snap["o"].append(None if not st else {k: (v.clone() if th.is_tensor(v) else v) for k, v in st.items()})
+        return snap
+
+    def _restore(self, snap):
+        with th.no_grad():
+            for p, saved, st_saved in zip(self.q_net.parameters(), snap["p"], snap["o"]):
+                p.copy_(saved)
+                st = self.q_optim.state.get(p, None)
+                if st:
+                    for k, v in st.items():
+                        if th.is_tensor(v):
+                            v.copy_(st_saved[k]) if st_saved is not None else v.zero_()
+
+    def _capture(self, mode: str):
+        """Warm up on a side stream, capture one step into a CUDA graph, then restore parameters and optimiser state IN
+        PLACE so the warm-up iterations leave no trace (parity with the reference's update count)."""
+        self._ensure_static()
+        if mode == "device":
+            self.replay_buffer.flush()
+        else:
+            self._ensure_stage()
+        snap = self._snapshot()
+        side = th.cuda.Stream()
+        side.wait_stream(th.cuda.current_stream())
+        with th.cuda.stream(side):
+            for _ in range(3):
+                self._step(mode)
+        th.cuda.current_stream().wait_stream(side)
+        g = th.cuda.CUDAGraph()
+        before = ops.launch_count
+        with th.cuda.graph(g):
+            self._step(mode)
+        self.launches_per_step = ops.launch_count - before
+        self._restore(snap)
+        self._graphs[mode] = g
+        return g
+
+    def _lambda_is_static(self):
+        return self.homotopy_decay_steps is None
+
+    def __sample_indices(self):
+        if self.per:
+            return self.replay_buffer.tree.sample(self.batch_size)
+        return self.replay_buffer._draw(self.batch_size)
+
+    def update(self):
+        """``gradient_updates`` gradient steps + target sync + schedules (reference envelope.py:266-367)."""
+        s = self._ensure_static()
+        rb = self.replay_buffer
+        has_mirror = getattr(rb, "_dev", None) is not None
+        critic_losses = []
+        priority = None
+        for _ in range(self.gradient_updates):
+            # RNG consumption order of the reference: replay indices (global numpy RNG) first, then the weights (self.np_random)
+            s["h2d_done"].synchronize()
+            if has_mirror:
+                b_inds = self.__sample_indices()
+                s["idx_pin"].copy_(th.from_numpy(np.ascontiguousarray(b_inds, dtype=np.int64)))
+                s["idx"].copy_(s["idx_pin"], non_blocking=True)
+            else:
+                smp = rb.sample(self.batch_size)  # host-resident buffer: the minibatch crosses PCIe every update
+                b_inds = smp[5]
+                self._stage_host_batch(smp)
+            w_np = random_weights(dim=self.reward_dim, n=self.num_sample_w, dist="gaussian", rng=self.np_random)
+            s["wset_pin"].copy_(th.from_numpy(np.asarray(w_np, dtype=np.float64).reshape(self.num_sample_w, -1)).float())
+            s["wset"].copy_(s["wset_pin"], non_blocking=True)
+            s["h2d_done"].record()
+
+            mode = "device" if has_mirror else "host"
+            if self.use_cuda_graph and self._lambda_is_static():
+                g = self._graphs.get(mode) or self._capture(mode)
+                if has_mirror:
+                    rb.flush()
+                g.replay()
+            else:
+                self._step(mode)
+            critic_losses.append(s["loss"])
+
+            if self.per:
+                s["prio_pin"].copy_(s["prio"], non_blocking=True)
+                th.cuda.current_stream().synchronize()
+                priority = s["prio_pin"].numpy().copy()
+                priority = (priority + rb.min_priority) ** self.per_alpha  # envelope.py:333
+                rb.update_priorities(b_inds, priority)
+
+        if self.tau != 1 or self.global_step % self.target_net_update_freq == 0:
+            polyak_update(self.q_net.parameters(), self.target_q_net.parameters(), self.tau)
+        if self.epsilon_decay_steps is not None:
+            self.epsilon = linearly_decaying_value(self.initial_epsilon, self.epsilon_decay_steps, self.global_step, self.learning_starts,
+                                                   self.final_epsilon)
+        if self.homotopy_decay_steps is not None:
+            self.homotopy_lambda = linearly_decaying_value(self.initial_homotopy_lambda, self.homotopy_decay_steps, self.global_step,
+                                                           self.learning_starts, self.final_homotopy_lambda)
+        self._last_loss = critic_losses[-1] if critic_losses else None
+        self._last_priority = priority
+        if self.log and self.global_step % 100 == 0:
+            import wandb
+
+            wandb.log({"losses/critic_loss": float(th.stack(critic_losses).mean()), "metrics/epsilon": self.epsilon,
+                       "metrics/homotopy_lambda": self.homotopy_lambda, "global_step": self.global_step})
+            wandb.log({"losses/grad_norm": get_grad_norm(self.q_net.parameters()).item(), "global_step": self.global_step})
+            if self.per:
+                wandb.log({"metrics/mean_priority": np.mean(priority)})
+
+    def _stage_host_batch(self, smp):
+        """Host minibatch (numpy) -> pinned staging -> device, asynchronously (replaces the reference's six synchronous
+        th.tensor(x, device) copies, buffer.py:93-94)."""
+        s = self._static
+        self._ensure_stage()
+        st = s["stage"]
+        obs, act, rew, nobs, done = smp[0], smp[1], smp[2], smp[3], smp[4]
+        for key, arr in (("obs", obs), ("act", np.asarray(act).astype(np.int32)), ("rew", rew), ("nobs", nobs), ("done", done)):
+            pin, dev = st[key]
+            pin.copy_(th.from_numpy(np.ascontiguousarray(arr)).reshape(pin.shape))
+            dev.copy_(pin, non_blocking=True)
+
+    def _ensure_stage(self):
+        s = self._ensure_static()
+        if s.get("stage") is None:
+            B = self.batch_size
+            shapes = {"obs": ((B,) + tuple(self.observation_shape), th.float32), "act": ((B, 1), th.int32),
+                      "rew": ((B, self.reward_dim), th.float32), "nobs": ((B,) + tuple(self.observation_shape), th.float32),
+                      "done": ((B, 1), th.float32)}
+            s["stage"] = {k: (th.zeros(sh, dtype=dt).pin_memory(), th.zeros(sh, dtype=dt, device=self.device)) for k, (sh, dt) in shapes.items()}
+        return s["stage"]
+
+    # ------------------------------------------------------------------------------------------ acting
+    def eval(self, obs: np.ndarray, w: np.ndarray) -> int:
+        obs = th.as_tensor(obs).float().to(self.device)
+        w = th.as_tensor(w).float().to(self.device)
+        return self.max_action(obs, w)
+
+    def act(self, obs: th.Tensor, w: th.Tensor) -> int:
+        """Epsilon-greedy action (reference envelope.py:375-387)."""
+        if self.np_random.random() < self.epsilon:
+            return self.env.action_space.sample()
+        return self.max_action(obs, w)
+
+    @th.no_grad()
+    def max_action(self, obs: th.Tensor, w: th.Tensor) -> int:
+        """argmax_a w . Q(obs, w)[a] (reference envelope.py:389-402); scalarise + argmax is one kernel."""
+        q = self.q_net(obs, w)  # [1, A, D]
+        _, _, act = ops.gpi_envelope(q.view(1, 1, 1, self.action_dim, self.reward_dim), w.reshape(1, -1), dot_mode=self.dot_mode)
+        return int(act.item())
+
+    @th.no_grad()
+    def envelope_target(self, obs: th.Tensor, w: th.Tensor, sampled_w: th.Tensor) -> th.Tensor:
+        """Reference calling convention (envelope.py:404-440): ``obs`` is the |W|-times tiled next-observation batch
+        [W*B, ...], ``w`` the repeat_interleaved weights [W*B, D]; returns max_next_q [W*B, D] in the reference row order.
+        Only the first B rows of ``obs`` are distinct; Q is evaluated on B*W rows."""
+        W = sampled_w.size(0)
+        B = obs.size(0) // W
+        nobs = obs[:B]
+        q_on = self.q_net.forward_pairs(nobs, sampled_w)
+        q_tg = self.target_q_net.forward_pairs(nobs, sampled_w)
+        zeros_r = th.zeros(B, self.reward_dim, device=obs.device)
+        out, _, _ = ops.envelope_td(q_on, q_tg, sampled_w, zeros_r, th.zeros(B, device=obs.device), 1.0, self.dot_mode, ops.ROWS_REFERENCE,
+                                    want_indices=False)
+        return out  # 0 + ((1 - 0) * 1) * q == q exactly
+
+    @th.no_grad()
+    def ddqn_target(self, obs: th.Tensor, w: th.Tensor) -> th.Tensor:
+        """Double-DQN target for paired rows (reference envelope.py:442-463)."""
+        q_sel = self.q_net(obs, w)
+        q_eval = self.target_q_net(obs, w)
+        out, _ = ops.greedy_td(q_sel, q_eval, w, dot_mode=self.dot_mode)
+        return out
+
+    # ------------------------------------------------------------------------------------------ training loop
+    def train(
+        self,
+        total_timesteps: int,
+        eval_env=None,
+        ref_point: Optional[np.ndarray] = None,
+        known_pareto_front: Optional[List[np.ndarray]] = None,
+        weight: Optional[np.ndarray] = None,
+        total_episodes: Optional[int] = None,
+        reset_num_timesteps: bool = True,
+        eval_freq: int = 10000,
+        num_eval_weights_for_front: int = 100,
+        num_eval_episodes_for_front: int = 5,
+        num_eval_weights_for_eval: int = 50,
+        reset_learning_starts: bool = False,
+        verbose: bool = False,
+    ):
+        """Interact with the (host) environment, one update per step after ``learning_starts`` (reference envelope.py:465-572)."""
+        if eval_env is not None:
+            assert ref_point is not None, "Reference point must be provided for the hypervolume computation."
+        if self.log:
+            self.register_additional_config({
+                "total_timesteps": total_timesteps, "ref_point": ref_point.tolist() if ref_point is not None else None,
+                "known_front": known_pareto_front, "weight": weight.tolist() if weight is not None else None,
+                "total_episodes": total_episodes, "reset_num_timesteps": reset_num_timesteps, "eval_freq": eval_freq,
+                "num_eval_weights_for_front": num_eval_weights_for_front, "num_eval_episodes_for_front": num_eval_episodes_for_front,
+                "num_eval_weights_for_eval": num_eval_weights_for_eval, "reset_learning_starts": reset_learning_starts})
+        self.global_step = 0 if reset_num_timesteps else self.global_step
+        self.num_episodes = 0 if reset_num_timesteps else self.num_episodes
+        if reset_learning_starts:
+            self.learning_starts = self.global_step
+        num_episodes = 0
+        eval_weights = equally_spaced_weights(self.reward_dim, n=num_eval_weights_for_front) if eval_env is not None else None
+        obs, _ = self.env.reset()
+        w = weight if weight is not None else random_weights(self.reward_dim, 1, dist="gaussian", rng=self.np_random)
+        tensor_w = th.tensor(w).float().to(self.device)
+
+        for _ in range(1, total_timesteps + 1):
+            if total_episodes is not None and num_episodes == total_episodes:
+                break
+            if self.global_step < self.learning_starts:
+                action = self.env.action_space.sample()
+            else:
+                action = self.act(th.as_tensor(obs).float().to(self.device), tensor_w)
+            next_obs, vec_reward, terminated, truncated, info = self.env.step(action)
+            self.global_step += 1
+            self.replay_buffer.add(obs, action, vec_reward, next_obs, terminated)
+            if self.global_step >= self.learning_starts:
+                self.update()
+            if eval_env is not None and self.log and self.global_step % eval_freq == 0:
+                from ...common.evaluation import log_all_multi_policy_metrics
+
+                front = [self.policy_eval(eval_env, weights=ew, num_episodes=num_eval_episodes_for_front, log=self.log)[3] for ew in eval_weights]
+                log_all_multi_policy_metrics(current_front=front, hv_ref_point=ref_point, reward_dim=self.reward_dim,
+                                             global_step=self.global_step, n_sample_weights=num_eval_weights_for_eval,
+                                             ref_front=known_pareto_front)
+            if terminated or truncated:
+                obs, _ = self.env.reset()
+                num_episodes += 1
+                self.num_episodes += 1
+                if self.log and "episode" in info.keys():
+                    from ...common.evaluation import log_episode_info
+
+                    log_episode_info(info["episode"], np.dot, w, self.global_step, verbose=verbose)
+                if weight is None:
+                    w = random_weights(self.reward_dim, 1, dist="gaussian", rng=self.np_random)
+                    tensor_w = th.tensor(w).float().to(self.device)
+            else:
+                obs = next_obs

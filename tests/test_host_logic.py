@@ -1,0 +1,189 @@
+"""CPU-only tests of the host-side mirror of the reference interface: replay buffers, the PER sum-tree, weight
+generation, indicators, schedules, and the N>1 front exchange over gloo (world_size 2)."""
+
+import os
+import pickle
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import oracle as orc
+from tests.golden import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_random_weights_consume_the_generator_like_the_reference(golden):
+    from morl_baselines_b200.common.weights import extrema_weights, random_weights
+
+    assert np.array_equal(random_weights(3, 64, "gaussian", rng=np.random.default_rng(5)), golden["random_weights_gauss"])
+    assert np.array_equal(random_weights(4, 10, "dirichlet", rng=np.random.default_rng(5)), golden["random_weights_dir"])
+    assert np.array_equal(random_weights(3, 1, "gaussian", rng=np.random.default_rng(9)), golden["random_weights_single"])
+    assert np.array_equal(np.array(extrema_weights(3)), np.eye(3, dtype=np.float32))
+    with pytest.raises(ValueError):
+        random_weights(3, 2, "uniform")
+
+
+@pytest.mark.parametrize("max_size,n0", [(1000, 700), (4096, 4096), (65536, 50000)])
+def test_host_sumtree_matches_reference(golden, max_size, n0):
+    from morl_baselines_b200.common.prioritized_buffer import SumTree
+
+    tree = SumTree(max_size)
+    rng = np.random.default_rng(max_size)
+    tree.batch_set(np.arange(n0), rng.random(n0) + 1e-5)
+    for rnd in range(4):
+        np.random.seed(100 + rnd)
+        idx = tree.sample(256)
+        assert np.array_equal(idx, golden[f"sumtree_{max_size}_samples"][rnd])
+        upd_idx = np.concatenate([idx, idx[:64]])
+        tree.batch_set(upd_idx, rng.random(len(upd_idx)) * 3.0)
+    assert tree.nodes[0][0] == float(golden[f"sumtree_{max_size}_root"])
+    assert cases.digest(np.concatenate(tree.nodes)) == str(golden[f"sumtree_{max_size}_levels_sha"])
+
+
+def test_replay_buffer_api_and_pickle_layout():
+    from morl_baselines_b200.common.buffer import ReplayBuffer
+    from morl_baselines_b200.common.prioritized_buffer import PrioritizedReplayBuffer
+
+    rb = ReplayBuffer((5,), 1, rew_dim=3, max_size=16, action_dtype=np.uint8)
+    for t in range(20):  # wraps around
+        rb.add(np.full(5, t, np.float32), t % 4, np.full(3, -t, np.float32), np.full(5, t + 1, np.float32), t % 7 == 0)
+    assert len(rb) == 16 and rb.ptr == 4
+    assert rb.obs[3, 0] == 19 and rb.obs[4, 0] == 4  # newest / oldest
+    np.random.seed(0)
+    obs, act, rew, nobs, done, idx = rb.sample(8)
+    np.random.seed(0)
+    assert np.array_equal(idx, np.random.choice(16, 8, replace=True))
+    assert np.array_equal(obs, rb.obs[idx]) and act.dtype == np.uint8 and rew.shape == (8, 3) and done.shape == (8, 1)
+    _, _, _, _, _, idx = rb.sample(4, use_cer=True)
+    assert idx[0] == rb.ptr - 1
+    t_obs = rb.sample(4, to_tensor=True, device="cpu")[0]
+    assert isinstance(t_obs, th.Tensor)
+    assert len(rb.get_all_data()) == 5 and rb.get_all_data(max_samples=5)[0].shape == (5, 5)
+    # pickling keeps the reference's numpy attribute layout
+    rb2 = pickle.loads(pickle.dumps(rb))
+    for name in ("obs", "next_obs", "actions", "rewards", "dones"):
+        assert np.array_equal(getattr(rb2, name), getattr(rb, name))
+    assert (rb2.ptr, rb2.size, rb2.max_size) == (rb.ptr, rb.size, rb.max_size)
+
+    prb = PrioritizedReplayBuffer((5,), 1, rew_dim=3, max_size=16, action_dtype=np.uint8)
+    for t in range(10):
+        prb.add(np.zeros(5), 1, np.zeros(3), np.zeros(5), False)
+    assert prb.tree.nodes[0][0] == pytest.approx(10 * 1e-5)
+    prb.update_priorities(np.array([1, 1, 3]), np.array([0.5, 0.9, 0.2]))
+    assert prb.tree.nodes[-1][1] == 0.5  # first occurrence wins
+    assert prb.min_priority == 0.9  # ratchet (reference prioritized_buffer.py:194)
+    prb.add(np.zeros(5), 1, np.zeros(3), np.zeros(5), False)
+    assert prb.tree.nodes[-1][10] == 0.9
+    np.random.seed(3)
+    smp = prb.sample(32)
+    assert smp[5].max() <= 10 and smp[0].shape == (32, 5)
+
+
+def test_hypervolume_and_indicators():
+    from morl_baselines_b200.common import performance_indicators as pi
+    from oracle.hv_oracle import hypervolume_min
+
+    assert pi.hypervolume(np.array([0.0, 0.0]), [np.array([1.0, 2.0]), np.array([2.0, 1.0])]) == pytest.approx(3.0)
+    rng = np.random.default_rng(0)
+    for d in (2, 3, 4):
+        pts = rng.random((30, d)) * 5
+        ref = -np.ones(d)
+        assert pi.hypervolume(ref, list(pts)) == pytest.approx(hypervolume_min(-pts, -ref), rel=1e-12)
+    front = [np.array([1.0, 0.0]), np.array([0.0, 1.0])]
+    assert pi.cardinality(front) == 2
+    assert pi.sparsity(front) == pytest.approx(2.0)
+    assert pi.expected_utility(front, [np.array([1.0, 0.0]), np.array([0.5, 0.5])]) == pytest.approx(0.75)
+    assert pi.igd(front, front) == 0.0
+    assert pi.maximum_utility_loss(front[:1], front, np.array([[0.0, 1.0]])) == pytest.approx(1.0)
+
+
+def test_schedules_and_unique_tol():
+    from morl_baselines_b200.common.utils import linearly_decaying_value, nearest_neighbors, unique_tol
+
+    assert linearly_decaying_value(1.0, 100, 0, 10, 0.1) == 1.0
+    assert linearly_decaying_value(1.0, 100, 60, 10, 0.1) == pytest.approx(0.55)
+    assert linearly_decaying_value(1.0, 100, 500, 10, 0.1) == pytest.approx(0.1)
+    u = unique_tol([np.array([1.0, 0.5]), np.array([1.00001, 0.5]), np.array([0.0, 1.0])])  # rtol semantics of np.allclose
+    assert len(u) == 2
+    ws = [np.array([1.0, 0.0]), np.array([0.9, 0.1]), np.array([0.0, 1.0]), np.array([0.5, 0.5])]
+    nn_ = nearest_neighbors(2, ws[0], ws, lambda a, b: float(np.abs(a - b).sum()))
+    assert nn_ == [1, 3]
+
+
+def test_envelope_requires_cuda():
+    """The product path fails loudly without a CUDA device -- no CPU fallback."""
+    from morl_baselines_b200 import _lib
+    from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
+    from oracle.ref_harness import FakeEnv
+
+    if th.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(_lib.MorlB200Error):
+        Envelope(FakeEnv(), log=False, device="cpu")
+    from morl_baselines_b200.common.pareto import filter_pareto_dominated
+
+    with pytest.raises(_lib.MorlB200Error):
+        filter_pareto_dominated(np.random.rand(5, 2))
+    assert filter_pareto_dominated(np.random.rand(1, 2)).shape == (1, 2)  # < 2 candidates: returned as is (pareto.py:71-72)
+
+
+def test_shard_range_and_front_records():
+    from morl_baselines_b200.parallel import pack_front, shard_range, unpack_fronts
+
+    spans = [shard_range(64, r, 8) for r in range(8)]
+    assert spans[0] == (0, 8) and spans[-1] == (56, 64)
+    spans = [shard_range(10, r, 4) for r in range(4)]
+    assert [b - a for a, b in spans] == [3, 3, 2, 2] and spans[-1][1] == 10
+    pts = th.arange(12, dtype=th.float64).view(4, 3)
+    rec = pack_front(pts, cap=8)
+    allp, counts = unpack_fronts(th.stack([rec, pack_front(pts[:1], 8)]), 2, 8, 3)
+    assert counts.tolist() == [4, 1] and allp.shape == (5, 3)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from morl_baselines_b200.parallel import allgather_fronts
+    from oracle import oracle as orc_
+
+    def prune(p):  # the CUDA kernel is not available on the CPU test host: inject the oracle as the dominance test
+        return th.from_numpy(orc_.pareto_mask(p.numpy(), True))
+
+    rng = np.random.default_rng(rank)
+    pts = np.abs(rng.standard_normal((300, 3)))
+    pts = th.from_numpy(pts / np.linalg.norm(pts, axis=1, keepdims=True))  # mutually non-dominated: 300 > cap forces grow-and-retry
+    stats = {}
+    front = allgather_fronts(pts, cap=64, prune=prune, stats=stats)
+    q.put((rank, front.numpy(), stats))
+    dist.destroy_process_group()
+
+
+def test_allgather_fronts_gloo_world2():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, f0, s0), (_, f1, s1) = res
+    assert np.array_equal(f0, f1)  # identical archive on every rank
+    assert s0["rounds"] == 2 and s0["cap"] == 512 and s0["counts"] == [300, 300]  # overflow was detected, never truncated
+    allpts = np.concatenate([np.abs(np.random.default_rng(r).standard_normal((300, 3))) for r in range(2)])
+    allpts = allpts / np.linalg.norm(allpts, axis=1, keepdims=True)
+    expect = allpts[orc.pareto_mask(allpts, True)]
+    assert {tuple(r) for r in f0} == {tuple(r) for r in expect}

@@ -1,0 +1,332 @@
+"""GPU parity tests: every CUDA operator, called through the C-ABI (morl_baselines_b200.ops -> ctypes -> libmorl_b200.so),
+against (1) the committed golden vectors of the unmodified reference and (2) the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact (np.array_equal / SHA-256) for targets, indices and masks -- the kernels use explicit round-to-nearest
+intrinsics in the documented order; 1e-6 relative for the reduced loss scalars (summation order differs), tolerance
+stated at the assert."""
+
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import oracle as orc
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(x, dev, dtype=None):
+    t = th.from_numpy(np.ascontiguousarray(x)).to(dev)
+    return t if dtype is None else t.to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ envelope TD
+@pytest.mark.parametrize("name", [c[0] for c in cases.ENVELOPE_CASES])
+def test_envelope_td_golden_and_oracle(cuda, golden, name):
+    from morl_baselines_b200 import ops
+
+    x = cases.envelope_inputs(name)
+    args = [_t(x[k], cuda) for k in ("q_on", "q_tg", "wset", "reward", "done")]
+    t, p, a = ops.envelope_td(*args, x["gamma"], ops.DOT_UNFUSED, ops.ROWS_REFERENCE)
+    t, p, a = t.cpu().numpy(), p.cpu().numpy(), a.cpu().numpy()
+    # (1) the reference's own output, bit for bit
+    assert cases.digest(t) == str(golden[f"env_{name}_target_sha"])
+    assert cases.digest(p) == str(golden[f"env_{name}_pref_sha"])
+    assert cases.digest(a) == str(golden[f"env_{name}_act_sha"])
+    # (2) every arithmetic mode and both row orders against the oracle
+    for mode in (ops.DOT_UNFUSED, ops.DOT_FMA, ops.DOT_PAIRFMA):
+        for order in (ops.ROWS_REFERENCE, ops.ROWS_BMAJOR):
+            t, p, a = ops.envelope_td(*args, x["gamma"], mode, order)
+            to, po, ao = orc.envelope_td(x["q_on"], x["q_tg"], x["wset"], x["reward"], x["done"], x["gamma"], mode, order)
+            assert np.array_equal(t.cpu().numpy(), to), (name, mode, order)
+            assert np.array_equal(p.cpu().numpy(), po) and np.array_equal(a.cpu().numpy(), ao), (name, mode, order)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (3, 2, 1, 3), (5, 33, 3, 3), (2, 300, 4, 3), (4, 70, 9, 8), (2, 600, 18, 3), (7, 64, 64, 2)])
+def test_envelope_td_edge_shapes(cuda, shape):
+    """Ragged / extreme shapes: W not a multiple of 32, W > 256 (several weight chunks), Q tile larger than one shared
+    memory stage (W*A*D > 10240 floats), D = 1 and D = 8, a single transition."""
+    from morl_baselines_b200 import ops
+
+    B, W, A, D = shape
+    rng = np.random.default_rng(B * 1000 + W)
+    q_on = rng.standard_normal((B, W, A, D)).astype(np.float32)
+    q_tg = rng.standard_normal((B, W, A, D)).astype(np.float32)
+    wset = cases.gaussian_weights(rng, W, D)
+    reward = rng.standard_normal((B, D)).astype(np.float32)
+    done = (rng.random(B) < 0.3).astype(np.float32)
+    for order in (ops.ROWS_REFERENCE, ops.ROWS_BMAJOR):
+        t, p, a = ops.envelope_td(_t(q_on, cuda), _t(q_tg, cuda), _t(wset, cuda), _t(reward, cuda), _t(done, cuda), 0.97, ops.DOT_UNFUSED, order)
+        to, po, ao = orc.envelope_td(q_on, q_tg, wset, reward, done, 0.97, orc.DOT_UNFUSED, order)
+        assert np.array_equal(t.cpu().numpy(), to) and np.array_equal(p.cpu().numpy(), po) and np.array_equal(a.cpu().numpy(), ao)
+
+
+def test_envelope_td_degenerate_values(cuda):
+    """All-equal Q (every candidate ties -> index (0,0)), -inf everywhere, and done = 1 rows (target == reward)."""
+    from morl_baselines_b200 import ops
+
+    B, W, A, D = 8, 16, 4, 3
+    rng = np.random.default_rng(3)
+    wset = _t(cases.gaussian_weights(rng, W, D), cuda)
+    reward = _t(rng.standard_normal((B, D)).astype(np.float32), cuda)
+    q_tg = _t(rng.standard_normal((B, W, A, D)).astype(np.float32), cuda)
+    ones = th.ones(B, device=cuda)
+    t, p, a = ops.envelope_td(th.zeros(B, W, A, D, device=cuda), q_tg, wset, reward, ones, 0.99)
+    assert int(p.abs().sum()) == 0 and int(a.abs().sum()) == 0
+    assert th.equal(t.view(W, B, D), reward.unsqueeze(0).expand(W, B, D))  # (1 - done) * gamma == 0
+    t, p, a = ops.envelope_td(th.full((B, W, A, D), -float("inf"), device=cuda), q_tg, wset, reward, th.zeros(B, device=cuda), 0.99)
+    assert int(p.abs().sum()) == 0 and int(a.abs().sum()) == 0
+
+
+def test_envelope_td_full_size_properties(cuda):
+    """North-star shape (B=1024, |W|=64, |A|=8, d=3): size-independent properties.
+      * optimality: the chosen (j*, a*) attains the maximum scalarised value and no earlier candidate equals it;
+      * permutation covariance: permuting the weight set permutes the output rows (REFERENCE order blocks);
+      * a weight set made of one repeated vector makes every block identical."""
+    from morl_baselines_b200 import ops
+
+    x = cases.envelope_inputs("north_star")
+    B, W, A, D = x["B"], x["W"], x["A"], x["D"]
+    q_on, q_tg, wset, reward, done = (_t(x[k], cuda) for k in ("q_on", "q_tg", "wset", "reward", "done"))
+    t, p, a = ops.envelope_td(q_on, q_tg, wset, reward, done, x["gamma"])
+    sc = (wset[:, None, None, None, 0] * q_on[None, ..., 0] + wset[:, None, None, None, 1] * q_on[None, ..., 1]) + wset[:, None, None, None, 2] * q_on[None, ..., 2]
+    sc = sc.reshape(W, B, W * A)  # [i, b, (j,a)] computed by torch with the same unfused order
+    flat = (p.long() * A + a.long()).view(W, B)
+    best = sc.max(dim=2).values
+    assert th.equal(sc.gather(2, flat.unsqueeze(2)).squeeze(2), best)
+    first = (sc == best.unsqueeze(2)).float().argmax(dim=2)
+    assert th.equal(first, flat)
+    perm = th.randperm(W, device=cuda)
+    t2, p2, a2 = ops.envelope_td(q_on, q_tg, wset[perm].contiguous(), reward, done, x["gamma"])
+    assert th.equal(t2.view(W, B, D), t.view(W, B, D)[perm])
+    t3, _, _ = ops.envelope_td(q_on, q_tg, wset[:1].expand(W, D).contiguous(), reward, done, x["gamma"])
+    assert th.equal(t3.view(W, B, D), t3.view(W, B, D)[:1].expand(W, B, D))
+
+
+# ------------------------------------------------------------------------------------------------ per-row targets
+@pytest.mark.parametrize("name", [c[0] for c in cases.ENVELOPE_CASES])
+def test_greedy_td_golden_and_oracle(cuda, golden, name):
+    from morl_baselines_b200 import ops
+
+    x = cases.envelope_inputs(name)
+    B, W, A, D = x["B"], x["W"], x["A"], x["D"]
+    qs = np.ascontiguousarray(x["q_on"].transpose(1, 0, 2, 3)).reshape(W * B, A, D)
+    qe = np.ascontiguousarray(x["q_tg"].transpose(1, 0, 2, 3)).reshape(W * B, A, D)
+    t, act = ops.greedy_td(_t(qs, cuda), _t(qe, cuda), _t(x["wset"], cuda), _t(x["reward"], cuda), _t(x["done"], cuda), x["gamma"])
+    assert cases.digest(t.cpu().numpy()) == str(golden[f"ddqn_{name}_target_sha"])
+    for mode in (0, 1, 2):
+        t, act = ops.greedy_td(_t(qs, cuda), _t(qe, cuda), _t(x["wset"], cuda), _t(x["reward"], cuda), _t(x["done"], cuda), x["gamma"], mode)
+        to, ao = orc.greedy_td(qs, qe, x["wset"], x["reward"], x["done"], x["gamma"], mode)
+        assert np.array_equal(t.cpu().numpy(), to) and np.array_equal(act.cpu().numpy(), ao)
+    # no Bellman (reward=None) and per-row weights
+    wfull = np.repeat(x["wset"], B, axis=0)
+    t, act = ops.greedy_td(_t(qs, cuda), _t(qe, cuda), _t(wfull, cuda))
+    to, ao = orc.greedy_td(qs, qe, wfull, None, None, 0.0)
+    assert np.array_equal(t.cpu().numpy(), to) and np.array_equal(act.cpu().numpy(), ao)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.GPI_CASES])
+def test_gpi_kernels_golden_and_oracle(cuda, golden, name):
+    from morl_baselines_b200 import ops
+
+    x = cases.gpi_inputs(name)
+    q, w = _t(x["q"], cuda), _t(x["w"], cuda)
+    o, p, a = ops.gpi_envelope(q, w)
+    assert np.array_equal(o.cpu().numpy(), golden[f"gpi_{name}_maxq"])
+    assert np.array_equal(p.cpu().numpy(), golden[f"gpi_{name}_policy"]) and np.array_equal(a.cpu().numpy(), golden[f"gpi_{name}_act"])
+    o1, a1 = ops.critic_min_td(q[:, :, 0].contiguous(), w)
+    assert np.array_equal(o1.cpu().numpy(), golden[f"gpi_{name}_criticmin"]) and np.array_equal(a1.cpu().numpy(), golden[f"gpi_{name}_criticmin_act"])
+    n16 = len(golden[f"gpi_{name}_action16"])
+    _, p16, a16 = ops.gpi_envelope(q[:1, :n16].contiguous(), w[:n16].contiguous())
+    assert np.array_equal(a16.cpu().numpy(), golden[f"gpi_{name}_action16"]) and np.array_equal(p16.cpu().numpy(), golden[f"gpi_{name}_policy16"])
+    # single observation, single shared weight (the shape GPIPD.gpi_action is called with every env step)
+    _, p1, a1_ = ops.gpi_envelope(q[:1, :1].contiguous(), w[:1].contiguous())
+    assert int(p1[0]) == int(golden[f"gpi_{name}_policy16"][0]) and int(a1_[0]) == int(golden[f"gpi_{name}_action16"][0])
+    # Bellman variants + all modes against the oracle
+    rew, dn = _t(x["reward"], cuda), _t(x["done"], cuda)
+    for mode in (0, 1, 2):
+        o, p, a = ops.gpi_envelope(q, w, rew, dn, x["gamma"], mode)
+        oo, po, ao = orc.gpi_envelope(x["q"], x["w"], x["reward"], x["done"], x["gamma"], mode)
+        assert np.array_equal(o.cpu().numpy(), oo) and np.array_equal(p.cpu().numpy(), po) and np.array_equal(a.cpu().numpy(), ao)
+        qc = x["q"][:, :, 0].copy()
+        o, a = ops.critic_min_td(_t(qc, cuda), w, rew, dn, x["gamma"], mode)
+        oo, ao = orc.critic_min_td(qc, x["w"], x["reward"], x["done"], x["gamma"], mode)
+        assert np.array_equal(o.cpu().numpy(), oo) and np.array_equal(a.cpu().numpy(), ao)
+
+
+def test_critic_min_td_tiled_rows(cuda):
+    """GPIPD.update doubles the batch (gpi_pd.py:425-432): rewards/dones tiled x2, weights per row."""
+    from morl_baselines_b200 import ops
+
+    rng = np.random.default_rng(11)
+    n_nets, B, A, D = 2, 128, 6, 3
+    q = rng.standard_normal((n_nets, 2 * B, A, D)).astype(np.float32)
+    w = cases.gaussian_weights(rng, 2 * B, D)
+    rew = rng.standard_normal((B, D)).astype(np.float32)
+    dn = (rng.random(B) < 0.2).astype(np.float32)
+    o, a = ops.critic_min_td(_t(q, cuda), _t(w, cuda), _t(rew, cuda), _t(dn, cuda), 0.99, 0, ops.MAP_BLOCK, ops.MAP_TILE)
+    oo, ao = orc.critic_min_td(q, w, rew, dn, 0.99, 0, orc.MAP_BLOCK, orc.MAP_TILE)
+    assert np.array_equal(o.cpu().numpy(), oo) and np.array_equal(a.cpu().numpy(), ao)
+    full = np.concatenate([rew, rew]), np.concatenate([dn, dn])
+    o2, _ = orc.critic_min_td(q, w, full[0], full[1], 0.99, 0)
+    assert np.array_equal(oo, o2)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("D", [2, 3])
+def test_actor_critic_td(cuda, variant, D):
+    from morl_baselines_b200 import ops
+
+    rng = np.random.default_rng(variant * 10 + D)
+    n_nets, N = 2, 257
+    q = rng.standard_normal((n_nets, N, D)).astype(np.float32)
+    w = cases.gaussian_weights(rng, N if variant != 1 else 1, D)
+    rew = rng.standard_normal((N, D)).astype(np.float32)
+    dn = (rng.random(N) < 0.2).astype(np.float32)
+    logp = rng.standard_normal(N).astype(np.float32) if variant != 2 else None
+    got = ops.actor_critic_td(_t(q, cuda), _t(w, cuda), _t(rew, cuda), _t(dn, cuda), None if logp is None else _t(logp, cuda), 0.2, 0.99, variant)
+    exp = orc.actor_critic_td(q, w, rew, dn, logp, 0.2, 0.99, variant)
+    assert np.array_equal(got.cpu().numpy(), exp)
+    # cross-check the oracle itself against a literal torch restatement of the reference lines
+    tq, tw, tr, td_ = map(th.from_numpy, (q, w, rew, dn))
+    if variant == 0:  # capql.py:329-331
+        ref = tr + (1 - td_.reshape(-1, 1)) * 0.99 * (th.min(tq, dim=0)[0] - 0.2 * th.from_numpy(logp).reshape(-1, 1))
+        assert np.array_equal(exp, ref.numpy())
+
+
+# ------------------------------------------------------------------------------------------------ TD loss
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("lam", [0.0, 0.35, 1.0])
+@pytest.mark.parametrize("shape", [(64, 8, 8, 3), (37, 5, 7, 3), (256, 32, 6, 2)])
+def test_td_mse_priority(cuda, order, lam, shape):
+    from morl_baselines_b200 import ops
+
+    B, W, A, D = shape
+    rng = np.random.default_rng(B + W)
+    qv = rng.standard_normal((B * W, A, D)).astype(np.float32)
+    tq = rng.standard_normal((B * W, D)).astype(np.float32)
+    wset = cases.gaussian_weights(rng, W, D)
+    act = rng.integers(0, A, size=B).astype(np.int32)
+    loss, grad, prio = ops.td_mse_priority(_t(qv, cuda), _t(act, cuda), _t(tq, cuda), _t(wset, cuda), lam, B, W, order)
+    lo, go, _, po = orc.td_mse(qv, act, tq, wset, lam, B, W, order)
+    # loss: float block partials + double final sum vs the oracle's all-double sum: 1e-6 relative
+    assert abs(float(loss) - lo) <= 1e-6 * max(1.0, abs(lo))
+    assert np.array_equal(prio.cpu().numpy(), po)  # |w . td| in the unfused order: bit-exact
+    # gradient: same formula in float vs double-then-rounded: 2 ulp
+    np.testing.assert_allclose(grad.cpu().numpy(), go, rtol=3e-7, atol=1e-12)
+    # and against torch autograd on the reference's literal loss (envelope.py:301-313) -- 1e-5 relative (north_star tolerance)
+    q_t = th.from_numpy(qv).requires_grad_(True)
+    i_of = np.arange(B * W) // B if order == 0 else np.arange(B * W) % W
+    b_of = np.arange(B * W) % B if order == 0 else np.arange(B * W) // W
+    a_rows = th.from_numpy(act[b_of].astype(np.int64))
+    q_taken = q_t.gather(1, a_rows.reshape(-1, 1, 1).expand(B * W, 1, D)).reshape(-1, D)
+    w_rows = th.from_numpy(wset[i_of])
+    ref = th.nn.functional.mse_loss(q_taken, th.from_numpy(tq))
+    if lam > 0:
+        aux = th.nn.functional.mse_loss(th.einsum("br,br->b", q_taken, w_rows), th.einsum("br,br->b", th.from_numpy(tq), w_rows))
+        ref = (1 - lam) * ref + lam * aux
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    np.testing.assert_allclose(grad.cpu().numpy(), q_t.grad.numpy(), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("gpi", [False, True])
+def test_td_huber_priority(cuda, gpi):
+    from morl_baselines_b200 import ops
+
+    rng = np.random.default_rng(5)
+    n_nets, B, A, D = 2, 96, 6, 3
+    N = 2 * B
+    qv = (rng.standard_normal((n_nets, N, A, D)) * 0.02).astype(np.float32)  # straddles min_priority = 0.01
+    tq = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+    tg = (rng.standard_normal((N, D)) * 0.02).astype(np.float32) if gpi else None
+    w = cases.gaussian_weights(rng, N, D)
+    act = rng.integers(0, A, size=B).astype(np.int32)
+    loss, grad, prio = ops.td_huber_priority(_t(qv, cuda), _t(act, cuda), _t(tq, cuda), None if tg is None else _t(tg, cuda), _t(w, cuda), 0.01, B)
+    lo, go, po = orc.td_huber(qv, act, tq, tg, w, 0.01, B)
+    assert abs(float(loss) - lo) <= 1e-6 * abs(lo)
+    assert np.array_equal(prio.cpu().numpy(), po)
+    np.testing.assert_allclose(grad.cpu().numpy(), go, rtol=3e-7, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ Pareto
+@pytest.mark.parametrize("name", cases.PARETO_CASES)
+@pytest.mark.parametrize("rd", [True, False])
+def test_pareto_mask_golden(cuda, golden, name, rd):
+    from morl_baselines_b200 import ops
+
+    pts = cases.pareto_points(name)
+    ref = np.unpackbits(golden[f"pareto_{name}_{int(rd)}"])[: len(pts)].astype(bool)
+    got = ops.pareto_mask(_t(pts, cuda), rd).cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert cases.digest(pts[got]) == str(golden[f"pareto_{name}_{int(rd)}_filtered_sha"])
+
+
+def test_pareto_mask_edge_cases(cuda):
+    from morl_baselines_b200 import ops
+
+    nan = float("nan")
+    m = ops.pareto_mask(th.tensor([[nan, 1.0], [0.0, 0.0], [1.0, 1.0]], device=cuda, dtype=th.float64), True)
+    assert m.tolist() == [False, False, True]
+    assert ops.pareto_mask(th.zeros(0, 3, device=cuda), True).numel() == 0
+    assert ops.pareto_mask(th.tensor([[1.0, 2.0]], device=cuda), True).tolist() == [True]
+    # float32 inputs are compared in float32, not promoted
+    a = np.float32(1.0)
+    b = np.nextafter(a, np.float32(2.0))
+    m = ops.pareto_mask(th.tensor([[a, a], [b, a]], device=cuda, dtype=th.float32), True)
+    assert m.tolist() == [False, True]
+
+
+def test_pareto_mask_large_properties(cuda):
+    """N = 20000, d = 4 (beyond anything the reference finishes quickly): idempotence, permutation invariance of the kept
+    SET, and agreement with the oracle on a 3000-point subset."""
+    from morl_baselines_b200 import ops
+
+    rng = np.random.default_rng(0)
+    pts = rng.standard_normal((20000, 4)).astype(np.float32)
+    pts[::7] = pts[3]  # heavy duplication of one point
+    x = _t(pts, cuda)
+    keep = ops.pareto_mask(x, True)
+    front = x[keep]
+    assert bool(ops.pareto_mask(front, True).all())  # idempotent
+    perm = th.randperm(len(pts), device=cuda)
+    keep_p = ops.pareto_mask(x[perm].contiguous(), True)
+    assert {tuple(r) for r in front.cpu().numpy()} == {tuple(r) for r in x[perm][keep_p].cpu().numpy()}
+    sub = pts[:3000]
+    assert np.array_equal(ops.pareto_mask(_t(sub, cuda), True).cpu().numpy(), orc.pareto_mask(sub, True))
+    assert np.array_equal(ops.pareto_mask(_t(sub, cuda), False).cpu().numpy(), orc.pareto_mask(sub, False))
+
+
+# ------------------------------------------------------------------------------------------------ replay / polyak
+@pytest.mark.parametrize("obs_dim,u8", [(32, True), (11, False), (17, True)])
+def test_replay_gather(cuda, obs_dim, u8):
+    from morl_baselines_b200 import ops
+
+    rng = np.random.default_rng(obs_dim)
+    cap, B, d = 5000, 1024, 3
+    obs = rng.standard_normal((cap, obs_dim)).astype(np.float32)
+    nobs = rng.standard_normal((cap, obs_dim)).astype(np.float32)
+    act = rng.integers(0, 8, size=(cap, 1)).astype(np.uint8) if u8 else rng.standard_normal((cap, 3)).astype(np.float32)
+    rew = rng.standard_normal((cap, d)).astype(np.float32)
+    done = (rng.random((cap, 1)) < 0.1).astype(np.float32)
+    idx = rng.integers(0, cap, size=B)
+    o, a, r, no, dn = ops.replay_gather(_t(obs, cuda), _t(nobs, cuda), _t(act, cuda), _t(rew, cuda), _t(done, cuda), _t(idx, cuda))
+    assert np.array_equal(o.cpu().numpy(), obs[idx]) and np.array_equal(no.cpu().numpy(), nobs[idx])
+    assert np.array_equal(a.cpu().numpy(), act[idx].astype(np.int32) if u8 else act[idx])
+    assert np.array_equal(r.cpu().numpy(), rew[idx]) and np.array_equal(dn.cpu().numpy(), done[idx])
+
+
+@pytest.mark.parametrize("tau", [0.005, 1.0, 0.3])
+def test_polyak_golden(cuda, golden, tau):
+    from morl_baselines_b200 import ops
+
+    p = _t(golden[f"polyak_{tau}_param"], cuda)
+    t = _t(golden[f"polyak_{tau}_target0"], cuda)
+    sizes = (24, 256 * 35, 1)
+    ps, ts, off = [], [], 0
+    for n in sizes:
+        ps.append(p[off : off + n].clone())
+        ts.append(t[off : off + n].clone())
+        off += n
+    ops.PolyakPlan(ps, ts).run(tau)
+    assert np.array_equal(th.cat(ts).cpu().numpy(), golden[f"polyak_{tau}_target1"])
