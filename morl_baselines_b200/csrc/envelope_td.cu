@@ -13,6 +13,7 @@
 // (value desc, flat index asc) order, which preserves first-occurrence semantics.  Q_tg is only touched at the
 // winning (j*, a*) (a D-float gather per output row), never streamed.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -124,6 +125,264 @@ __global__ void __launch_bounds__(512) envelope_td_kernel(const float* __restric
     }
 }
 
+
+// =================================================================================================================
+// v2 fast path: packed-FP32 (FMUL2 / FFMA2) scalarisation, 3-input FMNMX3 max tree, persistent CTAs with a
+// register-prefetched double buffer.  Bit-identical to the scalar arithmetic above:
+//   * mul.rn.f32x2 is two IEEE multiplies; the unfused add is issued as fma.rn.f32x2(acc, ONE, p) with ONE = 1.0f passed
+//     as a RUNTIME kernel argument -- ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false
+//     (observed with CUDA 12.9), but it cannot fold a multiplier it does not know; fl(acc * 1 + p) == fl(acc + p);
+//   * the Q_on[b] block is transposed once into shared memory as SoA planes Qs[r][c] (c = j*A + a), so one LDS.128 yields
+//     the r-th objective of four consecutive candidates already sitting in aligned register pairs;
+//   * candidates are scanned in groups of 8: four packed dot products, max of 8 with FMNMX3, and only the GROUP index of
+//     the running maximum is tracked (strict '>' keeps the first group); the exact (first) position inside the winning
+//     group is recovered afterwards by re-evaluating its 8 scores with the scalar path and testing equality.
+// =================================================================================================================
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// packed w . q for two candidates; `one2` = (1.0f, 1.0f) built from the runtime kernel argument
+template <int D, int MODE>
+__device__ __forceinline__ u64 dotw2(const u64 (&w2)[D], const u64 (&q2)[D], u64 one2) {
+    if constexpr (MODE == MORL_DOT_UNFUSED) {
+        u64 acc = mul2(w2[0], q2[0]);
+#pragma unroll
+        for (int r = 1; r < D; ++r) acc = fma2(acc, one2, mul2(w2[r], q2[r]));
+        return acc;
+    } else if constexpr (MODE == MORL_DOT_FMA) {
+        u64 acc = mul2(w2[0], q2[0]);
+#pragma unroll
+        for (int r = 1; r < D; ++r) acc = fma2(w2[r], q2[r], acc);
+        return acc;
+    } else {
+        u64 acc = 0;
+#pragma unroll
+        for (int r = 0; r + 1 < D; r += 2) {
+            const u64 p = fma2(w2[r + 1], q2[r + 1], mul2(w2[r], q2[r]));
+            acc = (r == 0) ? p : fma2(acc, one2, p);
+        }
+        if constexpr (D % 2 == 1) {
+            const u64 t = mul2(w2[D - 1], q2[D - 1]);
+            acc = (D == 1) ? t : fma2(acc, one2, t);
+        }
+        return acc;
+    }
+}
+
+constexpr int kV2MaxPrefetch = 4;  // float4 per thread held in registers for the next tile
+
+template <int D, int MODE, bool PIPE>
+__global__ void __launch_bounds__(256) envelope_td_v2_kernel(const float* __restrict__ q_on, const float* __restrict__ q_tg,
+                                                             const float* __restrict__ wset, const float* __restrict__ reward,
+                                                             const float* __restrict__ done, float gamma, float one, int B, int W,
+                                                             int A, int Cp, int CS, int gps, int row_order,
+                                                             float* __restrict__ target_out, int32_t* __restrict__ pref_out,
+                                                             int32_t* __restrict__ act_out) {
+    extern __shared__ __align__(16) float smem[];
+    const int C = W * A;               // candidates per transition
+    const int plane = Cp;              // floats per objective plane (multiple of 8, 16-byte aligned rows)
+    const int stage_floats = D * plane;
+    float* stage0 = smem;
+    float* stage1 = smem + stage_floats;
+    const int WI = blockDim.x / CS;    // weights handled per CTA (multiple of 32)
+    float* red_v = smem + 2 * stage_floats;                   // [CS][WI]
+    int* red_g = reinterpret_cast<int*>(red_v + CS * WI);     // [CS][WI]
+
+    const int il = threadIdx.x % WI;
+    const int cs = threadIdx.x / WI;
+    const int i = blockIdx.y * WI + il;
+    const bool active = i < W;
+    const u64 one2 = pk2(one, one);
+
+    float w[D];
+    u64 w2[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        w[r] = active ? __ldg(wset + (size_t)i * D + r) : 0.f;
+        w2[r] = pk2(w[r], w[r]);
+    }
+
+    const int n4 = (C * D) / 4;  // the launcher guarantees C*D % 4 == 0 and 16-byte aligned rows
+    const int ngroups = (C + 7) / 8;
+    const int g_begin = cs * gps;
+    const int g_end = min(g_begin + gps, ngroups);
+
+    // zero the padding columns [C, Cp) of both stages once (scores of padded candidates are masked, but must be finite)
+    for (int t = threadIdx.x; t < (Cp - C) * D; t += blockDim.x) {
+        const int r = t / (Cp - C), c = C + t % (Cp - C);
+        stage0[r * plane + c] = 0.f;
+        stage1[r * plane + c] = 0.f;
+    }
+
+    auto store_tile = [&](float* st, const float4& v, int e4) {
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = 4 * e4 + k;
+            const int c = e / D, r = e - c * D;
+            st[r * plane + c] = x[k];
+        }
+    };
+
+    // prologue: first tile straight to stage 0
+    int b = blockIdx.x;
+    if (b < B) {
+        const float4* src = reinterpret_cast<const float4*>(q_on + (size_t)b * C * D);
+        for (int t = threadIdx.x; t < n4; t += blockDim.x) store_tile(stage0, __ldg(src + t), t);
+    }
+    __syncthreads();
+
+    const bool can_prefetch = PIPE && (n4 <= kV2MaxPrefetch * (int)blockDim.x);
+    int it = 0;
+    for (; b < B; b += gridDim.x, ++it) {
+        float* cur = (it & 1) ? stage1 : stage0;
+        float* nxt = (it & 1) ? stage0 : stage1;
+        const int bn = b + gridDim.x;
+        float4 pf[PIPE ? kV2MaxPrefetch : 1];
+        if (PIPE && can_prefetch && bn < B) {
+            const float4* src = reinterpret_cast<const float4*>(q_on + (size_t)bn * C * D);
+#pragma unroll
+            for (int k = 0; k < kV2MaxPrefetch; ++k) {
+                const int t = threadIdx.x + k * blockDim.x;
+                if (t < n4) pf[k] = __ldg(src + t);
+            }
+        }
+
+        // ---- scan: groups of 8 candidates, packed arithmetic ----
+        float best = -INFINITY;
+        int bg = INT_MAX;
+        auto scan_group = [&](int g, bool tail) {
+            const int c0 = 8 * g;
+            u64 q2[4][D];
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                const float4 lo = *reinterpret_cast<const float4*>(cur + r * plane + c0);
+                const float4 hi = *reinterpret_cast<const float4*>(cur + r * plane + c0 + 4);
+                q2[0][r] = pk2(lo.x, lo.y);
+                q2[1][r] = pk2(lo.z, lo.w);
+                q2[2][r] = pk2(hi.x, hi.y);
+                q2[3][r] = pk2(hi.z, hi.w);
+            }
+            float x[8];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) upk2(dotw2<D, MODE>(w2, q2[p], one2), x[2 * p], x[2 * p + 1]);
+            if (tail) {  // last, partially filled group: padded candidates can never win
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (c0 + k >= C) x[k] = -INFINITY;
+            }
+            const float m = fmaxf(max3(x[0], x[1], x[2]), max3(max3(x[3], x[4], x[5]), x[6], x[7]));
+            if (m > best) {
+                best = m;
+                bg = g;
+            }
+        };
+        const int g_full = min(g_end, C / 8);  // groups entirely inside [0, C)
+        for (int g = g_begin; g < g_full; ++g) scan_group(g, false);
+        for (int g = max(g_begin, g_full); g < g_end; ++g) scan_group(g, true);
+
+        if (CS > 1) {
+            red_v[cs * WI + il] = best;
+            red_g[cs * WI + il] = bg;
+            __syncthreads();
+        }
+        if (cs == 0 && active) {
+            for (int s = 1; s < CS; ++s) argmax_merge(best, bg, red_v[s * WI + il], red_g[s * WI + il]);
+            int cstar = 0;
+            if (bg != INT_MAX) {
+                // exact first position inside the winning group: re-evaluate its scores with the scalar arithmetic
+                const int c0 = 8 * bg;
+                int kf = -1;
+#pragma unroll
+                for (int k = 7; k >= 0; --k) {
+                    float q[D];
+#pragma unroll
+                    for (int r = 0; r < D; ++r) q[r] = cur[r * plane + c0 + k];
+                    const float s = dotw<D, MODE>(w, q);
+                    if (s == best && c0 + k < C) kf = k;
+                }
+                cstar = c0 + (kf < 0 ? 0 : kf);
+            }
+            const int jstar = cstar / A;
+            const int astar = cstar - jstar * A;
+            const float* qt = q_tg + (((size_t)b * W + jstar) * A + astar) * D;
+            const size_t k = (row_order == MORL_ROWS_REFERENCE) ? ((size_t)i * B + b) : ((size_t)b * W + i);
+            const float dn = __ldg(done + b);
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+                target_out[k * D + r] = bellman(__ldg(reward + (size_t)b * D + r), dn, gamma, __ldg(qt + r));
+            if (pref_out) pref_out[k] = jstar;
+            if (act_out) act_out[k] = astar;
+        }
+
+        // ---- publish the next tile ----
+        if (bn < B) {
+            if (PIPE && can_prefetch) {
+#pragma unroll
+                for (int k = 0; k < (PIPE ? kV2MaxPrefetch : 1); ++k) {
+                    const int t = threadIdx.x + k * blockDim.x;
+                    if (t < n4) store_tile(nxt, pf[k], t);
+                }
+            } else {
+                const float4* src = reinterpret_cast<const float4*>(q_on + (size_t)bn * C * D);
+                for (int t = threadIdx.x; t < n4; t += blockDim.x) store_tile(nxt, __ldg(src + t), t);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct EnvelopeV2Plan {
+    bool ok;
+    int Cp, CS, gps, WI;
+    dim3 grid, block;
+    size_t smem;
+};
+
+static EnvelopeV2Plan plan_envelope_v2(int B, int W, int A, int D, int sm_count) {
+    EnvelopeV2Plan p{};
+    const long long C = (long long)W * A;
+    p.ok = false;
+    if ((C * D) % 4 != 0) return p;  // rows of Q_on[b] must stay 16-byte aligned for the float4 loads
+    const int Wp = (W + 31) / 32 * 32;
+    p.WI = Wp < 256 ? Wp : 256;
+    const int warps_i = p.WI / 32;
+    int cs = 4 / warps_i;
+    if (cs < 1) cs = 1;
+    const int ngroups = (int)((C + 7) / 8);
+    if (cs > ngroups) cs = ngroups;
+    p.CS = cs;
+    p.gps = (ngroups + cs - 1) / cs;
+    p.Cp = ngroups * 8;
+    p.block = dim3((unsigned)(p.WI * p.CS), 1, 1);
+    const size_t stage = (size_t)D * p.Cp * sizeof(float);
+    p.smem = 2 * stage + 2 * (size_t)p.CS * p.WI * sizeof(float);
+    if (p.smem > 96 * 1024) return p;
+    p.grid = dim3(1u, (unsigned)((W + p.WI - 1) / p.WI), 1);  // grid.x is set by the launcher from the measured occupancy
+    p.ok = true;
+    return p;
+}
+
 struct EnvelopePlan {
     int Wc, JS, JT;
     dim3 grid, block;
@@ -151,6 +410,8 @@ static EnvelopePlan plan_envelope(int B, int W, int A, int D) {
     return p;
 }
 
+static const bool g_force_v1 = (getenv("MORL_ENVELOPE_FORCE_V1") != nullptr);
+
 }  // namespace morl
 
 extern "C" int morl_envelope_td_f32(const float* q_online, const float* q_target, const float* wset, const float* reward,
@@ -169,8 +430,49 @@ extern "C" int morl_envelope_td_f32(const float* q_online, const float* q_target
                  "morl_envelope_td_f32: bad row_order %d", row_order);
     MORL_REQUIRE(aligned16(q_online) && aligned16(q_target) && aligned16(target_out), MORL_ERR_ALIGN,
                  "morl_envelope_td_f32: q_online/q_target/target_out must be 16-byte aligned");
-    const EnvelopePlan p = plan_envelope(B, W, A, D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static int sm_count_cached = 0;
+    if (sm_count_cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sm_count_cached = n;
+        else {
+            (void)cudaGetLastError();
+            sm_count_cached = 148;
+        }
+    }
+    EnvelopeV2Plan p2 = plan_envelope_v2(B, W, A, D, sm_count_cached);
+    if (p2.ok && !g_force_v1) {
+        bool launched2 = false;
+        MORL_DISPATCH_D(D, MORL_DISPATCH_MODE(dot_mode, {
+                            auto k1 = envelope_td_v2_kernel<kD, kMode, false>;  // one transition per CTA, everything co-resident
+                            auto kp = envelope_td_v2_kernel<kD, kMode, true>;   // persistent, register-prefetched double buffer
+                            if (p2.smem > 48 * 1024) {
+                                cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2.smem);
+                                cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2.smem);
+                            }
+                            int occ1 = 0, occp = 0;
+                            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, (int)p2.block.x, p2.smem);
+                            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, kp, (int)p2.block.x, p2.smem);
+                            const long long ctas_per_b = p2.grid.y;
+                            if (occ1 > 0 && (long long)B * ctas_per_b <= (long long)sm_count_cached * occ1) {
+                                p2.grid.x = (unsigned)B;  // a single wave: no tail, no pipeline needed
+                                k1<<<p2.grid, p2.block, p2.smem, st>>>(q_online, q_target, wset, reward, done, gamma, 1.0f, B, W, A, p2.Cp,
+                                                                        p2.CS, p2.gps, row_order, target_out, pref_out, act_out);
+                            } else {
+                                long long gx = (long long)sm_count_cached * (occp > 0 ? occp : 1) / ctas_per_b;
+                                if (gx < 1) gx = 1;
+                                if (gx > B) gx = B;
+                                p2.grid.x = (unsigned)gx;
+                                kp<<<p2.grid, p2.block, p2.smem, st>>>(q_online, q_target, wset, reward, done, gamma, 1.0f, B, W, A, p2.Cp,
+                                                                        p2.CS, p2.gps, row_order, target_out, pref_out, act_out);
+                            }
+                            launched2 = true;
+                        }));
+        MORL_REQUIRE(launched2, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: no v2 kernel for D=%d mode=%d", D, dot_mode);
+        return check_launch("morl_envelope_td_f32(v2)");
+    }
+    const EnvelopePlan p = plan_envelope(B, W, A, D);
     const bool vec4 = (A % 4 == 0);
     bool launched = false;
     MORL_DISPATCH_D(D, MORL_DISPATCH_MODE(dot_mode, {

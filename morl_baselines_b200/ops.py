@@ -238,6 +238,8 @@ def pareto_mask(points: th.Tensor, remove_duplicates: bool = True) -> th.Tensor:
     points = points.contiguous()
     N, D = points.shape
     keep = th.empty(N, device=points.device, dtype=th.uint8)
+    if N == 0:
+        return keep.bool()
     fn = _lib.load().morl_pareto_mask_f32 if points.dtype == th.float32 else _lib.load().morl_pareto_mask_f64
     rc = fn(_ptr(points), N, D, int(bool(remove_duplicates)), _ptr(keep), _stream())
     _lib.check(rc, "morl_pareto_mask")

@@ -212,8 +212,9 @@ def test_td_mse_priority(cuda, order, lam, shape):
     # loss: float block partials + double final sum vs the oracle's all-double sum: 1e-6 relative
     assert abs(float(loss) - lo) <= 1e-6 * max(1.0, abs(lo))
     assert np.array_equal(prio.cpu().numpy(), po)  # |w . td| in the unfused order: bit-exact
-    # gradient: same formula in float vs double-then-rounded: 2 ulp
-    np.testing.assert_allclose(grad.cpu().numpy(), go, rtol=3e-7, atol=1e-12)
+    # gradient: c1*d + c2*aux*w evaluated in float (kernel) vs double-then-rounded (oracle); the two terms may cancel, so the
+    # bound is 2 ulp of the larger term: atol = 3e-7 * max|g|
+    np.testing.assert_allclose(grad.cpu().numpy(), go, rtol=3e-7, atol=3e-7 * float(np.abs(go).max()))
     # and against torch autograd on the reference's literal loss (envelope.py:301-313) -- 1e-5 relative (north_star tolerance)
     q_t = th.from_numpy(qv).requires_grad_(True)
     i_of = np.arange(B * W) // B if order == 0 else np.arange(B * W) % W
