@@ -333,7 +333,7 @@ def run_b200(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "envelope_td_kernel<3,UNFUSED,vec4>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "envelope_td_v3_kernel<3,UNFUSED>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "us_per_launch": t_kernel * 1e6,
                      "peak_source": peak_src},
         "mlp": {"flop_per_step": mlp_flops, "tflops": mlp_flops / (ms / K * 1e-3) / 1e12, "path": "cuBLAS FP32 (TF32 off) via torch autograd",

@@ -189,95 +189,140 @@ __device__ __forceinline__ u64 dotw2(const u64 (&w2)[D], const u64 (&q2)[D], u64
     }
 }
 
-constexpr int kV2MaxPrefetch = 4;  // float4 per thread held in registers for the next tile
+// ---- 1-D bulk async copy (TMA, UBLKCP) + mbarrier helpers -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
-template <int D, int MODE, bool PIPE>
-__global__ void __launch_bounds__(256) envelope_td_v2_kernel(const float* __restrict__ q_on, const float* __restrict__ q_tg,
+// v3 kernel.  On top of the packed arithmetic described above:
+//   * FILTER (MODE != FMA): the scan uses the 3-op FMA chain t = fma(w2,q2, fma(w1,q1, w0*q0)) as an approximation of the
+//     contract arithmetic e (5 roundings).  |t - e| <= 6u * sum_r |w_r q_r| < eps := 2^-21 * (sum_r |w_r|) * max|Q_on[b]|.
+//     Per weight the scan keeps the best group maximum, its (first) group, and the runner-up group maximum.  If
+//     runner_up < best - thr (thr = 2^-19 * ..., a 4x margin over 2 eps) every candidate outside the best group is exactly
+//     smaller than the best group's maximum, so the exact first argmax lies in that group and is found by evaluating its 8
+//     candidates in the contract arithmetic.  Otherwise (near tie, ~1e-4 of the rows on continuous data; always for constant
+//     or non-finite Q) the row is re-scanned exactly by its whole warp.  The result is bit-identical to the exact scan.
+//   * Q_tg[b] is staged with one 1-D bulk async copy (TMA) that overlaps the scan; reward/done are pre-loaded;
+//   * the transposing Q_on load walks candidates (no div/mod), bank-conflict free.
+template <int D, int MODE>
+__global__ void __launch_bounds__(256) envelope_td_v3_kernel(const float* __restrict__ q_on, const float* __restrict__ q_tg,
                                                              const float* __restrict__ wset, const float* __restrict__ reward,
                                                              const float* __restrict__ done, float gamma, float one, int B, int W,
                                                              int A, int Cp, int CS, int gps, int row_order,
                                                              float* __restrict__ target_out, int32_t* __restrict__ pref_out,
                                                              int32_t* __restrict__ act_out) {
+    constexpr bool FILTER = (MODE != MORL_DOT_FMA);
+    constexpr int SCAN_MODE = MORL_DOT_FMA;  // arithmetic of the scan: the FMA chain (exact when MODE == FMA)
     extern __shared__ __align__(16) float smem[];
-    const int C = W * A;               // candidates per transition
-    const int plane = Cp;              // floats per objective plane (multiple of 8, 16-byte aligned rows)
-    const int stage_floats = D * plane;
-    float* stage0 = smem;
-    float* stage1 = smem + stage_floats;
-    const int WI = blockDim.x / CS;    // weights handled per CTA (multiple of 32)
-    float* red_v = smem + 2 * stage_floats;                   // [CS][WI]
-    int* red_g = reinterpret_cast<int*>(red_v + CS * WI);     // [CS][WI]
+    const int C = W * A;
+    const int plane = Cp;
+    float* Qs = smem;                                        // [D][Cp] SoA planes of Q_on[b]
+    float* Qt = smem + D * plane;                            // [C*D] AoS copy of Q_tg[b] (bulk async copy)
+    const int WI = blockDim.x / CS;
+    float* red_v = Qt + ((C * D + 3) & ~3);                  // [CS][WI] best
+    float* red_s = red_v + CS * WI;                          // [CS][WI] runner-up
+    int* red_g = reinterpret_cast<int*>(red_s + CS * WI);    // [CS][WI] group of best
+    float* red_amax = reinterpret_cast<float*>(red_g + CS * WI);  // [32] per-warp max |Q|
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red_amax + 32);
 
     const int il = threadIdx.x % WI;
     const int cs = threadIdx.x / WI;
     const int i = blockIdx.y * WI + il;
     const bool active = i < W;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
     const u64 one2 = pk2(one, one);
 
     float w[D];
     u64 w2[D];
+    float wsum = 0.f;
 #pragma unroll
     for (int r = 0; r < D; ++r) {
         w[r] = active ? __ldg(wset + (size_t)i * D + r) : 0.f;
         w2[r] = pk2(w[r], w[r]);
+        wsum += fabsf(w[r]);
     }
-
-    const int n4 = (C * D) / 4;  // the launcher guarantees C*D % 4 == 0 and 16-byte aligned rows
     const int ngroups = (C + 7) / 8;
     const int g_begin = cs * gps;
     const int g_end = min(g_begin + gps, ngroups);
+    const int g_full = min(g_end, C / 8);
+    const uint32_t qt_bytes = (uint32_t)(C * D) * 4u;  // multiple of 16 (launcher)
 
-    // zero the padding columns [C, Cp) of both stages once (scores of padded candidates are masked, but must be finite)
-    for (int t = threadIdx.x; t < (Cp - C) * D; t += blockDim.x) {
-        const int r = t / (Cp - C), c = C + t % (Cp - C);
-        stage0[r * plane + c] = 0.f;
-        stage1[r * plane + c] = 0.f;
-    }
-
-    auto store_tile = [&](float* st, const float4& v, int e4) {
-        const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int e = 4 * e4 + k;
-            const int c = e / D, r = e - c * D;
-            st[r * plane + c] = x[k];
-        }
-    };
-
-    // prologue: first tile straight to stage 0
-    int b = blockIdx.x;
-    if (b < B) {
-        const float4* src = reinterpret_cast<const float4*>(q_on + (size_t)b * C * D);
-        for (int t = threadIdx.x; t < n4; t += blockDim.x) store_tile(stage0, __ldg(src + t), t);
-    }
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    for (int t = threadIdx.x; t < (Cp - C) * D; t += blockDim.x) Qs[(t / (Cp - C)) * plane + C + t % (Cp - C)] = 0.f;
     __syncthreads();
 
-    const bool can_prefetch = PIPE && (n4 <= kV2MaxPrefetch * (int)blockDim.x);
-    int it = 0;
-    for (; b < B; b += gridDim.x, ++it) {
-        float* cur = (it & 1) ? stage1 : stage0;
-        float* nxt = (it & 1) ? stage0 : stage1;
-        const int bn = b + gridDim.x;
-        float4 pf[PIPE ? kV2MaxPrefetch : 1];
-        if (PIPE && can_prefetch && bn < B) {
-            const float4* src = reinterpret_cast<const float4*>(q_on + (size_t)bn * C * D);
+    uint32_t parity = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, parity ^= 1u) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, qt_bytes);
+            bulk_g2s(Qt, q_tg + (size_t)b * C * D, qt_bytes, bar);
+        }
+        // pre-load the per-transition scalars of the epilogue
+        float rw[D];
+        float dn = 0.f;
+        if (cs == 0) {
+            dn = __ldg(done + b);
 #pragma unroll
-            for (int k = 0; k < kV2MaxPrefetch; ++k) {
-                const int t = threadIdx.x + k * blockDim.x;
-                if (t < n4) pf[k] = __ldg(src + t);
+            for (int r = 0; r < D; ++r) rw[r] = __ldg(reward + (size_t)b * D + r);
+        }
+        // ---- transposing load of Q_on[b]: candidate-major walk, conflict-free STS, running max |q| ----
+        float amax = 0.f;
+        {
+            const float* src = q_on + (size_t)b * C * D;
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                float x[D];
+#pragma unroll
+                for (int r = 0; r < D; ++r) x[r] = __ldg(src + (size_t)c * D + r);
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    Qs[r * plane + c] = x[r];
+                    amax = fmaxf(amax, fabsf(x[r]));
+                    if (!(x[r] == x[r])) amax = INFINITY;  // NaN in the block: force the exact path
+                }
+            }
+            if (FILTER) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+                if (lane == 0) red_amax[threadIdx.x >> 5] = amax;
             }
         }
+        __syncthreads();
+        float qmax = 0.f;
+        if (FILTER)
+            for (int k = 0; k < nwarps; ++k) qmax = fmaxf(qmax, red_amax[k]);
 
-        // ---- scan: groups of 8 candidates, packed arithmetic ----
-        float best = -INFINITY;
+        // ---- scan: groups of 8 candidates, packed FMA-chain scores, best / runner-up group maxima ----
+        float best = -INFINITY, second = -INFINITY;
         int bg = INT_MAX;
         auto scan_group = [&](int g, bool tail) {
             const int c0 = 8 * g;
             u64 q2[4][D];
 #pragma unroll
             for (int r = 0; r < D; ++r) {
-                const float4 lo = *reinterpret_cast<const float4*>(cur + r * plane + c0);
-                const float4 hi = *reinterpret_cast<const float4*>(cur + r * plane + c0 + 4);
+                const float4 lo = *reinterpret_cast<const float4*>(Qs + r * plane + c0);
+                const float4 hi = *reinterpret_cast<const float4*>(Qs + r * plane + c0 + 4);
                 q2[0][r] = pk2(lo.x, lo.y);
                 q2[1][r] = pk2(lo.z, lo.w);
                 q2[2][r] = pk2(hi.x, hi.y);
@@ -285,70 +330,97 @@ __global__ void __launch_bounds__(256) envelope_td_v2_kernel(const float* __rest
             }
             float x[8];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) upk2(dotw2<D, MODE>(w2, q2[p], one2), x[2 * p], x[2 * p + 1]);
-            if (tail) {  // last, partially filled group: padded candidates can never win
+            for (int p = 0; p < 4; ++p) upk2(dotw2<D, SCAN_MODE>(w2, q2[p], one2), x[2 * p], x[2 * p + 1]);
+            if (tail) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     if (c0 + k >= C) x[k] = -INFINITY;
             }
             const float m = fmaxf(max3(x[0], x[1], x[2]), max3(max3(x[3], x[4], x[5]), x[6], x[7]));
+            if (FILTER) second = fmaxf(second, fminf(best, m));
             if (m > best) {
                 best = m;
                 bg = g;
             }
         };
-        const int g_full = min(g_end, C / 8);  // groups entirely inside [0, C)
         for (int g = g_begin; g < g_full; ++g) scan_group(g, false);
         for (int g = max(g_begin, g_full); g < g_end; ++g) scan_group(g, true);
 
         if (CS > 1) {
             red_v[cs * WI + il] = best;
             red_g[cs * WI + il] = bg;
+            if (FILTER) red_s[cs * WI + il] = second;
             __syncthreads();
         }
-        if (cs == 0 && active) {
-            for (int s = 1; s < CS; ++s) argmax_merge(best, bg, red_v[s * WI + il], red_g[s * WI + il]);
+        if (cs == 0) {  // warp-uniform: WI is a multiple of 32
+            for (int s = 1; s < CS; ++s) {
+                const float v2 = red_v[s * WI + il];
+                const int g2 = red_g[s * WI + il];
+                if (FILTER) second = fmaxf(fmaxf(second, red_s[s * WI + il]), fminf(best, v2));
+                argmax_merge(best, bg, v2, g2);
+            }
             int cstar = 0;
-            if (bg != INT_MAX) {
-                // exact first position inside the winning group: re-evaluate its scores with the scalar arithmetic
+            bool amb = false;
+            if (FILTER) {
+                const float thr = 1.9073486328125e-06f * wsum * qmax;  // 2^-19 * sum|w| * max|Q|
+                amb = active && !(second < best - thr);                // also true for NaN / inf
+            }
+            if (!amb && bg != INT_MAX) {
+                // exact first argmax inside the winning group, contract arithmetic (strict '>' from the left)
                 const int c0 = 8 * bg;
-                int kf = -1;
+                float ev = -INFINITY;
+                int kf = 0;
 #pragma unroll
-                for (int k = 7; k >= 0; --k) {
+                for (int k = 0; k < 8; ++k) {
                     float q[D];
 #pragma unroll
-                    for (int r = 0; r < D; ++r) q[r] = cur[r * plane + c0 + k];
+                    for (int r = 0; r < D; ++r) q[r] = Qs[r * plane + c0 + k];
                     const float s = dotw<D, MODE>(w, q);
-                    if (s == best && c0 + k < C) kf = k;
+                    if (c0 + k < C && s > ev) {
+                        ev = s;
+                        kf = k;
+                    }
                 }
-                cstar = c0 + (kf < 0 ? 0 : kf);
+                cstar = c0 + kf;
             }
-            const int jstar = cstar / A;
-            const int astar = cstar - jstar * A;
-            const float* qt = q_tg + (((size_t)b * W + jstar) * A + astar) * D;
-            const size_t k = (row_order == MORL_ROWS_REFERENCE) ? ((size_t)i * B + b) : ((size_t)b * W + i);
-            const float dn = __ldg(done + b);
+            if (FILTER) {
+                // near ties: the whole warp re-scans the row exactly (rare)
+                unsigned ambmask = __ballot_sync(0xffffffffu, amb);
+                while (ambmask) {
+                    const int L = __ffs(ambmask) - 1;
+                    ambmask &= ambmask - 1;
+                    float wl[D];
 #pragma unroll
-            for (int r = 0; r < D; ++r)
-                target_out[k * D + r] = bellman(__ldg(reward + (size_t)b * D + r), dn, gamma, __ldg(qt + r));
-            if (pref_out) pref_out[k] = jstar;
-            if (act_out) act_out[k] = astar;
-        }
-
-        // ---- publish the next tile ----
-        if (bn < B) {
-            if (PIPE && can_prefetch) {
+                    for (int r = 0; r < D; ++r) wl[r] = __shfl_sync(0xffffffffu, w[r], L);
+                    float bv = -INFINITY;
+                    int bc = INT_MAX;
+                    for (int c = lane; c < C; c += 32) {
+                        float q[D];
 #pragma unroll
-                for (int k = 0; k < (PIPE ? kV2MaxPrefetch : 1); ++k) {
-                    const int t = threadIdx.x + k * blockDim.x;
-                    if (t < n4) store_tile(nxt, pf[k], t);
+                        for (int r = 0; r < D; ++r) q[r] = Qs[r * plane + c];
+                        const float s = dotw<D, MODE>(wl, q);
+                        if (s > bv) {
+                            bv = s;
+                            bc = c;
+                        }
+                    }
+                    warp_argmax(bv, bc);
+                    if (lane == L) cstar = (bc == INT_MAX) ? 0 : bc;
                 }
-            } else {
-                const float4* src = reinterpret_cast<const float4*>(q_on + (size_t)bn * C * D);
-                for (int t = threadIdx.x; t < n4; t += blockDim.x) store_tile(nxt, __ldg(src + t), t);
+            }
+            mbar_wait(bar, parity);  // Q_tg[b] has landed in shared memory
+            if (active) {
+                const int jstar = cstar / A;
+                const int astar = cstar - jstar * A;
+                const float* qt = Qt + (size_t)cstar * D;
+                const size_t k = (row_order == MORL_ROWS_REFERENCE) ? ((size_t)i * B + b) : ((size_t)b * W + i);
+#pragma unroll
+                for (int r = 0; r < D; ++r) target_out[k * D + r] = bellman(rw[r], dn, gamma, qt[r]);
+                if (pref_out) pref_out[k] = jstar;
+                if (act_out) act_out[k] = astar;
             }
         }
-        __syncthreads();
+        __syncthreads();  // Qs / Qt / red_* are rewritten by the next transition
     }
 }
 
@@ -361,9 +433,11 @@ struct EnvelopeV2Plan {
 
 static EnvelopeV2Plan plan_envelope_v2(int B, int W, int A, int D, int sm_count) {
     EnvelopeV2Plan p{};
+    (void)B;
+    (void)sm_count;
     const long long C = (long long)W * A;
     p.ok = false;
-    if ((C * D) % 4 != 0) return p;  // rows of Q_on[b] must stay 16-byte aligned for the float4 loads
+    if ((C * D) % 4 != 0) return p;  // Q_tg[b] must be a 16-byte multiple for the bulk copy
     const int Wp = (W + 31) / 32 * 32;
     p.WI = Wp < 256 ? Wp : 256;
     const int warps_i = p.WI / 32;
@@ -375,8 +449,9 @@ static EnvelopeV2Plan plan_envelope_v2(int B, int W, int A, int D, int sm_count)
     p.gps = (ngroups + cs - 1) / cs;
     p.Cp = ngroups * 8;
     p.block = dim3((unsigned)(p.WI * p.CS), 1, 1);
-    const size_t stage = (size_t)D * p.Cp * sizeof(float);
-    p.smem = 2 * stage + 2 * (size_t)p.CS * p.WI * sizeof(float);
+    const size_t qs = (size_t)D * p.Cp * sizeof(float);
+    const size_t qt = (((size_t)C * D + 3) & ~(size_t)3) * sizeof(float);
+    p.smem = qs + qt + 3 * (size_t)p.CS * p.WI * sizeof(float) + 32 * sizeof(float) + 16;
     if (p.smem > 96 * 1024) return p;
     p.grid = dim3(1u, (unsigned)((W + p.WI - 1) / p.WI), 1);  // grid.x is set by the launcher from the measured occupancy
     p.ok = true;
@@ -445,32 +520,22 @@ extern "C" int morl_envelope_td_f32(const float* q_online, const float* q_target
     if (p2.ok && !g_force_v1) {
         bool launched2 = false;
         MORL_DISPATCH_D(D, MORL_DISPATCH_MODE(dot_mode, {
-                            auto k1 = envelope_td_v2_kernel<kD, kMode, false>;  // one transition per CTA, everything co-resident
-                            auto kp = envelope_td_v2_kernel<kD, kMode, true>;   // persistent, register-prefetched double buffer
-                            if (p2.smem > 48 * 1024) {
-                                cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2.smem);
-                                cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2.smem);
-                            }
-                            int occ1 = 0, occp = 0;
-                            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, (int)p2.block.x, p2.smem);
-                            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, kp, (int)p2.block.x, p2.smem);
-                            const long long ctas_per_b = p2.grid.y;
-                            if (occ1 > 0 && (long long)B * ctas_per_b <= (long long)sm_count_cached * occ1) {
-                                p2.grid.x = (unsigned)B;  // a single wave: no tail, no pipeline needed
-                                k1<<<p2.grid, p2.block, p2.smem, st>>>(q_online, q_target, wset, reward, done, gamma, 1.0f, B, W, A, p2.Cp,
-                                                                        p2.CS, p2.gps, row_order, target_out, pref_out, act_out);
-                            } else {
-                                long long gx = (long long)sm_count_cached * (occp > 0 ? occp : 1) / ctas_per_b;
-                                if (gx < 1) gx = 1;
-                                if (gx > B) gx = B;
-                                p2.grid.x = (unsigned)gx;
-                                kp<<<p2.grid, p2.block, p2.smem, st>>>(q_online, q_target, wset, reward, done, gamma, 1.0f, B, W, A, p2.Cp,
-                                                                        p2.CS, p2.gps, row_order, target_out, pref_out, act_out);
-                            }
+                            auto kern = envelope_td_v3_kernel<kD, kMode>;
+                            if (p2.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2.smem);
+                            int occ = 0;
+                            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)p2.block.x, p2.smem);
+                            if (occ < 1) occ = 1;
+                            // all transitions co-resident in one wave when they fit, else persistent CTAs striding over b
+                            long long gx = (long long)sm_count_cached * occ / (long long)p2.grid.y;
+                            if (gx < 1) gx = 1;
+                            if (gx > B) gx = B;
+                            p2.grid.x = (unsigned)gx;
+                            kern<<<p2.grid, p2.block, p2.smem, st>>>(q_online, q_target, wset, reward, done, gamma, 1.0f, B, W, A, p2.Cp,
+                                                                      p2.CS, p2.gps, row_order, target_out, pref_out, act_out);
                             launched2 = true;
                         }));
-        MORL_REQUIRE(launched2, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: no v2 kernel for D=%d mode=%d", D, dot_mode);
-        return check_launch("morl_envelope_td_f32(v2)");
+        MORL_REQUIRE(launched2, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: no fast-path kernel for D=%d mode=%d", D, dot_mode);
+        return check_launch("morl_envelope_td_f32(v3)");
     }
     const EnvelopePlan p = plan_envelope(B, W, A, D);
     const bool vec4 = (A % 4 == 0);

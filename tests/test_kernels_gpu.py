@@ -78,6 +78,33 @@ def test_envelope_td_degenerate_values(cuda):
     assert int(p.abs().sum()) == 0 and int(a.abs().sum()) == 0
 
 
+@pytest.mark.parametrize("shape", [(64, 64, 8, 3), (33, 32, 4, 3), (16, 16, 8, 2), (8, 40, 5, 4)])
+def test_envelope_td_near_ties(cuda, shape):
+    """Candidates a few ulps apart: the FMA-chain filter of the fast path cannot separate them, so rows must fall back to the
+    exact re-scan; FMA and unfused arithmetic genuinely pick different indices here, and every mode must match its oracle."""
+    from morl_baselines_b200 import ops
+
+    B, W, A, D = shape
+    rng = np.random.default_rng(B + 7 * W)
+    base = rng.standard_normal((B, 1, 1, D)).astype(np.float32)
+    q_on = (base * (1.0 + rng.integers(0, 6, size=(B, W, A, D)) * np.float32(2.0**-23))).astype(np.float32)
+    q_on[::3] = rng.standard_normal((len(q_on[::3]), W, A, D)).astype(np.float32)  # mix in well separated rows
+    q_tg = rng.standard_normal((B, W, A, D)).astype(np.float32)
+    wset = cases.gaussian_weights(rng, W, D)
+    reward = rng.standard_normal((B, D)).astype(np.float32)
+    done = np.zeros(B, np.float32)
+    n_diff = 0
+    ref = {}
+    for mode in (ops.DOT_UNFUSED, ops.DOT_FMA, ops.DOT_PAIRFMA):
+        t, p, a = ops.envelope_td(_t(q_on, cuda), _t(q_tg, cuda), _t(wset, cuda), _t(reward, cuda), _t(done, cuda), 0.99, mode, ops.ROWS_REFERENCE)
+        to, po, ao = orc.envelope_td(q_on, q_tg, wset, reward, done, 0.99, mode, orc.ROWS_REFERENCE)
+        assert np.array_equal(p.cpu().numpy(), po) and np.array_equal(a.cpu().numpy(), ao), mode
+        assert np.array_equal(t.cpu().numpy(), to), mode
+        ref[mode] = (po, ao)
+    n_diff = int((ref[ops.DOT_UNFUSED][0] != ref[ops.DOT_FMA][0]).sum() + (ref[ops.DOT_UNFUSED][1] != ref[ops.DOT_FMA][1]).sum())
+    assert n_diff > 0  # the construction really separates the arithmetics
+
+
 def test_envelope_td_full_size_properties(cuda):
     """North-star shape (B=1024, |W|=64, |A|=8, d=3): size-independent properties.
       * optimality: the chosen (j*, a*) attains the maximum scalarised value and no earlier candidate equals it;
