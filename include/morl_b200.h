@@ -193,6 +193,31 @@ MORL_API int morl_pareto_mask_f64(const double* pts, int N, int D, int remove_du
 MORL_API int morl_polyak_f32(const float* const* params, float* const* targets, const int64_t* sizes, int n_tensors,
                     int64_t max_size, double tau, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * FP32-accurate dense layers on the tcgen05 tensor cores.  Replace the fp32 GEMMs behind the reference's nn.Linear layers
+ * (common/networks.py:10-48; called from envelope.py:59-77 / :300, :420, :429 on the 65,536-row effective batch).
+ * Every fp32 operand is carried as three bf16 planes x = x0 + x1 + x2 ("bf16x3", [3][rows][ld] with `plane_stride`
+ * elements between planes); a product is six bf16 MMAs with fp32 accumulation in tensor memory (see csrc/gemm_bf16x3.cu).
+ *
+ * morl_split_bf16x3 : fp32 [rows, cols] (row stride ld_src; transposed read if `transpose`) -> planes [3][rows_pad][ldp],
+ *                     zero padded.
+ * morl_gemm_bf16x3_f32 : C = act(A . B^T + bias),  A planes [3][M][K] (K-major), B planes [3][N_pad][K] (K-major weights);
+ *                     K % 32 == 0, N_pad % 32 == 0, N_pad <= 256.  Outputs: c_f32 [M, ldc] and/or c_planes [3][M][ldp]
+ *                     (the operand format of the next layer).  relu != 0 applies max(x, 0); relu_mask_plane0 (plane 0 of a
+ *                     forward activation, [M][ld_mask] bf16) zeroes the outputs where that activation was <= 0 (ReLU backward).
+ */
+MORL_API int morl_split_bf16x3(const float* src, int rows, int cols, int ld_src, int transpose, void* dst_planes, int rows_pad,
+                               int ldp, long long plane_stride, void* stream);
+MORL_API int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stride, const void* b_planes, long long b_plane_stride,
+                                  int M, int N, int N_pad, int K, const float* bias, int relu, const void* relu_mask_plane0,
+                                  int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp, long long c_plane_stride,
+                                  void* stream);
+/* h[b*W + j, :] = relu(u[b, :] + v[j, :]) written directly as bf16x3 planes [3][B*W][H] (separable first layer of the
+ * weight-conditioned Q-network: W1 [s || w] + b1 = W1_s s + (W1_w w + b1); reference envelope.py:75 builds the concat). */
+MORL_API int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B, int W, int H, void* dst_planes,
+                                          long long plane_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

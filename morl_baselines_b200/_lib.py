@@ -39,6 +39,9 @@ SIGNATURES = {
     "morl_pareto_mask_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_pareto_mask_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_polyak_f32": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),
+    "morl_split_bf16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, C.c_longlong, _vp]),
+    "morl_gemm_bf16x3_f32": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_longlong, _vp]),
+    "morl_pairs_relu_split_bf16x3": (_i, [_vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
 }
 
 _lib = None

@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(256) envelope_td_v3_kernel(const float* __rest
     int* red_g = reinterpret_cast<int*>(red_s + CS * WI);    // [CS][WI] group of best
     float* red_amax = reinterpret_cast<float*>(red_g + CS * WI);  // [32] per-warp max |Q|
     uint64_t* bar = reinterpret_cast<uint64_t*>(red_amax + 32);
+    uint64_t* bar_on = bar + 1;
+    float* Qa = reinterpret_cast<float*>(bar + 2);           // [C*D] AoS staging of Q_on[b] (bulk async copy)
 
     const int il = threadIdx.x % WI;
     const int cs = threadIdx.x / WI;
@@ -269,13 +271,18 @@ __global__ void __launch_bounds__(256) envelope_td_v3_kernel(const float* __rest
     const int g_full = min(g_end, C / 8);
     const uint32_t qt_bytes = (uint32_t)(C * D) * 4u;  // multiple of 16 (launcher)
 
-    if (threadIdx.x == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar_on, 1);
+    }
     for (int t = threadIdx.x; t < (Cp - C) * D; t += blockDim.x) Qs[(t / (Cp - C)) * plane + C + t % (Cp - C)] = 0.f;
     __syncthreads();
 
     uint32_t parity = 0;
     for (int b = blockIdx.x; b < B; b += gridDim.x, parity ^= 1u) {
         if (threadIdx.x == 0) {
+            mbar_expect_tx(bar_on, qt_bytes);
+            bulk_g2s(Qa, q_on + (size_t)b * C * D, qt_bytes, bar_on);
             mbar_expect_tx(bar, qt_bytes);
             bulk_g2s(Qt, q_tg + (size_t)b * C * D, qt_bytes, bar);
         }
@@ -287,14 +294,15 @@ __global__ void __launch_bounds__(256) envelope_td_v3_kernel(const float* __rest
 #pragma unroll
             for (int r = 0; r < D; ++r) rw[r] = __ldg(reward + (size_t)b * D + r);
         }
-        // ---- transposing load of Q_on[b]: candidate-major walk, conflict-free STS, running max |q| ----
+        // ---- Q_on[b] arrives by the same bulk async copy (AoS staging); transpose smem -> smem into the SoA planes ----
+        // (reads at stride D words are bank-conflict free for odd D; the running max |q| feeds the filter threshold)
         float amax = 0.f;
         {
-            const float* src = q_on + (size_t)b * C * D;
+            mbar_wait(bar_on, parity);
             for (int c = threadIdx.x; c < C; c += blockDim.x) {
                 float x[D];
 #pragma unroll
-                for (int r = 0; r < D; ++r) x[r] = __ldg(src + (size_t)c * D + r);
+                for (int r = 0; r < D; ++r) x[r] = Qa[c * D + r];
 #pragma unroll
                 for (int r = 0; r < D; ++r) {
                     Qs[r * plane + c] = x[r];
@@ -343,6 +351,7 @@ __global__ void __launch_bounds__(256) envelope_td_v3_kernel(const float* __rest
                 bg = g;
             }
         };
+#pragma unroll 2
         for (int g = g_begin; g < g_full; ++g) scan_group(g, false);
         for (int g = max(g_begin, g_full); g < g_end; ++g) scan_group(g, true);
 
@@ -451,7 +460,7 @@ static EnvelopeV2Plan plan_envelope_v2(int B, int W, int A, int D, int sm_count)
     p.block = dim3((unsigned)(p.WI * p.CS), 1, 1);
     const size_t qs = (size_t)D * p.Cp * sizeof(float);
     const size_t qt = (((size_t)C * D + 3) & ~(size_t)3) * sizeof(float);
-    p.smem = qs + qt + 3 * (size_t)p.CS * p.WI * sizeof(float) + 32 * sizeof(float) + 16;
+    p.smem = qs + 2 * qt + 3 * (size_t)p.CS * p.WI * sizeof(float) + 32 * sizeof(float) + 16;
     if (p.smem > 96 * 1024) return p;
     p.grid = dim3(1u, (unsigned)((W + p.WI - 1) / p.WI), 1);  // grid.x is set by the launcher from the measured occupancy
     p.ok = true;

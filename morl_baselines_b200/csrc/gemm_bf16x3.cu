@@ -1,0 +1,433 @@
+// gemm_bf16x3.cu -- FP32-accurate dense layers on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces the cuBLAS SIMT sgemm calls behind the reference's nn.Linear layers (common/networks.py:10-48, called from
+// multi_policy/envelope/envelope.py:59-77, 300, 420, 429) on the 65,536-row effective batch.  The 1e-5 parity bar rules out
+// plain TF32/BF16, so every fp32 operand x is carried as three bf16 planes x = x0 + x1 + x2 (8 + 8 + 8 mantissa bits,
+// exact to 2^-24 relative) and a product A.B^T is evaluated as the six tensor-core MMAs
+//       A0B0 + A0B1 + A1B0 + A1B1 + A0B2 + A2B0            (dropped terms are O(2^-24))
+// accumulated in fp32 in tensor memory.  Each bf16 x bf16 product is exact in fp32, so the result differs from an fp32 GEMM
+// only by accumulation order -- the same class of difference as MKL vs cuBLAS.
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor.3d of a [3 planes x 128 rows x 32 k] A box and a [3 x BN x 32] B box per
+//              stage (64-byte swizzle), 3-stage mbarrier ring;
+//   warp 1   : MMA issuer     -- one elected thread issues 12 tcgen05.mma.kind::f16 (M=128, N=BN, K=16) per stage and commits
+//              the stage back to the producer; accumulators live in TMEM (2 x BN columns, double buffered);
+//   warps 2-5: epilogue       -- tcgen05.ld (32 lanes x 32 columns per warp-instruction), + bias, ReLU / ReLU-mask, then either an
+//              fp32 row-major store and/or a re-split into three bf16 planes (the operand format of the next layer), so
+//              intermediate activations never exist in fp32 in HBM.
+// Operands: A3 [3][M][K] bf16 (K-major), B3 [3][N_pad][K] bf16 (K-major), K % 32 == 0, N_pad % 16 == 0, N_pad <= 256.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace morl {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 32;        // bf16 elements per stage along K (= one 64-byte swizzle row)
+constexpr int kGemmStages = 3;
+constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug becomes a trap (launch error) instead of a hung GPU.
+__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(g_smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(g_smem_u32(dst)),
+        "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major canonical layout with 64-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
+//   rows of 64 B (32 bf16), 8-row groups of 512 B; SBO = 512 B between 8-row groups; LBO unused (1).
+__device__ __forceinline__ uint64_t make_desc_k_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                      // leading byte offset (ignored for swizzled K-major), 16-byte units
+    d |= (uint64_t)(512 >> 4) << 32;             // stride byte offset: 8 rows x 64 B
+    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                      // layout type: SWIZZLE_64B
+    return d;
+}
+
+struct GemmArgs {
+    int M, N, N_pad, K;          // N_pad = B rows covered by the tensor map box (multiple of 16, <= 256)
+    const float* bias;           // [N] or nullptr
+    float* c_f32;                // [M, ldc] or nullptr
+    int ldc;
+    __nv_bfloat16* c_planes;     // [3][M][ldp] or nullptr (re-split output: operand of the next layer)
+    int ldp;                     // columns of a plane row (>= N, multiple of 32; columns [N, ldp) are written as zero)
+    long long plane_stride;      // elements between planes
+    const __nv_bfloat16* mask;   // plane 0 of the forward activation [M][ld_mask] for the ReLU-backward mask, or nullptr
+    int ld_mask;
+    int relu;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    extern __shared__ uint8_t gsmem_raw[];
+    uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
+    const int BN = g.N_pad;
+    const uint32_t a_stage_bytes = 3u * kGemmBM * kGemmBK * 2u;      // 24 KB
+    const uint32_t b_stage_bytes = 3u * (uint32_t)BN * kGemmBK * 2u;  // <= 48 KB
+    const uint32_t b_stage_stride = 3u * 256u * kGemmBK * 2u;
+    uint8_t* smA = gsmem;
+    uint8_t* smB = gsmem + kGemmStages * a_stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kGemmStages * b_stage_stride);
+    uint64_t* empty = full + kGemmStages;
+    uint64_t* tfull = empty + kGemmStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [256]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = (g.M + kGemmBM - 1) / kGemmBM;
+    const int n_kblk = g.K / kGemmBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            g_mbar_init(&full[s], 1);
+            g_mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            g_mbar_init(&tfull[s], 1);
+            g_mbar_init(&tempty[s], 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) bias_s[t] = (g.bias && t < g.N) ? g.bias[t] : 0.f;
+    if (warp == 1) {  // TMEM: 512 columns (two BN-column accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < n_kblk; ++kb) {
+                    g_mbar_wait(&empty[stage], phase ^ 1u);
+                    g_mbar_expect_tx(&full[stage], a_stage_bytes + b_stage_bytes);
+                    tma_load_3d(smA + stage * a_stage_bytes, &tmA, &full[stage], kb * kGemmBK, tile * kGemmBM, 0);
+                    tma_load_3d(smB + stage * b_stage_stride, &tmB, &full[stage], kb * kGemmBK, 0, 0);
+                    if (++stage == kGemmStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+            const uint32_t a_plane = kGemmBM * kGemmBK * 2u;   // 8 KB
+            const uint32_t b_plane = (uint32_t)BN * kGemmBK * 2u;
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1u;
+                g_mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256u;
+                for (int kb = 0; kb < n_kblk; ++kb) {
+                    g_mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = g_smem_u32(smA + stage * a_stage_bytes);
+                    const uint32_t b0 = g_smem_u32(smB + stage * b_stage_stride);
+#pragma unroll
+                    for (int ks = 0; ks < kGemmBK / 16; ++ks) {
+                        // small terms first; the six products of the bf16x3 expansion
+                        const int pa[6] = {2, 0, 1, 1, 0, 0};
+                        const int pb[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+                        for (int t = 0; t < 6; ++t) {
+                            const uint64_t ad = make_desc_k_sw64(a0 + pa[t] * a_plane + ks * 32);
+                            const uint64_t bd = make_desc_k_sw64(b0 + pb[t] * b_plane + ks * 32);
+                            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&empty[stage]);  // frees the smem stage when the MMAs above have read it
+                    if (++stage == kGemmStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit(&tfull[as]);  // accumulator complete
+            }
+        }
+    } else {
+        // ================= epilogue warps (2..5) =================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1u;
+            g_mbar_wait(&tfull[as], (it >> 1) & 1u);
+            tc_fence_after();
+            const int row = tile * kGemmBM + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            const uint32_t t_row = tmem_base + as * 256u + ((uint32_t)(quad * 32) << 16);
+            for (int n0 = 0; n0 < BN; n0 += 32) {
+                uint32_t v[32];
+                tc_ld32(t_row + (uint32_t)n0, v);
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float f = __uint_as_float(v[j]) + bias_s[n0 + j];
+                    if (g.relu) f = fmaxf(f, 0.f);
+                    x[j] = f;
+                }
+                if (g.mask && row_ok) {
+                    const __nv_bfloat16* mrow = g.mask + (size_t)row * g.ld_mask + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < g.N && !(__bfloat162float(mrow[j]) > 0.f)) x[j] = 0.f;
+                }
+                if (row_ok && g.c_f32) {
+                    float* crow = g.c_f32 + (size_t)row * g.ldc + n0;
+                    if (n0 + 32 <= g.N && (g.ldc % 4 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < g.N) crow[j] = x[j];
+                    }
+                }
+                if (row_ok && g.c_planes && n0 < g.ldp) {
+                    // re-split into three bf16 planes: h0 = bf16(x), h1 = bf16(x - h0), h2 = bf16(x - h0 - h1)
+                    uint32_t p0[16], p1[16], p2[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float a = (n0 + j < g.N) ? x[j] : 0.f, b = (n0 + j + 1 < g.N) ? x[j + 1] : 0.f;
+                        const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
+                        const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
+                        const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
+                        const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
+                        const __nv_bfloat16 a2 = __float2bfloat16_rn(sa), b2 = __float2bfloat16_rn(sb);
+                        p0[j / 2] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+                        p1[j / 2] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                        p2[j / 2] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+                    }
+                    __nv_bfloat16* prow = g.c_planes + (size_t)row * g.ldp + n0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        *reinterpret_cast<uint4*>(prow + 8 * q) = make_uint4(p0[4 * q], p0[4 * q + 1], p0[4 * q + 2], p0[4 * q + 3]);
+                        *reinterpret_cast<uint4*>(prow + g.plane_stride + 8 * q) = make_uint4(p1[4 * q], p1[4 * q + 1], p1[4 * q + 2], p1[4 * q + 3]);
+                        *reinterpret_cast<uint4*>(prow + 2 * g.plane_stride + 8 * q) = make_uint4(p2[4 * q], p2[4 * q + 1], p2[4 * q + 2], p2[4 * q + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) g_mbar_arrive(&tempty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---- fp32 -> three bf16 planes (operands produced outside the GEMM epilogue: network inputs, weights, gradients) ---------
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, int transpose,
+                                                           __nv_bfloat16* __restrict__ dst, int rows_pad, int ldp, long long plane_stride) {
+    // dst[p][r][c] for r < rows_pad, c < ldp; source element (r, c) = transpose ? src[c * ld_src + r] : src[r * ld_src + c]
+    const long long total = (long long)rows_pad * ldp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / ldp), c = (int)(e - (long long)r * ldp);
+        float x = 0.f;
+        if (r < rows && c < cols) x = transpose ? src[(size_t)c * ld_src + r] : src[(size_t)r * ld_src + c];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x);
+        const float r1 = x - __bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+        dst[e] = h0;
+        dst[plane_stride + e] = h1;
+        dst[2 * plane_stride + e] = h2;
+    }
+}
+
+// ---- separable first layer: h[b*W + j] = relu(u[b] + v[j]) straight into bf16x3 planes --------------------------------------
+__global__ void __launch_bounds__(256) pairs_relu_split_kernel(const float* __restrict__ u, const float* __restrict__ v, int B, int W, int H,
+                                                               __nv_bfloat16* __restrict__ dst, long long plane_stride) {
+    const long long total = (long long)B * W * (H / 2);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int h2 = (int)(e % (H / 2));
+        const long long row = e / (H / 2);
+        const int b = (int)(row / W), j = (int)(row - (long long)b * W);
+        const float2 uu = *reinterpret_cast<const float2*>(u + (size_t)b * H + 2 * h2);
+        const float2 vv = *reinterpret_cast<const float2*>(v + (size_t)j * H + 2 * h2);
+        const float x0 = fmaxf(uu.x + vv.x, 0.f), x1 = fmaxf(uu.y + vv.y, 0.f);
+        uint32_t o[3];
+        float a = x0, c = x1;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const __nv_bfloat16 ha = __float2bfloat16_rn(a), hc = __float2bfloat16_rn(c);
+            o[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hc) << 16);
+            a -= __bfloat162float(ha);
+            c -= __bfloat162float(hc);
+        }
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+        const long long off = row * (H / 2) + h2;
+        d32[off] = o[0];
+        d32[plane_stride / 2 + off] = o[1];
+        d32[plane_stride + off] = o[2];
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) ----------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+static int make_plane_map(CUtensorMap* map, const void* base, int rows, int K, long long plane_stride_elems, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return -1;
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_stride_elems * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace morl
+
+extern "C" int morl_split_bf16x3(const float* src, int rows, int cols, int ld_src, int transpose, void* dst_planes, int rows_pad, int ldp,
+                                 long long plane_stride, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(src && dst_planes, MORL_ERR_NULL, "morl_split_bf16x3: NULL pointer argument");
+    MORL_REQUIRE(rows > 0 && cols > 0 && rows_pad >= rows && ldp >= cols && ld_src > 0, MORL_ERR_SHAPE,
+                 "morl_split_bf16x3: bad shape rows=%d cols=%d rows_pad=%d ldp=%d", rows, cols, rows_pad, ldp);
+    MORL_REQUIRE(plane_stride >= (long long)rows_pad * ldp, MORL_ERR_SHAPE, "morl_split_bf16x3: plane_stride too small");
+    const long long total = (long long)rows_pad * ldp;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    split_bf16x3_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, ld_src, transpose,
+                                                                                     static_cast<__nv_bfloat16*>(dst_planes), rows_pad, ldp, plane_stride);
+    return check_launch("morl_split_bf16x3");
+}
+
+extern "C" int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B, int W, int H, void* dst_planes, long long plane_stride,
+                                            void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(u && v && dst_planes, MORL_ERR_NULL, "morl_pairs_relu_split_bf16x3: NULL pointer argument");
+    MORL_REQUIRE(B > 0 && W > 0 && H > 0 && H % 2 == 0 && plane_stride % 2 == 0 && plane_stride >= (long long)B * W * H, MORL_ERR_SHAPE,
+                 "morl_pairs_relu_split_bf16x3: bad shape B=%d W=%d H=%d", B, W, H);
+    const long long total = (long long)B * W * (H / 2);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pairs_relu_split_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(u, v, B, W, H, static_cast<__nv_bfloat16*>(dst_planes),
+                                                                                         plane_stride);
+    return check_launch("morl_pairs_relu_split_bf16x3");
+}
+
+extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stride, const void* b_planes, long long b_plane_stride, int M, int N,
+                                    int N_pad, int K, const float* bias, int relu, const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc,
+                                    void* c_planes, int ldp, long long c_plane_stride, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(a_planes && b_planes && (c_f32 || c_planes), MORL_ERR_NULL, "morl_gemm_bf16x3_f32: NULL pointer argument");
+    MORL_REQUIRE(M > 0 && N > 0 && K > 0 && N_pad >= N, MORL_ERR_SHAPE, "morl_gemm_bf16x3_f32: bad shape M=%d N=%d N_pad=%d K=%d", M, N, N_pad, K);
+    MORL_REQUIRE(K % kGemmBK == 0 && N_pad % 32 == 0 && N_pad <= 256, MORL_ERR_UNSUPPORTED,
+                 "morl_gemm_bf16x3_f32: need K %% 32 == 0, N_pad %% 32 == 0, N_pad <= 256 (K=%d N_pad=%d)", K, N_pad);
+    MORL_REQUIRE(aligned16(a_planes) && aligned16(b_planes), MORL_ERR_ALIGN, "morl_gemm_bf16x3_f32: operand planes must be 16-byte aligned");
+    if (c_planes)
+        MORL_REQUIRE(ldp % 32 == 0 && ldp >= N && ldp <= N_pad && aligned16(c_planes) && c_plane_stride % 8 == 0, MORL_ERR_SHAPE,
+                     "morl_gemm_bf16x3_f32: ldp=%d must be a multiple of 32 with N <= ldp <= N_pad", ldp);
+    CUtensorMap tmA, tmB;
+    int rc = make_plane_map(&tmA, a_planes, M, K, a_plane_stride, kGemmBM);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
+    rc = make_plane_map(&tmB, b_planes, N_pad, K, b_plane_stride, N_pad);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+    GemmArgs g;
+    g.M = M; g.N = N; g.N_pad = N_pad; g.K = K;
+    g.bias = bias; g.c_f32 = c_f32; g.ldc = ldc;
+    g.c_planes = static_cast<__nv_bfloat16*>(c_planes); g.ldp = ldp; g.plane_stride = c_plane_stride;
+    g.mask = static_cast<const __nv_bfloat16*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
+    const size_t smem = (size_t)kGemmStages * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStages * (3u * 256u * kGemmBK * 2u) + 256 + 1024 + 1024 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    int sms = morl_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int n_tiles = (M + kGemmBM - 1) / kGemmBM;
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    gemm_bf16x3_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, g);
+    return check_launch("morl_gemm_bf16x3_f32");
+}

@@ -276,3 +276,62 @@ def sm_count() -> int:
     if n < 0:
         _lib.check(n, "morl_device_sm_count")
     return n
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 dense layers
+def _pad(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def split_bf16x3(x: th.Tensor, rows_pad: Optional[int] = None, ldp: Optional[int] = None, transpose: bool = False,
+                 out: Optional[th.Tensor] = None) -> th.Tensor:
+    """fp32 [rows, cols] -> bf16x3 planes [3, rows_pad, ldp] (zero padded); with ``transpose`` the planes hold x^T."""
+    x = _dev(x, "x")
+    r, c = (x.shape[1], x.shape[0]) if transpose else (x.shape[0], x.shape[1])
+    rows_pad = r if rows_pad is None else rows_pad
+    ldp = _pad(c, 32) if ldp is None else ldp
+    if out is None:
+        out = th.empty((3, rows_pad, ldp), device=x.device, dtype=th.bfloat16)
+    rc = _lib.load().morl_split_bf16x3(_ptr(x), r, c, x.shape[1], int(transpose), _ptr(out), rows_pad, ldp, out.stride(0), _stream())
+    _lib.check(rc, "morl_split_bf16x3")
+    _count()
+    return out
+
+
+def gemm_bf16x3(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Optional[th.Tensor] = None, relu: bool = False,
+                relu_mask: Optional[th.Tensor] = None, out_f32: bool = True, out_planes: bool = False, c_f32: Optional[th.Tensor] = None,
+                c_planes: Optional[th.Tensor] = None):
+    """C = act(A . B^T + bias) on the tcgen05 tensor cores with bf16x3 split operands (fp32-accurate).
+    a_planes [3, M, K], b_planes [3, N_pad, K] (bf16); returns (c_f32 [M, n_out] or None, c_planes [3, M, ldp] or None)."""
+    if a_planes.dtype != th.bfloat16 or b_planes.dtype != th.bfloat16 or not a_planes.is_cuda:
+        raise _lib.MorlB200Error("gemm_bf16x3: operands must be CUDA bfloat16 plane tensors")
+    _, M, K = a_planes.shape
+    _, n_pad, Kb = b_planes.shape
+    if Kb != K or a_planes.stride(1) != K or b_planes.stride(1) != K:
+        raise _lib.MorlB200Error("gemm_bf16x3: operand planes must be K-major with equal K")
+    dev = a_planes.device
+    if out_f32 and c_f32 is None:
+        c_f32 = th.empty((M, n_out), device=dev, dtype=th.float32)
+    if out_planes and c_planes is None:
+        c_planes = th.empty((3, M, _pad(n_out, 32)), device=dev, dtype=th.bfloat16)
+    mask0 = None if relu_mask is None else relu_mask[0]
+    rc = _lib.load().morl_gemm_bf16x3_f32(_ptr(a_planes), a_planes.stride(0), _ptr(b_planes), b_planes.stride(0), M, n_out, n_pad, K, _ptr(bias),
+                                          int(relu), _ptr(mask0), 0 if mask0 is None else mask0.stride(0), _ptr(c_f32),
+                                          0 if c_f32 is None else c_f32.stride(0), _ptr(c_planes), 0 if c_planes is None else c_planes.shape[2],
+                                          0 if c_planes is None else c_planes.stride(0), _stream())
+    _lib.check(rc, "morl_gemm_bf16x3_f32")
+    _count()
+    return c_f32, c_planes
+
+
+def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None) -> th.Tensor:
+    """relu(u[b] + v[j]) for every pair, written as bf16x3 planes [3, B*W, H] (row b*W + j)."""
+    u, v = _dev(u, "u"), _dev(v, "v")
+    B, H = u.shape
+    W = v.shape[0]
+    if out is None:
+        out = th.empty((3, B * W, H), device=u.device, dtype=th.bfloat16)
+    rc = _lib.load().morl_pairs_relu_split_bf16x3(_ptr(u), _ptr(v), B, W, H, _ptr(out), out.stride(0), _stream())
+    _lib.check(rc, "morl_pairs_relu_split_bf16x3")
+    _count()
+    return out

@@ -1,0 +1,96 @@
+"""GPU tests of the tcgen05 bf16x3 GEMM (csrc/gemm_bf16x3.cu) against a float64 reference.
+
+Tolerance: the six-term bf16x3 expansion is exact to ~2^-24 per product and accumulates in fp32, so the result must agree
+with the float64 product to fp32-GEMM accuracy: |err| <= 2e-6 * (|A| . |B|^T) elementwise (2e-6 ~ 32 ulp of headroom for the
+K = 256 accumulation; a plain BF16 or TF32 GEMM misses this bound by two to three orders of magnitude)."""
+
+import numpy as np
+import pytest
+import torch as th
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, bias):
+    r = a.double() @ b.double().t()
+    if bias is not None:
+        r = r + bias.double()
+    return r
+
+
+def _bound(a, b):
+    return 2e-6 * (a.abs().double() @ b.abs().double().t()) + 1e-30
+
+
+def test_split_planes_are_exact_to_2pow24(cuda):
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(0)
+    x = th.randn(300, 70, device=cuda, generator=g) * th.exp(3 * th.randn(300, 70, device=cuda, generator=g))
+    p = ops.split_bf16x3(x, rows_pad=320, ldp=96)
+    s = p[0].double() + p[1].double() + p[2].double()
+    assert th.all(s[300:] == 0) and th.all(s[:, 70:] == 0)
+    assert float(((s[:300, :70] - x.double()).abs() / x.abs().double()).max()) <= 2.0**-23
+    pt = ops.split_bf16x3(x, transpose=True)
+    assert th.equal(pt[0][:70, :300], p[0][:300, :70].t())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1000, 256, 256), (65536, 256, 256), (4096, 24, 256), (777, 256, 32), (513, 64, 64)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_gemm_bf16x3_matches_float64(cuda, M, N, K, relu):
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(M + N + K)
+    a = th.randn(M, K, device=cuda, generator=g)
+    b = th.randn(N, K, device=cuda, generator=g) / np.sqrt(K)
+    bias = th.randn(N, device=cuda, generator=g)
+    ap = ops.split_bf16x3(a)
+    bp = ops.split_bf16x3(b, rows_pad=(N + 31) // 32 * 32)
+    c, cp = ops.gemm_bf16x3(ap, bp, N, bias=bias, relu=relu, out_f32=True, out_planes=(N % 32 == 0))
+    ref = _ref(a, b, bias)
+    if relu:
+        ref = ref.clamp_min(0)
+    err = (c.double() - ref).abs()
+    bound = _bound(a, b) + 2e-6 * bias.abs().double()
+    assert bool((err <= bound).all()), float((err / bound).max())
+    # a plain fp32 cuBLAS product sits inside the same bound (sanity of the bound itself)
+    c32 = th.addmm(bias, a, b.t())
+    c32 = c32.clamp_min(0) if relu else c32
+    assert bool(((c32.double() - ref).abs() <= bound).all())
+    if cp is not None:
+        s = cp[0].double() + cp[1].double() + cp[2].double()
+        assert float((s - c.double()).abs().max()) <= 2.0**-22 * float(c.abs().max())
+
+
+def test_gemm_relu_mask_and_chaining(cuda):
+    """Two chained layers through the plane format (no fp32 round trip) and the ReLU-backward mask."""
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(5)
+    M, H = 2048, 256
+    x = th.randn(M, H, device=cuda, generator=g)
+    w1 = th.randn(H, H, device=cuda, generator=g) / 16
+    w2 = th.randn(H, H, device=cuda, generator=g) / 16
+    b1 = th.randn(H, device=cuda, generator=g) * 0.1
+    xp = ops.split_bf16x3(x)
+    _, h1p = ops.gemm_bf16x3(xp, ops.split_bf16x3(w1), H, bias=b1, relu=True, out_f32=False, out_planes=True)
+    y, _ = ops.gemm_bf16x3(h1p, ops.split_bf16x3(w2), H)
+    h1 = (x.double() @ w1.double().t() + b1.double()).clamp_min(0)
+    ref = h1 @ w2.double().t()
+    assert float((y.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    # backward of layer 2 w.r.t. h1, masked by relu'(h1):  dH = (dY . W2) * [h1 > 0]
+    dy = th.randn(M, H, device=cuda, generator=g)
+    dh, _ = ops.gemm_bf16x3(ops.split_bf16x3(dy), ops.split_bf16x3(w2, transpose=True), H, relu_mask=h1p)
+    ref_dh = (dy.double() @ w2.double()) * (h1 > 0)
+    assert float((dh.double() - ref_dh).abs().max()) <= 1e-5 * float(ref_dh.abs().max())
+
+
+def test_pairs_relu_split(cuda):
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(1)
+    u, v = th.randn(37, 256, device=cuda, generator=g), th.randn(5, 256, device=cuda, generator=g)
+    p = ops.pairs_relu_split(u, v)
+    ref = (u.unsqueeze(1) + v.unsqueeze(0)).clamp_min(0).view(-1, 256)
+    s = p[0].double() + p[1].double() + p[2].double()
+    assert float((s - ref.double()).abs().max()) <= 2.0**-22 * float(ref.abs().max())
