@@ -8,12 +8,12 @@
 // accumulated in fp32 in tensor memory.  Each bf16 x bf16 product is exact in fp32, so the result differs from an fp32 GEMM
 // only by accumulation order -- the same class of difference as MKL vs cuBLAS.
 //
-// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor.3d of a [3 planes x 128 rows x 32 k] A box and a [3 x BN x 32] B box per
 //              stage (64-byte swizzle), 3-stage mbarrier ring;
 //   warp 1   : MMA issuer     -- one elected thread issues 12 tcgen05.mma.kind::f16 (M=128, N=BN, K=16) per stage and commits
 //              the stage back to the producer; accumulators live in TMEM (2 x BN columns, double buffered);
-//   warps 2-5: epilogue       -- tcgen05.ld (32 lanes x 32 columns per warp-instruction), + bias, ReLU / ReLU-mask, then either an
+//   warps 2-9: epilogue       -- tcgen05.ld (32 lanes x 32 columns per warp-instruction), + bias, ReLU / ReLU-mask, then either an
 //              fp32 row-major store and/or a re-split into three bf16 planes (the operand format of the next layer), so
 //              intermediate activations never exist in fp32 in HBM.
 // Operands: A3 [3][M][K] bf16 (K-major), B3 [3][N_pad][K] bf16 (K-major), K % 32 == 0, N_pad % 16 == 0, N_pad <= 256.
@@ -27,7 +27,7 @@ namespace morl {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 32;        // bf16 elements per stage along K (= one 64-byte swizzle row)
 constexpr int kGemmStages = 3;
-constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quadrant)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,8 +84,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
           "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major canonical layout with 64-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
 //   rows of 64 B (32 bf16), 8-row groups of 512 B; SBO = 512 B between 8-row groups; LBO unused (1).
@@ -141,7 +141,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             g_mbar_init(&tfull[s], 1);
-            g_mbar_init(&tempty[s], 4);  // one arrival per epilogue warp
+            g_mbar_init(&tempty[s], 8);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -214,8 +214,67 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else {
-        // ================= epilogue warps (2..5) =================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        // ================= epilogue warps (2..9) =================
+        // warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a quadrant take alternating 32-column chunks
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        auto process = [&](const uint32_t (&v)[32], int n0, int row, bool row_ok) {
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float f = __uint_as_float(v[j]) + bias_s[n0 + j];
+                if (g.relu) f = fmaxf(f, 0.f);
+                x[j] = f;
+            }
+            if (g.mask && row_ok) {
+                const uint4* mrow = reinterpret_cast<const uint4*>(g.mask + (size_t)row * g.ld_mask + n0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 mm = __ldg(mrow + q);
+                    const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t bits = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xFFFFu);
+                        // bf16 > 0  <=>  sign bit clear and magnitude non-zero (NaN never occurs in a ReLU output)
+                        if ((bits & 0x8000u) || (bits & 0x7FFFu) == 0u) x[8 * q + e] = 0.f;
+                    }
+                }
+            }
+            if (row_ok && g.c_f32) {
+                float* crow = g.c_f32 + (size_t)row * g.ldc + n0;
+                if (n0 + 32 <= g.N && (g.ldc % 4 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < g.N) crow[j] = x[j];
+                }
+            }
+            if (row_ok && g.c_planes && n0 < g.ldp) {
+                // re-split into three bf16 planes: h0 = bf16(x), h1 = bf16(x - h0), h2 = bf16(x - h0 - h1)
+                uint32_t p0[16], p1[16], p2[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float a = (n0 + j < g.N) ? x[j] : 0.f, b = (n0 + j + 1 < g.N) ? x[j + 1] : 0.f;
+                    const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
+                    const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
+                    const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
+                    const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
+                    const __nv_bfloat16 a2 = __float2bfloat16_rn(sa), b2 = __float2bfloat16_rn(sb);
+                    p0[j / 2] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+                    p1[j / 2] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                    p2[j / 2] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+                }
+                __nv_bfloat16* prow = g.c_planes + (size_t)row * g.ldp + n0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    *reinterpret_cast<uint4*>(prow + 8 * q) = make_uint4(p0[4 * q], p0[4 * q + 1], p0[4 * q + 2], p0[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(prow + g.plane_stride + 8 * q) = make_uint4(p1[4 * q], p1[4 * q + 1], p1[4 * q + 2], p1[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(prow + 2 * g.plane_stride + 8 * q) = make_uint4(p2[4 * q], p2[4 * q + 1], p2[4 * q + 2], p2[4 * q + 3]);
+                }
+            }
+        };
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t as = it & 1u;
@@ -224,56 +283,25 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int row = tile * kGemmBM + quad * 32 + lane;
             const bool row_ok = row < g.M;
             const uint32_t t_row = tmem_base + as * 256u + ((uint32_t)(quad * 32) << 16);
-            for (int n0 = 0; n0 < BN; n0 += 32) {
-                uint32_t v[32];
-                tc_ld32(t_row + (uint32_t)n0, v);
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = __uint_as_float(v[j]) + bias_s[n0 + j];
-                    if (g.relu) f = fmaxf(f, 0.f);
-                    x[j] = f;
-                }
-                if (g.mask && row_ok) {
-                    const __nv_bfloat16* mrow = g.mask + (size_t)row * g.ld_mask + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + j < g.N && !(__bfloat162float(mrow[j]) > 0.f)) x[j] = 0.f;
-                }
-                if (row_ok && g.c_f32) {
-                    float* crow = g.c_f32 + (size_t)row * g.ldc + n0;
-                    if (n0 + 32 <= g.N && (g.ldc % 4 == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + j < g.N) crow[j] = x[j];
-                    }
-                }
-                if (row_ok && g.c_planes && n0 < g.ldp) {
-                    // re-split into three bf16 planes: h0 = bf16(x), h1 = bf16(x - h0), h2 = bf16(x - h0 - h1)
-                    uint32_t p0[16], p1[16], p2[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a = (n0 + j < g.N) ? x[j] : 0.f, b = (n0 + j + 1 < g.N) ? x[j + 1] : 0.f;
-                        const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
-                        const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
-                        const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
-                        const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
-                        const __nv_bfloat16 a2 = __float2bfloat16_rn(sa), b2 = __float2bfloat16_rn(sb);
-                        p0[j / 2] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-                        p1[j / 2] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-                        p2[j / 2] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
-                    }
-                    __nv_bfloat16* prow = g.c_planes + (size_t)row * g.ldp + n0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        *reinterpret_cast<uint4*>(prow + 8 * q) = make_uint4(p0[4 * q], p0[4 * q + 1], p0[4 * q + 2], p0[4 * q + 3]);
-                        *reinterpret_cast<uint4*>(prow + g.plane_stride + 8 * q) = make_uint4(p1[4 * q], p1[4 * q + 1], p1[4 * q + 2], p1[4 * q + 3]);
-                        *reinterpret_cast<uint4*>(prow + 2 * g.plane_stride + 8 * q) = make_uint4(p2[4 * q], p2[4 * q + 1], p2[4 * q + 2], p2[4 * q + 3]);
-                    }
-                }
+            // software pipeline over this warp's chunks n0 = 32*half, 32*half + 64, ...: the TMEM load of the next chunk is in
+            // flight while the current one is converted and stored
+            uint32_t va[32], vb[32];
+            int n0 = 32 * half;
+            if (n0 < BN) {
+                tc_ld32(t_row + (uint32_t)n0, va);
+                tc_ld_wait();
+            }
+            while (n0 < BN) {
+                const int n1 = n0 + 64;
+                if (n1 < BN) tc_ld32(t_row + (uint32_t)n1, vb);
+                process(va, n0, row, row_ok);
+                tc_ld_wait();
+                if (n1 >= BN) break;
+                const int n2 = n1 + 64;
+                if (n2 < BN) tc_ld32(t_row + (uint32_t)n2, va);
+                process(vb, n1, row, row_ok);
+                tc_ld_wait();
+                n0 = n2;
             }
             tc_fence_before();
             __syncwarp();

@@ -26,6 +26,7 @@ import torch.nn as nn
 import torch.optim as optim
 
 from ... import ops
+from ...tc_mlp import TCPairMlp
 from ...common.buffer import ReplayBuffer
 from ...common.morl_algorithm import MOAgent, MOPolicy
 from ...common.networks import NatureCNN, get_grad_norm, layer_init, mlp, polyak_update
@@ -123,6 +124,7 @@ class Envelope(MOPolicy, MOAgent):
         group: Optional[str] = None,
         use_cuda_graph: bool = True,
         replay_on_device: bool = True,
+        use_tensor_cores: bool = True,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
@@ -164,6 +166,9 @@ class Envelope(MOPolicy, MOAgent):
                                      device=self.device if replay_on_device else None)
         self.dot_mode = ops.DOT_UNFUSED
         self.use_cuda_graph = use_cuda_graph
+        # dense layers of the two no-grad target passes on the tcgen05 tensor cores (bf16x3 split, fp32-accurate)
+        self.use_tensor_cores = use_tensor_cores and self.q_net.feature_extractor is None and TCPairMlp.supported(self.q_net.net)
+        self._tc_on = self._tc_tg = None
         self._graphs = {}
         self._static = None
         self._last_loss = None
@@ -264,8 +269,17 @@ class Envelope(MOPolicy, MOAgent):
         s = self._static
         B, W, A, D = obs.shape[0], wset.shape[0], self.action_dim, self.reward_dim
         with th.no_grad():
-            q_on = self.q_net.forward_pairs(nobs, wset)  # online net selects   (envelope.py:420)
-            q_tg = self.target_q_net.forward_pairs(nobs, wset)  # target net evaluates (envelope.py:429)
+            if self.use_tensor_cores and B == self.batch_size and W == self.num_sample_w:
+                if self._tc_on is None:
+                    self._tc_on = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W)
+                    self._tc_tg = TCPairMlp(self.target_q_net.net, self.target_q_net.feat_dim, B, W)
+                self._tc_on.refresh_weights()
+                self._tc_tg.refresh_weights()
+                q_on = self._tc_on.forward_pairs(nobs, wset).view(B, W, A, D)  # online net selects   (envelope.py:420)
+                q_tg = self._tc_tg.forward_pairs(nobs, wset).view(B, W, A, D)  # target net evaluates (envelope.py:429)
+            else:
+                q_on = self.q_net.forward_pairs(nobs, wset)
+                q_tg = self.target_q_net.forward_pairs(nobs, wset)
             done1 = done.reshape(-1)
             if self.envelope:
                 target_q, _, _ = ops.envelope_td(q_on, q_tg, wset, rew, done1, self.gamma, self.dot_mode, ops.ROWS_BMAJOR, want_indices=False)
