@@ -218,6 +218,24 @@ MORL_API int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stride
 MORL_API int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B, int W, int H, void* dst_planes,
                                           long long plane_stride, void* stream);
 
+
+/* Weight-gradient GEMM (reduction over the batch rows), split-K, deterministic:
+ *   out[n, k] = sum_m G[m, n] * H[m, k]      G planes [3][M][ldg] (n < g_cols), H planes [3][M][ldh] (k < h_cols), bf16x3;
+ *   ldg, ldh multiples of 64, ldh <= 256;  transpose_out != 0 stores out[k, n] instead.  Replaces the dW = dY^T X products that
+ *   torch autograd issues for the nn.Linear layers of the reference networks (loss.backward(), envelope.py:316).
+ *   workspace: morl_gemm_mn_workspace_bytes(M, g_cols, h_cols) bytes. */
+MORL_API size_t morl_gemm_mn_workspace_bytes(int M, int a_cols, int b_cols);
+MORL_API int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_stride, int ldg, int g_cols, const void* h_planes,
+                                     long long h_plane_stride, int ldh, int h_cols, int M, int transpose_out, float* out,
+                                     int ld_out, void* workspace, void* stream);
+/* out[n] = sum_m sum_p planes[p][m][n]  (bias gradients); workspace: 296 * N floats */
+MORL_API int morl_colsum_bf16x3(const void* planes, long long plane_stride, int M, int ld, int N, float* out, void* workspace,
+                                void* stream);
+/* gradients of the separable first layer: dU[b,:] = sum_j G[b*W+j,:], dV[j,:] = sum_b G[b*W+j,:]  (G planes [3][B*W][H], W <= 64);
+ * workspace: 296 * W * H floats */
+MORL_API int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane_stride, int B, int W, int H, float* dU, float* dV,
+                                           void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

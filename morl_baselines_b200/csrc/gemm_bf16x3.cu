@@ -317,6 +317,205 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// =================================================================================================================
+// MN-major split-K variant: weight gradients  dW[n, k] = sum_m G[m, n] * H[m, k]  (reduction over the 65,536 batch rows).
+// Both operands are the row-major plane tensors the forward/backward GEMMs already produced, read "MN-major" (the MMA's M / N
+// index is the contiguous one), 128-byte swizzle:  A = G^T (M_mma = n, 128 per CTA), B = H^T (N_mma = k <= 256), K_mma = m.
+// One CTA per (128-row block of n, split s of the m range); fp32 partial tiles are summed by reduce_partials_kernel
+// (deterministic, no atomics).
+// =================================================================================================================
+constexpr int kMnKT = 32;  // batch rows (K_mma direction) per pipeline stage
+
+// canonical MN-major layout, SWIZZLE_128B: 64 contiguous MN elements (128 B) x 8 K-rows per 1 KB atom;
+// SBO = 1024 B (next 8 K-rows), LBO = distance between 64-element MN chunks.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+struct GemmMnArgs {
+    int M;            // reduction length (batch rows)
+    int n_tiles;      // ceil(A columns / 128)
+    int NB;           // N_mma = B columns covered (multiple of 64, <= 256)
+    int rows_per_split;
+    float* partial;   // [S][n_tiles*128][NB]
+};
+
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmMnArgs g) {
+    extern __shared__ uint8_t gsmem_raw[];
+    uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t chunk_bytes = 3u * kMnKT * 128u;            // one 64-element MN chunk, 3 planes: 12 KB
+    const uint32_t a_stage = 2u * chunk_bytes;                 // 24 KB
+    const uint32_t b_stage = 4u * chunk_bytes;                 // 48 KB (allocated for NB = 256)
+    const int nb_chunks = g.NB / 64;
+    uint8_t* smA = gsmem;
+    uint8_t* smB = gsmem + kGemmStages * a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kGemmStages * b_stage);
+    uint64_t* empty = full + kGemmStages;
+    uint64_t* tfull = empty + kGemmStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x % g.n_tiles;
+    const int split = blockIdx.x / g.n_tiles;
+    const int m_begin = split * g.rows_per_split;
+    const int m_end = min(g.M, m_begin + g.rows_per_split);
+    const int n_kblk = (m_end - m_begin + kMnKT - 1) / kMnKT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            g_mbar_init(&full[s], 1);
+            g_mbar_init(&empty[s], 1);
+        }
+        g_mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                g_mbar_wait(&empty[stage], phase ^ 1u);
+                g_mbar_expect_tx(&full[stage], (2u + (uint32_t)nb_chunks) * chunk_bytes);
+                const int m0 = m_begin + kb * kMnKT;
+                for (int c = 0; c < 2; ++c) tma_load_3d(smA + stage * a_stage + c * chunk_bytes, &tmA, &full[stage], nt * 128 + c * 64, m0, 0);
+                for (int c = 0; c < nb_chunks; ++c) tma_load_3d(smB + stage * b_stage + c * chunk_bytes, &tmB, &full[stage], c * 64, m0, 0);
+                if (++stage == kGemmStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=bf16, both MN-major, N = NB, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(g.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t plane = kMnKT * 128u;  // 4 KB: one plane of one chunk
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                g_mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a0 = g_smem_u32(smA + stage * a_stage);
+                const uint32_t b0 = g_smem_u32(smB + stage * b_stage);
+#pragma unroll
+                for (int ks = 0; ks < kMnKT / 16; ++ks) {
+                    const int pa[6] = {2, 0, 1, 1, 0, 0};
+                    const int pb[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        const uint64_t ad = make_desc_mn_sw128(a0 + pa[t] * plane + ks * 2048u, chunk_bytes);
+                        const uint64_t bd = make_desc_mn_sw128(b0 + pb[t] * plane + ks * 2048u, chunk_bytes);
+                        tc_mma_bf16(tmem_base, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty[stage]);
+                if (++stage == kGemmStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            tc_commit(tfull);
+        }
+    } else {
+        const int quad = warp & 3;
+        g_mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int row = nt * 128 + quad * 32 + lane;  // output row (n)
+        float* prow = g.partial + ((size_t)split * g.n_tiles * 128 + row) * g.NB;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int n0 = 0; n0 < g.NB; n0 += 32) {
+            uint32_t v[32];
+            tc_ld32(t_row + (uint32_t)n0, v);
+            tc_ld_wait();
+            if (n_kblk > 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(prow + n0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(prow + n0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// out[r][c] (or out[c][r] if transpose) = sum_s partial[s][r][c] for r < rows, c < cols
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int S, int prow, int pcol, int rows, int cols,
+                                                              int transpose, float* __restrict__ out, int ld_out) {
+    const int total = rows * cols;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int r = e / cols, c = e - r * cols;
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += partial[((size_t)s * prow + r) * pcol + c];
+        if (transpose)
+            out[(size_t)c * ld_out + r] = acc;
+        else
+            out[(size_t)r * ld_out + c] = acc;
+    }
+}
+
+// column sums of a plane tensor: part[chunk][n] = sum over the chunk's rows and the 3 planes of G[p][m][n]
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int M, int ld, int N,
+                                                            int rows_per_chunk, float* __restrict__ part) {
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m0 = blockIdx.x * rows_per_chunk, m1 = min(M, m0 + rows_per_chunk);
+    float acc = 0.f;
+    for (int m = m0; m < m1; ++m) {
+        const size_t o = (size_t)m * ld + n;
+        acc += (__bfloat162float(planes[o]) + __bfloat162float(planes[plane_stride + o])) + __bfloat162float(planes[2 * plane_stride + o]);
+    }
+    part[(size_t)blockIdx.x * N + n] = acc;
+}
+
+// gradients of the separable first layer: G1 planes [3][B*W][H] -> dU[b][h] = sum_j G1[b*W+j][h], dVpart[chunk][j][h] = sum_{b in chunk}
+template <int WMAX>
+__global__ void __launch_bounds__(256) pairs_grad_reduce_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int B, int W, int H,
+                                                                int b_per_chunk, float* __restrict__ dU, float* __restrict__ dVpart) {
+    const int h = blockIdx.y * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const int b0 = blockIdx.x * b_per_chunk, b1 = min(B, b0 + b_per_chunk);
+    float accv[WMAX];
+#pragma unroll
+    for (int j = 0; j < WMAX; ++j) accv[j] = 0.f;
+    for (int b = b0; b < b1; ++b) {
+        float accu = 0.f;
+#pragma unroll
+        for (int j = 0; j < WMAX; ++j) {
+            if (j < W) {
+                const size_t o = ((size_t)b * W + j) * H + h;
+                const float v = (__bfloat162float(planes[o]) + __bfloat162float(planes[plane_stride + o])) + __bfloat162float(planes[2 * plane_stride + o]);
+                accu += v;
+                accv[j] += v;
+            }
+        }
+        dU[(size_t)b * H + h] = accu;
+    }
+#pragma unroll
+    for (int j = 0; j < WMAX; ++j)
+        if (j < W) dVpart[((size_t)blockIdx.x * W + j) * H + h] = accv[j];
+}
+
 // ---- fp32 -> three bf16 planes (operands produced outside the GEMM epilogue: network inputs, weights, gradients) ---------
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, int transpose,
                                                            __nv_bfloat16* __restrict__ dst, int rows_pad, int ldp, long long plane_stride) {
@@ -393,6 +592,109 @@ static int make_plane_map(CUtensorMap* map, const void* base, int rows, int K, l
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+
+static int make_plane_map_mn(CUtensorMap* map, const void* base, int rows, int ld, long long plane_stride_elems) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return -1;
+    const cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride_elems * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)kMnKT, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace morl
+
+extern "C" size_t morl_gemm_mn_workspace_bytes(int M, int a_cols, int b_cols) {
+    if (M <= 0 || a_cols <= 0 || b_cols <= 0) return 0;
+    const int n_tiles = (a_cols + 127) / 128;
+    int S = 148 / n_tiles;
+    if (S < 1) S = 1;
+    int rps = ((M + S - 1) / S + 31) / 32 * 32;
+    S = (M + rps - 1) / rps;
+    const int NB = (b_cols + 63) / 64 * 64;
+    return (size_t)S * n_tiles * 128 * NB * sizeof(float) + (size_t)256 * 256 * sizeof(float);
+}
+
+extern "C" int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_stride, int ldg, int g_cols, const void* h_planes,
+                                       long long h_plane_stride, int ldh, int h_cols, int M, int transpose_out, float* out, int ld_out,
+                                       void* workspace, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(g_planes && h_planes && out && workspace, MORL_ERR_NULL, "morl_gemm_bf16x3_mn_f32: NULL pointer argument");
+    MORL_REQUIRE(M > 0 && g_cols > 0 && h_cols > 0, MORL_ERR_SHAPE, "morl_gemm_bf16x3_mn_f32: bad shape M=%d g_cols=%d h_cols=%d", M, g_cols, h_cols);
+    MORL_REQUIRE(ldg % 64 == 0 && ldh % 64 == 0 && ldh <= 256 && g_cols <= ldg && h_cols <= ldh, MORL_ERR_UNSUPPORTED,
+                 "morl_gemm_bf16x3_mn_f32: plane row lengths must be multiples of 64 (ldg=%d ldh=%d), ldh <= 256", ldg, ldh);
+    const int n_tiles = (g_cols + 127) / 128;
+    MORL_REQUIRE(n_tiles * 128 <= ldg || ldg % 128 == 0 || n_tiles * 128 - ldg <= 64, MORL_ERR_UNSUPPORTED, "morl_gemm_bf16x3_mn_f32: ldg=%d", ldg);
+    int S = 148 / n_tiles;
+    if (S < 1) S = 1;
+    const int rps = ((M + S - 1) / S + 31) / 32 * 32;
+    S = (M + rps - 1) / rps;
+    const int NB = (h_cols + 63) / 64 * 64;
+    CUtensorMap tmA, tmB;
+    int rc = make_plane_map_mn(&tmA, g_planes, M, ldg, g_plane_stride);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_mn_f32: cuTensorMapEncodeTiled(G) failed (%d)", rc);
+    rc = make_plane_map_mn(&tmB, h_planes, M, ldh, h_plane_stride);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_mn_f32: cuTensorMapEncodeTiled(H) failed (%d)", rc);
+    GemmMnArgs g;
+    g.M = M; g.n_tiles = n_tiles; g.NB = NB; g.rows_per_split = rps; g.partial = static_cast<float*>(workspace);
+    const size_t smem = (size_t)kGemmStages * (6u * 3u * kMnKT * 128u) + 256 + 1024 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gemm_bf16x3_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    gemm_bf16x3_mn_kernel<<<n_tiles * S, 192, smem, st>>>(tmA, tmB, g);
+    rc = check_launch("morl_gemm_bf16x3_mn_f32");
+    if (rc) return rc;
+    const int total = g_cols * h_cols;
+    reduce_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out);
+    return check_launch("morl_gemm_bf16x3_mn_f32(reduce)");
+}
+
+extern "C" int morl_colsum_bf16x3(const void* planes, long long plane_stride, int M, int ld, int N, float* out, void* workspace, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(planes && out && workspace, MORL_ERR_NULL, "morl_colsum_bf16x3: NULL pointer argument");
+    MORL_REQUIRE(M > 0 && N > 0 && ld >= N, MORL_ERR_SHAPE, "morl_colsum_bf16x3: bad shape M=%d N=%d ld=%d", M, N, ld);
+    const int chunks = 296;
+    const int rpc = (M + chunks - 1) / chunks;
+    const int nch = (M + rpc - 1) / rpc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* part = static_cast<float*>(workspace);
+    colsum_planes_kernel<<<dim3((unsigned)nch, (unsigned)((N + 255) / 256)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(planes), plane_stride, M, ld, N,
+                                                                                           rpc, part);
+    int rc = check_launch("morl_colsum_bf16x3");
+    if (rc) return rc;
+    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, nch, 1, N, 1, N, 0, out, N);
+    return check_launch("morl_colsum_bf16x3(reduce)");
+}
+
+extern "C" int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane_stride, int B, int W, int H, float* dU, float* dV, void* workspace,
+                                             void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(planes && dU && dV && workspace, MORL_ERR_NULL, "morl_pairs_grad_reduce_bf16x3: NULL pointer argument");
+    MORL_REQUIRE(B > 0 && W > 0 && W <= 64 && H > 0, MORL_ERR_UNSUPPORTED, "morl_pairs_grad_reduce_bf16x3: need W <= 64 (B=%d W=%d H=%d)", B, W, H);
+    const int chunks = 296;
+    const int bpc = (B + chunks - 1) / chunks;
+    const int nch = (B + bpc - 1) / bpc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* part = static_cast<float*>(workspace);
+    const dim3 grid((unsigned)nch, (unsigned)((H + 255) / 256));
+    if (W <= 8)
+        pairs_grad_reduce_kernel<8><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(planes), plane_stride, B, W, H, bpc, dU, part);
+    else
+        pairs_grad_reduce_kernel<64><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(planes), plane_stride, B, W, H, bpc, dU, part);
+    int rc = check_launch("morl_pairs_grad_reduce_bf16x3");
+    if (rc) return rc;
+    const int total = W * H;
+    reduce_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, nch, W, H, W, H, 0, dV, H);
+    return check_launch("morl_pairs_grad_reduce_bf16x3(reduce)");
+}
+
+namespace morl {
 }  // namespace morl
 
 extern "C" int morl_split_bf16x3(const float* src, int rows, int cols, int ld_src, int transpose, void* dst_planes, int rows_pad, int ldp,

@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.optim as optim
 
 from ... import ops
-from ...tc_mlp import TCPairMlp
+from ...tc_mlp import TCPairMlp, TCPairMlpFn
 from ...common.buffer import ReplayBuffer
 from ...common.morl_algorithm import MOAgent, MOPolicy
 from ...common.networks import NatureCNN, get_grad_norm, layer_init, mlp, polyak_update
@@ -168,7 +168,7 @@ class Envelope(MOPolicy, MOAgent):
         self.use_cuda_graph = use_cuda_graph
         # dense layers of the two no-grad target passes on the tcgen05 tensor cores (bf16x3 split, fp32-accurate)
         self.use_tensor_cores = use_tensor_cores and self.q_net.feature_extractor is None and TCPairMlp.supported(self.q_net.net)
-        self._tc_on = self._tc_tg = None
+        self._tc_on = self._tc_tg = self._tc_train = None
         self._graphs = {}
         self._static = None
         self._last_loss = None
@@ -273,6 +273,8 @@ class Envelope(MOPolicy, MOAgent):
                 if self._tc_on is None:
                     self._tc_on = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W)
                     self._tc_tg = TCPairMlp(self.target_q_net.net, self.target_q_net.feat_dim, B, W)
+                    if TCPairMlp.trainable_supported(self.q_net.net, W):
+                        self._tc_train = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W, share_weights_with=self._tc_on, trainable=True)
                 self._tc_on.refresh_weights()
                 self._tc_tg.refresh_weights()
                 q_on = self._tc_on.forward_pairs(nobs, wset).view(B, W, A, D)  # online net selects   (envelope.py:420)
@@ -286,7 +288,12 @@ class Envelope(MOPolicy, MOAgent):
             else:
                 target_q, _ = ops.greedy_td(q_on.view(B * W, A, D), q_tg.view(B * W, A, D), wset, rew, done1, self.gamma, self.dot_mode,
                                             ops.MAP_TILE, ops.MAP_BLOCK)
-        q_values = self.q_net.forward_pairs(obs, wset).view(B * W, A, D)
+        if self._tc_train is not None and B == self.batch_size and W == self.num_sample_w:
+            # training pass on the tensor cores too: hand-written backward (tc_mlp.TCPairMlpFn); weight planes were refreshed above
+            params = [p for l in self._tc_train.lin for p in (l.weight, l.bias)]
+            q_values = TCPairMlpFn.apply(self._tc_train, obs, wset, *params).view(B * W, A, D)
+        else:
+            q_values = self.q_net.forward_pairs(obs, wset).view(B * W, A, D)
         loss = _FusedTDLoss.apply(q_values, act.reshape(-1), target_q, wset, float(self.homotopy_lambda), B, W, s["ws"],
                                   s["prio"] if self.per else None)
         self.q_optim.zero_grad(set_to_none=True)

@@ -335,3 +335,51 @@ def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None
     _lib.check(rc, "morl_pairs_relu_split_bf16x3")
     _count()
     return out
+
+
+def gemm_mn_workspace(M: int, g_cols: int, h_cols: int, device) -> th.Tensor:
+    nbytes = _lib.load().morl_gemm_mn_workspace_bytes(int(M), int(g_cols), int(h_cols))
+    return th.empty((nbytes + 3) // 4, device=device, dtype=th.float32)
+
+
+def gemm_bf16x3_mn(g_planes: th.Tensor, g_cols: int, h_planes: th.Tensor, h_cols: int, transpose_out: bool = False,
+                   out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None) -> th.Tensor:
+    """out[n, k] = sum_m G[m, n] H[m, k] (weight gradient; reduction over the rows) from bf16x3 plane tensors [3, M, ld]."""
+    _, M, ldg = g_planes.shape
+    _, M2, ldh = h_planes.shape
+    if M != M2 or g_planes.dtype != th.bfloat16 or h_planes.dtype != th.bfloat16:
+        raise _lib.MorlB200Error("gemm_bf16x3_mn: plane tensors must be bfloat16 with the same number of rows")
+    dev = g_planes.device
+    if out is None:
+        out = th.empty((h_cols, g_cols) if transpose_out else (g_cols, h_cols), device=dev, dtype=th.float32)
+    ws = gemm_mn_workspace(M, g_cols, h_cols, dev) if workspace is None else workspace
+    rc = _lib.load().morl_gemm_bf16x3_mn_f32(_ptr(g_planes), g_planes.stride(0), ldg, g_cols, _ptr(h_planes), h_planes.stride(0), ldh, h_cols, M,
+                                             int(transpose_out), _ptr(out), out.stride(0), _ptr(ws), _stream())
+    _lib.check(rc, "morl_gemm_bf16x3_mn_f32")
+    _count(2)
+    return out
+
+
+def colsum_bf16x3(planes: th.Tensor, n_cols: int, out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None) -> th.Tensor:
+    """Column sums over the rows and the three planes (bias gradients)."""
+    _, M, ld = planes.shape
+    dev = planes.device
+    out = th.empty(n_cols, device=dev, dtype=th.float32) if out is None else out
+    ws = th.empty(296 * n_cols, device=dev, dtype=th.float32) if workspace is None else workspace
+    rc = _lib.load().morl_colsum_bf16x3(_ptr(planes), planes.stride(0), M, ld, n_cols, _ptr(out), _ptr(ws), _stream())
+    _lib.check(rc, "morl_colsum_bf16x3")
+    _count(2)
+    return out
+
+
+def pairs_grad_reduce(planes: th.Tensor, B: int, W: int, workspace: Optional[th.Tensor] = None):
+    """dU [B, H] and dV [W, H] from the planes of dL/dh1 [3, B*W, H] (gradient of relu(u[b] + v[j]) w.r.t. u and v)."""
+    _, M, H = planes.shape
+    dev = planes.device
+    dU = th.empty((B, H), device=dev, dtype=th.float32)
+    dV = th.empty((W, H), device=dev, dtype=th.float32)
+    ws = th.empty(296 * W * H, device=dev, dtype=th.float32) if workspace is None else workspace
+    rc = _lib.load().morl_pairs_grad_reduce_bf16x3(_ptr(planes), planes.stride(0), B, W, H, _ptr(dU), _ptr(dV), _ptr(ws), _stream())
+    _lib.check(rc, "morl_pairs_grad_reduce_bf16x3")
+    _count(2)
+    return dU, dV

@@ -8,7 +8,11 @@
     layers 2..: morl_gemm_bf16x3_f32 (TMA -> tcgen05.mma -> TMEM -> epilogue) with the activation re-split fused in the
                 epilogue; the last layer writes fp32 Q-values.
 
-Forward-only (no autograd) for now: it serves the two no-grad passes of the envelope target (online + target net on s').
+``forward_pairs`` alone serves the two no-grad passes of the envelope target (online + target net on s');
+``TCPairMlpFn`` wraps forward + a hand-written backward for the training pass:
+    G_L = dL/dQ;  dW_l = G_l^T H_{l-1} (MN-major split-K GEMM);  db_l = colsum(G_l);
+    G_{l-1} = (G_l W_l) * [H_{l-1} > 0] (K-major GEMM with the ReLU mask fused in the epilogue);
+    layer 1: dU = sum_j G_1, dV = sum_b G_1, dW1 = [dU^T feats | dV^T wset], db1 = sum_j dV.
 """
 
 from __future__ import annotations
@@ -39,7 +43,16 @@ class TCPairMlp:
         hidden = [l.out_features for l in lin[:-1]]
         return all(h % 32 == 0 and h <= 256 for h in hidden) and lin[-1].out_features <= 256
 
-    def __init__(self, net: nn.Sequential, feat_dim: int, n_obs: int, n_w: int):
+    @staticmethod
+    def trainable_supported(net: nn.Sequential, n_w: int) -> bool:
+        """The hand-written backward additionally needs equal hidden widths (multiples of 64) and at most 64 weight vectors."""
+        if not TCPairMlp.supported(net):
+            return False
+        hidden = {m.out_features for m in list(net)[:-1] if isinstance(m, nn.Linear)}
+        return len(hidden) == 1 and next(iter(hidden)) % 64 == 0 and n_w <= 64
+
+    def __init__(self, net: nn.Sequential, feat_dim: int, n_obs: int, n_w: int, share_weights_with: Optional["TCPairMlp"] = None,
+                 trainable: bool = False):
         self.net = net
         self.lin: List[nn.Linear] = [m for m in net if isinstance(m, nn.Linear)]
         self.feat_dim = feat_dim
@@ -47,8 +60,27 @@ class TCPairMlp:
         dev = self.lin[0].weight.device
         M = n_obs * n_w
         self.h = [th.empty((3, M, l.out_features), device=dev, dtype=th.bfloat16) for l in self.lin[:-1]]
-        self.wp = [th.empty((3, _pad32(l.out_features), l.in_features), device=dev, dtype=th.bfloat16) for l in self.lin[1:]]
+        if share_weights_with is not None:
+            self.wp = share_weights_with.wp  # same network: one set of weight planes, refreshed once per step
+        else:
+            self.wp = [th.empty((3, _pad32(l.out_features), l.in_features), device=dev, dtype=th.bfloat16) for l in self.lin[1:]]
         self.q = th.empty((M, self.lin[-1].out_features), device=dev, dtype=th.float32)
+        self.trainable = trainable
+        if trainable:
+            if n_w > 64:
+                raise ops._lib.MorlB200Error("TCPairMlp backward supports at most 64 weight vectors per minibatch")
+            out = self.lin[-1].out_features
+            self.ld_last = (out + 63) // 64 * 64
+            hid = max(l.out_features for l in self.lin[:-1])
+            self.g_last = th.empty((3, M, self.ld_last), device=dev, dtype=th.bfloat16)
+            self.g = [th.empty((3, M, hid), device=dev, dtype=th.bfloat16) for _ in range(2)]
+            # transposed weight planes W_l^T [3, in_l, K = padded out_l] for the dX products
+            self.wtp = []
+            for k, l in enumerate(self.lin[1:], start=1):
+                kdim = self.ld_last if k == len(self.lin) - 1 else l.out_features
+                self.wtp.append(th.empty((3, _pad32(l.in_features), kdim), device=dev, dtype=th.bfloat16))
+            self.ws_mn = ops.gemm_mn_workspace(M, 256, 256, dev)
+            self.ws_red = th.empty(296 * max(n_w * hid, 256), device=dev, dtype=th.float32)
 
     def refresh_weights(self):
         """Re-split the (fp32) weights of layers 2.. into bf16x3 planes; call after every optimiser step / target sync."""
@@ -69,3 +101,43 @@ class TCPairMlp:
         last = self.lin[-1]
         q, _ = ops.gemm_bf16x3(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q)
         return q
+
+    def refresh_transposed_weights(self):
+        for l, wt in zip(self.lin[1:], self.wtp):
+            ops.split_bf16x3(l.weight.detach(), rows_pad=wt.shape[1], ldp=wt.shape[2], transpose=True, out=wt)
+
+    @th.no_grad()
+    def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor):
+        """Gradients of all Linear parameters given dL/dQ [B*W, out]; uses the activations of the last forward_pairs()."""
+        n = len(self.lin)
+        grads = [None] * (2 * n)
+        self.refresh_transposed_weights()
+        G = ops.split_bf16x3(dq, rows_pad=dq.shape[0], ldp=self.ld_last, out=self.g_last)
+        for k in range(n - 1, 0, -1):
+            l = self.lin[k]
+            grads[2 * k] = ops.gemm_bf16x3_mn(G, l.out_features, self.h[k - 1], l.in_features, workspace=self.ws_mn)
+            grads[2 * k + 1] = ops.colsum_bf16x3(G, l.out_features, workspace=self.ws_red)
+            # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1})
+            _, G = ops.gemm_bf16x3(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
+                                   c_planes=self.g[k & 1])
+        dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red)
+        grads[0] = th.cat([dU.t() @ feats, dV.t() @ wset], dim=1)
+        grads[1] = dV.sum(0)
+        return grads
+
+
+class TCPairMlpFn(th.autograd.Function):
+    """Q = mlp(pairs(feats, wset)) with the dense layers on the tcgen05 tensor cores, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, plan: TCPairMlp, feats: th.Tensor, wset: th.Tensor, *params):
+        q = plan.forward_pairs(feats, wset)
+        ctx.plan = plan
+        ctx.save_for_backward(feats, wset)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        feats, wset = ctx.saved_tensors
+        grads = ctx.plan.backward(feats, wset, dq.contiguous())
+        return (None, None, None, *grads)

@@ -94,3 +94,37 @@ def test_pairs_relu_split(cuda):
     ref = (u.unsqueeze(1) + v.unsqueeze(0)).clamp_min(0).view(-1, 256)
     s = p[0].double() + p[1].double() + p[2].double()
     assert float((s - ref.double()).abs().max()) <= 2.0**-22 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("M,gc,hc", [(65536, 256, 256), (5000, 256, 256), (4096, 24, 256), (1000, 128, 64), (333, 256, 192)])
+def test_gemm_mn_weight_gradient(cuda, M, gc, hc):
+    """dW[n, k] = sum_m G[m, n] H[m, k] (MN-major operands, split-K) against float64."""
+    from morl_baselines_b200 import ops
+
+    g_ = th.Generator(device=cuda).manual_seed(M + gc)
+    G = th.randn(M, gc, device=cuda, generator=g_)
+    H = th.randn(M, hc, device=cuda, generator=g_).clamp_min(0)
+    Gp = ops.split_bf16x3(G, ldp=(gc + 63) // 64 * 64)
+    Hp = ops.split_bf16x3(H, ldp=(hc + 63) // 64 * 64)
+    dW = ops.gemm_bf16x3_mn(Gp, gc, Hp, hc)
+    ref = G.double().t() @ H.double()
+    bound = 2e-6 * (G.abs().double().t() @ H.abs().double()) * max(1.0, np.sqrt(M / 4096)) + 1e-30
+    err = (dW.double() - ref).abs()
+    assert bool((err <= bound).all()), float((err / bound).max())
+    dWt = ops.gemm_bf16x3_mn(Gp, gc, Hp, hc, transpose_out=True)
+    assert th.equal(dWt, dW.t().contiguous())
+    cs = ops.colsum_bf16x3(Gp, gc)
+    np.testing.assert_allclose(cs.cpu().numpy(), G.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5 * float(G.abs().sum(0).max()))
+
+
+def test_pairs_grad_reduce(cuda):
+    from morl_baselines_b200 import ops
+
+    g_ = th.Generator(device=cuda).manual_seed(2)
+    for B, W in ((37, 5), (64, 64)):
+        G = th.randn(B * W, 256, device=cuda, generator=g_)
+        Gp = ops.split_bf16x3(G)
+        dU, dV = ops.pairs_grad_reduce(Gp, B, W)
+        ref = G.double().view(B, W, 256)
+        np.testing.assert_allclose(dU.cpu().numpy(), ref.sum(1).cpu().numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(dV.cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5)
