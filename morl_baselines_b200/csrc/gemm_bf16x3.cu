@@ -459,61 +459,111 @@ gemm_bf16x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
-// out[r][c] (or out[c][r] if transpose) = sum_s partial[s][r][c] for r < rows, c < cols
+// out[r][c] (or out[c][r] if transpose) = sum_s partial[s][r][c] for r < rows, c < cols.
+// blockDim = (32, 8): 32 consecutive output elements per block, the S partials are strided over threadIdx.y (fixed order:
+// deterministic), then combined through shared memory.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int S, int prow, int pcol, int rows, int cols,
                                                               int transpose, float* __restrict__ out, int ld_out) {
+    __shared__ float red[8][33];
+    const int e = blockIdx.x * 32 + threadIdx.x;
     const int total = rows * cols;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int r = e / cols, c = e - r * cols;
-        float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += partial[((size_t)s * prow + r) * pcol + c];
+    float acc = 0.f;
+    int r = 0, c = 0;
+    if (e < total) {
+        r = e / cols;
+        c = e - r * cols;
+        const float* p = partial + (size_t)r * pcol + c;
+        const size_t stride = (size_t)prow * pcol;
+        float a0 = 0.f, a1 = 0.f;
+        int s = threadIdx.y;
+        for (; s + 8 < S; s += 16) {
+            a0 += p[(size_t)s * stride];
+            a1 += p[(size_t)(s + 8) * stride];
+        }
+        if (s < S) a0 += p[(size_t)s * stride];
+        acc = a0 + a1;
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < total) {
+        float t = red[0][threadIdx.x];
+#pragma unroll
+        for (int y = 1; y < 8; ++y) t += red[y][threadIdx.x];
         if (transpose)
-            out[(size_t)c * ld_out + r] = acc;
+            out[(size_t)c * ld_out + r] = t;
         else
-            out[(size_t)r * ld_out + c] = acc;
+            out[(size_t)r * ld_out + c] = t;
     }
 }
 
-// column sums of a plane tensor: part[chunk][n] = sum over the chunk's rows and the 3 planes of G[p][m][n]
+__device__ __forceinline__ void bf16x8_add(float (&acc)[8], const uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        acc[2 * q] += __uint_as_float(w[q] << 16);
+        acc[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+    }
+}
+
+// column sums of a plane tensor: part[chunk][n] = sum over the chunk's rows and the 3 planes of G[p][m][n].
+// blockDim = (32, 8): a thread owns 8 consecutive columns (one 16-byte load per plane per row) and every 8th row.
 __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int M, int ld, int N,
                                                             int rows_per_chunk, float* __restrict__ part) {
-    const int n = blockIdx.y * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    __shared__ float red[8][32][9];
+    const int n0 = (blockIdx.y * 32 + threadIdx.x) * 8;
     const int m0 = blockIdx.x * rows_per_chunk, m1 = min(M, m0 + rows_per_chunk);
-    float acc = 0.f;
-    for (int m = m0; m < m1; ++m) {
-        const size_t o = (size_t)m * ld + n;
-        acc += (__bfloat162float(planes[o]) + __bfloat162float(planes[plane_stride + o])) + __bfloat162float(planes[2 * plane_stride + o]);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (n0 < ld) {
+        for (int m = m0 + threadIdx.y; m < m1; m += 8) {
+            const size_t o = (size_t)m * ld + n0;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) bf16x8_add(acc, __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)));
+        }
     }
-    part[(size_t)blockIdx.x * N + n] = acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][j];
+            if (n0 + j < N) part[(size_t)blockIdx.x * N + n0 + j] = t;
+        }
+    }
 }
 
-// gradients of the separable first layer: G1 planes [3][B*W][H] -> dU[b][h] = sum_j G1[b*W+j][h], dVpart[chunk][j][h] = sum_{b in chunk}
-template <int WMAX>
-__global__ void __launch_bounds__(256) pairs_grad_reduce_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int B, int W, int H,
-                                                                int b_per_chunk, float* __restrict__ dU, float* __restrict__ dVpart) {
-    const int h = blockIdx.y * blockDim.x + threadIdx.x;
-    if (h >= H) return;
-    const int b0 = blockIdx.x * b_per_chunk, b1 = min(B, b0 + b_per_chunk);
-    float accv[WMAX];
+// dU[b][h] = sum_j sum_p G[p][b*W + j][h]   (one block per b; blockDim = (32, 8), 8 columns per thread, j strided over y)
+__global__ void __launch_bounds__(256) pairs_rowblock_sum_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int W, int H,
+                                                                 float* __restrict__ dU) {
+    __shared__ float red[8][32][9];
+    const int b = blockIdx.x;
+    const int h0 = (blockIdx.y * 32 + threadIdx.x) * 8;
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < WMAX; ++j) accv[j] = 0.f;
-    for (int b = b0; b < b1; ++b) {
-        float accu = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (h0 < H) {
+        for (int j = threadIdx.y; j < W; j += 8) {
+            const size_t o = ((size_t)b * W + j) * H + h0;
 #pragma unroll
-        for (int j = 0; j < WMAX; ++j) {
-            if (j < W) {
-                const size_t o = ((size_t)b * W + j) * H + h;
-                const float v = (__bfloat162float(planes[o]) + __bfloat162float(planes[plane_stride + o])) + __bfloat162float(planes[2 * plane_stride + o]);
-                accu += v;
-                accv[j] += v;
-            }
+            for (int p = 0; p < 3; ++p) bf16x8_add(acc, __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)));
         }
-        dU[(size_t)b * H + h] = accu;
     }
 #pragma unroll
-    for (int j = 0; j < WMAX; ++j)
-        if (j < W) dVpart[((size_t)blockIdx.x * W + j) * H + h] = accv[j];
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && h0 < H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][j];
+            dU[(size_t)b * H + h0 + j] = t;
+        }
+    }
 }
 
 // ---- fp32 -> three bf16 planes (operands produced outside the GEMM epilogue: network inputs, weights, gradients) ---------
@@ -538,28 +588,31 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
 // ---- separable first layer: h[b*W + j] = relu(u[b] + v[j]) straight into bf16x3 planes --------------------------------------
 __global__ void __launch_bounds__(256) pairs_relu_split_kernel(const float* __restrict__ u, const float* __restrict__ v, int B, int W, int H,
                                                                __nv_bfloat16* __restrict__ dst, long long plane_stride) {
-    const long long total = (long long)B * W * (H / 2);
+    const int hv = H / 8;  // 8 columns per thread: two float4 loads per operand, one 16-byte store per plane
+    const long long total = (long long)B * W * hv;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int h2 = (int)(e % (H / 2));
-        const long long row = e / (H / 2);
+        const int h8 = (int)(e % hv);
+        const long long row = e / hv;
         const int b = (int)(row / W), j = (int)(row - (long long)b * W);
-        const float2 uu = *reinterpret_cast<const float2*>(u + (size_t)b * H + 2 * h2);
-        const float2 vv = *reinterpret_cast<const float2*>(v + (size_t)j * H + 2 * h2);
-        const float x0 = fmaxf(uu.x + vv.x, 0.f), x1 = fmaxf(uu.y + vv.y, 0.f);
-        uint32_t o[3];
-        float a = x0, c = x1;
+        const float4* up = reinterpret_cast<const float4*>(u + (size_t)b * H + 8 * h8);
+        const float4* vp = reinterpret_cast<const float4*>(v + (size_t)j * H + 8 * h8);
+        const float4 u0 = __ldg(up), u1 = __ldg(up + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
+        float x[8] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w};
+        uint32_t o[3][4];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            const __nv_bfloat16 ha = __float2bfloat16_rn(a), hc = __float2bfloat16_rn(c);
-            o[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hc) << 16);
-            a -= __bfloat162float(ha);
-            c -= __bfloat162float(hc);
+        for (int q = 0; q < 4; ++q) {
+            float a = fmaxf(x[2 * q], 0.f), c = fmaxf(x[2 * q + 1], 0.f);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const __nv_bfloat16 ha = __float2bfloat16_rn(a), hc = __float2bfloat16_rn(c);
+                o[p][q] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hc) << 16);
+                a -= __bfloat162float(ha);
+                c -= __bfloat162float(hc);
+            }
         }
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        const long long off = row * (H / 2) + h2;
-        d32[off] = o[0];
-        d32[plane_stride / 2 + off] = o[1];
-        d32[plane_stride + off] = o[2];
+        const long long off = row * H + 8 * h8;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) *reinterpret_cast<uint4*>(dst + p * plane_stride + off) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
     }
 }
 
@@ -651,24 +704,24 @@ extern "C" int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_s
     rc = check_launch("morl_gemm_bf16x3_mn_f32");
     if (rc) return rc;
     const int total = g_cols * h_cols;
-    reduce_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out);
+    reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out);
     return check_launch("morl_gemm_bf16x3_mn_f32(reduce)");
 }
 
 extern "C" int morl_colsum_bf16x3(const void* planes, long long plane_stride, int M, int ld, int N, float* out, void* workspace, void* stream) {
     using namespace morl;
     MORL_REQUIRE(planes && out && workspace, MORL_ERR_NULL, "morl_colsum_bf16x3: NULL pointer argument");
-    MORL_REQUIRE(M > 0 && N > 0 && ld >= N, MORL_ERR_SHAPE, "morl_colsum_bf16x3: bad shape M=%d N=%d ld=%d", M, N, ld);
+    MORL_REQUIRE(M > 0 && N > 0 && ld >= N && ld % 8 == 0 && plane_stride % 8 == 0, MORL_ERR_SHAPE, "morl_colsum_bf16x3: bad shape M=%d N=%d ld=%d", M, N, ld);
     const int chunks = 296;
     const int rpc = (M + chunks - 1) / chunks;
     const int nch = (M + rpc - 1) / rpc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* part = static_cast<float*>(workspace);
-    colsum_planes_kernel<<<dim3((unsigned)nch, (unsigned)((N + 255) / 256)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(planes), plane_stride, M, ld, N,
-                                                                                           rpc, part);
+    colsum_planes_kernel<<<dim3((unsigned)nch, (unsigned)((ld + 255) / 256)), dim3(32, 8), 0, st>>>(static_cast<const __nv_bfloat16*>(planes), plane_stride,
+                                                                                                    M, ld, N, rpc, part);
     int rc = check_launch("morl_colsum_bf16x3");
     if (rc) return rc;
-    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, nch, 1, N, 1, N, 0, out, N);
+    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, out, N);
     return check_launch("morl_colsum_bf16x3(reduce)");
 }
 
@@ -676,21 +729,23 @@ extern "C" int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane
                                              void* stream) {
     using namespace morl;
     MORL_REQUIRE(planes && dU && dV && workspace, MORL_ERR_NULL, "morl_pairs_grad_reduce_bf16x3: NULL pointer argument");
-    MORL_REQUIRE(B > 0 && W > 0 && W <= 64 && H > 0, MORL_ERR_UNSUPPORTED, "morl_pairs_grad_reduce_bf16x3: need W <= 64 (B=%d W=%d H=%d)", B, W, H);
-    const int chunks = 296;
-    const int bpc = (B + chunks - 1) / chunks;
-    const int nch = (B + bpc - 1) / bpc;
+    MORL_REQUIRE(B > 0 && W > 0 && H > 0 && H % 8 == 0 && plane_stride % 8 == 0, MORL_ERR_SHAPE, "morl_pairs_grad_reduce_bf16x3: bad shape B=%d W=%d H=%d", B, W, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float* part = static_cast<float*>(workspace);
-    const dim3 grid((unsigned)nch, (unsigned)((H + 255) / 256));
-    if (W <= 8)
-        pairs_grad_reduce_kernel<8><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(planes), plane_stride, B, W, H, bpc, dU, part);
-    else
-        pairs_grad_reduce_kernel<64><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(planes), plane_stride, B, W, H, bpc, dU, part);
-    int rc = check_launch("morl_pairs_grad_reduce_bf16x3");
+    const __nv_bfloat16* pl = static_cast<const __nv_bfloat16*>(planes);
+    // dU[b] = sum over the W rows of transition b
+    pairs_rowblock_sum_kernel<<<dim3((unsigned)B, (unsigned)((H + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, W, H, dU);
+    int rc = check_launch("morl_pairs_grad_reduce_bf16x3(dU)");
     if (rc) return rc;
-    const int total = W * H;
-    reduce_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, nch, W, H, W, H, 0, dV, H);
+    // dV[j] = sum over b: column sums of the [B, W*H] view
+    const int N = W * H;
+    const int chunks = 74;
+    const int rpc = (B + chunks - 1) / chunks;
+    const int nch = (B + rpc - 1) / rpc;
+    float* part = static_cast<float*>(workspace);
+    colsum_planes_kernel<<<dim3((unsigned)nch, (unsigned)((N + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, B, N, N, rpc, part);
+    rc = check_launch("morl_pairs_grad_reduce_bf16x3(dV)");
+    if (rc) return rc;
+    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, dV, N);
     return check_launch("morl_pairs_grad_reduce_bf16x3(reduce)");
 }
 
@@ -716,9 +771,9 @@ extern "C" int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int 
                                             void* stream) {
     using namespace morl;
     MORL_REQUIRE(u && v && dst_planes, MORL_ERR_NULL, "morl_pairs_relu_split_bf16x3: NULL pointer argument");
-    MORL_REQUIRE(B > 0 && W > 0 && H > 0 && H % 2 == 0 && plane_stride % 2 == 0 && plane_stride >= (long long)B * W * H, MORL_ERR_SHAPE,
+    MORL_REQUIRE(B > 0 && W > 0 && H > 0 && H % 8 == 0 && plane_stride % 8 == 0 && plane_stride >= (long long)B * W * H, MORL_ERR_SHAPE,
                  "morl_pairs_relu_split_bf16x3: bad shape B=%d W=%d H=%d", B, W, H);
-    const long long total = (long long)B * W * (H / 2);
+    const long long total = (long long)B * W * (H / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     pairs_relu_split_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(u, v, B, W, H, static_cast<__nv_bfloat16*>(dst_planes),

@@ -71,6 +71,8 @@ class Box(_Space):
         self.dtype = dtype
 
     def sample(self):
+        if not (np.all(np.isfinite(self.low)) and np.all(np.isfinite(self.high))):
+            return self._rng.standard_normal(self.shape).astype(self.dtype)  # unbounded box: gymnasium samples a normal as well
         return self._rng.uniform(self.low, self.high).astype(self.dtype)
 
 

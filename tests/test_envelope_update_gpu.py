@@ -93,7 +93,8 @@ def test_envelope_api_surface(cuda):
     w = np.array([0.3, 0.7], dtype=np.float32)
     a = agent.eval(obs, w)
     assert isinstance(a, int) and 0 <= a < 3
-    q = agent.q_net(th.as_tensor(obs).float().to(cuda), th.as_tensor(w).to(cuda))
+    with th.no_grad():  # (a grad-tracking forward kept alive on the default stream would pin AccumulateGrad nodes to it)
+        q = agent.q_net(th.as_tensor(obs).float().to(cuda), th.as_tensor(w).to(cuda))
     assert a == int(th.argmax(th.einsum("r,bar->ba", th.as_tensor(w).to(cuda), q), dim=1).item())
     # reference calling convention of envelope_target: tiled obs [W*B, ...], repeat_interleaved weights
     B, W = 5, 4
