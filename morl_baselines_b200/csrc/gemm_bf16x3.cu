@@ -19,6 +19,7 @@
 // Operands: A3 [3][M][K] bf16 (K-major), B3 [3][N_pad][K] bf16 (K-major), K % 32 == 0, N_pad % 16 == 0, N_pad <= 256.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -26,7 +27,8 @@ namespace morl {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 32;        // bf16 elements per stage along K (= one 64-byte swizzle row)
-constexpr int kGemmStages = 3;
+constexpr int kGemmStages = 3;        // MN-major (weight-gradient) kernel
+constexpr int kGemmStagesK = 2;       // K-major kernel: 2 x 72 KB stages + 48 KB of TMA-store staging
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quadrant)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -113,7 +115,8 @@ struct GemmArgs {
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                   const GemmArgs g) {
     extern __shared__ uint8_t gsmem_raw[];
     uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
     const int BN = g.N_pad;
@@ -121,13 +124,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t b_stage_bytes = 3u * (uint32_t)BN * kGemmBK * 2u;  // <= 48 KB
     const uint32_t b_stage_stride = 3u * 256u * kGemmBK * 2u;
     uint8_t* smA = gsmem;
-    uint8_t* smB = gsmem + kGemmStages * a_stage_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kGemmStages * b_stage_stride);
-    uint64_t* empty = full + kGemmStages;
-    uint64_t* tfull = empty + kGemmStages;
+    uint8_t* smB = gsmem + kGemmStagesK * a_stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kGemmStagesK * b_stage_stride);
+    uint64_t* empty = full + kGemmStagesK;
+    uint64_t* tfull = empty + kGemmStagesK;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [256]
+    // per-epilogue-warp staging tile for the TMA store of the re-split activations: 3 planes x 32 rows x 64 B, 64-byte swizzle
+    uint8_t* stage_c = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bias_s + 256) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -135,7 +140,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int n_kblk = g.K / kGemmBK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStages; ++s) {
+        for (int s = 0; s < kGemmStagesK; ++s) {
             g_mbar_init(&full[s], 1);
             g_mbar_init(&empty[s], 1);
         }
@@ -167,7 +172,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     g_mbar_expect_tx(&full[stage], a_stage_bytes + b_stage_bytes);
                     tma_load_3d(smA + stage * a_stage_bytes, &tmA, &full[stage], kb * kGemmBK, tile * kGemmBM, 0);
                     tma_load_3d(smB + stage * b_stage_stride, &tmB, &full[stage], kb * kGemmBK, 0, 0);
-                    if (++stage == kGemmStages) {
+                    if (++stage == kGemmStagesK) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -205,7 +210,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                     }
                     tc_commit(&empty[stage]);  // frees the smem stage when the MMAs above have read it
-                    if (++stage == kGemmStages) {
+                    if (++stage == kGemmStagesK) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -218,6 +223,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a quadrant take alternating 32-column chunks
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
+        uint8_t* my_stage = stage_c + (warp - 2) * 6144;
         auto process = [&](const uint32_t (&v)[32], int n0, int row, bool row_ok) {
             float x[32];
 #pragma unroll
@@ -251,7 +257,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         if (n0 + j < g.N) crow[j] = x[j];
                 }
             }
-            if (row_ok && g.c_planes && n0 < g.ldp) {
+            if (g.c_planes && n0 < g.ldp) {
                 // re-split into three bf16 planes: h0 = bf16(x), h1 = bf16(x - h0), h2 = bf16(x - h0 - h1)
                 uint32_t p0[16], p1[16], p2[16];
 #pragma unroll
@@ -266,12 +272,26 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     p1[j / 2] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
                     p2[j / 2] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
                 }
-                __nv_bfloat16* prow = g.c_planes + (size_t)row * g.ldp + n0;
+                // stage the warp's [32 rows x 32 cols] x 3 planes in shared memory (TMA SWIZZLE_64B pattern: 16-byte chunk index
+                // XOR ((row >> 1) & 3), bank-conflict free), then ONE bulk tensor store writes it out coalesced and asynchronously
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has read the staging tile
+                __syncwarp();
+                uint8_t* st = my_stage + lane * 64;
+                const int sw = (lane >> 1) & 3;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    *reinterpret_cast<uint4*>(prow + 8 * q) = make_uint4(p0[4 * q], p0[4 * q + 1], p0[4 * q + 2], p0[4 * q + 3]);
-                    *reinterpret_cast<uint4*>(prow + g.plane_stride + 8 * q) = make_uint4(p1[4 * q], p1[4 * q + 1], p1[4 * q + 2], p1[4 * q + 3]);
-                    *reinterpret_cast<uint4*>(prow + 2 * g.plane_stride + 8 * q) = make_uint4(p2[4 * q], p2[4 * q + 1], p2[4 * q + 2], p2[4 * q + 3]);
+                    const int off = ((q ^ sw) << 4);
+                    *reinterpret_cast<uint4*>(st + off) = make_uint4(p0[4 * q], p0[4 * q + 1], p0[4 * q + 2], p0[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(st + 2048 + off) = make_uint4(p1[4 * q], p1[4 * q + 1], p1[4 * q + 2], p1[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(st + 4096 + off) = make_uint4(p2[4 * q], p2[4 * q + 1], p2[4 * q + 2], p2[4 * q + 3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmC), "r"(g_smem_u32(my_stage)),
+                                 "r"(n0), "r"(row - lane), "r"(0)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         };
@@ -307,6 +327,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             __syncwarp();
             if (lane == 0) g_mbar_arrive(&tempty[as]);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp have completed
     }
 
     tc_fence_before();
@@ -633,12 +654,12 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int make_plane_map(CUtensorMap* map, const void* base, int rows, int K, long long plane_stride_elems, int box_rows) {
+static int make_plane_map(CUtensorMap* map, const void* base, int rows, int K, long long plane_stride_elems, int box_rows, int box_k = kGemmBK) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return -1;
     const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 3};
     const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_stride_elems * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows, 3};
+    const cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 3};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -798,12 +819,19 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
     rc = make_plane_map(&tmB, b_planes, N_pad, K, b_plane_stride, N_pad);
     MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+    CUtensorMap tmC;
+    memset(&tmC, 0, sizeof(tmC));
+    if (c_planes) {  // store map of the re-split output: [3][M][ldp], box 32 cols x 32 rows x 3 planes
+        rc = make_plane_map(&tmC, c_planes, M, ldp, c_plane_stride, 32, 32);
+        MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(C) failed (%d)", rc);
+    }
     GemmArgs g;
     g.M = M; g.N = N; g.N_pad = N_pad; g.K = K;
     g.bias = bias; g.c_f32 = c_f32; g.ldc = ldc;
     g.c_planes = static_cast<__nv_bfloat16*>(c_planes); g.ldp = ldp; g.plane_stride = c_plane_stride;
     g.mask = static_cast<const __nv_bfloat16*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
-    const size_t smem = (size_t)kGemmStages * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStages * (3u * 256u * kGemmBK * 2u) + 256 + 1024 + 1024 + 64;
+    const size_t smem = (size_t)kGemmStagesK * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStagesK * (3u * 256u * kGemmBK * 2u) + 256 + 1024 + 1024 + 64 +
+                        1024 + 8 * 6144;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -813,6 +841,6 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     if (sms <= 0) sms = 148;
     const int n_tiles = (M + kGemmBM - 1) / kGemmBM;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    gemm_bf16x3_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, g);
+    gemm_bf16x3_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmC, g);
     return check_launch("morl_gemm_bf16x3_f32");
 }
