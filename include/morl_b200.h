@@ -236,6 +236,16 @@ MORL_API int morl_colsum_bf16x3(const void* planes, long long plane_stride, int 
 MORL_API int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane_stride, int B, int W, int H, float* dU, float* dV,
                                            void* workspace, void* stream);
 
+
+/* Fused gradient clipping + Adam step over a list of tensors (two launches).  Replaces th.nn.utils.clip_grad_norm_ +
+ * optim.Adam.step (envelope.py:324-326; torch/optim/adam.py _single_tensor_adam arithmetic, amsgrad = False, weight_decay = 0).
+ *   params/grads/exp_avg/exp_avg_sq/steps : device arrays of n_tensors device pointers (steps[t] -> float32 scalar, incremented here)
+ *   max_grad_norm <= 0 disables clipping;  workspace: morl_adam_workspace_bytes(n_tensors, max_size) bytes */
+MORL_API size_t morl_adam_workspace_bytes(int n_tensors, int64_t max_size);
+MORL_API int morl_adam_clip_f32(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                                float* const* steps, const int64_t* sizes, int n_tensors, int64_t max_size, float max_grad_norm,
+                                float lr, float beta1, float beta2, float eps, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,81 @@
+"""Adam with gradient clipping as two CUDA launches (morl_adam_clip_f32) instead of ~25 foreach / elementwise kernels.
+
+``FusedClipAdam`` IS a ``torch.optim.Adam`` (same param groups, same ``state_dict`` layout: per-parameter ``step`` (float32
+device scalar), ``exp_avg``, ``exp_avg_sq``), so checkpoints interchange with the reference's optimiser state
+(reference multi_policy/envelope/envelope.py:183, 240-247).  ``step_fused(max_grad_norm)`` performs
+``clip_grad_norm_(params, max_grad_norm)`` + ``step()`` (reference envelope.py:324-326) with the arithmetic of the reference's
+non-capturable single-tensor Adam.  Parameter gradients must already be populated and keep their storage between steps (they
+do under CUDA-graph replay; in eager mode the pointer table is refreshed when a gradient tensor moves)."""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch as th
+from torch import optim
+
+from .. import _lib, ops
+
+
+class FusedClipAdam(optim.Adam):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, capturable=True)
+        self._tables = None
+        self._cache = {}
+
+    def _ensure_state(self):
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = th.zeros((), dtype=th.float32, device=p.device)
+                    st["exp_avg"] = th.zeros_like(p, memory_format=th.preserve_format)
+                    st["exp_avg_sq"] = th.zeros_like(p, memory_format=th.preserve_format)
+
+    def _build_tables(self, params):
+        """Device-side pointer tables for one set of gradient buffers.  Built through PINNED staging + async copies so that it
+        is legal inside a CUDA-graph capture (the copy becomes a graph node that re-writes the same pointers on every replay);
+        tables are cached per gradient-pointer tuple and never freed, because a captured graph keeps referencing them."""
+        dev = params[0].device
+        grads = [p.grad for p in params]
+        key = tuple(g.data_ptr() for g in grads)
+        if key in self._cache:
+            self._tables = self._cache[key]
+            return
+        lists = {
+            "p": [t.data_ptr() for t in params], "g": list(key), "m": [self.state[p]["exp_avg"].data_ptr() for p in params],
+            "v": [self.state[p]["exp_avg_sq"].data_ptr() for p in params], "s": [self.state[p]["step"].data_ptr() for p in params],
+            "n": [p.numel() for p in params],
+        }
+        pinned = th.tensor([lists[k] for k in ("p", "g", "m", "v", "s", "n")], dtype=th.int64).pin_memory()
+        table = th.empty_like(pinned, device=dev)
+        table.copy_(pinned, non_blocking=True)
+        t = {k: table[i] for i, k in enumerate(("p", "g", "m", "v", "s", "n"))}
+        t["max"] = max(lists["n"])
+        t["keep"] = (params, grads, pinned, table)
+        t["key"] = key
+        nbytes = _lib.load().morl_adam_workspace_bytes(len(params), t["max"])
+        t["ws"] = th.empty((nbytes + 3) // 4, dtype=th.float32, device=dev)
+        self._cache[key] = t
+        self._tables = t
+
+    @th.no_grad()
+    def step_fused(self, max_grad_norm: Optional[float] = None):
+        assert len(self.param_groups) == 1, "FusedClipAdam.step_fused supports a single parameter group"
+        group = self.param_groups[0]
+        params = [p for p in group["params"] if p.grad is not None]
+        if not params:
+            return
+        if any(not (p.is_cuda and p.dtype == th.float32 and p.is_contiguous() and p.grad.is_contiguous()) for p in params):
+            raise _lib.MorlB200Error("FusedClipAdam: parameters and gradients must be contiguous float32 CUDA tensors")
+        self._ensure_state()
+        if self._tables is None or self._tables["key"] != tuple(p.grad.data_ptr() for p in params):
+            self._build_tables(params)
+        t = self._tables
+        b1, b2 = group["betas"]
+        rc = _lib.load().morl_adam_clip_f32(t["p"].data_ptr(), t["g"].data_ptr(), t["m"].data_ptr(), t["v"].data_ptr(), t["s"].data_ptr(),
+                                            t["n"].data_ptr(), len(params), t["max"], float(max_grad_norm) if max_grad_norm is not None else 0.0,
+                                            float(group["lr"]), float(b1), float(b2), float(group["eps"]), t["ws"].data_ptr(),
+                                            th.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "morl_adam_clip_f32")
+        ops._count(2)

@@ -28,6 +28,7 @@ import torch.optim as optim
 from ... import ops
 from ...tc_mlp import TCPairMlp, TCPairMlpFn
 from ...common.buffer import ReplayBuffer
+from ...common.fused_adam import FusedClipAdam
 from ...common.morl_algorithm import MOAgent, MOPolicy
 from ...common.networks import NatureCNN, get_grad_norm, layer_init, mlp, polyak_update
 from ...common.prioritized_buffer import PrioritizedReplayBuffer
@@ -156,7 +157,7 @@ class Envelope(MOPolicy, MOAgent):
         self.target_q_net.load_state_dict(self.q_net.state_dict())
         for p in self.target_q_net.parameters():
             p.requires_grad = False
-        self.q_optim = optim.Adam(self.q_net.parameters(), lr=self.learning_rate, capturable=True)
+        self.q_optim = FusedClipAdam(self.q_net.parameters(), lr=self.learning_rate)  # an optim.Adam with a fused clip+step
 
         self.envelope = envelope
         self.num_sample_w = num_sample_w
@@ -298,9 +299,7 @@ class Envelope(MOPolicy, MOAgent):
                                   s["prio"] if self.per else None)
         self.q_optim.zero_grad(set_to_none=True)
         loss.backward()
-        if self.max_grad_norm is not None:
-            th.nn.utils.clip_grad_norm_(self.q_net.parameters(), self.max_grad_norm)
-        self.q_optim.step()
+        self.q_optim.step_fused(self.max_grad_norm)  # clip_grad_norm_ + Adam.step (envelope.py:324-326) in two launches
         s["loss"].copy_(loss.detach())
 
     def _step(self, mode: str):

@@ -358,3 +358,33 @@ def test_polyak_golden(cuda, golden, tau):
         off += n
     ops.PolyakPlan(ps, ts).run(tau)
     assert np.array_equal(th.cat(ts).cpu().numpy(), golden[f"polyak_{tau}_target1"])
+
+
+@pytest.mark.parametrize("max_norm", [None, 1.0, 1e6])
+def test_fused_clip_adam_matches_torch(cuda, max_norm):
+    """Three steps of clip_grad_norm_ + Adam on the CPU (the reference's optimiser path) vs FusedClipAdam.step_fused.
+    Tolerance 2e-6 relative to the parameter scale: same formula, fp32, different operation fusion."""
+    from morl_baselines_b200.common.fused_adam import FusedClipAdam
+
+    th.manual_seed(0)
+    shapes = [(256, 35), (256,), (256, 256), (24, 256), (24,)]
+    ref = [th.nn.Parameter(th.randn(*s)) for s in shapes]
+    mine = [th.nn.Parameter(p.detach().clone().to(cuda)) for p in ref]
+    o_ref = th.optim.Adam(ref, lr=3e-4)
+    o_mine = FusedClipAdam(mine, lr=3e-4)
+    for step in range(3):
+        for p, q in zip(ref, mine):
+            g = th.randn_like(p) * (10.0 if step == 1 else 0.1)
+            p.grad = g.clone()
+            if q.grad is None:
+                q.grad = g.to(cuda)
+            else:
+                q.grad.copy_(g)
+        if max_norm is not None:
+            th.nn.utils.clip_grad_norm_(ref, max_norm)
+        o_ref.step()
+        o_mine.step_fused(max_norm)
+    for p, q in zip(ref, mine):
+        np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().numpy(), rtol=2e-6, atol=2e-6)
+    sd = o_mine.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 3.0
