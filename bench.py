@@ -141,6 +141,31 @@ def time_envelope_kernel(dev, iters=400):
     return e0.elapsed_time(e1) * 1e-3 / iters
 
 
+def time_gemm_kernel(dev, iters=200):
+    """Average launch duration of the dominant kernel of the step, morl_gemm_bf16x3_f32 on one hidden layer of the pair batch
+    (65,536 x 256 x 256, bias + ReLU + plane re-split epilogue), CUDA events, 4 rotating activation sets (4 x 2 x 100 MB > L2)."""
+    import torch as th
+
+    from morl_baselines_b200 import ops
+
+    M, H = B * W, NET[0]
+    g = th.Generator(device=dev).manual_seed(2)
+    wp = ops.split_bf16x3(th.randn(H, H, device=dev, generator=g) / 16.0, rows_pad=H, ldp=H)
+    bias = th.randn(H, device=dev, generator=g) * 0.1
+    a_sets = [ops.split_bf16x3(th.randn(M, H, device=dev, generator=g).relu_(), rows_pad=M, ldp=H) for _ in range(4)]
+    c_sets = [th.empty_like(a_sets[0]) for _ in range(4)]
+    for i in range(8):
+        ops.gemm_bf16x3(a_sets[i % 4], wp, H, bias=bias, relu=True, out_f32=False, out_planes=True, c_planes=c_sets[i % 4])
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ops.gemm_bf16x3(a_sets[i % 4], wp, H, bias=bias, relu=True, out_f32=False, out_planes=True, c_planes=c_sets[i % 4])
+    e1.record()
+    th.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters, 6 * 2 * M * H * H
+
+
 def cpu_reference_steps(steps, warmup, sample_b=CPU_SAMPLE_B):
     """Time the reference's CPU update on a bounded sample (sample_b of the 1024 transitions, all 64 weights); returns
     (seconds per sampled step, kind, cores).  Uses the unmodified reference when /root/reference is mounted, else the port."""
@@ -312,6 +337,7 @@ def run_b200(args, rank, local_rank, world):
     # ---------------- roofline of the fused envelope-TD kernel (rank 0) ------------------------------------------
     hbm_peak, bf16_peak, peak_src = _peaks()
     t_kernel = time_envelope_kernel(dev)
+    t_gemm, gemm_flops = time_gemm_kernel(dev)
     alg_bytes = 2 * B * W * A * D * 4 + W * D * 4 + B * D * 4 + B * 4 + W * B * D * 4  # 13,386,496 B
     achieved = alg_bytes / t_kernel / 1e9
     traffic = None
@@ -336,7 +362,12 @@ def run_b200(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "kernel": "envelope_td_v3_kernel<3,UNFUSED>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "us_per_launch": t_kernel * 1e6,
                      "peak_source": peak_src},
-        "mlp": {"flop_per_step": mlp_flops, "tflops": mlp_flops / (ms / K * 1e-3) / 1e12, "path": "cuBLAS FP32 (TF32 off) via torch autograd",
+        "roofline_gemm": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel (65536x256x256, 6 bf16 tcgen05 products per fp32 product)",
+                          "achieved": gemm_flops / t_gemm / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "frac": gemm_flops / t_gemm / 1e12 / bf16_peak,
+                          "us_per_launch": t_gemm * 1e6, "fp32_equivalent_tflops": gemm_flops / 6 / t_gemm / 1e12, "peak_source": peak_src,
+                          "note": "dominant kernel of the step (about 2/3 of its time); the envelope kernel above is the one north_star names"},
+        "mlp": {"flop_per_step": mlp_flops, "fp32_equivalent_tflops": mlp_flops / (ms / K * 1e-3) / 1e12,
+                "path": "layer 1 separable (library sgemm on B + |W| rows), layers 2.. tcgen05 bf16x3 forward and backward",
                 "note": "whole-step time used, so this is a lower bound on the dense-layer rate"},
         "loss": loss_dev,
     }

@@ -1,0 +1,145 @@
+"""Whole-update parity of GPIPD / GPILS, CAPQL and MOSAC (CUDA engine) against golden vectors produced by the UNMODIFIED
+reference on CPU (tests/golden/make_golden_updates.py -> tests/golden/updates.npz).  Same initial parameters, same replay
+contents, same RNG streams (python `random`, numpy global, injected Gaussian noise); tolerance 1e-4 relative / 2e-6 absolute
+on parameters after the updates (Adam amplifies fp32 GEMM-order differences of ~1e-6 in the gradients), 1e-4 on priorities."""
+
+import os
+import random
+
+import numpy as np
+import pytest
+import torch as th
+
+from oracle.ref_harness import FakeEnv
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "updates.npz"))
+
+
+def _load_sd(module, gold, prefix, dev):
+    sd = {k[len(prefix) + 1:]: th.from_numpy(gold[k]).to(dev) for k in gold.files if k.startswith(prefix + "/")}
+    module.load_state_dict(sd)
+
+
+def _cmp_sd(module, gold, prefix, rtol=1e-4, atol=2e-6):
+    for k, v in module.state_dict().items():
+        np.testing.assert_allclose(v.detach().cpu().numpy(), gold[f"{prefix}/{k}"], rtol=rtol, atol=atol, err_msg=f"{prefix}/{k}")
+
+
+class _Noise:
+    def __init__(self, seed, dev):
+        self.rng, self.dev = np.random.default_rng(seed), dev
+
+    def __call__(self, shape):
+        return th.from_numpy(self.rng.standard_normal(tuple(shape)).astype(np.float32)).to(self.dev)
+
+
+@pytest.mark.parametrize("gpi_pd", [True, False])
+def test_gpipd_update_matches_reference(cuda, gold, gpi_pd):
+    from morl_baselines_b200.multi_policy.gpi_pd.gpi_pd import GPIPD
+
+    tag = f"gpipd{int(gpi_pd)}"
+    OBS, A, D, B, N = 10, 4, 3, 16, 256
+    agent = GPIPD(FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D), batch_size=B, net_arch=[32, 32, 32], num_nets=2, gradient_updates=2, dyna=False,
+                  per=True, gpi_pd=gpi_pd, drop_rate=0.0, layer_norm=True, buffer_size=N, log=False, seed=1, device=cuda, target_net_update_freq=3)
+    for i, (net, tnet) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
+        _load_sd(net, gold, f"{tag}/init{i}", cuda)
+        tnet.load_state_dict(net.state_dict())
+    rb = agent.replay_buffer
+    for k in ("obs", "next_obs", "actions", "rewards", "dones"):
+        getattr(rb, k)[:] = gold[f"{tag}/rb_{k}"]
+    rb.size, rb.ptr = N, 0
+    rb.mark_all_dirty()
+    rb.tree.batch_set(np.arange(N), gold[f"{tag}/tree_leaves0"][:N])
+    support = gold[f"{tag}/support"]
+    agent.set_weight_support(list(support))
+    w = th.tensor(support[2]).to(cuda)
+    agent.global_step = 3
+    random.seed(5)
+    np.random.seed(6)
+    for _ in range(2):
+        agent.update(w)
+        agent.global_step += 1
+    for i, (net, tnet) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
+        _cmp_sd(net, gold, f"{tag}/final{i}")
+        _cmp_sd(tnet, gold, f"{tag}/final_target{i}")
+    np.testing.assert_allclose(rb.tree.nodes[-1][:N], gold[f"{tag}/tree_leaves1"][:N], rtol=2e-4, atol=1e-7)
+    assert rb.min_priority == pytest.approx(float(gold[f"{tag}/min_priority1"]), rel=2e-4)
+    acts = np.array([agent.eval(o, support[1]) for o in gold[f"{tag}/eval_obs"]], np.int32)
+    assert np.array_equal(acts, gold[f"{tag}/eval_act"])
+    agent._reset_priorities(w)
+    np.testing.assert_allclose(rb.tree.nodes[-1][:N], gold[f"{tag}/tree_leaves_reset"][:N], rtol=2e-4, atol=1e-7)
+
+
+def test_capql_update_matches_reference(cuda, gold):
+    from morl_baselines_b200.multi_policy.capql.capql import CAPQL
+
+    OBS, ACT, D, B = 9, 3, 2, 16
+    agent = CAPQL(FakeEnv(obs_dim=OBS, continuous_action_dim=ACT, reward_dim=D), batch_size=B, net_arch=[32, 32], log=False, seed=2, device=cuda,
+                  gradient_updates=2)
+    _load_sd(agent.policy, gold, "capql/init_policy", cuda)
+    for i, (q, tq) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
+        _load_sd(q, gold, f"capql/init_q{i}", cuda)
+        tq.load_state_dict(q.state_dict())
+    for row in gold["capql/transitions"]:
+        o = 0
+        parts = []
+        for n in (OBS, ACT, D, D, OBS, 1):
+            parts.append(row[o:o + n])
+            o += n
+        agent.replay_buffer.push(parts[0], parts[1], parts[2], parts[3], parts[4], parts[5][0])
+    agent._noise_hook = _Noise(77, cuda)
+    random.seed(9)
+    agent.update()
+    _cmp_sd(agent.policy, gold, "capql/final_policy")
+    for i, (q, tq) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
+        _cmp_sd(q, gold, f"capql/final_q{i}")
+        _cmp_sd(tq, gold, f"capql/final_tq{i}")
+    a = agent.eval(np.zeros(OBS, np.float32), np.array([0.5, 0.5], np.float32))
+    assert a.shape == (ACT,) and np.all(np.abs(a) <= 1.0)
+
+
+def test_mosac_update_matches_reference(cuda, gold):
+    from morl_baselines_b200.single_policy.ser.mosac_continuous_action import MOSAC
+
+    OBS, ACT, D, B, N = 9, 3, 3, 16, 128
+    w = np.array([0.2, 0.5, 0.3], dtype=np.float32)
+    agent = MOSAC(FakeEnv(obs_dim=OBS, continuous_action_dim=ACT, reward_dim=D), weights=w, batch_size=B, net_arch=[32, 32], log=False, seed=4,
+                  device=cuda, buffer_size=N)
+    for name in ("actor", "qf1", "qf2"):
+        _load_sd(getattr(agent, name), gold, f"mosac/init_{name}", cuda)
+    agent.qf1_target.load_state_dict(agent.qf1.state_dict())
+    agent.qf2_target.load_state_dict(agent.qf2.state_dict())
+    buf = agent.buffer
+    for k in ("obs", "next_obs", "actions", "rewards", "dones"):
+        getattr(buf, k)[:] = gold[f"mosac/rb_{k}"]
+    buf.size, buf.ptr = N, 0
+    buf.mark_all_dirty()
+    agent._noise_hook = _Noise(88, cuda)
+    np.random.seed(12)
+    for step in range(2):
+        agent.global_step = 2 * step
+        agent.update()
+    for name in ("actor", "qf1", "qf2", "qf1_target", "qf2_target"):
+        _cmp_sd(getattr(agent, name), gold, f"mosac/final_{name}")
+    np.testing.assert_allclose(agent.log_alpha.detach().cpu().numpy(), gold["mosac/final_log_alpha"], rtol=1e-4, atol=1e-7)
+
+
+def test_morld_population_smoke(cuda):
+    """MORL/D with MOSAC learners on the stand-in MOMDP: one outer iteration (train, update the others, evaluate, archive)."""
+    from morl_baselines_b200.multi_policy.morld.morld import MORLD
+
+    env = FakeEnv(obs_dim=6, continuous_action_dim=2, reward_dim=2, horizon=20)
+    eval_env = FakeEnv(obs_dim=6, continuous_action_dim=2, reward_dim=2, horizon=20, seed=1)
+    algo = MORLD(env, pop_size=3, exchange_every=60, update_passes=2, log=False, device=cuda, seed=0, weight_init_method="random",
+                 policy_args={"learning_starts": 20, "batch_size": 16, "net_arch": [32, 32], "buffer_size": 512}, neighborhood_size=1)
+    algo.train(total_timesteps=60, eval_env=eval_env, ref_point=np.array([-100.0, -100.0]), num_eval_episodes_for_front=1, checkpoints=False)
+    assert len(algo.archive.evaluations) >= 1 and algo.global_front.shape[1] == 2
+    from morl_baselines_b200.common.performance_indicators import hypervolume
+
+    assert hypervolume(np.array([-100.0, -100.0]), list(algo.global_front)) > 0
