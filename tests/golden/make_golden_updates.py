@@ -25,7 +25,7 @@ from oracle import ref_harness as rh  # noqa: E402
 
 def sd_to_npz(out, prefix, sd):
     for k, v in sd.items():
-        out[f"{prefix}/{k}"] = v.detach().cpu().numpy()
+        out[f"{prefix}/{k}"] = v.detach().cpu().numpy().copy()
 
 
 def gen_gpipd(out):
