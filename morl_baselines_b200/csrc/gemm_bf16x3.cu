@@ -19,6 +19,7 @@
 // Operands: A3 [3][M][K] bf16 (K-major), B3 [3][N_pad][K] bf16 (K-major), K % 32 == 0, N_pad % 16 == 0, N_pad <= 256.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -29,6 +30,7 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 32;        // bf16 elements per stage along K (= one 64-byte swizzle row)
 constexpr int kGemmStages = 3;        // MN-major (weight-gradient) kernel
 constexpr int kGemmStagesK = 2;       // K-major kernel: 2 x 72 KB stages + 48 KB of TMA-store staging
+constexpr int kGemmStagesPair = 3;    // K-major CTA-pair kernel: 3 x 48 KB stages per CTA + 48 KB of TMA-store staging
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quadrant)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -62,6 +64,44 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(g_smem_u32(dst)),
         "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// ---- CTA-pair (cta_group::2) flavours: the pair's TMA loads signal the LEADER's (cluster rank 0) mbarrier, the leader's MMA
+// commit is multicast to the same barrier offset in both CTAs, the peer's epilogue releases the accumulator remotely ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t smem_addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_addr));
+    return r;
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            g_smem_u32(dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(g_smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -114,20 +154,26 @@ struct GemmArgs {
     int relu;
 };
 
+// NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2 on one TPC) per 256-row tile, tcgen05 cta_group::2 --
+// each CTA stages its own 128 A rows and HALF of the B (weight) rows, the pair's tensor cores read both halves, so the L2 -> smem
+// traffic of the weight planes (2/3 of a stage in the 1-CTA kernel) is halved and a third pipeline stage fits.
+template <int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                    const GemmArgs g) {
+    constexpr int kStages = NCTA == 2 ? kGemmStagesPair : kGemmStagesK;
     extern __shared__ uint8_t gsmem_raw[];
     uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
     const int BN = g.N_pad;
+    const int BNL = BN / NCTA;                                        // B rows staged by this CTA
     const uint32_t a_stage_bytes = 3u * kGemmBM * kGemmBK * 2u;      // 24 KB
-    const uint32_t b_stage_bytes = 3u * (uint32_t)BN * kGemmBK * 2u;  // <= 48 KB
-    const uint32_t b_stage_stride = 3u * 256u * kGemmBK * 2u;
+    const uint32_t b_stage_bytes = 3u * (uint32_t)BNL * kGemmBK * 2u;  // <= 48 KB (24 KB in a pair)
+    const uint32_t b_stage_stride = 3u * (256u / NCTA) * kGemmBK * 2u;
     uint8_t* smA = gsmem;
-    uint8_t* smB = gsmem + kGemmStagesK * a_stage_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kGemmStagesK * b_stage_stride);
-    uint64_t* empty = full + kGemmStagesK;
-    uint64_t* tfull = empty + kGemmStagesK;
+    uint8_t* smB = gsmem + kStages * a_stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kStages * b_stage_stride);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [256]
@@ -136,27 +182,35 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tiles = (g.M + kGemmBM - 1) / kGemmBM;
+    const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+    const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;  // a unit = one CTA (NCTA = 1) or one CTA pair
+    const int n_tiles = (g.M + kGemmBM * NCTA - 1) / (kGemmBM * NCTA);
     const int n_kblk = g.K / kGemmBK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStagesK; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             g_mbar_init(&full[s], 1);
             g_mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             g_mbar_init(&tfull[s], 1);
-            g_mbar_init(&tempty[s], 8);  // one arrival per epilogue warp
+            g_mbar_init(&tempty[s], 8 * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's barrier)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int t = threadIdx.x; t < 256; t += blockDim.x) bias_s[t] = (g.bias && t < g.N) ? g.bias[t] : 0.f;
-    if (warp == 1) {  // TMEM: 512 columns (two BN-column accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {  // TMEM: 512 columns (two BN-column accumulators); in a pair both CTAs' warp 1 execute the paired allocation
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -166,13 +220,22 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < n_tiles; tile += n_units) {
+                const int row0 = (tile * NCTA + (int)cta_rank) * kGemmBM;
                 for (int kb = 0; kb < n_kblk; ++kb) {
                     g_mbar_wait(&empty[stage], phase ^ 1u);
-                    g_mbar_expect_tx(&full[stage], a_stage_bytes + b_stage_bytes);
-                    tma_load_3d(smA + stage * a_stage_bytes, &tmA, &full[stage], kb * kGemmBK, tile * kGemmBM, 0);
-                    tma_load_3d(smB + stage * b_stage_stride, &tmB, &full[stage], kb * kGemmBK, 0, 0);
-                    if (++stage == kGemmStagesK) {
+                    if (NCTA == 2) {
+                        // one expect_tx (leader) covers the four boxes of the pair; every box completes on the leader's barrier
+                        if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + b_stage_bytes));
+                        const uint32_t lbar = mapa_rank0(g_smem_u32(&full[stage]));
+                        tma_load_3d_pair(smA + stage * a_stage_bytes, &tmA, lbar, kb * kGemmBK, row0, 0);
+                        tma_load_3d_pair(smB + stage * b_stage_stride, &tmB, lbar, kb * kGemmBK, (int)cta_rank * BNL, 0);
+                    } else {
+                        g_mbar_expect_tx(&full[stage], a_stage_bytes + b_stage_bytes);
+                        tma_load_3d(smA + stage * a_stage_bytes, &tmA, &full[stage], kb * kGemmBK, row0, 0);
+                        tma_load_3d(smB + stage * b_stage_stride, &tmB, &full[stage], kb * kGemmBK, 0, 0);
+                    }
+                    if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -181,13 +244,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+        if (lane == 0 && cta_rank == 0) {  // in a pair only the leader issues; its MMAs drive both CTAs' tensor cores
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128 (256 across a pair)
+            const uint32_t idesc =
+                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((kGemmBM * NCTA) >> 4) << 24);
             const uint32_t a_plane = kGemmBM * kGemmBK * 2u;   // 8 KB
-            const uint32_t b_plane = (uint32_t)BN * kGemmBK * 2u;
+            const uint32_t b_plane = (uint32_t)BNL * kGemmBK * 2u;
             uint32_t stage = 0, phase = 0, it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = unit; tile < n_tiles; tile += n_units, ++it) {
                 const uint32_t as = it & 1u;
                 g_mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -206,16 +270,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         for (int t = 0; t < 6; ++t) {
                             const uint64_t ad = make_desc_k_sw64(a0 + pa[t] * a_plane + ks * 32);
                             const uint64_t bd = make_desc_k_sw64(b0 + pb[t] * b_plane + ks * 32);
-                            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
+                            if (NCTA == 2)
+                                tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
+                            else
+                                tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
                         }
                     }
-                    tc_commit(&empty[stage]);  // frees the smem stage when the MMAs above have read it
-                    if (++stage == kGemmStagesK) {
+                    // frees the smem stage (in both CTAs of a pair) when the MMAs above have read it
+                    if (NCTA == 2) tc_commit_pair(&empty[stage]); else tc_commit(&empty[stage]);
+                    if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc_commit(&tfull[as]);  // accumulator complete
+                if (NCTA == 2) tc_commit_pair(&tfull[as]); else tc_commit(&tfull[as]);  // accumulator complete
             }
         }
     } else {
@@ -296,11 +364,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         };
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = unit; tile < n_tiles; tile += n_units, ++it) {
             const uint32_t as = it & 1u;
             g_mbar_wait(&tfull[as], (it >> 1) & 1u);
             tc_fence_after();
-            const int row = tile * kGemmBM + quad * 32 + lane;
+            const int row = (tile * NCTA + (int)cta_rank) * kGemmBM + quad * 32 + lane;
             const bool row_ok = row < g.M;
             const uint32_t t_row = tmem_base + as * 256u + ((uint32_t)(quad * 32) << 16);
             // software pipeline over this warp's chunks n0 = 32*half, 32*half + 64, ...: the TMEM load of the next chunk is in
@@ -325,16 +393,22 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) g_mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                if (NCTA == 2) mbar_arrive_remote(mapa_rank0(g_smem_u32(&tempty[as]))); else g_mbar_arrive(&tempty[as]);
+            }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp have completed
     }
 
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();  // no CTA of a pair exits (or frees TMEM) while its peer can still signal it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        if (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
@@ -814,10 +888,16 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     if (c_planes)
         MORL_REQUIRE(ldp % 32 == 0 && ldp >= N && ldp <= N_pad && aligned16(c_planes) && c_plane_stride % 8 == 0, MORL_ERR_SHAPE,
                      "morl_gemm_bf16x3_f32: ldp=%d must be a multiple of 32 with N <= ldp <= N_pad", ldp);
+    int sms = morl_device_sm_count();
+    if (sms <= 0) sms = 148;
+    // CTA pairs (tcgen05 cta_group::2) whenever there are at least two 128-row tiles; MORL_GEMM_FORCE_1CTA=1 keeps the 1-CTA kernel
+    static const bool force_1cta = [] { const char* e = getenv("MORL_GEMM_FORCE_1CTA"); return e && e[0] == '1'; }();
+    const bool pair = !force_1cta && M > kGemmBM && sms >= 2;
+    const int ncta = pair ? 2 : 1;
     CUtensorMap tmA, tmB;
     int rc = make_plane_map(&tmA, a_planes, M, K, a_plane_stride, kGemmBM);
     MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
-    rc = make_plane_map(&tmB, b_planes, N_pad, K, b_plane_stride, N_pad);
+    rc = make_plane_map(&tmB, b_planes, N_pad, K, b_plane_stride, N_pad / ncta);
     MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
     CUtensorMap tmC;
     memset(&tmC, 0, sizeof(tmC));
@@ -830,17 +910,36 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     g.bias = bias; g.c_f32 = c_f32; g.ldc = ldc;
     g.c_planes = static_cast<__nv_bfloat16*>(c_planes); g.ldp = ldp; g.plane_stride = c_plane_stride;
     g.mask = static_cast<const __nv_bfloat16*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
-    const size_t smem = (size_t)kGemmStagesK * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStagesK * (3u * 256u * kGemmBK * 2u) + 256 + 1024 + 1024 + 64 +
-                        1024 + 8 * 6144;
+    const size_t tail = 256 + 1024 + 1024 + 64 + 1024 + 8 * 6144;  // barriers, bias, alignment slack, 8 epilogue staging tiles
+    const size_t smem1 = (size_t)kGemmStagesK * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStagesK * (3u * 256u * kGemmBK * 2u) + tail;
+    const size_t smem2 = (size_t)kGemmStagesPair * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStagesPair * (3u * 128u * kGemmBK * 2u) + tail;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(gemm_bf16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        cudaFuncSetAttribute(gemm_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         attr_set = true;
     }
-    int sms = morl_device_sm_count();
-    if (sms <= 0) sms = 148;
-    const int n_tiles = (M + kGemmBM - 1) / kGemmBM;
-    const int grid = n_tiles < sms ? n_tiles : sms;
-    gemm_bf16x3_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmC, g);
+    if (pair) {
+        const int n_tiles = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+        const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem2;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<2>, tmA, tmB, tmC, g);
+    } else {
+        const int n_tiles = (M + kGemmBM - 1) / kGemmBM;
+        const int grid = n_tiles < sms ? n_tiles : sms;
+        gemm_bf16x3_kernel<1><<<grid, kGemmThreads, smem1, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmC, g);
+    }
     return check_launch("morl_gemm_bf16x3_f32");
 }

@@ -128,3 +128,29 @@ def test_pairs_grad_reduce(cuda):
         ref = G.double().view(B, W, 256)
         np.testing.assert_allclose(dU.cpu().numpy(), ref.sum(1).cpu().numpy(), rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(dV.cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_gemm_single_cta_kernel_still_correct(cuda):
+    """Large shapes use the CTA-pair (cta_group::2) kernel; MORL_GEMM_FORCE_1CTA=1 keeps the one-CTA kernel alive as a cross-check.
+    The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch as th, numpy as np\n"
+        "from morl_baselines_b200 import ops\n"
+        "g = th.Generator(device='cuda').manual_seed(3)\n"
+        "a = th.randn(5000, 256, device='cuda', generator=g); b = th.randn(256, 256, device='cuda', generator=g) / 16\n"
+        "c, _ = ops.gemm_bf16x3(ops.split_bf16x3(a), ops.split_bf16x3(b), 256)\n"
+        "ref = a.double() @ b.double().t()\n"
+        "err = float((c.double() - ref).abs().max()); print('ERR', err); assert err < 2e-5\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for flag in ("1", "0"):
+        env = dict(os.environ, MORL_GEMM_FORCE_1CTA=flag, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[flag] = r.stdout
+    assert "ERR" in outs["1"] and "ERR" in outs["0"]
