@@ -223,11 +223,13 @@ MORL_API int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B,
  *   out[n, k] = sum_m G[m, n] * H[m, k]      G planes [3][M][ldg] (n < g_cols), H planes [3][M][ldh] (k < h_cols), bf16x3;
  *   ldg, ldh multiples of 64, ldh <= 256;  transpose_out != 0 stores out[k, n] instead.  Replaces the dW = dY^T X products that
  *   torch autograd issues for the nn.Linear layers of the reference networks (loss.backward(), envelope.py:316).
+ *   colsum_out (nullable, [g_cols]): out_b[n] = sum_m G[m, n], the bias gradient db = colsum(dY), evaluated in the same pass as
+ *   G^T . ones on the tensor cores (replaces a separate 100 MB sweep of the G planes).
  *   workspace: morl_gemm_mn_workspace_bytes(M, g_cols, h_cols) bytes. */
 MORL_API size_t morl_gemm_mn_workspace_bytes(int M, int a_cols, int b_cols);
 MORL_API int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_stride, int ldg, int g_cols, const void* h_planes,
                                      long long h_plane_stride, int ldh, int h_cols, int M, int transpose_out, float* out,
-                                     int ld_out, void* workspace, void* stream);
+                                     int ld_out, float* colsum_out, void* workspace, void* stream);
 /* out[n] = sum_m sum_p planes[p][m][n]  (bias gradients); workspace: 296 * N floats */
 MORL_API int morl_colsum_bf16x3(const void* planes, long long plane_stride, int M, int ld, int N, float* out, void* workspace,
                                 void* stream);

@@ -159,8 +159,8 @@ struct GemmArgs {
 // traffic of the weight planes (2/3 of a stage in the 1-CTA kernel) is halved and a third pipeline stage fits.
 template <int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                   const GemmArgs g) {
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
+                   const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
     constexpr int kStages = NCTA == 2 ? kGemmStagesPair : kGemmStagesK;
     extern __shared__ uint8_t gsmem_raw[];
     uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
@@ -186,6 +186,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;  // a unit = one CTA (NCTA = 1) or one CTA pair
     const int n_tiles = (g.M + kGemmBM * NCTA - 1) / (kGemmBM * NCTA);
     const int n_kblk = g.K / kGemmBK;
+    // Work units.  A static round-robin over `n_units` workers leaves a tail of L = n_tiles % n_units tiles that costs a whole
+    // extra round (65,536 rows: 256 pair tiles on 74 pairs = 3.46 -> 4 rounds).  When 2L <= n_units the tail tiles are split into
+    // two half-width (N/2) units each, so the tail costs half a round.  All three roles enumerate the same sequence.
+    const int full_units = (n_tiles / n_units) * n_units;
+    const int tail = n_tiles - full_units;
+    const bool split_tail = NCTA == 2 && tail > 0 && 2 * tail <= n_units && (BN % 64) == 0;
+    const int n_work = split_tail ? full_units + 2 * tail : n_tiles;
+    auto unit_of = [&](int u, int& tile, int& n_begin, int& n_cnt) {
+        if (!split_tail || u < full_units) {
+            tile = u; n_begin = 0; n_cnt = BN;
+        } else {
+            const int r = u - full_units;
+            tile = full_units + (r >> 1); n_cnt = BN >> 1; n_begin = (r & 1) * n_cnt;
+        }
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -220,16 +235,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             uint32_t stage = 0, phase = 0;
-            for (int tile = unit; tile < n_tiles; tile += n_units) {
+            for (int u = unit; u < n_work; u += n_units) {
+                int tile, n_begin, n_cnt;
+                unit_of(u, tile, n_begin, n_cnt);
                 const int row0 = (tile * NCTA + (int)cta_rank) * kGemmBM;
+                const int b_rows = n_cnt / NCTA;  // B rows this CTA stages for the unit
                 for (int kb = 0; kb < n_kblk; ++kb) {
                     g_mbar_wait(&empty[stage], phase ^ 1u);
                     if (NCTA == 2) {
                         // one expect_tx (leader) covers the four boxes of the pair; every box completes on the leader's barrier
-                        if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + b_stage_bytes));
+                        if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + 3u * (uint32_t)b_rows * kGemmBK * 2u));
                         const uint32_t lbar = mapa_rank0(g_smem_u32(&full[stage]));
                         tma_load_3d_pair(smA + stage * a_stage_bytes, &tmA, lbar, kb * kGemmBK, row0, 0);
-                        tma_load_3d_pair(smB + stage * b_stage_stride, &tmB, lbar, kb * kGemmBK, (int)cta_rank * BNL, 0);
+                        tma_load_3d_pair(smB + stage * b_stage_stride, n_cnt == BN ? &tmB : &tmBh, lbar, kb * kGemmBK,
+                                         n_begin + (int)cta_rank * b_rows, 0);
                     } else {
                         g_mbar_expect_tx(&full[stage], a_stage_bytes + b_stage_bytes);
                         tma_load_3d(smA + stage * a_stage_bytes, &tmA, &full[stage], kb * kGemmBK, row0, 0);
@@ -246,12 +265,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ================= MMA issuer =================
         if (lane == 0 && cta_rank == 0) {  // in a pair only the leader issues; its MMAs drive both CTAs' tensor cores
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128 (256 across a pair)
-            const uint32_t idesc =
-                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((kGemmBM * NCTA) >> 4) << 24);
             const uint32_t a_plane = kGemmBM * kGemmBK * 2u;   // 8 KB
-            const uint32_t b_plane = (uint32_t)BNL * kGemmBK * 2u;
             uint32_t stage = 0, phase = 0, it = 0;
-            for (int tile = unit; tile < n_tiles; tile += n_units, ++it) {
+            for (int u = unit; u < n_work; u += n_units, ++it) {
+                int tile, n_begin, n_cnt;
+                unit_of(u, tile, n_begin, n_cnt);
+                const uint32_t idesc =
+                    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cnt >> 3) << 17) | ((uint32_t)((kGemmBM * NCTA) >> 4) << 24);
+                const uint32_t b_plane = (uint32_t)(n_cnt / NCTA) * kGemmBK * 2u;
                 const uint32_t as = it & 1u;
                 g_mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -364,7 +385,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         };
         uint32_t it = 0;
-        for (int tile = unit; tile < n_tiles; tile += n_units, ++it) {
+        for (int u = unit; u < n_work; u += n_units, ++it) {
+            int tile, n_begin, n_cnt;
+            unit_of(u, tile, n_begin, n_cnt);
             const uint32_t as = it & 1u;
             g_mbar_wait(&tfull[as], (it >> 1) & 1u);
             tc_fence_after();
@@ -374,20 +397,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // software pipeline over this warp's chunks n0 = 32*half, 32*half + 64, ...: the TMEM load of the next chunk is in
             // flight while the current one is converted and stored
             uint32_t va[32], vb[32];
-            int n0 = 32 * half;
-            if (n0 < BN) {
+            int n0 = 32 * half;  // accumulator column of the unit; the output column is n_begin + n0
+            if (n0 < n_cnt) {
                 tc_ld32(t_row + (uint32_t)n0, va);
                 tc_ld_wait();
             }
-            while (n0 < BN) {
+            while (n0 < n_cnt) {
                 const int n1 = n0 + 64;
-                if (n1 < BN) tc_ld32(t_row + (uint32_t)n1, vb);
-                process(va, n0, row, row_ok);
+                if (n1 < n_cnt) tc_ld32(t_row + (uint32_t)n1, vb);
+                process(va, n_begin + n0, row, row_ok);
                 tc_ld_wait();
-                if (n1 >= BN) break;
+                if (n1 >= n_cnt) break;
                 const int n2 = n1 + 64;
-                if (n2 < BN) tc_ld32(t_row + (uint32_t)n2, va);
-                process(vb, n1, row, row_ok);
+                if (n2 < n_cnt) tc_ld32(t_row + (uint32_t)n2, va);
+                process(vb, n_begin + n1, row, row_ok);
                 tc_ld_wait();
                 n0 = n2;
             }
@@ -439,6 +462,7 @@ struct GemmMnArgs {
     int NB;           // N_mma = B columns covered (multiple of 64, <= 256)
     int rows_per_split;
     float* partial;   // [S][n_tiles*128][NB]
+    float* colsum_partial;  // [S][n_tiles*128] or nullptr: per-split column sums of G (bias gradient), fused as G^T . ones
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -455,6 +479,11 @@ gemm_bf16x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* empty = full + kGemmStages;
     uint64_t* tfull = empty + kGemmStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    // 4 KB of bf16 1.0: the B operand of the fused bias-gradient product  colsum(G) = G^T . ones  (N = 16; every element is 1,
+    // so the swizzle pattern is irrelevant)
+    uint32_t* ones = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+    for (int t = threadIdx.x; t < 1024; t += blockDim.x) ones[t] = 0x3F803F80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.x % g.n_tiles;
@@ -471,8 +500,8 @@ gemm_bf16x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         g_mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+    if (warp == 1) {  // 256 accumulator columns + 16 for the fused column sums (allocation granularity: power of two)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -499,6 +528,8 @@ gemm_bf16x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {
             // D=f32, A=B=bf16, both MN-major, N = NB, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(g.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t ones_desc = make_desc_mn_sw128(g_smem_u32(ones), chunk_bytes);
             const uint32_t plane = kMnKT * 128u;  // 4 KB: one plane of one chunk
             uint32_t stage = 0, phase = 0;
             for (int kb = 0; kb < n_kblk; ++kb) {
@@ -515,6 +546,12 @@ gemm_bf16x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         const uint64_t ad = make_desc_mn_sw128(a0 + pa[t] * plane + ks * 2048u, chunk_bytes);
                         const uint64_t bd = make_desc_mn_sw128(b0 + pb[t] * plane + ks * 2048u, chunk_bytes);
                         tc_mma_bf16(tmem_base, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
+                    }
+                    if (g.colsum_partial) {  // (G2 + G1 + G0)^T . ones -> 16 identical columns at TMEM column 256
+#pragma unroll
+                        for (int pl = 2; pl >= 0; --pl)
+                            tc_mma_bf16(tmem_base + 256u, make_desc_mn_sw128(a0 + pl * plane + ks * 2048u, chunk_bytes), ones_desc, idesc_ones,
+                                        (kb | ks | (2 - pl)) != 0 ? 1u : 0u);
                     }
                 }
                 tc_commit(&empty[stage]);
@@ -545,22 +582,35 @@ gemm_bf16x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(prow + n0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        if (g.colsum_partial) {
+            uint32_t v[32];
+            tc_ld32(t_row + 256u, v);
+            tc_ld_wait();
+            g.colsum_partial[(size_t)split * g.n_tiles * 128 + row] = n_kblk > 0 ? __uint_as_float(v[0]) : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
 // out[r][c] (or out[c][r] if transpose) = sum_s partial[s][r][c] for r < rows, c < cols.
 // blockDim = (32, 8): 32 consecutive output elements per block, the S partials are strided over threadIdx.y (fixed order:
 // deterministic), then combined through shared memory.
+// Blocks beyond the matrix (blockIdx.x >= main_blocks) reduce the fused column-sum partials vec_partial[s][prow] into vec_out[rows].
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int S, int prow, int pcol, int rows, int cols,
-                                                              int transpose, float* __restrict__ out, int ld_out) {
+                                                              int transpose, float* __restrict__ out, int ld_out, int main_blocks,
+                                                              const float* __restrict__ vec_partial, float* __restrict__ vec_out) {
     __shared__ float red[8][33];
-    const int e = blockIdx.x * 32 + threadIdx.x;
+    if ((int)blockIdx.x >= main_blocks) {  // uniform per block
+        partial = vec_partial;
+        out = vec_out;
+        pcol = 1; cols = 1; transpose = 0; ld_out = 1;
+    }
+    const int e = ((int)blockIdx.x >= main_blocks ? (int)blockIdx.x - main_blocks : (int)blockIdx.x) * 32 + threadIdx.x;
     const int total = rows * cols;
     float acc = 0.f;
     int r = 0, c = 0;
@@ -763,12 +813,12 @@ extern "C" size_t morl_gemm_mn_workspace_bytes(int M, int a_cols, int b_cols) {
     int rps = ((M + S - 1) / S + 31) / 32 * 32;
     S = (M + rps - 1) / rps;
     const int NB = (b_cols + 63) / 64 * 64;
-    return (size_t)S * n_tiles * 128 * NB * sizeof(float) + (size_t)256 * 256 * sizeof(float);
+    return (size_t)S * n_tiles * 128 * NB * sizeof(float) + (size_t)256 * 256 * sizeof(float);  // tail: [S][n_tiles*128] column-sum partials
 }
 
 extern "C" int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_stride, int ldg, int g_cols, const void* h_planes,
                                        long long h_plane_stride, int ldh, int h_cols, int M, int transpose_out, float* out, int ld_out,
-                                       void* workspace, void* stream) {
+                                       float* colsum_out, void* workspace, void* stream) {
     using namespace morl;
     MORL_REQUIRE(g_planes && h_planes && out && workspace, MORL_ERR_NULL, "morl_gemm_bf16x3_mn_f32: NULL pointer argument");
     MORL_REQUIRE(M > 0 && g_cols > 0 && h_cols > 0, MORL_ERR_SHAPE, "morl_gemm_bf16x3_mn_f32: bad shape M=%d g_cols=%d h_cols=%d", M, g_cols, h_cols);
@@ -788,7 +838,8 @@ extern "C" int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_s
     MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_mn_f32: cuTensorMapEncodeTiled(H) failed (%d)", rc);
     GemmMnArgs g;
     g.M = M; g.n_tiles = n_tiles; g.NB = NB; g.rows_per_split = rps; g.partial = static_cast<float*>(workspace);
-    const size_t smem = (size_t)kGemmStages * (6u * 3u * kMnKT * 128u) + 256 + 1024 + 64;
+    g.colsum_partial = colsum_out ? g.partial + (size_t)S * n_tiles * 128 * NB : nullptr;  // S * n_tiles * 128 <= 148 * 128 floats < 256 KB tail
+    const size_t smem = (size_t)kGemmStages * (6u * 3u * kMnKT * 128u) + 256 + 1024 + 64 + 1024 + 4096;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_bf16x3_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -799,7 +850,9 @@ extern "C" int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_s
     rc = check_launch("morl_gemm_bf16x3_mn_f32");
     if (rc) return rc;
     const int total = g_cols * h_cols;
-    reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out);
+    const int main_blocks = (total + 31) / 32, vec_blocks = colsum_out ? (g_cols + 31) / 32 : 0;
+    reduce_partials_kernel<<<main_blocks + vec_blocks, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out,
+                                                                             main_blocks, g.colsum_partial, colsum_out);
     return check_launch("morl_gemm_bf16x3_mn_f32(reduce)");
 }
 
@@ -816,7 +869,7 @@ extern "C" int morl_colsum_bf16x3(const void* planes, long long plane_stride, in
                                                                                                     M, ld, N, rpc, part);
     int rc = check_launch("morl_colsum_bf16x3");
     if (rc) return rc;
-    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, out, N);
+    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, out, N, 1 << 30, nullptr, nullptr);
     return check_launch("morl_colsum_bf16x3(reduce)");
 }
 
@@ -840,7 +893,7 @@ extern "C" int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane
     colsum_planes_kernel<<<dim3((unsigned)nch, (unsigned)((N + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, B, N, N, rpc, part);
     rc = check_launch("morl_pairs_grad_reduce_bf16x3(dV)");
     if (rc) return rc;
-    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, dV, N);
+    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, dV, N, 1 << 30, nullptr, nullptr);
     return check_launch("morl_pairs_grad_reduce_bf16x3(reduce)");
 }
 
@@ -899,6 +952,11 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
     rc = make_plane_map(&tmB, b_planes, N_pad, K, b_plane_stride, N_pad / ncta);
     MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+    CUtensorMap tmBh = tmB;  // half-width units of the tail split: boxes of N_pad / 4 rows
+    if (pair && N_pad % 64 == 0) {
+        rc = make_plane_map(&tmBh, b_planes, N_pad, K, b_plane_stride, N_pad / 4);
+        MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_bf16x3_f32: cuTensorMapEncodeTiled(B half) failed (%d)", rc);
+    }
     CUtensorMap tmC;
     memset(&tmC, 0, sizeof(tmC));
     if (c_planes) {  // store map of the re-split output: [3][M][ldp], box 32 cols x 32 rows x 3 planes
@@ -935,11 +993,11 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<2>, tmA, tmB, tmC, g);
+        cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<2>, tmA, tmB, tmBh, tmC, g);
     } else {
         const int n_tiles = (M + kGemmBM - 1) / kGemmBM;
         const int grid = n_tiles < sms ? n_tiles : sms;
-        gemm_bf16x3_kernel<1><<<grid, kGemmThreads, smem1, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmC, g);
+        gemm_bf16x3_kernel<1><<<grid, kGemmThreads, smem1, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmBh, tmC, g);
     }
     return check_launch("morl_gemm_bf16x3_f32");
 }

@@ -343,8 +343,9 @@ def gemm_mn_workspace(M: int, g_cols: int, h_cols: int, device) -> th.Tensor:
 
 
 def gemm_bf16x3_mn(g_planes: th.Tensor, g_cols: int, h_planes: th.Tensor, h_cols: int, transpose_out: bool = False,
-                   out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None) -> th.Tensor:
-    """out[n, k] = sum_m G[m, n] H[m, k] (weight gradient; reduction over the rows) from bf16x3 plane tensors [3, M, ld]."""
+                   out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None, colsum: Optional[th.Tensor] = None) -> th.Tensor:
+    """out[n, k] = sum_m G[m, n] H[m, k] (weight gradient; reduction over the rows) from bf16x3 plane tensors [3, M, ld].
+    ``colsum`` ([g_cols] fp32, optional) additionally receives sum_m G[m, n] (the bias gradient) from the same pass."""
     _, M, ldg = g_planes.shape
     _, M2, ldh = h_planes.shape
     if M != M2 or g_planes.dtype != th.bfloat16 or h_planes.dtype != th.bfloat16:
@@ -354,7 +355,7 @@ def gemm_bf16x3_mn(g_planes: th.Tensor, g_cols: int, h_planes: th.Tensor, h_cols
         out = th.empty((h_cols, g_cols) if transpose_out else (g_cols, h_cols), device=dev, dtype=th.float32)
     ws = gemm_mn_workspace(M, g_cols, h_cols, dev) if workspace is None else workspace
     rc = _lib.load().morl_gemm_bf16x3_mn_f32(_ptr(g_planes), g_planes.stride(0), ldg, g_cols, _ptr(h_planes), h_planes.stride(0), ldh, h_cols, M,
-                                             int(transpose_out), _ptr(out), out.stride(0), _ptr(ws), _stream())
+                                             int(transpose_out), _ptr(out), out.stride(0), _ptr(colsum), _ptr(ws), _stream())
     _lib.check(rc, "morl_gemm_bf16x3_mn_f32")
     _count(2)
     return out

@@ -115,8 +115,9 @@ class TCPairMlp:
         G = ops.split_bf16x3(dq, rows_pad=dq.shape[0], ldp=self.ld_last, out=self.g_last)
         for k in range(n - 1, 0, -1):
             l = self.lin[k]
-            grads[2 * k] = ops.gemm_bf16x3_mn(G, l.out_features, self.h[k - 1], l.in_features, workspace=self.ws_mn)
-            grads[2 * k + 1] = ops.colsum_bf16x3(G, l.out_features, workspace=self.ws_red)
+            # dW_k = G_k^T H_{k-1} and db_k = colsum(G_k) in one pass over the G planes
+            grads[2 * k + 1] = th.empty(l.out_features, device=dq.device, dtype=th.float32)
+            grads[2 * k] = ops.gemm_bf16x3_mn(G, l.out_features, self.h[k - 1], l.in_features, workspace=self.ws_mn, colsum=grads[2 * k + 1])
             # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1})
             _, G = ops.gemm_bf16x3(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
                                    c_planes=self.g[k & 1])

@@ -115,6 +115,11 @@ def test_gemm_mn_weight_gradient(cuda, M, gc, hc):
     assert th.equal(dWt, dW.t().contiguous())
     cs = ops.colsum_bf16x3(Gp, gc)
     np.testing.assert_allclose(cs.cpu().numpy(), G.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5 * float(G.abs().sum(0).max()))
+    # bias gradient fused into the same pass (G^T . ones on the tensor cores); the weight gradient must be unchanged by it
+    cs2 = th.full((gc,), float("nan"), device=cuda)
+    dW2 = ops.gemm_bf16x3_mn(Gp, gc, Hp, hc, colsum=cs2)
+    assert th.equal(dW2, dW)
+    np.testing.assert_allclose(cs2.cpu().numpy(), G.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5 * float(G.abs().sum(0).max()))
 
 
 def test_pairs_grad_reduce(cuda):
