@@ -166,6 +166,23 @@ MORL_API int morl_td_huber_priority_f32(const float* q_values, int n_nets, const
                                float* grad_q, float* prio_out, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Host halves of the replay path (CPU code in the same library; no CUDA call, usable without a device).
+ *
+ * Prioritised replay sum tree, reference common/prioritized_buffer.py:12-82 (class SumTree).  `tree` is ONE float64 array of
+ * 2^n_levels - 1 nodes: level l (2^l nodes, l = 0 the root, l = n_levels - 1 the leaves) starts at element 2^l - 1.
+ *   morl_host_sumtree_walk      : SumTree.sample after the uniform draw (:35-49): descend for each query value -> leaf index.
+ *   morl_host_sumtree_batch_set : SumTree.batch_set (:73-82): np.unique(index, return_index) then node += (new - old) on every
+ *                                 level in array order -- the same float64 operations in the same order, so the tree (and the
+ *                                 indices later sampled from it) is bit-identical to the reference's.
+ * Minibatch packing, reference common/buffer.py:84-94 (fancy-index gathers before the host->device copies):
+ *   morl_host_gather_rows       : dst[i, :] = src[index[i], :] for rows of row_bytes bytes (dst: pinned staging memory).
+ *   morl_host_gather_u8_to_i32  : same for uint8 action rows, widened to int32 (the reference's callers call .long()). */
+MORL_API int morl_host_sumtree_walk(const double* tree, int n_levels, const double* queries, int n, long long* out_index);
+MORL_API int morl_host_sumtree_batch_set(double* tree, int n_levels, const long long* index, const double* priority, int n);
+MORL_API int morl_host_gather_rows(const void* src, long long row_bytes, const long long* index, int n, void* dst);
+MORL_API int morl_host_gather_u8_to_i32(const unsigned char* src, long long row_elems, const long long* index, int n, int* dst);
+
+/* ------------------------------------------------------------------------------------------------
  * Device-resident replay: index gather.  Replaces the 5 fancy-index gathers + 6 host->device copies of
  * ReplayBuffer.sample (common/buffer.py:82-94) / PrioritizedReplayBuffer.sample (common/prioritized_buffer.py:160-166).
  *   stores: obs/next_obs f32 [cap, obs_dim], action u8|f32 [cap, act_dim], reward f32 [cap, rew_dim], done f32 [cap]
@@ -206,13 +223,30 @@ MORL_API int morl_polyak_f32(const float* const* params, float* const* targets, 
  *                     K % 32 == 0, N_pad % 32 == 0, N_pad <= 256.  Outputs: c_f32 [M, ldc] and/or c_planes [3][M][ldp]
  *                     (the operand format of the next layer).  relu != 0 applies max(x, 0); relu_mask_plane0 (plane 0 of a
  *                     forward activation, [M][ld_mask] bf16) zeroes the outputs where that activation was <= 0 (ReLU backward).
+ *                     reverse_tiles != 0 walks the 128-row tiles from the last to the first: alternate it between the layers of
+ *                     a chain so that a layer starts on the rows its producer wrote last (still in the 126 MB L2).
+ * morl_split_bf16x3_multi : up to MORL_SPLIT_MAX_JOBS independent splits (all weight matrices of a network, plain and
+ *                     transposed) in one launch.
  */
+#define MORL_SPLIT_MAX_JOBS 16
+typedef struct MorlSplitJob {
+    const float* src;       /* fp32 [rows, cols], row stride ld_src */
+    void* dst_planes;       /* bf16 [3][rows_pad][ldp] */
+    long long plane_stride; /* elements between planes */
+    int rows, cols, ld_src, transpose, rows_pad, ldp;
+} MorlSplitJob;
+MORL_API int morl_split_bf16x3_multi(const MorlSplitJob* jobs, int n_jobs, void* stream);
 MORL_API int morl_split_bf16x3(const float* src, int rows, int cols, int ld_src, int transpose, void* dst_planes, int rows_pad,
                                int ldp, long long plane_stride, void* stream);
 MORL_API int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stride, const void* b_planes, long long b_plane_stride,
                                   int M, int N, int N_pad, int K, const float* bias, int relu, const void* relu_mask_plane0,
                                   int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp, long long c_plane_stride,
-                                  void* stream);
+                                  int reverse_tiles, void* stream);
+/* Diagnostics (not part of the reference surface): per-role cycle counters of morl_gemm_bf16x3_f32, summed over CTAs and launches
+ * since the last reset; collected only when the environment variable MORL_GEMM_STATS=1 is set before the first GEMM call.
+ * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,
+ * [3] TMA thread waiting for a free stage, [4] epilogue waiting for an accumulator, [5] epilogue busy; [6], [7] reserved. */
+MORL_API int morl_debug_gemm_stats(unsigned long long* out8, int reset);
 /* h[b*W + j, :] = relu(u[b, :] + v[j, :]) written directly as bf16x3 planes [3][B*W][H] (separable first layer of the
  * weight-conditioned Q-network: W1 [s || w] + b1 = W1_s s + (W1_w w + b1); reference envelope.py:75 builds the concat). */
 MORL_API int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B, int W, int H, void* dst_planes,

@@ -35,12 +35,18 @@ SIGNATURES = {
     "morl_td_workspace_bytes": (_sz, [_i]),
     "morl_td_mse_priority_f32": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "morl_td_huber_priority_f32": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "morl_host_sumtree_walk": (_i, [_vp, _i, _vp, _i, _vp]),
+    "morl_host_sumtree_batch_set": (_i, [_vp, _i, _vp, _vp, _i]),
+    "morl_host_gather_rows": (_i, [_vp, C.c_longlong, _vp, _i, _vp]),
+    "morl_host_gather_u8_to_i32": (_i, [_vp, C.c_longlong, _vp, _i, _vp]),
     "morl_replay_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "morl_pareto_mask_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_pareto_mask_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_polyak_f32": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),
     "morl_split_bf16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, C.c_longlong, _vp]),
-    "morl_gemm_bf16x3_f32": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_longlong, _vp]),
+    "morl_gemm_bf16x3_f32": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_longlong, _i, _vp]),
+    "morl_split_bf16x3_multi": (_i, [_vp, _i, _vp]),
+    "morl_debug_gemm_stats": (_i, [_vp, _i]),
     "morl_pairs_relu_split_bf16x3": (_i, [_vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
     "morl_gemm_mn_workspace_bytes": (_sz, [_i, _i, _i]),
     "morl_gemm_bf16x3_mn_f32": (_i, [_vp, C.c_longlong, _i, _i, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
@@ -49,6 +55,16 @@ SIGNATURES = {
     "morl_adam_workspace_bytes": (_sz, [_i, _i64]),
     "morl_adam_clip_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _vp, _vp]),
 }
+
+SPLIT_MAX_JOBS = 16
+
+
+class SplitJob(C.Structure):
+    """MorlSplitJob of include/morl_b200.h"""
+
+    _fields_ = [("src", _vp), ("dst_planes", _vp), ("plane_stride", C.c_longlong), ("rows", _i), ("cols", _i), ("ld_src", _i), ("transpose", _i),
+                ("rows_pad", _i), ("ldp", _i)]
+
 
 _lib = None
 

@@ -1,7 +1,7 @@
 """Prioritised replay (mirrors reference morl_baselines/common/prioritized_buffer.py).
 
-The sum-tree keeps the reference's layout -- one float64 array per level, root first (prioritized_buffer.py:19-28) -- and
-its exact semantics: proportional sampling by a batched level walk with the GLOBAL numpy RNG (:40-54, strict '>' goes
+The sum-tree keeps the reference's layout -- one float64 array per level, root first (prioritized_buffer.py:19-28; here views
+of one flat array so that the walk and the update run in C, csrc/host_replay.cu) -- and its exact semantics: proportional sampling by a batched level walk with the GLOBAL numpy RNG (:40-54, strict '>' goes
 right), duplicate-safe ``batch_set`` where the first occurrence of an index wins (:76-82), new transitions entering with
 ``min_priority`` which ratchets up to the largest priority ever written (:194).  Transition storage and the minibatch
 gather are inherited from the device-mirrored ReplayBuffer.
@@ -12,47 +12,56 @@ from __future__ import annotations
 import numpy as np
 import torch as th
 
+from .. import _lib
 from .buffer import ReplayBuffer, ReplayBufferSamplesNp
 
 
 class SumTree:
-    """Fixed-size sum tree over float64 level arrays (reference prioritized_buffer.py:12-82)."""
+    """Fixed-size sum tree over float64 level arrays (reference prioritized_buffer.py:12-82).
+
+    ``nodes`` is the reference's list of per-level arrays (root first); here they are views of ONE flat float64 array so that
+    the walk and the batched update run in C (csrc/host_replay.cu: morl_host_sumtree_walk / _batch_set) with the same float64
+    operations in the same order -- the tree sits on the critical path between two GPU steps."""
 
     def __init__(self, max_size):
-        self.nodes = []
-        level_size = 1
-        for _ in range(int(np.ceil(np.log2(max_size))) + 1):
-            self.nodes.append(np.zeros(level_size))
-            level_size *= 2
+        self.n_levels = int(np.ceil(np.log2(max_size))) + 1
+        self._alloc(np.zeros((1 << self.n_levels) - 1))
+
+    def _alloc(self, flat):
+        self._flat = np.ascontiguousarray(flat, dtype=np.float64)
+        self.nodes = [self._flat[(1 << l) - 1 : (1 << (l + 1)) - 1] for l in range(self.n_levels)]
+        self._lib = _lib.load()
+
+    def __getstate__(self):
+        return {"n_levels": self.n_levels, "flat": self._flat}
+
+    def __setstate__(self, state):
+        self.n_levels = state["n_levels"]
+        self._alloc(state["flat"])
 
     def sample(self, batch_size):
-        query = np.random.uniform(0, self.nodes[0][0], size=batch_size)
+        query = np.random.uniform(0, self.nodes[0][0], size=batch_size)  # global numpy RNG, as the reference (:40)
         return self.walk(query)
 
     def walk(self, query):
-        """Descend the tree for given query values (the deterministic part of ``sample``)."""
-        query = np.array(query, dtype=np.float64)
-        node = np.zeros(len(query), dtype=int)
-        for nodes in self.nodes[1:]:
-            node *= 2
-            left = nodes[node]
-            greater = np.greater(query, left)
-            node += greater
-            query -= left * greater
-        return node
+        """Descend the tree for given query values (the deterministic part of ``sample``; strict '>' goes right)."""
+        query = np.ascontiguousarray(query, dtype=np.float64)
+        out = np.empty(query.shape[0], dtype=np.int64)
+        _lib.check(self._lib.morl_host_sumtree_walk(self._flat.ctypes.data, self.n_levels, query.ctypes.data, query.shape[0], out.ctypes.data),
+                   "morl_host_sumtree_walk")
+        return out
 
     def set(self, node_index, new_priority):
-        diff = new_priority - self.nodes[-1][node_index]
-        for nodes in self.nodes[::-1]:
-            np.add.at(nodes, node_index, diff)
-            node_index //= 2
+        self.batch_set(np.array([node_index], dtype=np.int64), np.array([new_priority], dtype=np.float64))
 
     def batch_set(self, node_index, new_priority):
-        node_index, unique_index = np.unique(node_index, return_index=True)
-        diff = new_priority[unique_index] - self.nodes[-1][node_index]
-        for nodes in self.nodes[::-1]:
-            np.add.at(nodes, node_index, diff)
-            node_index //= 2
+        """np.unique(node_index, return_index=True) + np.add.at on every level (:73-82), in C."""
+        idx = np.ascontiguousarray(node_index, dtype=np.int64).reshape(-1)
+        pr = np.ascontiguousarray(new_priority, dtype=np.float64).reshape(-1)
+        if pr.shape[0] != idx.shape[0]:
+            raise ValueError("batch_set: node_index and new_priority must have the same length")
+        _lib.check(self._lib.morl_host_sumtree_batch_set(self._flat.ctypes.data, self.n_levels, idx.ctypes.data, pr.ctypes.data, idx.shape[0]),
+                   "morl_host_sumtree_batch_set")
 
 
 class PrioritizedReplayBuffer(ReplayBuffer):

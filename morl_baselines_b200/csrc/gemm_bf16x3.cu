@@ -152,7 +152,12 @@ struct GemmArgs {
     const __nv_bfloat16* mask;   // plane 0 of the forward activation [M][ld_mask] for the ReLU-backward mask, or nullptr
     int ld_mask;
     int relu;
+    int reverse;                 // walk the row tiles from the last to the first (see morl_gemm_bf16x3_f32: L2 reuse between chained layers)
+    unsigned long long* stats;   // diagnostics (MORL_GEMM_STATS=1), else nullptr: [0] MMA wait-on-TMA cycles, [1] MMA wait-on-epilogue,
+                                 // [2] MMA loop total, [3] producer wait-on-free-stage, [4] epilogue wait-on-accumulator, [5] epilogue busy
 };
+
+__device__ unsigned long long g_gemm_stats[8];
 
 // NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2 on one TPC) per 256-row tile, tcgen05 cta_group::2 --
 // each CTA stages its own 128 A rows and HALF of the B (weight) rows, the pair's tensor cores read both halves, so the L2 -> smem
@@ -200,6 +205,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int r = u - full_units;
             tile = full_units + (r >> 1); n_cnt = BN >> 1; n_begin = (r & 1) * n_cnt;
         }
+        if (g.reverse) tile = n_tiles - 1 - tile;
     };
 
     if (threadIdx.x == 0) {
@@ -235,13 +241,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             uint32_t stage = 0, phase = 0;
+            long long w_empty = 0;
             for (int u = unit; u < n_work; u += n_units) {
                 int tile, n_begin, n_cnt;
                 unit_of(u, tile, n_begin, n_cnt);
                 const int row0 = (tile * NCTA + (int)cta_rank) * kGemmBM;
                 const int b_rows = n_cnt / NCTA;  // B rows this CTA stages for the unit
                 for (int kb = 0; kb < n_kblk; ++kb) {
+                    const long long c0 = g.stats ? clock64() : 0;
                     g_mbar_wait(&empty[stage], phase ^ 1u);
+                    if (g.stats) w_empty += clock64() - c0;
                     if (NCTA == 2) {
                         // one expect_tx (leader) covers the four boxes of the pair; every box completes on the leader's barrier
                         if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + 3u * (uint32_t)b_rows * kGemmBK * 2u));
@@ -260,6 +269,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
+            if (g.stats) atomicAdd(&g.stats[3], (unsigned long long)w_empty);
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -267,6 +277,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128 (256 across a pair)
             const uint32_t a_plane = kGemmBM * kGemmBK * 2u;   // 8 KB
             uint32_t stage = 0, phase = 0, it = 0;
+            long long w_full = 0, w_tempty = 0;
+            const long long t_begin = g.stats ? clock64() : 0;
             for (int u = unit; u < n_work; u += n_units, ++it) {
                 int tile, n_begin, n_cnt;
                 unit_of(u, tile, n_begin, n_cnt);
@@ -274,11 +286,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cnt >> 3) << 17) | ((uint32_t)((kGemmBM * NCTA) >> 4) << 24);
                 const uint32_t b_plane = (uint32_t)(n_cnt / NCTA) * kGemmBK * 2u;
                 const uint32_t as = it & 1u;
+                long long c0 = g.stats ? clock64() : 0;
                 g_mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
+                if (g.stats) w_tempty += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256u;
                 for (int kb = 0; kb < n_kblk; ++kb) {
+                    c0 = g.stats ? clock64() : 0;
                     g_mbar_wait(&full[stage], phase);
+                    if (g.stats) w_full += clock64() - c0;
                     tc_fence_after();
                     const uint32_t a0 = g_smem_u32(smA + stage * a_stage_bytes);
                     const uint32_t b0 = g_smem_u32(smB + stage * b_stage_stride);
@@ -305,6 +321,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
                 if (NCTA == 2) tc_commit_pair(&tfull[as]); else tc_commit(&tfull[as]);  // accumulator complete
+            }
+            if (g.stats) {
+                atomicAdd(&g.stats[0], (unsigned long long)w_full);
+                atomicAdd(&g.stats[1], (unsigned long long)w_tempty);
+                atomicAdd(&g.stats[2], (unsigned long long)(clock64() - t_begin));
             }
         }
     } else {
@@ -385,11 +406,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         };
         uint32_t it = 0;
+        long long w_tfull = 0, busy = 0;
         for (int u = unit; u < n_work; u += n_units, ++it) {
             int tile, n_begin, n_cnt;
             unit_of(u, tile, n_begin, n_cnt);
             const uint32_t as = it & 1u;
+            const long long c0 = g.stats ? clock64() : 0;
             g_mbar_wait(&tfull[as], (it >> 1) & 1u);
+            const long long c1 = g.stats ? clock64() : 0;
+            w_tfull += c1 - c0;
             tc_fence_after();
             const int row = (tile * NCTA + (int)cta_rank) * kGemmBM + quad * 32 + lane;
             const bool row_ok = row < g.M;
@@ -419,6 +444,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (lane == 0) {
                 if (NCTA == 2) mbar_arrive_remote(mapa_rank0(g_smem_u32(&tempty[as]))); else g_mbar_arrive(&tempty[as]);
             }
+            if (g.stats) busy += clock64() - c1;
+        }
+        if (g.stats && warp == 2 && lane == 0) {
+            atomicAdd(&g.stats[4], (unsigned long long)w_tfull);
+            atomicAdd(&g.stats[5], (unsigned long long)busy);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp have completed
     }
@@ -730,6 +760,29 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
     }
 }
 
+// several small matrices (the weight matrices of a network, plain and transposed) in ONE launch: blockIdx.y selects the job
+struct SplitJobs {
+    MorlSplitJob job[MORL_SPLIT_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) split_bf16x3_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+    const MorlSplitJob& j = jobs.job[blockIdx.y];
+    const float* __restrict__ src = j.src;
+    __nv_bfloat16* __restrict__ dst = static_cast<__nv_bfloat16*>(j.dst_planes);
+    const long long total = (long long)j.rows_pad * j.ldp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / j.ldp), c = (int)(e - (long long)r * j.ldp);
+        float x = 0.f;
+        if (r < j.rows && c < j.cols) x = j.transpose ? src[(size_t)c * j.ld_src + r] : src[(size_t)r * j.ld_src + c];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x);
+        const float r1 = x - __bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+        dst[e] = h0;
+        dst[j.plane_stride + e] = h1;
+        dst[2 * j.plane_stride + e] = h2;
+    }
+}
+
 // ---- separable first layer: h[b*W + j] = relu(u[b] + v[j]) straight into bf16x3 planes --------------------------------------
 __global__ void __launch_bounds__(256) pairs_relu_split_kernel(const float* __restrict__ u, const float* __restrict__ v, int B, int W, int H,
                                                                __nv_bfloat16* __restrict__ dst, long long plane_stride) {
@@ -915,6 +968,29 @@ extern "C" int morl_split_bf16x3(const float* src, int rows, int cols, int ld_sr
     return check_launch("morl_split_bf16x3");
 }
 
+extern "C" int morl_split_bf16x3_multi(const MorlSplitJob* jobs, int n_jobs, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(jobs, MORL_ERR_NULL, "morl_split_bf16x3_multi: NULL pointer argument");
+    MORL_REQUIRE(n_jobs > 0 && n_jobs <= MORL_SPLIT_MAX_JOBS, MORL_ERR_SHAPE, "morl_split_bf16x3_multi: n_jobs=%d out of range", n_jobs);
+    SplitJobs sj;
+    memset(&sj, 0, sizeof(sj));
+    long long max_total = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        const MorlSplitJob& j = jobs[i];
+        MORL_REQUIRE(j.src && j.dst_planes, MORL_ERR_NULL, "morl_split_bf16x3_multi: job %d has a NULL pointer", i);
+        MORL_REQUIRE(j.rows > 0 && j.cols > 0 && j.rows_pad >= j.rows && j.ldp >= j.cols && j.ld_src > 0 &&
+                         j.plane_stride >= (long long)j.rows_pad * j.ldp,
+                     MORL_ERR_SHAPE, "morl_split_bf16x3_multi: job %d bad shape rows=%d cols=%d rows_pad=%d ldp=%d", i, j.rows, j.cols, j.rows_pad, j.ldp);
+        sj.job[i] = j;
+        const long long t = (long long)j.rows_pad * j.ldp;
+        if (t > max_total) max_total = t;
+    }
+    long long bx = (max_total + 255) / 256;
+    if (bx > 148) bx = 148;
+    split_bf16x3_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(sj);
+    return check_launch("morl_split_bf16x3_multi");
+}
+
 extern "C" int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B, int W, int H, void* dst_planes, long long plane_stride,
                                             void* stream) {
     using namespace morl;
@@ -929,9 +1005,23 @@ extern "C" int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int 
     return check_launch("morl_pairs_relu_split_bf16x3");
 }
 
+// Diagnostics: cycle counters of the K-major GEMM roles, accumulated over all CTAs and launches since the last reset
+// (only when MORL_GEMM_STATS=1 was set before the first GEMM call).
+extern "C" int morl_debug_gemm_stats(unsigned long long* out8, int reset) {
+    using namespace morl;
+    MORL_REQUIRE(out8, MORL_ERR_NULL, "morl_debug_gemm_stats: NULL pointer argument");
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_gemm_stats, 8 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_gemm_stats, z, sizeof(z));
+    }
+    return check_launch("morl_debug_gemm_stats");
+}
+
 extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stride, const void* b_planes, long long b_plane_stride, int M, int N,
                                     int N_pad, int K, const float* bias, int relu, const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc,
-                                    void* c_planes, int ldp, long long c_plane_stride, void* stream) {
+                                    void* c_planes, int ldp, long long c_plane_stride, int reverse_tiles, void* stream) {
     using namespace morl;
     MORL_REQUIRE(a_planes && b_planes && (c_f32 || c_planes), MORL_ERR_NULL, "morl_gemm_bf16x3_f32: NULL pointer argument");
     MORL_REQUIRE(M > 0 && N > 0 && K > 0 && N_pad >= N, MORL_ERR_SHAPE, "morl_gemm_bf16x3_f32: bad shape M=%d N=%d N_pad=%d K=%d", M, N, N_pad, K);
@@ -968,6 +1058,14 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     g.bias = bias; g.c_f32 = c_f32; g.ldc = ldc;
     g.c_planes = static_cast<__nv_bfloat16*>(c_planes); g.ldp = ldp; g.plane_stride = c_plane_stride;
     g.mask = static_cast<const __nv_bfloat16*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
+    g.reverse = reverse_tiles ? 1 : 0;
+    static const bool want_stats = [] { const char* e = getenv("MORL_GEMM_STATS"); return e && e[0] == '1'; }();
+    g.stats = nullptr;
+    if (want_stats) {
+        void* sp = nullptr;
+        cudaGetSymbolAddress(&sp, g_gemm_stats);
+        g.stats = static_cast<unsigned long long*>(sp);
+    }
     const size_t tail = 256 + 1024 + 1024 + 64 + 1024 + 8 * 6144;  // barriers, bias, alignment slack, 8 epilogue staging tiles
     const size_t smem1 = (size_t)kGemmStagesK * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStagesK * (3u * 256u * kGemmBK * 2u) + tail;
     const size_t smem2 = (size_t)kGemmStagesPair * (3u * kGemmBM * kGemmBK * 2u) + (size_t)kGemmStagesPair * (3u * 128u * kGemmBK * 2u) + tail;

@@ -248,20 +248,48 @@ class Envelope(MOPolicy, MOAgent):
 
     # ------------------------------------------------------------------------------------------ the update
     def _ensure_static(self):
+        """Static tensors of the update.  All per-step host inputs live in ONE pinned buffer mirrored by one device buffer:
+            [ replay indices int64 B | weight vectors W x D | obs | next_obs | rewards | dones | actions int32 ]
+        so a step issues a single host->device copy: indices + weights when the replay store is mirrored in HBM, weights +
+        minibatch when it is host-resident (the reference makes six synchronous pageable copies, buffer.py:93-94)."""
         if self._static is not None:
             return self._static
         dev, B, W, D = self.device, self.batch_size, self.num_sample_w, self.reward_dim
+        obs_n = int(np.prod(self.observation_shape))
+        seg = lambda n: (n + 3) // 4 * 4  # noqa: E731  (16-byte aligned segments)
+        sizes = [("idx", 2 * B), ("wset", W * D), ("obs", B * obs_n), ("nobs", B * obs_n), ("rew", B * D), ("done", B), ("act", B)]
+        off, o = {}, 0
+        for k, n in sizes:
+            off[k] = (o, n)
+            o += seg(n)
+        total = o
+        pin = th.zeros(total, dtype=th.float32).pin_memory()
+        pdev = th.zeros(total, dtype=th.float32, device=dev)
+        pnp = pin.numpy()
+        cut = lambda buf, k: buf[off[k][0] : off[k][0] + off[k][1]]  # noqa: E731
+        shp = {"wset": (W, D), "obs": (B,) + tuple(self.observation_shape), "nobs": (B,) + tuple(self.observation_shape), "rew": (B, D),
+               "done": (B, 1), "act": (B, 1)}
+        host = {k: cut(pnp, k).reshape(shp[k]) for k in shp if k != "act"}
+        host["act"] = cut(pnp, "act").view(np.int32).reshape(B, 1)
+        host["idx"] = cut(pnp, "idx").view(np.int64)
+        stage = {k: cut(pdev, k).view(shp[k]) for k in ("obs", "nobs", "rew", "done")}
+        stage["act"] = cut(pdev, "act").view(th.int32).view(B, 1)
+        head_end = off["wset"][0] + seg(off["wset"][1])
         s = {
-            "idx": th.zeros(B, dtype=th.int64, device=dev),
-            "wset": th.full((W, D), 1.0 / D, dtype=th.float32, device=dev),
+            "idx": cut(pdev, "idx").view(th.int64),
+            "wset": cut(pdev, "wset").view(W, D),
             "loss": th.zeros((), dtype=th.float32, device=dev),
             "prio": th.zeros(B, dtype=th.float32, device=dev),
             "ws": ops.td_workspace(B * W, dev),
-            "idx_pin": th.zeros(B, dtype=th.int64).pin_memory(),
-            "wset_pin": th.zeros((W, D), dtype=th.float32).pin_memory(),
+            "pack_pin": pin, "pack_dev": pdev, "host": host, "stage": stage,
+            # (device slice, pinned slice) of the one copy a step makes
+            "copy_device": (pdev[:head_end], pin[:head_end]),
+            "copy_host": (pdev[off["wset"][0] :], pin[off["wset"][0] :]),
             "prio_pin": th.zeros(B, dtype=th.float32).pin_memory(),
-            "h2d_done": th.cuda.Event(),  # guards the pinned staging buffers against being overwritten while a copy is pending
+            "h2d_done": th.cuda.Event(),  # guards the pinned staging buffer against being overwritten while a copy is pending
         }
+        s["wset"].fill_(1.0 / D)
+        s["prio_np"] = s["prio_pin"].numpy()
         self._static = s
         return s
 
@@ -276,8 +304,8 @@ class Envelope(MOPolicy, MOAgent):
                     self._tc_tg = TCPairMlp(self.target_q_net.net, self.target_q_net.feat_dim, B, W)
                     if TCPairMlp.trainable_supported(self.q_net.net, W):
                         self._tc_train = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W, share_weights_with=self._tc_on, trainable=True)
-                self._tc_on.refresh_weights()
-                self._tc_tg.refresh_weights()
+                # every weight plane this step needs (online, target, transposed-for-backward) in one launch
+                TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
                 q_on = self._tc_on.forward_pairs(nobs, wset).view(B, W, A, D)  # online net selects   (envelope.py:420)
                 q_tg = self._tc_tg.forward_pairs(nobs, wset).view(B, W, A, D)  # target net evaluates (envelope.py:429)
             else:
@@ -311,7 +339,7 @@ class Envelope(MOPolicy, MOAgent):
             obs, act, rew, nobs, done = ops.replay_gather(obs_s, nobs_s, act_s, rew_s, done_s, s["idx"])
         else:
             st = s["stage"]
-            obs, act, rew, nobs, done = st["obs"][1], st["act"][1], st["rew"][1], st["nobs"][1], st["done"][1]
+            obs, act, rew, nobs, done = st["obs"], st["act"], st["rew"], st["nobs"], st["done"]
         self._gradient_step(obs, act, rew, nobs, done, s["wset"])
 
     def _snapshot(self):
@@ -337,8 +365,6 @@ class Envelope(MOPolicy, MOAgent):
         self._ensure_static()
         if mode == "device":
             self.replay_buffer.flush()
-        else:
-            self._ensure_stage()
         snap = self._snapshot()
         side = th.cuda.Stream()
         side.wait_stream(th.cuda.current_stream())
@@ -373,20 +399,19 @@ class Envelope(MOPolicy, MOAgent):
         for _ in range(self.gradient_updates):
             # RNG consumption order of the reference: replay indices (global numpy RNG) first, then the weights (self.np_random)
             s["h2d_done"].synchronize()
+            b_inds = self.__sample_indices()
+            host = s["host"]
             if has_mirror:
-                b_inds = self.__sample_indices()
-                s["idx_pin"].copy_(th.from_numpy(np.ascontiguousarray(b_inds, dtype=np.int64)))
-                s["idx"].copy_(s["idx_pin"], non_blocking=True)
-            else:
-                smp = rb.sample(self.batch_size)  # host-resident buffer: the minibatch crosses PCIe every update
-                b_inds = smp[5]
-                self._stage_host_batch(smp)
+                host["idx"][:] = b_inds
+            else:  # host-resident buffer: the minibatch crosses PCIe every update, packed into the pinned staging buffer
+                self._stage_host_batch(b_inds)
             w_np = random_weights(dim=self.reward_dim, n=self.num_sample_w, dist="gaussian", rng=self.np_random)
-            s["wset_pin"].copy_(th.from_numpy(np.asarray(w_np, dtype=np.float64).reshape(self.num_sample_w, -1)).float())
-            s["wset"].copy_(s["wset_pin"], non_blocking=True)
+            host["wset"][:] = np.asarray(w_np).reshape(self.num_sample_w, -1)  # float64 -> float32, as th.tensor(w).float() (envelope.py:278)
+            mode = "device" if has_mirror else "host"
+            dst, src = s["copy_" + mode]
+            dst.copy_(src, non_blocking=True)
             s["h2d_done"].record()
 
-            mode = "device" if has_mirror else "host"
             if self.use_cuda_graph and self._lambda_is_static():
                 g = self._graphs.get(mode) or self._capture(mode)
                 if has_mirror:
@@ -399,8 +424,7 @@ class Envelope(MOPolicy, MOAgent):
             if self.per:
                 s["prio_pin"].copy_(s["prio"], non_blocking=True)
                 th.cuda.current_stream().synchronize()
-                priority = s["prio_pin"].numpy().copy()
-                priority = (priority + rb.min_priority) ** self.per_alpha  # envelope.py:333
+                priority = (s["prio_np"] + rb.min_priority) ** self.per_alpha  # envelope.py:333 (float32, as the reference's tensor math)
                 rb.update_priorities(b_inds, priority)
 
         if self.tau != 1 or self.global_step % self.target_net_update_freq == 0:
@@ -422,27 +446,26 @@ class Envelope(MOPolicy, MOAgent):
             if self.per:
                 wandb.log({"metrics/mean_priority": np.mean(priority)})
 
-    def _stage_host_batch(self, smp):
-        """Host minibatch (numpy) -> pinned staging -> device, asynchronously (replaces the reference's six synchronous
-        th.tensor(x, device) copies, buffer.py:93-94)."""
-        s = self._static
-        self._ensure_stage()
-        st = s["stage"]
-        obs, act, rew, nobs, done = smp[0], smp[1], smp[2], smp[3], smp[4]
-        for key, arr in (("obs", obs), ("act", np.asarray(act).astype(np.int32)), ("rew", rew), ("nobs", nobs), ("done", done)):
-            pin, dev = st[key]
-            pin.copy_(th.from_numpy(np.ascontiguousarray(arr)).reshape(pin.shape))
-            dev.copy_(pin, non_blocking=True)
-
-    def _ensure_stage(self):
-        s = self._ensure_static()
-        if s.get("stage") is None:
-            B = self.batch_size
-            shapes = {"obs": ((B,) + tuple(self.observation_shape), th.float32), "act": ((B, 1), th.int32),
-                      "rew": ((B, self.reward_dim), th.float32), "nobs": ((B,) + tuple(self.observation_shape), th.float32),
-                      "done": ((B, 1), th.float32)}
-            s["stage"] = {k: (th.zeros(sh, dtype=dt).pin_memory(), th.zeros(sh, dtype=dt, device=self.device)) for k, (sh, dt) in shapes.items()}
-        return s["stage"]
+    def _stage_host_batch(self, inds):
+        """Gather the host-resident minibatch for ``inds`` straight into the pinned staging buffer (C row gathers,
+        csrc/host_replay.cu); replaces the reference's fancy-index temporaries + six synchronous th.tensor(x, device) copies
+        (buffer.py:84-94)."""
+        rb, host = self.replay_buffer, self._static["host"]
+        lib = ops._lib.load()
+        idx = np.ascontiguousarray(inds, dtype=np.int64)
+        n = idx.shape[0]
+        for key, arr in (("obs", rb.obs), ("nobs", rb.next_obs), ("rew", rb.rewards), ("done", rb.dones)):
+            if arr.dtype != np.float32 or not arr.flags.c_contiguous:
+                host[key][:] = arr[idx].reshape(host[key].shape)
+                continue
+            row_bytes = arr.strides[0]
+            ops._lib.check(lib.morl_host_gather_rows(arr.ctypes.data, row_bytes, idx.ctypes.data, n, host[key].ctypes.data), "morl_host_gather_rows")
+        act = rb.actions
+        if act.dtype == np.uint8 and act.flags.c_contiguous:
+            ops._lib.check(lib.morl_host_gather_u8_to_i32(act.ctypes.data, act.shape[1], idx.ctypes.data, n, host["act"].ctypes.data),
+                           "morl_host_gather_u8_to_i32")
+        else:
+            host["act"][:] = act[idx].astype(np.int32).reshape(host["act"].shape)
 
     # ------------------------------------------------------------------------------------------ acting
     def eval(self, obs: np.ndarray, w: np.ndarray) -> int:

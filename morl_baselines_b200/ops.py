@@ -298,9 +298,28 @@ def split_bf16x3(x: th.Tensor, rows_pad: Optional[int] = None, ldp: Optional[int
     return out
 
 
+def split_bf16x3_multi(jobs) -> None:
+    """One launch for several splits.  jobs: iterable of (src [rows, cols] fp32 CUDA, out [3, rows_pad, ldp] bf16, transpose)."""
+    jobs = list(jobs)
+    if not jobs:
+        return
+    if len(jobs) > _lib.SPLIT_MAX_JOBS:
+        raise _lib.MorlB200Error(f"split_bf16x3_multi: at most {_lib.SPLIT_MAX_JOBS} jobs per call")
+    arr = (_lib.SplitJob * len(jobs))()
+    for k, (src, out, transpose) in enumerate(jobs):
+        src = _dev(src, "src")
+        rows, cols = (src.shape[1], src.shape[0]) if transpose else (src.shape[0], src.shape[1])
+        arr[k].src, arr[k].dst_planes, arr[k].plane_stride = src.data_ptr(), out.data_ptr(), out.stride(0)
+        arr[k].rows, arr[k].cols, arr[k].ld_src, arr[k].transpose = rows, cols, src.stride(0), int(bool(transpose))
+        arr[k].rows_pad, arr[k].ldp = out.shape[1], out.shape[2]
+    rc = _lib.load().morl_split_bf16x3_multi(arr, len(jobs), _stream())
+    _lib.check(rc, "morl_split_bf16x3_multi")
+    _count()
+
+
 def gemm_bf16x3(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Optional[th.Tensor] = None, relu: bool = False,
                 relu_mask: Optional[th.Tensor] = None, out_f32: bool = True, out_planes: bool = False, c_f32: Optional[th.Tensor] = None,
-                c_planes: Optional[th.Tensor] = None):
+                c_planes: Optional[th.Tensor] = None, reverse_tiles: bool = False):
     """C = act(A . B^T + bias) on the tcgen05 tensor cores with bf16x3 split operands (fp32-accurate).
     a_planes [3, M, K], b_planes [3, N_pad, K] (bf16); returns (c_f32 [M, n_out] or None, c_planes [3, M, ldp] or None)."""
     if a_planes.dtype != th.bfloat16 or b_planes.dtype != th.bfloat16 or not a_planes.is_cuda:
@@ -318,7 +337,7 @@ def gemm_bf16x3(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Opti
     rc = _lib.load().morl_gemm_bf16x3_f32(_ptr(a_planes), a_planes.stride(0), _ptr(b_planes), b_planes.stride(0), M, n_out, n_pad, K, _ptr(bias),
                                           int(relu), _ptr(mask0), 0 if mask0 is None else mask0.stride(0), _ptr(c_f32),
                                           0 if c_f32 is None else c_f32.stride(0), _ptr(c_planes), 0 if c_planes is None else c_planes.shape[2],
-                                          0 if c_planes is None else c_planes.stride(0), _stream())
+                                          0 if c_planes is None else c_planes.stride(0), int(reverse_tiles), _stream())
     _lib.check(rc, "morl_gemm_bf16x3_f32")
     _count()
     return c_f32, c_planes

@@ -25,6 +25,12 @@ import torch.nn as nn
 from . import ops
 
 
+import os
+
+_SNAKE = os.environ.get("MORL_TC_SNAKE", "1") == "1"          # alternate the GEMM tile order between chained layers
+_MULTI_SPLIT = os.environ.get("MORL_TC_MULTI_SPLIT", "1") == "1"  # one launch for all weight splits of a step
+
+
 def _pad32(n: int) -> int:
     return (n + 31) // 32 * 32
 
@@ -84,8 +90,32 @@ class TCPairMlp:
 
     def refresh_weights(self):
         """Re-split the (fp32) weights of layers 2.. into bf16x3 planes; call after every optimiser step / target sync."""
-        for l, wp in zip(self.lin[1:], self.wp):
-            ops.split_bf16x3(l.weight.detach(), rows_pad=wp.shape[1], ldp=wp.shape[2], out=wp)
+        ops.split_bf16x3_multi(self._weight_jobs())
+
+    def _weight_jobs(self):
+        return [(l.weight.detach(), wp, False) for l, wp in zip(self.lin[1:], self.wp)]
+
+    def _transposed_jobs(self):
+        return [(l.weight.detach(), wt, True) for l, wt in zip(self.lin[1:], self.wtp)]
+
+    @staticmethod
+    def refresh_many(plans, transposed_of=()):
+        """All weight planes of several plans (and the transposed planes of the trainable ones) in a single launch per 16 matrices.
+        Plans sharing their planes (``share_weights_with``) are split once."""
+        jobs, seen = [], set()
+        for p in plans:
+            if id(p.wp) not in seen:
+                seen.add(id(p.wp))
+                jobs += p._weight_jobs()
+        for p in transposed_of:
+            jobs += p._transposed_jobs()
+            p._wt_fresh = True
+        if not _MULTI_SPLIT:
+            for src, out, tr in jobs:
+                ops.split_bf16x3(src, rows_pad=out.shape[1], ldp=out.shape[2], transpose=tr, out=out)
+            return
+        for i in range(0, len(jobs), 16):
+            ops.split_bf16x3_multi(jobs[i:i + 16])
 
     @th.no_grad()
     def forward_pairs(self, feats: th.Tensor, wset: th.Tensor) -> th.Tensor:
@@ -97,21 +127,26 @@ class TCPairMlp:
         n = len(self.lin)
         for k in range(1, n - 1):
             l = self.lin[k]
-            _, a = ops.gemm_bf16x3(a, self.wp[k - 1], l.out_features, bias=l.bias, relu=True, out_f32=False, out_planes=True, c_planes=self.h[k])
+            # alternate the tile order: a layer starts on the rows its producer wrote last (L2-resident)
+            _, a = ops.gemm_bf16x3(a, self.wp[k - 1], l.out_features, bias=l.bias, relu=True, out_f32=False, out_planes=True, c_planes=self.h[k],
+                                   reverse_tiles=_SNAKE and bool(k & 1))
         last = self.lin[-1]
-        q, _ = ops.gemm_bf16x3(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q)
+        q, _ = ops.gemm_bf16x3(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
+                               reverse_tiles=_SNAKE and bool((n - 1) & 1))
         return q
 
     def refresh_transposed_weights(self):
-        for l, wt in zip(self.lin[1:], self.wtp):
-            ops.split_bf16x3(l.weight.detach(), rows_pad=wt.shape[1], ldp=wt.shape[2], transpose=True, out=wt)
+        ops.split_bf16x3_multi(self._transposed_jobs())
 
     @th.no_grad()
     def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor):
         """Gradients of all Linear parameters given dL/dQ [B*W, out]; uses the activations of the last forward_pairs()."""
         n = len(self.lin)
         grads = [None] * (2 * n)
-        self.refresh_transposed_weights()
+        if getattr(self, "_wt_fresh", False):
+            self._wt_fresh = False  # refreshed together with the forward planes of this step (refresh_many)
+        else:
+            self.refresh_transposed_weights()
         G = ops.split_bf16x3(dq, rows_pad=dq.shape[0], ldp=self.ld_last, out=self.g_last)
         for k in range(n - 1, 0, -1):
             l = self.lin[k]
@@ -120,7 +155,7 @@ class TCPairMlp:
             grads[2 * k] = ops.gemm_bf16x3_mn(G, l.out_features, self.h[k - 1], l.in_features, workspace=self.ws_mn, colsum=grads[2 * k + 1])
             # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1})
             _, G = ops.gemm_bf16x3(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
-                                   c_planes=self.g[k & 1])
+                                   c_planes=self.g[k & 1], reverse_tiles=_SNAKE and bool(k & 1))
         dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red)
         grads[0] = th.cat([dU.t() @ feats, dV.t() @ wset], dim=1)
         grads[1] = dV.sum(0)

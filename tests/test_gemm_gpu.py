@@ -159,3 +159,20 @@ def test_gemm_single_cta_kernel_still_correct(cuda):
         assert r.returncode == 0, r.stdout + r.stderr
         outs[flag] = r.stdout
     assert "ERR" in outs["1"] and "ERR" in outs["0"]
+
+
+def test_reverse_tile_order_and_multi_split_are_bit_identical(cuda):
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(11)
+    a = th.randn(40000, 256, device=cuda, generator=g)
+    ws = [th.randn(256, 256, device=cuda, generator=g) / 16, th.randn(24, 256, device=cuda, generator=g), th.randn(256, 64, device=cuda, generator=g)]
+    ap = ops.split_bf16x3(a)
+    singles = [ops.split_bf16x3(ws[0]), ops.split_bf16x3(ws[1], rows_pad=32), ops.split_bf16x3(ws[2], rows_pad=64, ldp=256, transpose=True)]
+    multi = [th.empty_like(s) for s in singles]
+    ops.split_bf16x3_multi([(ws[0], multi[0], False), (ws[1], multi[1], False), (ws[2], multi[2], True)])
+    for s, m in zip(singles, multi):
+        assert th.equal(s, m)
+    c0, p0 = ops.gemm_bf16x3(ap, singles[0], 256, relu=True, out_f32=True, out_planes=True)
+    c1, p1 = ops.gemm_bf16x3(ap, singles[0], 256, relu=True, out_f32=True, out_planes=True, reverse_tiles=True)
+    assert th.equal(c0, c1) and th.equal(p0, p1)

@@ -187,3 +187,77 @@ def test_allgather_fronts_gloo_world2():
     allpts = allpts / np.linalg.norm(allpts, axis=1, keepdims=True)
     expect = allpts[orc.pareto_mask(allpts, True)]
     assert {tuple(r) for r in f0} == {tuple(r) for r in expect}
+
+
+class _NumpySumTree:
+    """Restatement of the reference's SumTree (prioritized_buffer.py:12-82) with its own numpy calls, level arrays root first."""
+
+    def __init__(self, max_size):
+        self.nodes, level = [], 1
+        for _ in range(int(np.ceil(np.log2(max_size))) + 1):
+            self.nodes.append(np.zeros(level))
+            level *= 2
+
+    def walk(self, query):
+        query = np.array(query, dtype=np.float64)
+        node = np.zeros(len(query), dtype=int)
+        for nodes in self.nodes[1:]:
+            node *= 2
+            left = nodes[node]
+            greater = np.greater(query, left)
+            node += greater
+            query -= left * greater
+        return node
+
+    def batch_set(self, node_index, new_priority):
+        node_index, unique_index = np.unique(node_index, return_index=True)
+        diff = new_priority[unique_index] - self.nodes[-1][node_index]
+        for nodes in self.nodes[::-1]:
+            np.add.at(nodes, node_index, diff)
+            node_index //= 2
+
+
+@pytest.mark.parametrize("size", [5, 100, 4096, 100000])
+def test_native_sum_tree_is_bit_identical_to_numpy_semantics(size):
+    """The C sum tree (csrc/host_replay.cu) performs the reference's float64 operations in the reference's order: every level
+    array and every sampled index is bit-identical, duplicates included (first occurrence wins)."""
+    from morl_baselines_b200.common.prioritized_buffer import SumTree
+
+    rng = np.random.default_rng(size)
+    a, b = SumTree(size), _NumpySumTree(size)
+    for _ in range(25):
+        n = int(rng.integers(1, 1500))
+        idx = rng.integers(0, size, n)
+        pr = rng.random(n) * 10
+        a.batch_set(idx, pr)
+        b.batch_set(idx.copy(), pr)
+        for la, lb in zip(a.nodes, b.nodes):
+            assert np.array_equal(la, lb)
+        q = rng.uniform(0, a.nodes[0][0], 777)
+        assert np.array_equal(a.walk(q), b.walk(q))
+    a.set(3 % size, 0.25)
+    b.batch_set(np.array([3 % size]), np.array([0.25]))
+    assert np.array_equal(a.nodes[0], b.nodes[0])
+    import pickle
+
+    c = pickle.loads(pickle.dumps(a))
+    assert all(np.array_equal(x, y) for x, y in zip(a.nodes, c.nodes))
+    c.batch_set(np.array([0]), np.array([1.5]))  # views still alias the flat array after unpickling
+    assert c.nodes[-1][0] == 1.5 and c.nodes[0][0] != a.nodes[0][0]
+
+
+def test_native_row_gather_matches_fancy_indexing():
+    from morl_baselines_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    src = rng.standard_normal((500, 7)).astype(np.float32)
+    idx = rng.integers(0, 500, 64).astype(np.int64)
+    dst = np.empty((64, 7), np.float32)
+    _lib.check(lib.morl_host_gather_rows(src.ctypes.data, src.strides[0], idx.ctypes.data, 64, dst.ctypes.data), "gather")
+    assert np.array_equal(dst, src[idx])
+    act = rng.integers(0, 255, (500, 1)).astype(np.uint8)
+    d32 = np.empty((64, 1), np.int32)
+    _lib.check(lib.morl_host_gather_u8_to_i32(act.ctypes.data, 1, idx.ctypes.data, 64, d32.ctypes.data), "gather u8")
+    assert np.array_equal(d32, act[idx].astype(np.int32))
+    assert lib.morl_host_gather_rows(None, 4, idx.ctypes.data, 1, dst.ctypes.data) == -1
