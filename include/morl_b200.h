@@ -247,6 +247,10 @@ MORL_API int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stride
  * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,
  * [3] TMA thread waiting for a free stage, [4] epilogue waiting for an accumulator, [5] epilogue busy; [6], [7] reserved. */
 MORL_API int morl_debug_gemm_stats(unsigned long long* out8, int reset);
+/* Diagnostics of the tensor-core envelope kernel (MORL_ENVELOPE_STATS=1 before the first call): cycles summed over CTAs and launches,
+ * one thread per role: [0] converter waiting, [1] converter busy, [2] MMA thread waiting, [3] scanner waiting, [4] scanner busy,
+ * [5] finisher waiting, [6] finisher busy, [7] kernel start -> last finisher iteration. */
+MORL_API int morl_debug_envelope_stats(unsigned long long* out8, int reset);
 /* h[b*W + j, :] = relu(u[b, :] + v[j, :]) written directly as bf16x3 planes [3][B*W][H] (separable first layer of the
  * weight-conditioned Q-network: W1 [s || w] + b1 = W1_s s + (W1_w w + b1); reference envelope.py:75 builds the concat). */
 MORL_API int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B, int W, int H, void* dst_planes,

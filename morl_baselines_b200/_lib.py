@@ -47,6 +47,7 @@ SIGNATURES = {
     "morl_gemm_bf16x3_f32": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_longlong, _i, _vp]),
     "morl_split_bf16x3_multi": (_i, [_vp, _i, _vp]),
     "morl_debug_gemm_stats": (_i, [_vp, _i]),
+    "morl_debug_envelope_stats": (_i, [_vp, _i]),
     "morl_pairs_relu_split_bf16x3": (_i, [_vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
     "morl_gemm_mn_workspace_bytes": (_sz, [_i, _i, _i]),
     "morl_gemm_bf16x3_mn_f32": (_i, [_vp, C.c_longlong, _i, _i, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),

@@ -494,7 +494,23 @@ static EnvelopePlan plan_envelope(int B, int W, int A, int D) {
     return p;
 }
 
-static const bool g_force_v1 = (getenv("MORL_ENVELOPE_FORCE_V1") != nullptr);
+// Path selection, read on every call: MORL_ENVELOPE_PATH = "v1" (generic kernel), "v3" (CUDA-core fast path; the default whenever the
+// shape fits), "tc" (tensor-core filter, envelope_td_tc.cu: opt-in -- bit-identical, but measured SLOWER on B200 because reading the
+// 128 KB score tile back from tensor memory is limited to 64 B/clk per SM).  MORL_ENVELOPE_FORCE_V1 is the older
+// spelling of "v1".
+static int envelope_path_override() {
+    if (getenv("MORL_ENVELOPE_FORCE_V1") != nullptr) return 1;
+    const char* e = getenv("MORL_ENVELOPE_PATH");
+    if (!e) return 0;
+    if (e[0] == 'v' && e[1] == '1') return 1;
+    if (e[0] == 'v' && e[1] == '3') return 3;
+    if (e[0] == 't' && e[1] == 'c') return 4;
+    return 0;
+}
+
+int envelope_td_tc_try_launch(const float* q_online, const float* q_target, const float* wset, const float* reward, const float* done,
+                              float gamma, int B, int W, int A, int D, int dot_mode, int row_order, float* target_out, int32_t* pref_out,
+                              int32_t* act_out, cudaStream_t st, int sm_count);
 
 }  // namespace morl
 
@@ -525,8 +541,15 @@ extern "C" int morl_envelope_td_f32(const float* q_online, const float* q_target
             sm_count_cached = 148;
         }
     }
+    const int path = envelope_path_override();
+    if (path == 4) {
+        if (envelope_td_tc_try_launch(q_online, q_target, wset, reward, done, gamma, B, W, A, D, dot_mode, row_order, target_out, pref_out,
+                                      act_out, st, sm_count_cached))
+            return check_launch("morl_envelope_td_f32(tc)");
+        MORL_REQUIRE(false, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: MORL_ENVELOPE_PATH=tc but the shape W=%d A=%d D=%d is outside the tensor-core path", W, A, D);
+    }
     EnvelopeV2Plan p2 = plan_envelope_v2(B, W, A, D, sm_count_cached);
-    if (p2.ok && !g_force_v1) {
+    if (p2.ok && path != 1) {
         bool launched2 = false;
         MORL_DISPATCH_D(D, MORL_DISPATCH_MODE(dot_mode, {
                             auto kern = envelope_td_v3_kernel<kD, kMode>;

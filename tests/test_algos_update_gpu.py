@@ -143,3 +143,77 @@ def test_morld_population_smoke(cuda):
     from morl_baselines_b200.common.performance_indicators import hypervolume
 
     assert hypervolume(np.array([-100.0, -100.0]), list(algo.global_front)) > 0
+
+
+@pytest.mark.parametrize("tag,n_support", [("m5", 5), ("m1", 1)])
+def test_gpipd_continuous_update_matches_reference(cuda, tag, n_support):
+    """GPILSContinuousAction: three critic steps + two delayed actor steps, PER write-back, target syncs and the GPI evaluation against
+    the unmodified reference (tests/golden/make_golden_gpipd_continuous.py), hopper dimensions (BASELINE.json configs[2])."""
+    from morl_baselines_b200.multi_policy.gpi_pd.gpi_pd_continuous_action import GPILSContinuousAction
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "gpipd_continuous.npz"))
+    OBS, ACT, D, B, N = 11, 3, 3, 16, 128
+    agent = GPILSContinuousAction(FakeEnv(obs_dim=OBS, continuous_action_dim=ACT, reward_dim=D), batch_size=B, net_arch=[32, 32], num_q_nets=2,
+                                  gradient_updates=3, per=True, buffer_size=N, log=False, seed=3, device=cuda)
+    for net in agent.q_nets + agent.target_q_nets:
+        for m in net.modules():
+            if isinstance(m, th.nn.Dropout):
+                m.p = 0.0
+    _load_sd(agent.policy, g, f"{tag}/init_policy", cuda)
+    agent.target_policy.load_state_dict(agent.policy.state_dict())
+    for i, (q, tq) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
+        _load_sd(q, g, f"{tag}/init_q{i}", cuda)
+        tq.load_state_dict(q.state_dict())
+    rb = agent.replay_buffer
+    for k in ("obs", "next_obs", "actions", "rewards", "dones"):
+        getattr(rb, k)[:] = g[f"{tag}/rb_{k}"]
+    rb.size, rb.ptr = N, 0
+    rb.mark_all_dirty()
+    rb.tree.batch_set(np.arange(N), g[f"{tag}/tree_leaves0"][:N])
+    support = g[f"{tag}/support"]
+    assert support.shape[0] == n_support
+    agent.set_weight_support(list(support))
+    w = th.tensor(support[min(2, n_support - 1)]).to(cuda)
+    agent._noise_hook = _Noise(99, cuda)
+    random.seed(15)
+    np.random.seed(16)
+    agent.global_step = 5
+    agent.update(w)
+    _cmp_sd(agent.policy, g, f"{tag}/final_policy")
+    _cmp_sd(agent.target_policy, g, f"{tag}/final_target_policy")
+    for i, (q, tq) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
+        _cmp_sd(q, g, f"{tag}/final_q{i}")
+        _cmp_sd(tq, g, f"{tag}/final_tq{i}")
+    np.testing.assert_allclose(rb.tree.nodes[-1][:N], g[f"{tag}/tree_leaves1"][:N], rtol=2e-4, atol=1e-7)
+    assert rb.min_priority == pytest.approx(float(g[f"{tag}/min_priority1"]), rel=2e-4)
+    wq = support[0]
+    agent.use_gpi = False
+    plain = np.stack([agent.eval(o, wq) for o in g[f"{tag}/eval_obs"]])
+    np.testing.assert_allclose(plain, g[f"{tag}/eval_plain"], rtol=1e-4, atol=1e-5)
+    agent.use_gpi = True
+    gpi = np.stack([agent.eval(o, wq) for o in g[f"{tag}/eval_obs"]])
+    np.testing.assert_allclose(gpi, g[f"{tag}/eval_gpi"], rtol=1e-4, atol=1e-5)
+
+
+def test_gpipd_continuous_train_iteration_and_checkpoint(cuda, tmp_path):
+    """train_iteration on the stand-in MOMDP (rollout -> replay -> update), save / load round trip with the reference's keys."""
+    from morl_baselines_b200.multi_policy.gpi_pd.gpi_pd_continuous_action import GPIPDContinuousAction, GPILSContinuousAction
+
+    env = FakeEnv(obs_dim=11, continuous_action_dim=3, reward_dim=3, horizon=20)
+    with pytest.raises(NotImplementedError):
+        GPIPDContinuousAction(env, log=False, device=cuda)  # dyna=True is the reference default; the Dyna path is out of scope
+    agent = GPILSContinuousAction(env, batch_size=16, net_arch=[32, 32], gradient_updates=2, learning_starts=20, buffer_size=512, log=False,
+                                  seed=0, device=cuda)
+    M = [np.array([1.0, 0.0, 0.0], np.float32), np.array([0.0, 1.0, 0.0], np.float32), np.array([0.3, 0.3, 0.4], np.float32)]
+    agent.train_iteration(total_timesteps=60, weight=M[2], weight_support=M, change_weight_every_episode=True)
+    assert agent.global_step == 60 and agent._n_updates == 2 * 41 and len(agent.replay_buffer) == 60
+    assert all(bool(th.isfinite(p).all()) for p in agent.policy.parameters())
+    agent.save(save_dir=str(tmp_path), filename="ckpt", save_replay_buffer=False)
+    params = th.load(str(tmp_path / "ckpt.tar"), map_location="cpu", weights_only=False)
+    assert {"policy_state_dict", "policy_optimizer_state_dict", "q_net_0_state_dict", "target_q_net_0_state_dict", "q_net_1_state_dict",
+            "target_q_net_1_state_dict", "q_nets_optimizer_state_dict", "M"} <= set(params)
+    other = GPILSContinuousAction(env, batch_size=16, net_arch=[32, 32], buffer_size=512, log=False, seed=1, device=cuda)
+    other.load(str(tmp_path / "ckpt.tar"))
+    a1 = agent.eval(np.ones(11, np.float32), M[2])
+    a2 = other.eval(np.ones(11, np.float32), M[2])
+    np.testing.assert_array_equal(a1, a2)

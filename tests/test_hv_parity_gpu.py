@@ -1,0 +1,65 @@
+"""Hypervolume parity after equal updates (SURVEY.md section 8(d) "HV parity protocol"; BASELINE.json: "hypervolume within 1 % of
+reference after equal updates").
+
+The unmodified reference Envelope was trained on CPU in the build container (tests/golden/make_golden_hv.py -> hv_parity.json) on
+the stand-in vector-reward MDP of tests/golden/standin_env.py (mo-gymnasium is not installed, so BOTH engines use the stand-in, as
+the protocol prescribes).  Here the B200 engine is trained with the same hyper-parameters, seeds, environment, number of
+environment steps (= gradient updates) and evaluation-weight list; both fronts go through the same exact hypervolume routine.
+Bar: |mean_seeds HV_b200 - mean_seeds HV_ref| / mean HV_ref <= 1 %  (3 seeds).
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+from tests.golden.standin_env import HV_REF_POINT, TreasureChain
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _evaluate(agent, gamma, weights):
+    from morl_baselines_b200.common.pareto import filter_pareto_dominated
+    from morl_baselines_b200.common.performance_indicators import hypervolume
+
+    env = TreasureChain(seed=123)
+    returns = []
+    for w in weights:
+        obs, _ = env.reset()
+        done, g, disc = False, 1.0, np.zeros(3)
+        while not done:
+            obs, r, term, trunc, _ = env.step(agent.eval(obs, w))
+            disc += g * r
+            g *= gamma
+            done = term or trunc
+        returns.append(disc)
+    front = filter_pareto_dominated(returns)
+    return front, hypervolume(HV_REF_POINT, list(front))
+
+
+def test_envelope_hypervolume_within_one_percent_of_reference(cuda):
+    from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "hv_parity.json")))
+    hp = gold["hyper_parameters"]
+    hvs = []
+    for seed_s, ref in sorted(gold["seeds"].items()):
+        seed = int(seed_s)
+        th.manual_seed(seed)
+        np.random.seed(seed)
+        env = TreasureChain(seed=seed)
+        agent = Envelope(env, log=False, seed=seed, device=cuda, **hp)
+        agent.train(total_timesteps=gold["total_timesteps"])
+        assert agent.global_step == gold["total_timesteps"]
+        front, hv = _evaluate(agent, hp["gamma"], [np.asarray(w, dtype=np.float32) for w in gold["eval_weights"]])
+        hvs.append(hv)
+        print(f"seed {seed}: hv b200 {hv:.4f} vs reference {ref['hv']:.4f} (true front {gold['true_front_hv']:.4f}), |front| {len(front)} vs {ref['n_front']}")
+    mean_b200, mean_ref = float(np.mean(hvs)), float(gold["hv_mean"])
+    rel = abs(mean_b200 - mean_ref) / mean_ref
+    print(f"mean hv b200 {mean_b200:.4f}, reference {mean_ref:.4f}, relative difference {rel * 100:.3f} %")
+    assert rel <= 0.01
+    # sanity: neither engine can exceed the hypervolume of the true Pareto front of the deterministic MDP
+    assert max(hvs) <= gold["true_front_hv"] * (1 + 1e-9)

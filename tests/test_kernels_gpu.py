@@ -130,6 +130,73 @@ def test_envelope_td_full_size_properties(cuda):
     assert th.equal(t3.view(W, B, D), t3.view(W, B, D)[:1].expand(W, B, D))
 
 
+def _env_path(path, *a, **k):
+    """Run morl_envelope_td_f32 with the kernel family forced by MORL_ENVELOPE_PATH (read by the library on every call)."""
+    import os
+
+    from morl_baselines_b200 import ops
+
+    os.environ["MORL_ENVELOPE_PATH"] = path
+    try:
+        return ops.envelope_td(*a, **k)
+    finally:
+        os.environ.pop("MORL_ENVELOPE_PATH", None)
+
+
+@pytest.mark.parametrize("shape", [(1024, 64, 8, 3), (256, 32, 6, 3), (96, 16, 4, 2), (33, 50, 8, 3), (7, 64, 8, 1), (300, 2, 8, 3), (600, 62, 8, 3)])
+@pytest.mark.parametrize("kind", ["plain", "ties", "neartie", "signed", "special"])
+def test_envelope_td_kernel_families_agree_bitwise(cuda, shape, kind):
+    """The three kernel families of morl_envelope_td_f32 -- generic (v1), CUDA-core fast path (v3: FMA-chain filter + exact re-check),
+    tensor-core filter (tc: bf16x3 scores from tcgen05.mma, exact re-check) -- return bit-identical targets and indices, in every
+    arithmetic mode and row order, on continuous data, exact ties, candidates a few ulps apart, mixed-sign weights / large values,
+    and NaN / +-inf / all-zero / huge / tiny blocks.  v1 is pinned to the oracle and the reference's golden vectors above."""
+    from morl_baselines_b200 import ops
+
+    B, W, A, D = shape
+    g = th.Generator(device=cuda).manual_seed(sum(shape) + len(kind))
+    if kind == "ties":
+        q_on = th.randint(-2, 3, (B, W, A, D), device=cuda, generator=g).float()
+        wset = th.randint(1, 4, (W, D), device=cuda, generator=g).float() / 8.0
+    elif kind == "neartie":
+        q_on = th.randn(B, 1, A, D, device=cuda, generator=g).repeat(1, W, 1, 1) * (1.0 + 1e-7 * th.randn(B, W, A, D, device=cuda, generator=g))
+        wset = th.rand(W, D, device=cuda, generator=g)
+    elif kind == "signed":
+        q_on = th.randn(B, W, A, D, device=cuda, generator=g) * 100.0
+        wset = th.randn(W, D, device=cuda, generator=g)
+    elif kind == "special":
+        q_on = th.randn(B, W, A, D, device=cuda, generator=g)
+        fills = [lambda t: t.fill_(float("nan")), lambda t: t.view(-1)[:1].fill_(float("inf")), lambda t: t.fill_(-float("inf")),
+                 lambda t: t.fill_(0.0), lambda t: t.mul_(1e38), lambda t: t.mul_(1e-38), lambda t: t.view(-1)[-1:].fill_(float("nan"))]
+        for b, f in enumerate(fills[:B]):
+            f(q_on[b])
+        wset = th.rand(W, D, device=cuda, generator=g)
+    else:
+        q_on = th.randn(B, W, A, D, device=cuda, generator=g) * 3.0
+        wset = th.rand(W, D, device=cuda, generator=g)
+        wset = wset / wset.sum(1, keepdim=True)
+    q_tg = th.randn(B, W, A, D, device=cuda, generator=g)
+    rew = th.randn(B, D, device=cuda, generator=g)
+    done = (th.rand(B, device=cuda, generator=g) < 0.1).float()
+    combos = [(ops.DOT_UNFUSED, ops.ROWS_BMAJOR)]
+    if kind in ("plain", "ties"):
+        combos += [(ops.DOT_UNFUSED, ops.ROWS_REFERENCE), (ops.DOT_FMA, ops.ROWS_BMAJOR), (ops.DOT_PAIRFMA, ops.ROWS_REFERENCE)]
+    for mode, order in combos:
+        ref = _env_path("v1", q_on, q_tg, wset, rew, done, 0.99, mode, order)
+        for path in ("v3", "tc"):
+            got = _env_path(path, q_on, q_tg, wset, rew, done, 0.99, mode, order)
+            assert th.equal(ref[0].view(th.int32), got[0].view(th.int32)), (path, mode, order)  # bit pattern (NaN-safe)
+            assert th.equal(ref[1], got[1]) and th.equal(ref[2], got[2]), (path, mode, order)
+
+
+def test_envelope_td_tc_path_rejects_unsupported_shapes(cuda):
+    from morl_baselines_b200 import _lib, ops
+
+    B, W, A, D = 4, 70, 9, 4  # |W| > 64, D > 3
+    z = th.zeros(B, W, A, D, device=cuda)
+    with pytest.raises(_lib.MorlB200Error):
+        _env_path("tc", z, z, th.ones(W, D, device=cuda), th.zeros(B, D, device=cuda), th.zeros(B, device=cuda), 0.99)
+
+
 # ------------------------------------------------------------------------------------------------ per-row targets
 @pytest.mark.parametrize("name", [c[0] for c in cases.ENVELOPE_CASES])
 def test_greedy_td_golden_and_oracle(cuda, golden, name):
