@@ -433,6 +433,226 @@ __global__ void __launch_bounds__(256) envelope_td_v3_kernel(const float* __rest
     }
 }
 
+// =================================================================================================================
+// v5 kernel ("weight pairs"): the same FMA-chain filter + exact re-check as v3, re-blocked so that
+//   * a thread owns TWO scalarising weights packed in f32x2 registers and the candidate value is the scalar operand of the packed
+//     FMUL2 / FFMA2 (SASS form  FFMA2 Rd, Rw.F32x2, Rq.F32, Rc.F32x2): one LDS.128 of the AoS block feeds two weights, so the
+//     shared-memory traffic per score halves and Q_on[b] is consumed exactly as the bulk copy (TMA) delivered it -- the
+//     AoS -> SoA transposition pass of v3 (and its barrier) disappears;
+//   * a warp covers all 64 weights of a weight block (lane = weight pair) and one quarter of the candidates, so every
+//     shared-memory read is a warp-wide broadcast;
+//   * groups of 16 candidates (book-keeping amortised over twice as many scores); the winner group is re-evaluated in the
+//     contract arithmetic by two threads per weight.
+// 2.9 instructions per score instead of 3.8.  Shapes: W*A a multiple of 16, 16-byte multiple Q blocks, |W| > 32 (below that half of
+// the lanes would idle and v3 is used).  Bit-identical to v1 / v3 / the oracle (tests/test_kernels_gpu.py).
+// =================================================================================================================
+template <int D, int MODE>
+__global__ void __launch_bounds__(128) envelope_td_wp_kernel(const float* __restrict__ q_on, const float* __restrict__ q_tg,
+                                                             const float* __restrict__ wset, const float* __restrict__ reward,
+                                                             const float* __restrict__ done, float gamma, int B, int W, int A,
+                                                             int row_order, float* __restrict__ target_out,
+                                                             int32_t* __restrict__ pref_out, int32_t* __restrict__ act_out) {
+    constexpr bool FILTER = (MODE != MORL_DOT_FMA);
+    extern __shared__ __align__(16) float smem[];
+    const int C = W * A;
+    const int CDp = (C * D + 3) & ~3;
+    float* Qa = smem;                                         // [C*D] AoS Q_on[b]  (bulk async copy)
+    float* Qt = Qa + CDp;                                     // [C*D] AoS Q_tg[b]  (bulk async copy)
+    float* red_v = Qt + CDp;                                  // [4][64] best group maximum per (candidate quarter, weight)
+    float* red_s = red_v + 256;                               // [4][64] runner-up
+    int* red_g = reinterpret_cast<int*>(red_s + 256);         // [4][64] group of best
+    unsigned* red_amax = reinterpret_cast<unsigned*>(red_g + 256);  // [4]
+    uint64_t* bar_on = reinterpret_cast<uint64_t*>(red_amax + 4);
+    uint64_t* bar_tg = bar_on + 1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wbase = blockIdx.y * 64;
+    // scan role: lane = weight pair, warp = candidate quarter
+    const int i0 = wbase + 2 * lane, i1 = i0 + 1;
+    u64 wp2[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) wp2[r] = pk2(i0 < W ? __ldg(wset + (size_t)i0 * D + r) : 0.f, i1 < W ? __ldg(wset + (size_t)i1 * D + r) : 0.f);
+    // finish role: thread pair (2 k, 2 k + 1) finishes weight wbase + k
+    const int fi = wbase + (tid >> 1), part = tid & 1;
+    const bool f_active = fi < W;
+    float fw[D];
+    float wsum = 0.f;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        fw[r] = f_active ? __ldg(wset + (size_t)fi * D + r) : 0.f;
+        wsum += fabsf(fw[r]);
+    }
+    const int ngroups = C >> 4;
+    const int gpw = (ngroups + 3) >> 2;
+    const int g_begin = warp * gpw, g_end = min(g_begin + gpw, ngroups);
+    const uint32_t q_bytes = (uint32_t)(C * D) * 4u;  // multiple of 16 (launcher)
+
+    if (tid == 0) {
+        mbar_init(bar_on, 1);
+        mbar_init(bar_tg, 1);
+    }
+    __syncthreads();
+
+    uint32_t parity = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, parity ^= 1u) {
+        if (tid == 0) {
+            mbar_expect_tx(bar_on, q_bytes);
+            bulk_g2s(Qa, q_on + (size_t)b * C * D, q_bytes, bar_on);
+            mbar_expect_tx(bar_tg, q_bytes);
+            bulk_g2s(Qt, q_tg + (size_t)b * C * D, q_bytes, bar_tg);
+        }
+        float rw[D];
+        const float dn = __ldg(done + b);
+#pragma unroll
+        for (int r = 0; r < D; ++r) rw[r] = __ldg(reward + (size_t)b * D + r);
+        mbar_wait(bar_on, parity);
+
+        // ---- max |Q_on[b]| for the filter threshold (integer max of the magnitude bits: NaN / inf sort above every finite value) ----
+        if (FILTER) {
+            unsigned am = 0u;
+            for (int t = tid; t < (C * D) >> 2; t += 128) {
+                const uint4 x = *reinterpret_cast<const uint4*>(Qa + 4 * t);
+                am = max(max(am, x.x & 0x7FFFFFFFu), max(x.y & 0x7FFFFFFFu, max(x.z & 0x7FFFFFFFu, x.w & 0x7FFFFFFFu)));
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) am = max(am, __shfl_xor_sync(0xffffffffu, am, off));
+            if (lane == 0) red_amax[warp] = am;
+        }
+
+        // ---- scan: groups of 16 candidates, two weights per thread, FMA-chain scores ----
+        float best0 = -INFINITY, second0 = -INFINITY, best1 = -INFINITY, second1 = -INFINITY;
+        int bg0 = INT_MAX, bg1 = INT_MAX;
+#pragma unroll 1
+        for (int g = g_begin; g < g_end; ++g) {
+            const float4* src = reinterpret_cast<const float4*>(Qa + (size_t)g * 16 * D);
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {
+                float f[4 * D];
+#pragma unroll
+                for (int v = 0; v < D; ++v) {
+                    const float4 x = src[sub * D + v];
+                    f[4 * v + 0] = x.x;
+                    f[4 * v + 1] = x.y;
+                    f[4 * v + 2] = x.z;
+                    f[4 * v + 3] = x.w;
+                }
+                float lo[4], hi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    u64 acc = mul2(wp2[0], pk2(f[k * D], f[k * D]));
+#pragma unroll
+                    for (int r = 1; r < D; ++r) acc = fma2(wp2[r], pk2(f[k * D + r], f[k * D + r]), acc);
+                    upk2(acc, lo[k], hi[k]);
+                }
+                m0 = max3(max3(m0, lo[0], lo[1]), lo[2], lo[3]);
+                m1 = max3(max3(m1, hi[0], hi[1]), hi[2], hi[3]);
+            }
+            if (FILTER) {
+                second0 = fmaxf(second0, fminf(best0, m0));
+                second1 = fmaxf(second1, fminf(best1, m1));
+            }
+            if (m0 > best0) {
+                best0 = m0;
+                bg0 = g;
+            }
+            if (m1 > best1) {
+                best1 = m1;
+                bg1 = g;
+            }
+        }
+        {
+            const int k0 = warp * 64 + 2 * lane;
+            *reinterpret_cast<float2*>(red_v + k0) = make_float2(best0, best1);
+            *reinterpret_cast<int2*>(red_g + k0) = make_int2(bg0, bg1);
+            if (FILTER) *reinterpret_cast<float2*>(red_s + k0) = make_float2(second0, second1);
+        }
+        __syncthreads();
+
+        // ---- finish weight fi: merge the four quarters (candidate order), exact re-check of the winning group ----
+        const int fl = tid >> 1;
+        float bb = -INFINITY, ss = -INFINITY;
+        int g = INT_MAX;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float pb = red_v[k * 64 + fl];
+            if (FILTER) ss = fmaxf(fmaxf(ss, red_s[k * 64 + fl]), fminf(bb, pb));
+            if (pb > bb) {
+                bb = pb;
+                g = red_g[k * 64 + fl];
+            }
+        }
+        bool amb = false;
+        if (FILTER) {
+            const unsigned am = max(max(red_amax[0], red_amax[1]), max(red_amax[2], red_amax[3]));
+            const float qmax = am >= 0x7F800000u ? INFINITY : __uint_as_float(am);
+            const float thr = 1.9073486328125e-06f * wsum * qmax;  // 2^-19 * sum|w| * max|Q|
+            amb = f_active && !(ss < bb - thr);                    // also true for NaN / inf
+        }
+        int cstar = 0;
+        {
+            const int gg = (g == INT_MAX) ? 0 : g;  // every candidate was -inf / NaN: th.argmax returns 0 (found by the re-check below)
+            const int c0 = 16 * gg + 8 * part;
+            float ev = -INFINITY;
+            int ei = INT_MAX;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float q[D];
+#pragma unroll
+                for (int r = 0; r < D; ++r) q[r] = Qa[(c0 + k) * D + r];
+                const float s = dotw<D, MODE>(fw, q);
+                if (s > ev) {
+                    ev = s;
+                    ei = c0 + k;
+                }
+            }
+            const float ev2 = __shfl_xor_sync(0xffffffffu, ev, 1);
+            const int ei2 = __shfl_xor_sync(0xffffffffu, ei, 1);
+            argmax_merge(ev, ei, ev2, ei2);
+            cstar = (ei == INT_MAX) ? 0 : ei;
+        }
+        if (FILTER) {
+            // near ties: the whole warp re-scans the row exactly (rare)
+            unsigned ambmask = __ballot_sync(0xffffffffu, amb && part == 0);
+            while (ambmask) {
+                const int L = __ffs(ambmask) - 1;
+                ambmask &= ambmask - 1;
+                float wl[D];
+#pragma unroll
+                for (int r = 0; r < D; ++r) wl[r] = __shfl_sync(0xffffffffu, fw[r], L);
+                float bv = -INFINITY;
+                int bc = INT_MAX;
+                for (int c = lane; c < C; c += 32) {
+                    float q[D];
+#pragma unroll
+                    for (int r = 0; r < D; ++r) q[r] = Qa[c * D + r];
+                    const float s = dotw<D, MODE>(wl, q);
+                    if (s > bv) {
+                        bv = s;
+                        bc = c;
+                    }
+                }
+                warp_argmax(bv, bc);
+                if ((lane & ~1) == L) cstar = (bc == INT_MAX) ? 0 : bc;
+            }
+        }
+        mbar_wait(bar_tg, parity);  // Q_tg[b] has landed in shared memory
+        if (f_active) {
+            const size_t k = (row_order == MORL_ROWS_REFERENCE) ? ((size_t)fi * B + b) : ((size_t)b * W + fi);
+            if (part == 0) {
+                const float* qt = Qt + (size_t)cstar * D;
+#pragma unroll
+                for (int r = 0; r < D; ++r) target_out[k * D + r] = bellman(rw[r], dn, gamma, qt[r]);
+            } else {
+                const int jstar = cstar / A;
+                if (pref_out) pref_out[k] = jstar;
+                if (act_out) act_out[k] = cstar - jstar * A;
+            }
+        }
+        __syncthreads();  // Qa / Qt / red_* are rewritten by the next transition
+    }
+}
+
 struct EnvelopeV2Plan {
     bool ok;
     int Cp, CS, gps, WI;
@@ -494,8 +714,8 @@ static EnvelopePlan plan_envelope(int B, int W, int A, int D) {
     return p;
 }
 
-// Path selection, read on every call: MORL_ENVELOPE_PATH = "v1" (generic kernel), "v3" (CUDA-core fast path; the default whenever the
-// shape fits), "tc" (tensor-core filter, envelope_td_tc.cu: opt-in -- bit-identical, but measured SLOWER on B200 because reading the
+// Path selection, read on every call: MORL_ENVELOPE_PATH = "v1" (generic kernel), "v3" (CUDA-core fast path), "wp" (v5, weight-pair
+// re-blocking of v3; the default whenever the shape fits, then v3, then v1), "tc" (tensor-core filter, envelope_td_tc.cu: opt-in -- bit-identical, but measured SLOWER on B200 because reading the
 // 128 KB score tile back from tensor memory is limited to 64 B/clk per SM).  MORL_ENVELOPE_FORCE_V1 is the older
 // spelling of "v1".
 static int envelope_path_override() {
@@ -505,6 +725,7 @@ static int envelope_path_override() {
     if (e[0] == 'v' && e[1] == '1') return 1;
     if (e[0] == 'v' && e[1] == '3') return 3;
     if (e[0] == 't' && e[1] == 'c') return 4;
+    if (e[0] == 'w' && e[1] == 'p') return 5;
     return 0;
 }
 
@@ -547,6 +768,30 @@ extern "C" int morl_envelope_td_f32(const float* q_online, const float* q_target
                                       act_out, st, sm_count_cached))
             return check_launch("morl_envelope_td_f32(tc)");
         MORL_REQUIRE(false, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: MORL_ENVELOPE_PATH=tc but the shape W=%d A=%d D=%d is outside the tensor-core path", W, A, D);
+    }
+    // v5 (weight pairs): the default fast path when the shape fits; "wp" forces it, "v3" / "v1" skip it
+    const long long Cw = (long long)W * A;
+    const bool wp_ok = W > 32 && (Cw % 16) == 0 && ((Cw * D) % 4) == 0 && (2 * ((Cw * D + 3) & ~3LL) + 3 * 256 + 16) * 4 <= 96 * 1024;
+    MORL_REQUIRE(path != 5 || wp_ok, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: MORL_ENVELOPE_PATH=wp but the shape W=%d A=%d D=%d is outside the weight-pair path", W, A, D);
+    if (wp_ok && (path == 0 || path == 5)) {
+        bool launched5 = false;
+        const size_t smem5 = (size_t)(2 * ((Cw * D + 3) & ~3LL) + 3 * 256 + 16) * 4;
+        MORL_DISPATCH_D(D, MORL_DISPATCH_MODE(dot_mode, {
+                            auto kern = envelope_td_wp_kernel<kD, kMode>;
+                            if (smem5 > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+                            int occ = 0;
+                            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem5);
+                            if (occ < 1) occ = 1;
+                            const unsigned gy = (unsigned)((W + 63) / 64);
+                            long long gx = (long long)sm_count_cached * occ / gy;
+                            if (gx < 1) gx = 1;
+                            if (gx > B) gx = B;
+                            kern<<<dim3((unsigned)gx, gy, 1), 128, smem5, st>>>(q_online, q_target, wset, reward, done, gamma, B, W, A, row_order,
+                                                                              target_out, pref_out, act_out);
+                            launched5 = true;
+                        }));
+        MORL_REQUIRE(launched5, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: no weight-pair kernel for D=%d mode=%d", D, dot_mode);
+        return check_launch("morl_envelope_td_f32(wp)");
     }
     EnvelopeV2Plan p2 = plan_envelope_v2(B, W, A, D, sm_count_cached);
     if (p2.ok && path != 1) {

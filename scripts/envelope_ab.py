@@ -71,15 +71,16 @@ for shape in shapes:
                     continue
                 inp = make(*shape, kind, seed=sum(shape) + len(kind))
                 ref = run("v1", *inp, 0.99, mode, order)
-                got = run("tc", *inp, 0.99, mode, order)
-                th.cuda.synchronize()
-                ok = all(same(r, g) for r, g in zip(ref, got))
-                if not ok:
-                    bad += 1
-                    nt = int((ref[0].view(th.int32) != got[0].view(th.int32)).any(1).sum())
-                    np_ = int((ref[1] != got[1]).sum())
-                    na = int((ref[2] != got[2]).sum())
-                    print(f"MISMATCH shape={shape} kind={kind} mode={mode} order={order}: target rows {nt}, pref {np_}, act {na} of {ref[1].numel()}", flush=True)
+                for path in (["tc", "wp"] if shape[1] > 32 else ["tc"]):
+                    got = run(path, *inp, 0.99, mode, order)
+                    th.cuda.synchronize()
+                    ok = all(same(r, g) for r, g in zip(ref, got))
+                    if not ok:
+                        bad += 1
+                        nt = int((ref[0].view(th.int32) != got[0].view(th.int32)).any(1).sum())
+                        np_ = int((ref[1] != got[1]).sum())
+                        na = int((ref[2] != got[2]).sum())
+                        print(f"MISMATCH path={path} shape={shape} kind={kind} mode={mode} order={order}: target rows {nt}, pref {np_}, act {na} of {ref[1].numel()}", flush=True)
 print("agreement sweep:", "OK" if bad == 0 else f"{bad} FAILED", flush=True)
 
 # ---- timing at the north-star shape ----
@@ -124,7 +125,7 @@ for (B, W, A, D) in [(1024, 64, 8, 3), (148, 64, 8, 3), (2048, 64, 8, 3)]:
     sets = [make(B, W, A, D, "plain", 100 + i) for i in range(16)]
     out = th.empty(W * B, D, device=dev)
     alg = 2 * B * W * A * D * 4 + W * D * 4 + B * D * 4 + B * 4 + W * B * D * 4
-    for path in ["v3", "tc", "v3", "tc"]:
+    for path in ["v3", "wp", "tc", "v3", "wp"]:
         t_loop, t_graph = timed(path, B, W, A, D, sets, out)
         print(f"B={B} path {path}: python loop {t_loop * 1e6:.2f} us/launch, graph replay {t_graph * 1e6:.2f} us/launch = {alg / t_graph / 1e9:.0f} GB/s algorithmic",
               flush=True)

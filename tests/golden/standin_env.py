@@ -3,7 +3,8 @@ build box, use an in-repo stand-in vector-reward MDP for *both* engines and say 
 reference (CPU, golden generation) and the B200 engine (GPU test) are both trained on this environment.
 
 TreasureChain: a 3-objective chain in the spirit of deep-sea-treasure.  Positions x = 0..2; every step costs TIME_COST units of
-time (objective 2).  Actions: 0 = move right, 1 = collect treasure A (terminal), 2 = collect treasure B (terminal), 3 = wait.
+time (objective 2).  Actions: 0 = move right (walking off the end of the chain terminates the episode empty-handed), 1 = collect
+treasure A (terminal), 2 = collect treasure B (terminal) -- every episode terminates within N_POS steps, no time-limit truncation.
 Both treasures grow with x (concave), so the 6 "go to x, collect A|B" policies are mutually non-dominated and each is optimal for
 some linear weight.  The constants were chosen (random search) so that every policy has an evaluation weight for which it beats the
 runner-up by more than 1.0 in scalarised discounted return (about 6 % of the value scale): the hypervolume of a correctly trained
@@ -21,13 +22,13 @@ TA = np.array([10.0, 18.0, 21.0])
 TB = np.array([12.0, 22.0, 25.5])
 TIME_COST = 4.0
 N_POS = 3
-HORIZON = 6
+HORIZON = 3
 
 
 class TreasureChain:
     def __init__(self, seed: int = 0):
         self.observation_space = Box(0.0, 1.0, shape=(N_POS + 1,))
-        self.action_space = Discrete(4)
+        self.action_space = Discrete(3)
         self.action_space.seed(seed)
         self.reward_space = Box(-np.inf, np.inf, shape=(3,))
         self.reward_dim = 3
@@ -52,7 +53,10 @@ class TreasureChain:
         r = np.array([0.0, 0.0, -TIME_COST], dtype=np.float32)
         terminated = False
         if a == 0:
-            self._x = min(self._x + 1, N_POS - 1)
+            if self._x == N_POS - 1:
+                terminated = True
+            else:
+                self._x += 1
         elif a == 1:
             r[0] = TA[self._x]
             terminated = True

@@ -61,5 +61,6 @@ def test_envelope_hypervolume_within_one_percent_of_reference(cuda):
     rel = abs(mean_b200 - mean_ref) / mean_ref
     print(f"mean hv b200 {mean_b200:.4f}, reference {mean_ref:.4f}, relative difference {rel * 100:.3f} %")
     assert rel <= 0.01
-    # sanity: neither engine can exceed the hypervolume of the true Pareto front of the deterministic MDP
-    assert max(hvs) <= gold["true_front_hv"] * (1 + 1e-9)
+    # sanity: neither engine can exceed the hypervolume of the true Pareto front of the deterministic MDP (returns are accumulated
+    # from float32 rewards, the true front in float64: allow rounding)
+    assert max(hvs) <= gold["true_front_hv"] * (1 + 1e-6)

@@ -146,8 +146,8 @@ def _env_path(path, *a, **k):
 @pytest.mark.parametrize("shape", [(1024, 64, 8, 3), (256, 32, 6, 3), (96, 16, 4, 2), (33, 50, 8, 3), (7, 64, 8, 1), (300, 2, 8, 3), (600, 62, 8, 3)])
 @pytest.mark.parametrize("kind", ["plain", "ties", "neartie", "signed", "special"])
 def test_envelope_td_kernel_families_agree_bitwise(cuda, shape, kind):
-    """The three kernel families of morl_envelope_td_f32 -- generic (v1), CUDA-core fast path (v3: FMA-chain filter + exact re-check),
-    tensor-core filter (tc: bf16x3 scores from tcgen05.mma, exact re-check) -- return bit-identical targets and indices, in every
+    """The kernel families of morl_envelope_td_f32 -- generic (v1), CUDA-core fast paths (v3: FMA-chain filter + exact re-check; wp: its
+    weight-pair re-blocking, the default at |W| > 32), tensor-core filter (tc: bf16x3 scores from tcgen05.mma, exact re-check) -- return bit-identical targets and indices, in every
     arithmetic mode and row order, on continuous data, exact ties, candidates a few ulps apart, mixed-sign weights / large values,
     and NaN / +-inf / all-zero / huge / tiny blocks.  v1 is pinned to the oracle and the reference's golden vectors above."""
     from morl_baselines_b200 import ops
@@ -182,7 +182,7 @@ def test_envelope_td_kernel_families_agree_bitwise(cuda, shape, kind):
         combos += [(ops.DOT_UNFUSED, ops.ROWS_REFERENCE), (ops.DOT_FMA, ops.ROWS_BMAJOR), (ops.DOT_PAIRFMA, ops.ROWS_REFERENCE)]
     for mode, order in combos:
         ref = _env_path("v1", q_on, q_tg, wset, rew, done, 0.99, mode, order)
-        for path in ("v3", "tc"):
+        for path in (("v3", "wp", "tc") if W > 32 else ("v3", "tc")):
             got = _env_path(path, q_on, q_tg, wset, rew, done, 0.99, mode, order)
             assert th.equal(ref[0].view(th.int32), got[0].view(th.int32)), (path, mode, order)  # bit pattern (NaN-safe)
             assert th.equal(ref[1], got[1]) and th.equal(ref[2], got[2]), (path, mode, order)
