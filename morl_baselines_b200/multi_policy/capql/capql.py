@@ -6,10 +6,14 @@ entropy term, stack -> min -> (alpha * logp) broadcast -> Bellman (capql.py:326-
 (morl_actor_critic_td_f32, variant ELEMENTWISE_MIN); the target sync of all critics is one multi-tensor launch per net.
 The transition store keeps the reference's semantics (python ``random.sample`` over the stored tuples, capql.py:51-58) but
 lives in preallocated arrays mirrored in HBM, so a minibatch is one index gather instead of six np.stack + six copies.
+The reference's update is ~200 tiny tensor operations (8.4 ms on its CPU path, 3.9 ms eager on a B200, launch bound): the device side
+of one gradient update -- gather, target, critic step, policy step, target syncs -- is captured in a CUDA graph over static index /
+noise buffers (``use_cuda_graph``, common/graphed.py) and replayed with one host call per update.
 """
 
 from __future__ import annotations
 
+import math
 import os
 import random
 from itertools import chain
@@ -20,9 +24,10 @@ import torch as th
 import torch.nn as nn
 import torch.nn.functional as F
 import torch.optim as optim
-from torch.distributions import Normal
 
 from ... import ops
+from ...common.fused_adam import FusedClipAdam
+from ...common.graphed import GraphedStep, optimizer_tensors
 from ...common.morl_algorithm import MOAgent, MOPolicy
 from ...common.networks import layer_init, mlp, polyak_update
 from ...common.weights import equally_spaced_weights
@@ -80,12 +85,21 @@ class ReplayMemory:
         out[5] = out[5].reshape(-1)  # the reference stacks 0-d `done`s into a [B] vector
         return tuple(out)
 
-    def sample(self, batch_size, to_tensor=True, device=None):
-        idx = random.sample(range(self._len), batch_size)
-        if to_tensor and self._dev is not None:
+    def flush(self):
+        """Copy the rows pushed since the last call to the HBM mirror."""
+        if self._dev is not None:
             for a, b in self._dirty:
                 self._dev[a:b].copy_(self._packed_t[a:b], non_blocking=True)
             self._dirty = []
+
+    def draw(self, batch_size):
+        """The reference's sampling rule (capql.py:51-58): ``random.sample`` without replacement over the stored transitions."""
+        return random.sample(range(self._len), batch_size)
+
+    def sample(self, batch_size, to_tensor=True, device=None):
+        idx = self.draw(batch_size)
+        if to_tensor and self._dev is not None:
+            self.flush()
             rows = self._dev.index_select(0, th.tensor(idx, device=self.device))
             return self._split(rows)
         rows = self._packed[np.asarray(idx)]
@@ -139,14 +153,18 @@ class Policy(nn.Module):
         return th.tanh(mean) * self.action_scale + self.action_bias
 
     def sample(self, obs, w, noise: Optional[th.Tensor] = None):
-        """Reparameterised sample; ``noise`` (standard normal, same shape as the mean) may be injected for parity tests."""
+        """Reparameterised sample; ``noise`` (standard normal, same shape as the mean) may be injected for parity tests.  The Gaussian is
+        written out with the arithmetic of ``torch.distributions.Normal`` (rsample: loc + eps * scale; log_prob: -((v - loc)^2) /
+        (2 var) - log(scale) - log(sqrt(2 pi))) without the distribution object, whose argument validation synchronises with the host
+        (illegal under CUDA-graph capture)."""
         mean, log_std = self.forward(obs, w)
         std = log_std.exp()
-        normal = Normal(mean, std)
-        x_t = normal.rsample() if noise is None else mean + std * noise
+        eps = th.randn_like(mean) if noise is None else noise
+        x_t = mean + eps * std
         y_t = th.tanh(x_t)
         action = y_t * self.action_scale + self.action_bias
-        log_prob = normal.log_prob(x_t).sum(dim=1)
+        var = std**2
+        log_prob = (-((x_t - mean) ** 2) / (2 * var) - std.log() - math.log(math.sqrt(2 * math.pi))).sum(dim=1)
         log_prob = log_prob - th.log(self.action_scale * (1 - y_t.pow(2)) + EPSILON).sum(dim=1)
         log_prob = log_prob.clamp(-1e3, 1e3)
         return action, log_prob, th.tanh(mean) * self.action_scale + self.action_bias
@@ -186,6 +204,7 @@ class CAPQL(MOAgent, MOPolicy):
         log: bool = True,
         seed: Optional[int] = None,
         device: Union[th.device, str] = "auto",
+        use_cuda_graph: bool = True,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
@@ -211,10 +230,13 @@ class CAPQL(MOAgent, MOPolicy):
             for p in tq.parameters():
                 p.requires_grad = False
         self.policy = Policy(self.observation_dim, self.reward_dim, self.action_dim, self.env.action_space, net_arch=net_arch).to(self.device)
-        self.q_optim = optim.Adam(chain(*[net.parameters() for net in self.q_nets]), lr=self.learning_rate)
-        self.policy_optim = optim.Adam(list(self.policy.parameters()), lr=self.learning_rate)
+        # torch.optim.Adam subclasses with the reference's arithmetic and state_dict layout, two launches per step, capture-safe
+        self.q_optim = FusedClipAdam(chain(*[net.parameters() for net in self.q_nets]), lr=self.learning_rate)
+        self.policy_optim = FusedClipAdam(list(self.policy.parameters()), lr=self.learning_rate)
         self._n_updates = 0
         self._noise_hook = None  # tests may set a callable(shape) -> standard-normal tensor to make rsample reproducible
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
         self.log = log
         if self.log:
             self.setup_wandb(project_name, experiment_name, wandb_entity)
@@ -248,6 +270,7 @@ class CAPQL(MOAgent, MOPolicy):
         self.q_optim.load_state_dict(params["q_nets_optimizer_state_dict"])
         if load_replay_buffer and "replay_buffer" in params:
             self.replay_buffer = params["replay_buffer"]
+        self._graphs = {}  # optimiser state tensors / the buffer may have been replaced
 
     def _sample_batch_experiences(self):
         return self.replay_buffer.sample(self.batch_size, to_tensor=True, device=self.device)
@@ -255,36 +278,71 @@ class CAPQL(MOAgent, MOPolicy):
     def _noise(self, shape):
         return None if self._noise_hook is None else self._noise_hook(shape)
 
+    def _device_update(self, s_obs, s_actions, w, s_rewards, s_next_obs, s_dones, noise):
+        """The device side of one gradient update (reference capql.py:323-362) on an already gathered minibatch."""
+        with th.no_grad():
+            next_actions, log_pi, _ = self.policy.sample(s_next_obs, w, noise(0))
+            q_targets = th.stack([tq(s_next_obs, next_actions, w) for tq in self.target_q_nets])  # [n, B, D]
+            # per-objective min over critics - alpha * logp, vector Bellman: one kernel (capql.py:329-331)
+            target_q = ops.actor_critic_td(q_targets, None, s_rewards, s_dones, log_pi, self.alpha, self.gamma, ops.AC_ELEMENTWISE_MIN)
+        q_values = [q(s_obs, s_actions, w) for q in self.q_nets]
+        critic_loss = (1 / self.num_q_nets) * sum([F.mse_loss(qv, target_q) for qv in q_values])
+        self.q_optim.zero_grad(set_to_none=True)
+        critic_loss.backward()
+        self.q_optim.step_fused(None)
+
+        pi, log_pi, _ = self.policy.sample(s_obs, w, noise(1))
+        q_pi = th.stack([q(s_obs, pi, w) for q in self.q_nets])
+        min_q = (th.min(q_pi, dim=0)[0] * w).sum(dim=-1, keepdim=True)
+        policy_loss = ((self.alpha * log_pi) - min_q).mean()
+        self.policy_optim.zero_grad(set_to_none=True)
+        policy_loss.backward()
+        self.policy_optim.step_fused(None)
+        for q, tq in zip(self.q_nets, self.target_q_nets):
+            polyak_update(q.parameters(), tq.parameters(), self.tau)
+        self._last_losses = (critic_loss.detach(), policy_loss.detach())
+
+    def _mutated_tensors(self):
+        ts = [p for m in [self.policy] + self.q_nets + self.target_q_nets for p in m.parameters()]
+        return ts + optimizer_tensors(self.q_optim) + optimizer_tensors(self.policy_optim)
+
     def update(self):
         """Critic and policy update (reference capql.py:321-362)."""
+        B, hook = self.batch_size, self._noise_hook
+        rb = self.replay_buffer
+        graphable = self.use_cuda_graph and getattr(rb, "_dev", None) is not None
         for _ in range(self.gradient_updates):
-            s_obs, s_actions, w, s_rewards, s_next_obs, s_dones = self._sample_batch_experiences()
-            with th.no_grad():
-                next_actions, log_pi, _ = self.policy.sample(s_next_obs, w, self._noise((s_obs.shape[0], self.action_dim)))
-                q_targets = th.stack([tq(s_next_obs, next_actions, w) for tq in self.target_q_nets])  # [n, B, D]
-                # per-objective min over critics - alpha * logp, vector Bellman: one kernel (capql.py:329-331)
-                target_q = ops.actor_critic_td(q_targets, None, s_rewards, s_dones, log_pi, self.alpha, self.gamma, ops.AC_ELEMENTWISE_MIN)
-            q_values = [q(s_obs, s_actions, w) for q in self.q_nets]
-            critic_loss = (1 / self.num_q_nets) * sum([F.mse_loss(qv, target_q) for qv in q_values])
-            self.q_optim.zero_grad()
-            critic_loss.backward()
-            self.q_optim.step()
+            if not graphable:
+                s_obs, s_actions, w, s_rewards, s_next_obs, s_dones = self._sample_batch_experiences()
+                self._device_update(s_obs, s_actions, w, s_rewards, s_next_obs, s_dones,
+                                    (lambda k: hook((B, self.action_dim))) if hook is not None else (lambda k: None))
+            else:
+                key = (hook is not None, id(rb))
+                st = self._graphs.get(key)
+                if st is None:
+                    st = {"idx_pin": th.zeros(B, dtype=th.int64).pin_memory(), "idx": th.zeros(B, dtype=th.int64, device=self.device),
+                          "noise": [th.zeros(B, self.action_dim, device=self.device) for _ in range(2)] if hook is not None else None}
 
-            pi, log_pi, _ = self.policy.sample(s_obs, w, self._noise((s_obs.shape[0], self.action_dim)))
-            q_pi = th.stack([q(s_obs, pi, w) for q in self.q_nets])
-            min_q = (th.min(q_pi, dim=0)[0] * w).sum(dim=-1, keepdim=True)
-            policy_loss = ((self.alpha * log_pi) - min_q).mean()
-            self.policy_optim.zero_grad()
-            policy_loss.backward()
-            self.policy_optim.step()
-            for q, tq in zip(self.q_nets, self.target_q_nets):
-                polyak_update(q.parameters(), tq.parameters(), self.tau)
+                    def step(st=st):
+                        parts = rb._split(rb._dev.index_select(0, st["idx"]))
+                        nz = st["noise"]
+                        self._device_update(*parts, (lambda k: nz[k]) if nz is not None else (lambda k: None))
+
+                    st["graph"] = GraphedStep(step, self._mutated_tensors)
+                    self._graphs[key] = st
+                st["idx_pin"].numpy()[:] = rb.draw(B)  # python `random`, as the reference's random.sample(self.buffer, batch_size)
+                st["idx"].copy_(st["idx_pin"], non_blocking=True)
+                if hook is not None:
+                    for t in st["noise"]:
+                        t.copy_(hook((B, self.action_dim)))
+                rb.flush()
+                st["graph"]()
             self._n_updates += 1
-        self._last_losses = (critic_loss.detach(), policy_loss.detach())
         if self.log and self.global_step % 100 == 0:
             import wandb
 
-            wandb.log({"losses/critic_loss": critic_loss.item(), "losses/policy_loss": policy_loss.item(), "global_step": self.global_step})
+            wandb.log({"losses/critic_loss": self._last_losses[0].item(), "losses/policy_loss": self._last_losses[1].item(),
+                       "global_step": self.global_step})
 
     @th.no_grad()
     def eval(self, obs, w, torch_action=False):

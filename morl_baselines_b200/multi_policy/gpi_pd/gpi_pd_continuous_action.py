@@ -9,7 +9,11 @@ Hot-path row a11 of SURVEY.md section 8 (BASELINE.json configs[2]: GPI-PD on mo-
   (``morl_actor_critic_td_f32``, variant ARGMIN_GATHER);
 * the GPI evaluation over the |M| x |M| (critic-conditioning weight, candidate action) pairs (``eval``, :463-478) is one batched
   critic call followed by the fused double-argmax kernel (``morl_gpi_envelope_f32`` with B = 1);
-* target-network syncs are one multi-tensor launch per network (``polyak_update``).
+* target-network syncs are one multi-tensor launch per network (``polyak_update``), Adam steps the fused two-launch optimiser;
+* the reference's update is ~200 tiny tensor operations (13.4 ms on its CPU path, 3.3 ms eager on a B200, launch bound): the device
+  side of one gradient update -- gather from the HBM replay mirror, weight tiling, target, critic step, priorities, target syncs and
+  the delayed actor step -- is captured in CUDA graphs over static index / weight / noise buffers (``use_cuda_graph``,
+  common/graphed.py); per update the host only walks the PER sum-tree, replays one graph and writes the priorities back.
 
 The Dyna path (probabilistic ensemble + ModelEnv, :348-391 and :545-562) is outside the accelerated hot path (SURVEY.md section 2,
 component 20): ``dyna=True`` raises, use ``GPILSContinuousAction`` / ``dyna=False``.
@@ -30,6 +34,8 @@ import torch.optim as optim
 
 from ... import ops
 from ...common.buffer import ReplayBuffer
+from ...common.fused_adam import FusedClipAdam
+from ...common.graphed import GraphedStep, optimizer_tensors
 from ...common.morl_algorithm import MOAgent, MOPolicy
 from ...common.networks import layer_init, mlp, polyak_update
 from ...common.prioritized_buffer import PrioritizedReplayBuffer
@@ -111,6 +117,7 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
         log: bool = True,
         seed: Optional[int] = None,
         device: Union[th.device, str] = "auto",
+        use_cuda_graph: bool = True,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
@@ -156,8 +163,11 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
         self.target_policy.load_state_dict(self.policy.state_dict())
         for param in self.target_policy.parameters():
             param.requires_grad = False
-        self.q_optim = optim.Adam(chain(*[net.parameters() for net in self.q_nets]), lr=self.learning_rate)
-        self.policy_optim = optim.Adam(list(self.policy.parameters()), lr=self.learning_rate)
+        # torch.optim.Adam subclasses with the reference's arithmetic and state_dict layout, two launches per step, capture-safe
+        self.q_optim = FusedClipAdam(chain(*[net.parameters() for net in self.q_nets]), lr=self.learning_rate)
+        self.policy_optim = FusedClipAdam(list(self.policy.parameters()), lr=self.learning_rate)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
 
         self.dyna = False
         self.dynamics = None
@@ -220,6 +230,7 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
             self.replay_buffer = params["replay_buffer"]
             if hasattr(self.replay_buffer, "to"):
                 self.replay_buffer.to(self.device)
+        self._graphs = {}  # optimiser state tensors / the buffer / the support may have been replaced
 
     # ------------------------------------------------------------------------------------------ the update
     def _sample_batch_experiences(self):
@@ -228,71 +239,122 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
     def _eps(self, shape):
         return None if self._noise_hook is None else self._noise_hook(shape)
 
+    def _tile_weights(self, weight, picks, B0):
+        """Effective-batch weights: ``weight`` for the first B0 rows, support weights ``picks`` for the doubled half (:381-391)."""
+        D = self.reward_dim
+        if picks is not None:
+            return th.cat([weight.reshape(1, D).expand(B0, D), self.stacked_weight_support.index_select(0, picks)], dim=0).contiguous()
+        return weight.reshape(1, D).repeat(B0, 1)
+
+    def _device_update(self, s_obs, s_actions, s_rewards, s_next_obs, s_dones, w, with_policy: bool, eps, n_prio: int, prio_out=None):
+        """The device side of one gradient update (reference :393-446) on the effective batch."""
+        with th.no_grad():
+            next_actions = self.target_policy(s_next_obs, w, noise=self.policy_noise, noise_clip=self.noise_clip, eps=eps)
+            q_targets = th.stack([q_target(s_next_obs, next_actions, w) for q_target in self.target_q_nets])  # [n, N, D]
+            # argmin_n w . Q_n -> gather -> r + (1 - done) * gamma * Q: one kernel (:396-403)
+            target_q = ops.actor_critic_td(q_targets, w, s_rewards, s_dones, None, 0.0, self.gamma, ops.AC_ARGMIN_GATHER)
+        q_values = [q_net(s_obs, s_actions, w) for q_net in self.q_nets]
+        critic_loss = (1 / self.num_q_nets) * sum([F.mse_loss(q_value, target_q) for q_value in q_values])
+        self.q_optim.zero_grad(set_to_none=True)
+        critic_loss.backward()
+        self.q_optim.step_fused(None)
+        prio = None
+        if n_prio > 0:
+            per = (q_values[0] - target_q)[:n_prio].detach().abs() * 0.05
+            prio = th.einsum("br,br->b", per, w[:n_prio])
+            if prio_out is not None:
+                prio_out.copy_(prio)
+        for q_net, target_q_net in zip(self.q_nets, self.target_q_nets):
+            polyak_update(q_net.parameters(), target_q_net.parameters(), self.tau)
+        if with_policy:
+            actions = self.policy(s_obs, w)
+            q_values_pi = (1 / self.num_q_nets) * sum(q_net(s_obs, actions, w) for q_net in self.q_nets)
+            policy_loss = -th.einsum("br,br->b", q_values_pi, w).mean()
+            self.policy_optim.zero_grad(set_to_none=True)
+            policy_loss.backward()
+            self.policy_optim.step_fused(None)
+            polyak_update(self.policy.parameters(), self.target_policy.parameters(), self.tau)
+            self._last_policy_loss = policy_loss.detach()
+        self._last_critic_loss = critic_loss.detach()
+        return prio
+
+    def _mutated_tensors(self):
+        ts = [p for m in [self.policy, self.target_policy] + self.q_nets + self.target_q_nets for p in m.parameters()]
+        return ts + optimizer_tensors(self.q_optim) + optimizer_tensors(self.policy_optim)
+
     def update(self, weight: th.Tensor):
         """``gradient_updates`` critic steps (+ delayed actor steps) for the given weight (reference :373-452)."""
-        D = self.reward_dim
+        D, B0, rb = self.reward_dim, self.batch_size, self.replay_buffer
+        hook = self._noise_hook
+        graphable = self.use_cuda_graph and getattr(rb, "_dev", None) is not None and B0 <= len(rb)
+        priority = None
         for _ in range(self.gradient_updates):
-            if self.per:
-                s_obs, s_actions, s_rewards, s_next_obs, s_dones, idxes = self._sample_batch_experiences()
-            else:
-                s_obs, s_actions, s_rewards, s_next_obs, s_dones = self._sample_batch_experiences()[:5]
-                idxes = None
-            B0 = s_obs.size(0)
             P = len(self.weight_support)
-            if P > 1:
-                # half of the effective batch uses `weight`, the other half weights drawn from the support (:381-391);
-                # random.choices on range(P) consumes python's RNG exactly like random.choices(self.weight_support, k=B)
-                picks = random.choices(range(P), k=B0)
-                s_obs, s_actions, s_rewards, s_next_obs, s_dones = (s_obs.repeat(2, 1), s_actions.repeat(2, 1), s_rewards.repeat(2, 1),
-                                                                    s_next_obs.repeat(2, 1), s_dones.repeat(2, 1))
-                w = th.cat([weight.reshape(1, D).expand(B0, D), self.stacked_weight_support[th.tensor(picks, device=self.device)]], dim=0).contiguous()
+            N = 2 * B0 if P > 1 else B0
+            with_policy = self._n_updates % self.delay_policy_update == 0
+            if not graphable:
+                smp = self._sample_batch_experiences()
+                s_obs, s_actions, s_rewards, s_next_obs, s_dones = smp[:5]
+                idxes = smp[5] if self.per else None
+                picks = None
+                if P > 1:
+                    # half of the effective batch uses `weight`, the other half weights drawn from the support (:381-391);
+                    # random.choices on range(P) consumes python's RNG exactly like random.choices(self.weight_support, k=B)
+                    picks = th.tensor(random.choices(range(P), k=B0), device=self.device)
+                    s_obs, s_actions, s_rewards, s_next_obs, s_dones = (s_obs.repeat(2, 1), s_actions.repeat(2, 1), s_rewards.repeat(2, 1),
+                                                                        s_next_obs.repeat(2, 1), s_dones.repeat(2, 1))
+                w = self._tile_weights(weight, picks, B0)
+                prio = self._device_update(s_obs, s_actions, s_rewards, s_next_obs, s_dones, w, with_policy,
+                                           hook((N, self.action_dim)) if hook is not None else None, len(idxes) if self.per else 0)
+                if self.per:
+                    priority = prio.cpu().numpy().flatten().clip(min=self.min_priority) ** self.alpha
+                    rb.update_priorities(np.asarray(idxes.cpu() if th.is_tensor(idxes) else idxes), priority)
             else:
-                w = weight.reshape(1, D).repeat(B0, 1)
-            N = s_obs.size(0)
+                # graph path: the host walks the PER tree / draws the support picks (same RNG consumption and order as the reference),
+                # fills the static buffers, replays one graph, and writes the priorities back
+                key = (P > 1, with_policy, hook is not None, id(rb), id(self.stacked_weight_support) if P > 1 else 0)
+                st = self._graphs.get(key)
+                if st is None:
+                    st = {"host": th.zeros(2 * B0, dtype=th.int64).pin_memory(), "dev": th.zeros(2 * B0, dtype=th.int64, device=self.device),
+                          "w": th.zeros(D, device=self.device), "eps": th.zeros(N, self.action_dim, device=self.device) if hook is not None else None,
+                          "prio": th.zeros(B0, device=self.device), "prio_pin": th.zeros(B0).pin_memory()}
 
-            with th.no_grad():
-                next_actions = self.target_policy(s_next_obs, w, noise=self.policy_noise, noise_clip=self.noise_clip,
-                                                  eps=self._eps((N, self.action_dim)))
-                q_targets = th.stack([q_target(s_next_obs, next_actions, w) for q_target in self.target_q_nets])  # [n, N, D]
-                # argmin_n w . Q_n -> gather -> r + (1 - done) * gamma * Q: one kernel (:396-403)
-                target_q = ops.actor_critic_td(q_targets, w, s_rewards, s_dones, None, 0.0, self.gamma, ops.AC_ARGMIN_GATHER)
+                    def step(st=st, doubled=P > 1, with_policy=with_policy):
+                        obs_s, nobs_s, act_s, rew_s, done_s = rb._dev
+                        obs, act, rew, nobs, done = ops.replay_gather(obs_s, nobs_s, act_s, rew_s, done_s, st["dev"][:B0])
+                        if doubled:
+                            obs, act, rew, nobs, done = obs.repeat(2, 1), act.repeat(2, 1), rew.repeat(2, 1), nobs.repeat(2, 1), done.repeat(2, 1)
+                        w = self._tile_weights(st["w"], st["dev"][B0:] if doubled else None, B0)
+                        self._device_update(obs, act, rew, nobs, done, w, with_policy, st["eps"], B0 if self.per else 0, st["prio"])
 
-            q_values = [q_net(s_obs, s_actions, w) for q_net in self.q_nets]
-            critic_loss = (1 / self.num_q_nets) * sum([F.mse_loss(q_value, target_q) for q_value in q_values])
-            self.q_optim.zero_grad()
-            critic_loss.backward()
-            self.q_optim.step()
-
-            if self.per:
-                n = len(idxes)
-                per = (q_values[0] - target_q)[:n].detach().abs() * 0.05
-                per = th.einsum("br,br->b", per, w[:n])
-                priority = per.cpu().numpy().flatten()
-                priority = priority.clip(min=self.min_priority) ** self.alpha
-                self.replay_buffer.update_priorities(np.asarray(idxes.cpu() if th.is_tensor(idxes) else idxes), priority)
-
-            for q_net, target_q_net in zip(self.q_nets, self.target_q_nets):
-                polyak_update(q_net.parameters(), target_q_net.parameters(), self.tau)
-
-            if self._n_updates % self.delay_policy_update == 0:
-                actions = self.policy(s_obs, w)
-                q_values_pi = (1 / self.num_q_nets) * sum(q_net(s_obs, actions, w) for q_net in self.q_nets)
-                policy_loss = -th.einsum("br,br->b", q_values_pi, w).mean()
-                self.policy_optim.zero_grad()
-                policy_loss.backward()
-                self.policy_optim.step()
-                polyak_update(self.policy.parameters(), self.target_policy.parameters(), self.tau)
-                self._last_policy_loss = policy_loss.detach()
+                    st["graph"] = GraphedStep(step, self._mutated_tensors)
+                    self._graphs[key] = st
+                hostv = st["host"].numpy()
+                idxes = rb.tree.sample(B0) if self.per else rb._draw(B0)
+                hostv[:B0] = idxes
+                if P > 1:
+                    hostv[B0:] = random.choices(range(P), k=B0)
+                st["dev"].copy_(st["host"], non_blocking=True)
+                st["w"].copy_(weight.reshape(-1))
+                if hook is not None:
+                    st["eps"].copy_(hook((N, self.action_dim)))
+                rb.flush()
+                st["graph"]()
+                if self.per:
+                    st["prio_pin"].copy_(st["prio"], non_blocking=True)
+                    th.cuda.current_stream().synchronize()
+                    priority = st["prio_pin"].numpy().copy().clip(min=self.min_priority) ** self.alpha
+                    rb.update_priorities(np.asarray(idxes), priority)
             self._n_updates += 1
 
-        self._last_losses = (critic_loss.detach(), getattr(self, "_last_policy_loss", None))
+        self._last_losses = (getattr(self, "_last_critic_loss", None), getattr(self, "_last_policy_loss", None))
         if self.log and self.global_step % 100 == 0:
             import wandb
 
-            if self.per:
+            if self.per and priority is not None:
                 wandb.log({"metrics/mean_priority": np.mean(priority), "metrics/max_priority": np.max(priority),
                            "metrics/min_priority": np.min(priority)}, commit=False)
-            wandb.log({"losses/critic_loss": critic_loss.item(), "losses/policy_loss": float(self._last_losses[1]),
+            wandb.log({"losses/critic_loss": self._last_losses[0].item(), "losses/policy_loss": float(self._last_losses[1]),
                        "global_step": self.global_step})
 
     @th.no_grad()
@@ -325,6 +387,7 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
         self.weight_support = [th.tensor(w).float().to(self.device) for w in weights_no_repeat]
         if len(self.weight_support) > 0:
             self.stacked_weight_support = th.stack(self.weight_support)
+        self._graphs = {}  # captured graphs read the previous support matrix
 
     def train_iteration(self, total_timesteps: int, weight: np.ndarray, weight_support: List[np.ndarray],
                         change_weight_every_episode: bool = False, eval_env=None, eval_freq: int = 1000, reset_num_timesteps: bool = False):

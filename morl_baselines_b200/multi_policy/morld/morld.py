@@ -239,7 +239,13 @@ class MORLD(MOAgent):
                     dst_policy = self.population[n]
                     dst = dst_policy.wrapped.get_policy_net()
                     polyak_update(params=src.parameters(), target_params=dst.parameters(), tau=1.0)
-                    dst_policy.wrapped.actor_optimizer = optim.Adam(dst.parameters(), lr=dst_policy.wrapped.policy_lr)
+                    if hasattr(dst_policy.wrapped, "_graphs"):  # MOSAC: capture-safe fused Adam; captured graphs reference the old optimiser
+                        from ...common.fused_adam import FusedClipAdam
+
+                        dst_policy.wrapped.actor_optimizer = FusedClipAdam(dst.parameters(), lr=dst_policy.wrapped.policy_lr)
+                        dst_policy.wrapped._graphs = {}
+                    else:
+                        dst_policy.wrapped.actor_optimizer = optim.Adam(dst.parameters(), lr=dst_policy.wrapped.policy_lr)
 
     def _adapt_weights(self, evals: List[np.ndarray]):
         """PSA weight adaptation (reference morld.py:368-417)."""

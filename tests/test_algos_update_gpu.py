@@ -76,12 +76,14 @@ def test_gpipd_update_matches_reference(cuda, gold, gpi_pd):
     np.testing.assert_allclose(rb.tree.nodes[-1][:N], gold[f"{tag}/tree_leaves_reset"][:N], rtol=2e-4, atol=1e-7)
 
 
-def test_capql_update_matches_reference(cuda, gold):
+@pytest.mark.parametrize("graph", [True, False])
+def test_capql_update_matches_reference(cuda, gold, graph):
+    """``graph``: the CUDA-graph replay path (default) and the eager path run the same kernels; both are held to the reference."""
     from morl_baselines_b200.multi_policy.capql.capql import CAPQL
 
     OBS, ACT, D, B = 9, 3, 2, 16
     agent = CAPQL(FakeEnv(obs_dim=OBS, continuous_action_dim=ACT, reward_dim=D), batch_size=B, net_arch=[32, 32], log=False, seed=2, device=cuda,
-                  gradient_updates=2)
+                  gradient_updates=2, use_cuda_graph=graph)
     _load_sd(agent.policy, gold, "capql/init_policy", cuda)
     for i, (q, tq) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
         _load_sd(q, gold, f"capql/init_q{i}", cuda)
@@ -104,13 +106,14 @@ def test_capql_update_matches_reference(cuda, gold):
     assert a.shape == (ACT,) and np.all(np.abs(a) <= 1.0)
 
 
-def test_mosac_update_matches_reference(cuda, gold):
+@pytest.mark.parametrize("graph", [True, False])
+def test_mosac_update_matches_reference(cuda, gold, graph):
     from morl_baselines_b200.single_policy.ser.mosac_continuous_action import MOSAC
 
     OBS, ACT, D, B, N = 9, 3, 3, 16, 128
     w = np.array([0.2, 0.5, 0.3], dtype=np.float32)
     agent = MOSAC(FakeEnv(obs_dim=OBS, continuous_action_dim=ACT, reward_dim=D), weights=w, batch_size=B, net_arch=[32, 32], log=False, seed=4,
-                  device=cuda, buffer_size=N)
+                  device=cuda, buffer_size=N, use_cuda_graph=graph)
     for name in ("actor", "qf1", "qf2"):
         _load_sd(getattr(agent, name), gold, f"mosac/init_{name}", cuda)
     agent.qf1_target.load_state_dict(agent.qf1.state_dict())
@@ -145,8 +148,9 @@ def test_morld_population_smoke(cuda):
     assert hypervolume(np.array([-100.0, -100.0]), list(algo.global_front)) > 0
 
 
+@pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("tag,n_support", [("m5", 5), ("m1", 1)])
-def test_gpipd_continuous_update_matches_reference(cuda, tag, n_support):
+def test_gpipd_continuous_update_matches_reference(cuda, tag, n_support, graph):
     """GPILSContinuousAction: three critic steps + two delayed actor steps, PER write-back, target syncs and the GPI evaluation against
     the unmodified reference (tests/golden/make_golden_gpipd_continuous.py), hopper dimensions (BASELINE.json configs[2])."""
     from morl_baselines_b200.multi_policy.gpi_pd.gpi_pd_continuous_action import GPILSContinuousAction
@@ -154,7 +158,7 @@ def test_gpipd_continuous_update_matches_reference(cuda, tag, n_support):
     g = np.load(os.path.join(ROOT, "tests", "golden", "gpipd_continuous.npz"))
     OBS, ACT, D, B, N = 11, 3, 3, 16, 128
     agent = GPILSContinuousAction(FakeEnv(obs_dim=OBS, continuous_action_dim=ACT, reward_dim=D), batch_size=B, net_arch=[32, 32], num_q_nets=2,
-                                  gradient_updates=3, per=True, buffer_size=N, log=False, seed=3, device=cuda)
+                                  gradient_updates=3, per=True, buffer_size=N, log=False, seed=3, device=cuda, use_cuda_graph=graph)
     for net in agent.q_nets + agent.target_q_nets:
         for m in net.modules():
             if isinstance(m, th.nn.Dropout):
@@ -217,3 +221,44 @@ def test_gpipd_continuous_train_iteration_and_checkpoint(cuda, tmp_path):
     a1 = agent.eval(np.ones(11, np.float32), M[2])
     a2 = other.eval(np.ones(11, np.float32), M[2])
     np.testing.assert_array_equal(a1, a2)
+
+
+def test_mosac_graph_replay_matches_eager(cuda):
+    """The CUDA-graph path of MOSAC.update (gather + critic step + actor / temperature steps + target syncs in one replay) and the
+    eager path apply the same kernels: after 6 updates from the same state with the same injected noise the parameters agree to
+    float32 round-off (1e-6 relative), and the number of applied updates is exact (warm-up / capture passes leave no trace)."""
+    from morl_baselines_b200.single_policy.ser.mosac_continuous_action import MOSAC
+
+    OBS, ACT, D, B, N = 11, 3, 3, 32, 256
+    w = np.array([0.2, 0.5, 0.3], dtype=np.float32)
+    agents = []
+    for graph in (True, False):
+        th.manual_seed(7)
+        a = MOSAC(FakeEnv(obs_dim=OBS, continuous_action_dim=ACT, reward_dim=D), weights=w, batch_size=B, net_arch=[64, 64], log=False, seed=4,
+                  device=cuda, buffer_size=N, use_cuda_graph=graph)
+        rng = np.random.default_rng(5)
+        buf = a.buffer
+        buf.obs[:] = rng.standard_normal((N, OBS)).astype(np.float32)
+        buf.next_obs[:] = rng.standard_normal((N, OBS)).astype(np.float32)
+        buf.actions[:] = rng.uniform(-1, 1, (N, ACT)).astype(np.float32)
+        buf.rewards[:] = rng.standard_normal((N, D)).astype(np.float32)
+        buf.dones[:] = (rng.random((N, 1)) < 0.1).astype(np.float32)
+        buf.size, buf.ptr = N, 0
+        buf.mark_all_dirty()
+        a._noise_hook = _Noise(123, cuda)
+        np.random.seed(3)
+        for step in range(6):
+            a.global_step = step  # policy_freq = 2: actor + temperature steps on even steps (two graph variants)
+            a.update()
+        agents.append(a)
+    g, e = agents
+    assert len(g._graphs) == 2 and len(e._graphs) == 0
+    for name in ("actor", "qf1", "qf2", "qf1_target", "qf2_target"):
+        for (k, pg), (_, pe) in zip(getattr(g, name).state_dict().items(), getattr(e, name).state_dict().items()):
+            np.testing.assert_allclose(pg.cpu().numpy(), pe.cpu().numpy(), rtol=1e-6, atol=1e-7, err_msg=f"{name}.{k}")
+    np.testing.assert_allclose(g.log_alpha.detach().cpu().numpy(), e.log_alpha.detach().cpu().numpy(), rtol=1e-6, atol=1e-8)
+    assert g.alpha == pytest.approx(e.alpha, rel=1e-6)
+    for og, oe in ((g.q_optimizer, e.q_optimizer), (g.actor_optimizer, e.actor_optimizer), (g.a_optimizer, e.a_optimizer)):
+        sg, se = [s["step"].item() for s in og.state.values()], [s["step"].item() for s in oe.state.values()]
+        assert sg == se and len(sg) > 0
+    assert [s["step"].item() for s in g.q_optimizer.state.values()][0] == 6.0
