@@ -27,6 +27,8 @@ import torch.nn as nn
 import torch.optim as optim
 
 from ... import ops
+from ...common.fused_adam import FusedClipAdam
+from ...common.graphed import GraphedStep, optimizer_tensors
 from ...common.buffer import ReplayBuffer
 from ...common.morl_algorithm import MOAgent, MOPolicy
 from ...common.networks import NatureCNN, layer_init, mlp, polyak_update
@@ -82,7 +84,10 @@ class _FusedHuberLoss(th.autograd.Function):
 
 
 class GPIPD(MOPolicy, MOAgent):
-    """GPI-PD / GPI-LS (Alegre et al., AAMAS 2023), model-free path."""
+    """GPI-PD / GPI-LS (Alegre et al., AAMAS 2023), model-free path.  One gradient step (gather from the HBM replay mirror, weight
+    tiling, critic-min target, GPI envelope target, Huber loss, backward, Adam, raw priorities) is captured in a CUDA graph over static
+    index / weight buffers (``use_cuda_graph``, common/graphed.py): per step the host walks the PER tree, replays one graph and writes
+    the priorities back."""
 
     def __init__(
         self,
@@ -115,6 +120,7 @@ class GPIPD(MOPolicy, MOAgent):
         log: bool = True,
         seed: Optional[int] = None,
         device: Union[th.device, str] = "auto",
+        use_cuda_graph: bool = True,
         **dyna_kwargs,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
@@ -151,7 +157,11 @@ class GPIPD(MOPolicy, MOAgent):
             tq.load_state_dict(q.state_dict())
             for p in tq.parameters():
                 p.requires_grad = False
-        self.q_optim = optim.Adam(chain(*[net.parameters() for net in self.q_nets]), lr=self.learning_rate)
+        # a torch.optim.Adam subclass with the reference's arithmetic and state_dict layout, two launches per step, capture-safe
+        self.q_optim = FusedClipAdam(chain(*[net.parameters() for net in self.q_nets]), lr=self.learning_rate)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self._support_cache = None
         self.per = per
         self.gpi_pd = gpi_pd
         buf_cls = PrioritizedReplayBuffer if per else ReplayBuffer
@@ -205,61 +215,116 @@ class GPIPD(MOPolicy, MOAgent):
             self.replay_buffer = params["replay_buffer"]
             if hasattr(self.replay_buffer, "to"):
                 self.replay_buffer.to(self.device)
+        self._graphs, self._support_cache = {}, None  # optimiser state / buffer / support may have been replaced
 
     # ------------------------------------------------------------------------------------------ the update
     def _sample_batch_experiences(self):
         return self.replay_buffer.sample(self.batch_size, to_tensor=True, device=self.device)
 
     def _support_matrix(self) -> th.Tensor:
-        return th.stack(self.weight_support)
+        """[P, D] matrix of the support set, cached per support list (captured graphs read it)."""
+        c = self._support_cache
+        if c is None or c[0] is not self.weight_support or c[1].shape[0] != len(self.weight_support):
+            self._support_cache = c = (self.weight_support, th.stack(self.weight_support))
+            self._graphs = {}
+        return c[1]
+
+    def _device_update(self, s_obs, s_actions, s_rewards, s_next_obs, s_dones, weight, picks, sampled_idx, p_rows: int, prio_out=None):
+        """The device side of one gradient step (reference gpi_pd.py:425-505) on a gathered minibatch of B0 transitions.
+        picks: int64 [B0] support indices of the doubled half (None: no doubling); sampled_idx: int64 [4] support indices of the
+        sampled GPI weights (None: the whole support, or ``weight`` alone when the support is empty)."""
+        B0, D = s_obs.shape[0], self.reward_dim
+        P = len(self.weight_support)
+        if picks is not None:
+            # half of the effective batch uses `weight`, the other half weights drawn from the support set (gpi_pd.py:425-436)
+            M = self._support_matrix()
+            w = th.cat([weight.reshape(1, D).expand(B0, D), M.index_select(0, picks)], dim=0).contiguous()
+            rep = (2,) + tuple(1 for _ in range(s_obs.dim() - 1))
+            obs, nobs = s_obs.repeat(*rep), s_next_obs.repeat(*rep)
+        else:
+            w = weight.reshape(1, D).expand(B0, D).contiguous()
+            obs, nobs = s_obs, s_next_obs
+        if sampled_idx is not None:
+            sampled_w = th.cat([weight.reshape(1, D), self._support_matrix().index_select(0, sampled_idx)], dim=0)
+        else:
+            sampled_w = self._support_matrix() if P > 0 else weight.reshape(1, D)
+        with th.no_grad():
+            # min_i Q_i(s', a, w) . w, greedy action, Bellman (gpi_pd.py:445-463) -- rewards / dones stay un-tiled (TILE map)
+            next_q = th.stack([tn(nobs, w) for tn in self.target_q_nets])  # [n, N, A, D]
+            target_q, _ = ops.critic_min_td(next_q, w, s_rewards, s_dones, self.gamma, self.dot_mode, ops.MAP_BLOCK, ops.MAP_TILE)
+            target_gpi = None
+            if self.gpi_pd:
+                target_gpi, _ = self._envelope_target(nobs, w, sampled_w, rewards=s_rewards, dones=s_dones)
+        psi = th.stack([net(obs, w) for net in self.q_nets])  # [n, N, A, D], train mode (dropout active as in the reference)
+        holder = {}
+        loss = _FusedHuberLoss.apply(psi, s_actions, target_q, target_gpi, w, float(self.min_priority), p_rows, holder)
+        self.q_optim.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.max_grad_norm is not None:
+            for net in self.q_nets:
+                th.nn.utils.clip_grad_norm_(net.parameters(), self.max_grad_norm)
+        self.q_optim.step_fused(None)
+        self._last_loss = loss.detach()
+        if p_rows > 0 and prio_out is not None:
+            prio_out.copy_(holder["prio"].reshape(-1))
+        return holder.get("prio")
+
+    def _mutated_tensors(self):
+        return [p for m in self.q_nets for p in m.parameters()] + optimizer_tensors(self.q_optim)
 
     def update(self, weight: th.Tensor):
         """``gradient_updates`` gradient steps for the given weight vector (reference gpi_pd.py:416-562)."""
         critic_losses = []
-        B0, D, A = self.batch_size, self.reward_dim, self.action_dim
-        P = len(self.weight_support)
+        B0, D, rb = self.batch_size, self.reward_dim, self.replay_buffer
+        graphable = self.use_cuda_graph and getattr(rb, "_dev", None) is not None and self.max_grad_norm is None
         for _ in range(self.gradient_updates):
-            s_obs, s_actions, s_rewards, s_next_obs, s_dones, idxes = self._sample_batch_experiences()
-            s_actions = s_actions.to(th.int32).reshape(-1)
-            if P > 1:
-                # half of the effective batch uses `weight`, the other half weights drawn from the support set (gpi_pd.py:425-436);
-                # random.choices on range(P) consumes python's RNG exactly like random.choices(self.weight_support, k=B)
-                picks = random.choices(range(P), k=B0)
-                M = self._support_matrix()
-                w = th.cat([weight.reshape(1, D).expand(B0, D), M[th.tensor(picks, device=self.device)]], dim=0).contiguous()
-                obs, nobs = s_obs.repeat(2, *(1 for _ in range(s_obs.dim() - 1))), s_next_obs.repeat(2, *(1 for _ in range(s_obs.dim() - 1)))
+            P = len(self.weight_support)
+            want_prio = self.per or self.gpi_pd
+            if not graphable:
+                s_obs, s_actions, s_rewards, s_next_obs, s_dones, idxes = self._sample_batch_experiences()
+                s_actions = s_actions.to(th.int32).reshape(-1)
+                # random.choices / random.sample on range(P) consume python's RNG exactly like the reference's calls on the weight list
+                picks = th.tensor(random.choices(range(P), k=B0), device=self.device) if P > 1 else None
+                sampled_idx = th.tensor(random.sample(range(P), k=4), device=self.device) if P > 5 else None
+                prio = self._device_update(s_obs, s_actions, s_rewards, s_next_obs, s_dones, weight, picks, sampled_idx, len(idxes) if want_prio else 0)
+                pr = prio.cpu().numpy().flatten() if want_prio else None
             else:
-                w = weight.reshape(1, D).expand(B0, D).contiguous()
-                obs, nobs = s_obs, s_next_obs
-            N = w.shape[0]
-            if P > 5:
-                sampled_w = th.stack([weight] + [self.weight_support[i] for i in random.sample(range(P), k=4)])
-            else:
-                sampled_w = self._support_matrix() if P > 0 else weight.reshape(1, D)
+                # graph path: the host walks the PER tree and draws the support indices (same RNG consumption and order as the
+                # reference), fills the static buffers, replays one graph, and reads the raw priorities back
+                M = self._support_matrix() if P > 0 else None
+                key = (P > 1, P > 5, P, id(rb), id(M))
+                st = self._graphs.get(key)
+                if st is None:
+                    st = {"host": th.zeros(2 * B0 + 4, dtype=th.int64).pin_memory(), "dev": th.zeros(2 * B0 + 4, dtype=th.int64, device=self.device),
+                          "w": th.zeros(D, device=self.device), "prio": th.zeros(B0, device=self.device), "prio_pin": th.zeros(B0).pin_memory()}
 
-            with th.no_grad():
-                # min_i Q_i(s', a, w) . w, greedy action, Bellman (gpi_pd.py:445-463) -- rewards / dones stay un-tiled (TILE map)
-                next_q = th.stack([tn(nobs, w) for tn in self.target_q_nets])  # [n, N, A, D]
-                target_q, _ = ops.critic_min_td(next_q, w, s_rewards, s_dones, self.gamma, self.dot_mode, ops.MAP_BLOCK, ops.MAP_TILE)
-                target_gpi = None
-                if self.gpi_pd:
-                    target_gpi, _ = self._envelope_target(nobs, w, sampled_w, rewards=s_rewards, dones=s_dones)
+                    def step(st=st, doubled=P > 1, sampled=P > 5, want_prio=want_prio):
+                        obs_s, nobs_s, act_s, rew_s, done_s = rb._dev
+                        obs, act, rew, nobs, done = ops.replay_gather(obs_s, nobs_s, act_s, rew_s, done_s, st["dev"][:B0])
+                        self._device_update(obs, act.reshape(-1), rew, nobs, done, st["w"], st["dev"][B0:2 * B0] if doubled else None,
+                                            st["dev"][2 * B0:] if sampled else None, B0 if want_prio else 0, st["prio"])
 
-            psi = th.stack([net(obs, w) for net in self.q_nets])  # [n, N, A, D], train mode (dropout active as in the reference)
-            holder = {}
-            p_rows = len(idxes) if (self.per or self.gpi_pd) else 0
-            loss = _FusedHuberLoss.apply(psi, s_actions, target_q, target_gpi, w, float(self.min_priority), p_rows, holder)
-            self.q_optim.zero_grad()
-            loss.backward()
-            if self.max_grad_norm is not None:
-                for net in self.q_nets:
-                    th.nn.utils.clip_grad_norm_(net.parameters(), self.max_grad_norm)
-            self.q_optim.step()
-            critic_losses.append(loss.detach())
-
-            if self.per or self.gpi_pd:
+                    st["graph"] = GraphedStep(step, self._mutated_tensors)
+                    self._graphs[key] = st
+                hostv = st["host"].numpy()
+                idxes = rb.tree.sample(B0) if self.per else rb._draw(B0)
+                hostv[:B0] = idxes
+                if P > 1:
+                    hostv[B0:2 * B0] = random.choices(range(P), k=B0)
+                if P > 5:
+                    hostv[2 * B0:] = random.sample(range(P), k=4)
+                st["dev"].copy_(st["host"], non_blocking=True)
+                st["w"].copy_(weight.reshape(-1))
+                rb.flush()
+                st["graph"]()
+                pr = None
+                if want_prio:
+                    st["prio_pin"].copy_(st["prio"], non_blocking=True)
+                    th.cuda.current_stream().synchronize()
+                    pr = st["prio_pin"].numpy().copy()
+            critic_losses.append(self._last_loss)
+            if want_prio:
                 # priorities: |w . max_n err_n| of the first len(idxes) rows, clip(min)^alpha on the host (gpi_pd.py:507-525)
-                pr = holder["prio"].cpu().numpy().flatten()
                 priority = pr.clip(min=self.min_priority) ** self.alpha
                 if self.per:
                     self.replay_buffer.update_priorities(np.asarray(idxes), priority)

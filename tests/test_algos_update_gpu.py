@@ -39,14 +39,16 @@ class _Noise:
         return th.from_numpy(self.rng.standard_normal(tuple(shape)).astype(np.float32)).to(self.dev)
 
 
+@pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("gpi_pd", [True, False])
-def test_gpipd_update_matches_reference(cuda, gold, gpi_pd):
+def test_gpipd_update_matches_reference(cuda, gold, gpi_pd, graph):
     from morl_baselines_b200.multi_policy.gpi_pd.gpi_pd import GPIPD
 
     tag = f"gpipd{int(gpi_pd)}"
     OBS, A, D, B, N = 10, 4, 3, 16, 256
     agent = GPIPD(FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D), batch_size=B, net_arch=[32, 32, 32], num_nets=2, gradient_updates=2, dyna=False,
-                  per=True, gpi_pd=gpi_pd, drop_rate=0.0, layer_norm=True, buffer_size=N, log=False, seed=1, device=cuda, target_net_update_freq=3)
+                  per=True, gpi_pd=gpi_pd, drop_rate=0.0, layer_norm=True, buffer_size=N, log=False, seed=1, device=cuda, target_net_update_freq=3,
+                  use_cuda_graph=graph)
     for i, (net, tnet) in enumerate(zip(agent.q_nets, agent.target_q_nets)):
         _load_sd(net, gold, f"{tag}/init{i}", cuda)
         tnet.load_state_dict(net.state_dict())
