@@ -276,8 +276,8 @@ def run_b200(args, rank, local_rank, world):
     from morl_baselines_b200.common.networks import polyak_update
 
     def dev_step(t):
-        s["idx"].copy_(idx_all[t])
-        s["wset"].copy_(w_all[t])
+        s["in"]["idx"].copy_(idx_all[t])
+        s["in"]["wset"].copy_(w_all[t])
         graph.replay()
         if (t + 1) % agent.target_net_update_freq == 0:
             polyak_update(agent.q_net.parameters(), agent.target_q_net.parameters(), 1.0)
@@ -325,7 +325,7 @@ def run_b200(args, rank, local_rank, world):
     agent_h = _make_agent(dev, seed=rank, on_device=False)
     _fill_store(agent_h.replay_buffer, store)
     agent_h.global_step = 1
-    loss_pin = th.zeros((), dtype=th.float32).pin_memory()
+    loss_host = 0.0
     for _ in range(max(Wm, 3)):
         agent_h.update()
     if world > 1:
@@ -334,8 +334,8 @@ def run_b200(args, rank, local_rank, world):
     e2, e3 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(K):
-        agent_h.update()  # H2D minibatch + weights, graph replay, D2H priorities (sync) -> host sum-tree
-        loss_pin.copy_(agent_h._last_loss)  # the reference reads critic_loss.item() every update (envelope.py:327)
+        agent_h.update()  # H2D minibatch + weights, graph replay, D2H priorities + loss (event sync) -> host sum-tree
+        loss_host = agent_h.last_loss_host()  # the reference reads critic_loss.item() every update (envelope.py:327): a python float here too
     e3.record()
     if world > 1:
         dist.barrier()
@@ -398,7 +398,7 @@ def run_b200(args, rank, local_rank, world):
         "mlp": {"flop_per_step": mlp_flops, "fp32_equivalent_tflops": mlp_flops / (ms / K * 1e-3) / 1e12,
                 "path": "layer 1 separable (library sgemm on B + |W| rows), layers 2.. tcgen05 bf16x3 forward and backward",
                 "note": "whole-step time used, so this is a lower bound on the dense-layer rate"},
-        "loss": loss_dev,
+        "loss": loss_dev, "loss_e2e_last": loss_host,
     }
     if world == 1:
         t_step, kind, cores = cpu_reference_steps(steps=3, warmup=1)

@@ -741,6 +741,69 @@ __global__ void __launch_bounds__(256) pairs_rowblock_sum_kernel(const __nv_bflo
     }
 }
 
+// dU and the per-chunk partials of dV in ONE pass over the planes of dL/dh1 (|W| <= 64): block = (chunk of transitions, 256 columns),
+// thread (x, y) owns 8 columns and the weights j = y, y + 8, ...; per transition the 8 y-partials of dU are reduced through shared
+// memory (same order as pairs_rowblock_sum_kernel), dV[j] accumulates over the transitions of the chunk in registers.
+__global__ void __launch_bounds__(256) pairs_grad_reduce_fused_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int B, int W,
+                                                                      int H, int b_per_chunk, float* __restrict__ dU, float* __restrict__ partV) {
+    __shared__ float red[8][32][9];
+    const int h0 = (blockIdx.y * 32 + threadIdx.x) * 8;
+    const int b0 = blockIdx.x * b_per_chunk, b1 = min(B, b0 + b_per_chunk);
+    float accV[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) accV[k][c] = 0.f;
+    for (int b = b0; b < b1; ++b) {
+        float accU[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) accU[c] = 0.f;
+        if (h0 < H) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int j = threadIdx.y + 8 * k;
+                if (j < W) {
+                    const size_t o = ((size_t)b * W + j) * H + h0;
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) bf16x8_add(v, __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        accU[c] += v[c];
+                        accV[k][c] += v[c];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red[threadIdx.y][threadIdx.x][c] = accU[c];
+        __syncthreads();
+        if (threadIdx.y == 0 && h0 < H) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float t = 0.f;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][c];
+                dU[(size_t)b * H + h0 + c] = t;
+            }
+        }
+        __syncthreads();
+    }
+    if (h0 < H) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = threadIdx.y + 8 * k;
+            if (j < W) {
+                float* dst = partV + ((size_t)blockIdx.x * W + j) * H + h0;
+                *reinterpret_cast<float4*>(dst) = make_float4(accV[k][0], accV[k][1], accV[k][2], accV[k][3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(accV[k][4], accV[k][5], accV[k][6], accV[k][7]);
+            }
+        }
+    }
+}
+
 // ---- fp32 -> three bf16 planes (operands produced outside the GEMM epilogue: network inputs, weights, gradients) ---------
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, int transpose,
                                                            __nv_bfloat16* __restrict__ dst, int rows_pad, int ldp, long long plane_stride) {
@@ -757,6 +820,42 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
         dst[e] = h0;
         dst[plane_stride + e] = h1;
         dst[2 * plane_stride + e] = h2;
+    }
+}
+
+// non-transposed, ldp % 8 == 0: one thread converts 8 consecutive columns (two 128-bit loads when the source row allows it) and writes one
+// 128-bit store per plane -- the gradient seed dL/dQ [65,536 x 24] of every step goes through here (23 -> ~5 us)
+__global__ void __launch_bounds__(256) split_bf16x3_vec8_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
+                                                                __nv_bfloat16* __restrict__ dst, int rows_pad, int ldp, long long plane_stride) {
+    const int cpr = ldp >> 3;  // 8-column chunks per row
+    const long long total = (long long)rows_pad * cpr;
+    const bool vec_ok = (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(t / cpr), c0 = (int)(t - (long long)r * cpr) << 3;
+        float x[8];
+        if (r < rows && c0 + 8 <= cols && vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c0 + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = (r < rows && c0 + k < cols) ? __ldg(src + (size_t)r * ld_src + c0 + k) : 0.f;
+        }
+        uint32_t p0[4], p1[4], p2[4];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const __nv_bfloat16 a0 = __float2bfloat16_rn(x[k]), b0 = __float2bfloat16_rn(x[k + 1]);
+            const float ra = x[k] - __bfloat162float(a0), rb = x[k + 1] - __bfloat162float(b0);
+            const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
+            const __nv_bfloat16 a2 = __float2bfloat16_rn(ra - __bfloat162float(a1)), b2 = __float2bfloat16_rn(rb - __bfloat162float(b1));
+            p0[k >> 1] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+            p1[k >> 1] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+            p2[k >> 1] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+        }
+        const size_t e = (size_t)r * ldp + c0;
+        *reinterpret_cast<uint4*>(dst + e) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+        *reinterpret_cast<uint4*>(dst + plane_stride + e) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+        *reinterpret_cast<uint4*>(dst + 2 * plane_stride + e) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
     }
 }
 
@@ -933,6 +1032,19 @@ extern "C" int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane
     MORL_REQUIRE(B > 0 && W > 0 && H > 0 && H % 8 == 0 && plane_stride % 8 == 0, MORL_ERR_SHAPE, "morl_pairs_grad_reduce_bf16x3: bad shape B=%d W=%d H=%d", B, W, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __nv_bfloat16* pl = static_cast<const __nv_bfloat16*>(planes);
+    if (W <= 64) {
+        // one pass: dU directly, dV as per-chunk partials [chunks][W*H] reduced in a fixed order
+        const int chunks_f = B < 148 ? B : 148;
+        const int bpc = (B + chunks_f - 1) / chunks_f;
+        const int nchf = (B + bpc - 1) / bpc;
+        const int Nf = W * H;
+        float* partf = static_cast<float*>(workspace);  // nchf * W * H floats (<= 296 * W * H, the documented workspace size)
+        pairs_grad_reduce_fused_kernel<<<dim3((unsigned)nchf, (unsigned)((H + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, B, W, H, bpc, dU, partf);
+        int rcf = check_launch("morl_pairs_grad_reduce_bf16x3(fused)");
+        if (rcf) return rcf;
+        reduce_partials_kernel<<<(Nf + 31) / 32, dim3(32, 8), 0, st>>>(partf, nchf, 1, Nf, 1, Nf, 0, dV, Nf, 1 << 30, nullptr, nullptr);
+        return check_launch("morl_pairs_grad_reduce_bf16x3(reduce)");
+    }
     // dU[b] = sum over the W rows of transition b
     pairs_rowblock_sum_kernel<<<dim3((unsigned)B, (unsigned)((H + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, W, H, dU);
     int rc = check_launch("morl_pairs_grad_reduce_bf16x3(dU)");
@@ -961,6 +1073,14 @@ extern "C" int morl_split_bf16x3(const float* src, int rows, int cols, int ld_sr
                  "morl_split_bf16x3: bad shape rows=%d cols=%d rows_pad=%d ldp=%d", rows, cols, rows_pad, ldp);
     MORL_REQUIRE(plane_stride >= (long long)rows_pad * ldp, MORL_ERR_SHAPE, "morl_split_bf16x3: plane_stride too small");
     const long long total = (long long)rows_pad * ldp;
+    if (!transpose && (ldp & 7) == 0 && (plane_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(dst_planes) & 15u) == 0) {
+        const long long chunks = total >> 3;
+        long long vb = (chunks + 255) / 256;
+        if (vb > 148 * 8) vb = 148 * 8;
+        split_bf16x3_vec8_kernel<<<(int)vb, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, ld_src, static_cast<__nv_bfloat16*>(dst_planes),
+                                                                                          rows_pad, ldp, plane_stride);
+        return check_launch("morl_split_bf16x3(vec8)");
+    }
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     split_bf16x3_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, ld_src, transpose,

@@ -272,24 +272,37 @@ class Envelope(MOPolicy, MOAgent):
         host = {k: cut(pnp, k).reshape(shp[k]) for k in shp if k != "act"}
         host["act"] = cut(pnp, "act").view(np.int32).reshape(B, 1)
         host["idx"] = cut(pnp, "idx").view(np.int64)
-        stage = {k: cut(pdev, k).view(shp[k]) for k in ("obs", "nobs", "rew", "done")}
-        stage["act"] = cut(pdev, "act").view(th.int32).view(B, 1)
+        # the captured step reads a PRIVATE copy (`work`, refreshed by the first node of the graph), so the next step's host->device
+        # copy may overwrite `pdev` while the backward half of this step is still running
+        work = th.zeros(total, dtype=th.float32, device=dev)
+        stage = {k: cut(work, k).view(shp[k]) for k in ("obs", "nobs", "rew", "done")}
+        stage["act"] = cut(work, "act").view(th.int32).view(B, 1)
         head_end = off["wset"][0] + seg(off["wset"][1])
         s = {
-            "idx": cut(pdev, "idx").view(th.int64),
-            "wset": cut(pdev, "wset").view(W, D),
-            "loss": th.zeros((), dtype=th.float32, device=dev),
-            "prio": th.zeros(B, dtype=th.float32, device=dev),
+            "idx": cut(work, "idx").view(th.int64),
+            "wset": cut(work, "wset").view(W, D),
+            "work": work,
+            "result": th.zeros(B + 1, dtype=th.float32, device=dev),  # [priorities (B) | loss]: one device->host copy per step
             "ws": ops.td_workspace(B * W, dev),
             "pack_pin": pin, "pack_dev": pdev, "host": host, "stage": stage,
             # (device slice, pinned slice) of the one copy a step makes
             "copy_device": (pdev[:head_end], pin[:head_end]),
             "copy_host": (pdev[off["wset"][0] :], pin[off["wset"][0] :]),
-            "prio_pin": th.zeros(B, dtype=th.float32).pin_memory(),
+            "result_pin": th.zeros(B + 1, dtype=th.float32).pin_memory(),
             "h2d_done": th.cuda.Event(),  # guards the pinned staging buffer against being overwritten while a copy is pending
+            # recorded INSIDE the captured step right after the fused TD-loss kernel (external event node): the host waits for the
+            # priorities only, writes them back to the sum-tree and prepares the next minibatch while the GPU runs backward + Adam
+            "prio_ready": th.cuda.Event(external=True),
+            "copy_stream": th.cuda.Stream(device=dev),
         }
+        # where a caller that stages inputs on the device itself (bench.py's `value` arm) must write them: the staging buffer, not the
+        # private copy the graph refreshes from it
+        s["in"] = {"idx": cut(pdev, "idx").view(th.int64), "wset": cut(pdev, "wset").view(W, D)}
+        s["in"]["wset"].fill_(1.0 / D)
         s["wset"].fill_(1.0 / D)
-        s["prio_np"] = s["prio_pin"].numpy()
+        s["prio"], s["loss"] = s["result"][:B], s["result"][B]
+        s["prio_np"] = s["result_pin"].numpy()[:B]
+        s["loss_pin"] = s["result_pin"][B]
         self._static = s
         return s
 
@@ -325,15 +338,20 @@ class Envelope(MOPolicy, MOAgent):
             q_values = self.q_net.forward_pairs(obs, wset).view(B * W, A, D)
         loss = _FusedTDLoss.apply(q_values, act.reshape(-1), target_q, wset, float(self.homotopy_lambda), B, W, s["ws"],
                                   s["prio"] if self.per else None)
+        # loss and priorities are final here (the loss kernel wrote them): ship them to the host before the backward half starts
+        s["loss"].copy_(loss.detach())
+        s["result_pin"].copy_(s["result"], non_blocking=True)
+        s["prio_ready"].record()
         self.q_optim.zero_grad(set_to_none=True)
         loss.backward()
         self.q_optim.step_fused(self.max_grad_norm)  # clip_grad_norm_ + Adam.step (envelope.py:324-326) in two launches
-        s["loss"].copy_(loss.detach())
 
     def _step(self, mode: str):
         """What one CUDA graph captures.  mode "device": gather from the HBM-resident store by the static index buffer, then
         the gradient step; mode "host": the gradient step on the static staging tensors the host minibatch was copied into."""
         s = self._static
+        src = s["copy_" + mode][0]  # the segment of the staging buffer this mode's host->device copy fills
+        s["work"][src.storage_offset() : src.storage_offset() + src.numel()].copy_(src)
         if mode == "device":
             obs_s, nobs_s, act_s, rew_s, done_s = self.replay_buffer.device_stores()
             obs, act, rew, nobs, done = ops.replay_gather(obs_s, nobs_s, act_s, rew_s, done_s, s["idx"])
@@ -409,8 +427,18 @@ class Envelope(MOPolicy, MOAgent):
             host["wset"][:] = np.asarray(w_np).reshape(self.num_sample_w, -1)  # float64 -> float32, as th.tensor(w).float() (envelope.py:278)
             mode = "device" if has_mirror else "host"
             dst, src = s["copy_" + mode]
-            dst.copy_(src, non_blocking=True)
-            s["h2d_done"].record()
+            # the copy runs on its own stream: the previous step's graph has already consumed `pack_dev` (its first node; the host
+            # waited for that step's priorities, which come later in the graph), so the copy overlaps that step's backward half
+            # (only with PER -- without it the host never waits on the GPU, so the copy simply stays in stream order)
+            if self.per:
+                cs = s["copy_stream"]
+                with th.cuda.stream(cs):
+                    dst.copy_(src, non_blocking=True)
+                    s["h2d_done"].record(cs)
+                th.cuda.current_stream().wait_event(s["h2d_done"])
+            else:
+                dst.copy_(src, non_blocking=True)
+                s["h2d_done"].record()
 
             if self.use_cuda_graph and self._lambda_is_static():
                 g = self._graphs.get(mode) or self._capture(mode)
@@ -422,8 +450,7 @@ class Envelope(MOPolicy, MOAgent):
             critic_losses.append(s["loss"])
 
             if self.per:
-                s["prio_pin"].copy_(s["prio"], non_blocking=True)
-                th.cuda.current_stream().synchronize()
+                s["prio_ready"].synchronize()  # the priorities of THIS step have landed in pinned memory; backward + Adam still run
                 priority = (s["prio_np"] + rb.min_priority) ** self.per_alpha  # envelope.py:333 (float32, as the reference's tensor math)
                 rb.update_priorities(b_inds, priority)
 
@@ -445,6 +472,15 @@ class Envelope(MOPolicy, MOAgent):
             wandb.log({"losses/grad_norm": get_grad_norm(self.q_net.parameters()).item(), "global_step": self.global_step})
             if self.per:
                 wandb.log({"metrics/mean_priority": np.mean(priority)})
+
+    def last_loss_host(self, wait: bool = True) -> float:
+        """Critic loss of the most recent gradient update as a python float (the reference reads ``critic_loss.item()`` every update,
+        envelope.py:327).  The value is copied to pinned host memory INSIDE the captured step right after the loss kernel, so reading it
+        waits for the forward half of the step only, not for backward + Adam."""
+        s = self._static
+        if wait:
+            s["prio_ready"].synchronize()
+        return float(s["loss_pin"])
 
     def _stage_host_batch(self, inds):
         """Gather the host-resident minibatch for ``inds`` straight into the pinned staging buffer (C row gathers,
