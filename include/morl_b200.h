@@ -276,6 +276,12 @@ MORL_API int morl_colsum_bf16x3(const void* planes, long long plane_stride, int 
 MORL_API int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane_stride, int B, int W, int H, float* dU, float* dV,
                                            void* workspace, void* stream);
 
+/* Separable first layer of the weight-conditioned Q-network on the pair batch (reference envelope.py:59-77 builds [s || w] rows for
+ * nn.Linear):  u[b, :] = W1[:, :F] feats[b],  v[j, :] = W1[:, F:] wset[j] + b1  in ONE launch (replaces two library
+ * sgemms and their epilogue kernels).  W1 is the row-major nn.Linear weight [H, F + D]; u [B, H], v [W, H]. */
+MORL_API int morl_pair_layer1_uv_f32(const float* feats, const float* wset, const float* W1, const float* b1, int B, int W, int F, int D, int H,
+                                     float* u, float* v, void* stream);
+
 
 /* Fused gradient clipping + Adam step over a list of tensors (two launches).  Replaces th.nn.utils.clip_grad_norm_ +
  * optim.Adam.step (envelope.py:324-326; torch/optim/adam.py _single_tensor_adam arithmetic, amsgrad = False, weight_decay = 0).

@@ -53,6 +53,7 @@ SIGNATURES = {
     "morl_gemm_bf16x3_mn_f32": (_i, [_vp, C.c_longlong, _i, _i, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "morl_colsum_bf16x3": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
     "morl_pairs_grad_reduce_bf16x3": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "morl_pair_layer1_uv_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "morl_adam_workspace_bytes": (_sz, [_i, _i64]),
     "morl_adam_clip_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _vp, _vp]),
 }

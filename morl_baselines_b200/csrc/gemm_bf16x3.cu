@@ -741,12 +741,14 @@ __global__ void __launch_bounds__(256) pairs_rowblock_sum_kernel(const __nv_bflo
     }
 }
 
-// dU and the per-chunk partials of dV in ONE pass over the planes of dL/dh1 (|W| <= 64): block = (chunk of transitions, 256 columns),
-// thread (x, y) owns 8 columns and the weights j = y, y + 8, ...; per transition the 8 y-partials of dU are reduced through shared
-// memory (same order as pairs_rowblock_sum_kernel), dV[j] accumulates over the transitions of the chunk in registers.
+// dU and the per-chunk partials of dV in ONE pass over the planes of dL/dh1 (|W| <= 64): block = (chunk of <= kPgrMaxB transitions, 256
+// columns), thread (x, y) owns 8 columns and the weights j = y, y + 8, ...; the 8 y-partials of dU of every transition of the chunk are
+// parked in shared memory and reduced after ONE barrier (same order as pairs_rowblock_sum_kernel), dV[j] accumulates over the
+// transitions of the chunk in registers.
+constexpr int kPgrMaxB = 8;
 __global__ void __launch_bounds__(256) pairs_grad_reduce_fused_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int B, int W,
                                                                       int H, int b_per_chunk, float* __restrict__ dU, float* __restrict__ partV) {
-    __shared__ float red[8][32][9];
+    extern __shared__ float red_dyn[];  // [kPgrMaxB][8][32][9]
     const int h0 = (blockIdx.y * 32 + threadIdx.x) * 8;
     const int b0 = blockIdx.x * b_per_chunk, b1 = min(B, b0 + b_per_chunk);
     float accV[8][8];
@@ -777,21 +779,21 @@ __global__ void __launch_bounds__(256) pairs_grad_reduce_fused_kernel(const __nv
                 }
             }
         }
+        float* r = red_dyn + (((size_t)(b - b0) * 8 + threadIdx.y) * 32 + threadIdx.x) * 9;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) red[threadIdx.y][threadIdx.x][c] = accU[c];
-        __syncthreads();
-        if (threadIdx.y == 0 && h0 < H) {
+        for (int c = 0; c < 8; ++c) r[c] = accU[c];
+    }
+    __syncthreads();
+    if (h0 < H) {
+        for (int bl = threadIdx.y; bl < b1 - b0; bl += 8) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float t = 0.f;
 #pragma unroll
-                for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][c];
-                dU[(size_t)b * H + h0 + c] = t;
+                for (int y = 0; y < 8; ++y) t += red_dyn[(((size_t)bl * 8 + y) * 32 + threadIdx.x) * 9 + c];
+                dU[(size_t)(b0 + bl) * H + h0 + c] = t;
             }
         }
-        __syncthreads();
-    }
-    if (h0 < H) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int j = threadIdx.y + 8 * k;
@@ -1034,16 +1036,25 @@ extern "C" int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane
     const __nv_bfloat16* pl = static_cast<const __nv_bfloat16*>(planes);
     if (W <= 64) {
         // one pass: dU directly, dV as per-chunk partials [chunks][W*H] reduced in a fixed order
-        const int chunks_f = B < 148 ? B : 148;
-        const int bpc = (B + chunks_f - 1) / chunks_f;
+        int bpc = (B + 295) / 296;  // <= 296 chunks (the documented workspace size), at most kPgrMaxB transitions per chunk
+        if (bpc > kPgrMaxB) bpc = kPgrMaxB;
         const int nchf = (B + bpc - 1) / bpc;
-        const int Nf = W * H;
-        float* partf = static_cast<float*>(workspace);  // nchf * W * H floats (<= 296 * W * H, the documented workspace size)
-        pairs_grad_reduce_fused_kernel<<<dim3((unsigned)nchf, (unsigned)((H + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, B, W, H, bpc, dU, partf);
-        int rcf = check_launch("morl_pairs_grad_reduce_bf16x3(fused)");
-        if (rcf) return rcf;
-        reduce_partials_kernel<<<(Nf + 31) / 32, dim3(32, 8), 0, st>>>(partf, nchf, 1, Nf, 1, Nf, 0, dV, Nf, 1 << 30, nullptr, nullptr);
-        return check_launch("morl_pairs_grad_reduce_bf16x3(reduce)");
+        if (nchf <= 296) {
+            const int Nf = W * H;
+            float* partf = static_cast<float*>(workspace);
+            const size_t smemf = (size_t)kPgrMaxB * 8 * 32 * 9 * sizeof(float);  // 73,728 B
+            static bool configured = false;
+            if (!configured) {
+                cudaFuncSetAttribute(pairs_grad_reduce_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf);
+                configured = true;
+            }
+            pairs_grad_reduce_fused_kernel<<<dim3((unsigned)nchf, (unsigned)((H + 255) / 256)), dim3(32, 8), smemf, st>>>(pl, plane_stride, B, W, H, bpc,
+                                                                                                                           dU, partf);
+            int rcf = check_launch("morl_pairs_grad_reduce_bf16x3(fused)");
+            if (rcf) return rcf;
+            reduce_partials_kernel<<<(Nf + 31) / 32, dim3(32, 8), 0, st>>>(partf, nchf, 1, Nf, 1, Nf, 0, dV, Nf, 1 << 30, nullptr, nullptr);
+            return check_launch("morl_pairs_grad_reduce_bf16x3(reduce)");
+        }
     }
     // dU[b] = sum over the W rows of transition b
     pairs_rowblock_sum_kernel<<<dim3((unsigned)B, (unsigned)((H + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, W, H, dU);

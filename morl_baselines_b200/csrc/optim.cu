@@ -78,15 +78,24 @@ __global__ void __launch_bounds__(kOptBlock) adam_clip_kernel(float* const* __re
                                                               const float* __restrict__ partials, int n_partials, float max_norm, float lr,
                                                               float beta1, float beta2, float eps) {
     __shared__ float s_coef;
-    if (threadIdx.x == 0) {
-        float coef = 1.0f;
-        if (max_norm > 0.f) {
-            double tot = 0.0;
-            for (int i = 0; i < n_partials; ++i) tot += (double)partials[i];  // fixed order: deterministic
-            const float total_norm = (float)sqrt(tot);
-            coef = fminf(max_norm / (total_norm + 1e-6f), 1.0f);
+    __shared__ double s_red[kOptBlock / 32];
+    if (max_norm > 0.f) {
+        // total squared norm: every block re-reduces the (few hundred) partials with the whole block, in a fixed tree order
+        // (deterministic); a single thread walking them serially was ~10 us of latency in front of every block
+        double tot = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += kOptBlock) tot += (double)partials[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t2 = 0.0;
+            for (int w = 0; w < kOptBlock / 32; ++w) t2 += s_red[w];
+            const float total_norm = (float)sqrt(t2);
+            s_coef = fminf(max_norm / (total_norm + 1e-6f), 1.0f);
         }
-        s_coef = coef;
+    } else if (threadIdx.x == 0) {
+        s_coef = 1.0f;
     }
     __syncthreads();
     const float coef = s_coef;

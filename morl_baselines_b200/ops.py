@@ -356,6 +356,23 @@ def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None
     return out
 
 
+def pair_layer1_uv(feats: th.Tensor, wset: th.Tensor, weight: th.Tensor, bias: th.Tensor, u: Optional[th.Tensor] = None,
+                   v: Optional[th.Tensor] = None):
+    """u = feats @ W1[:, :F]^T [B, H] and v = wset @ W1[:, F:]^T + b1 [W, H] in one launch (separable first layer of the pair batch)."""
+    feats, wset, weight, bias = _dev(feats, "feats"), _dev(wset, "wset"), _dev(weight, "weight"), _dev(bias, "bias")
+    B, F = feats.shape
+    W, D = wset.shape
+    H = weight.shape[0]
+    if weight.shape[1] != F + D or bias.numel() != H:
+        raise _lib.MorlB200Error(f"pair_layer1_uv: weight {tuple(weight.shape)} does not match F={F}, D={D}")
+    u = th.empty((B, H), device=feats.device, dtype=th.float32) if u is None else u
+    v = th.empty((W, H), device=feats.device, dtype=th.float32) if v is None else v
+    rc = _lib.load().morl_pair_layer1_uv_f32(_ptr(feats), _ptr(wset), _ptr(weight), _ptr(bias), B, W, F, D, H, _ptr(u), _ptr(v), _stream())
+    _lib.check(rc, "morl_pair_layer1_uv_f32")
+    _count()
+    return u, v
+
+
 def gemm_mn_workspace(M: int, g_cols: int, h_cols: int, device) -> th.Tensor:
     nbytes = _lib.load().morl_gemm_mn_workspace_bytes(int(M), int(g_cols), int(h_cols))
     return th.empty((nbytes + 3) // 4, device=device, dtype=th.float32)

@@ -29,6 +29,7 @@ import os
 
 _SNAKE = os.environ.get("MORL_TC_SNAKE", "1") == "1"          # alternate the GEMM tile order between chained layers
 _MULTI_SPLIT = os.environ.get("MORL_TC_MULTI_SPLIT", "1") == "1"  # one launch for all weight splits of a step
+_FUSED_L1 = os.environ.get("MORL_TC_FUSED_L1", "1") == "1"        # separable first layer as custom launches instead of library sgemms
 
 
 def _pad32(n: int) -> int:
@@ -121,8 +122,11 @@ class TCPairMlp:
     def forward_pairs(self, feats: th.Tensor, wset: th.Tensor) -> th.Tensor:
         """feats [B, F], wset [W, D] -> Q [B*W, out] (fp32, row b*W + j).  Uses the planes of the last refresh_weights()."""
         first = self.lin[0]
-        u = feats @ first.weight[:, : self.feat_dim].t()
-        v = th.addmm(first.bias, wset, first.weight[:, self.feat_dim :].t())
+        if _FUSED_L1 and feats.shape[1] == self.feat_dim and first.in_features == self.feat_dim + wset.shape[1]:
+            u, v = ops.pair_layer1_uv(feats, wset, first.weight.detach(), first.bias.detach())  # one launch (csrc/pair_layer1.cu)
+        else:
+            u = feats @ first.weight[:, : self.feat_dim].t()
+            v = th.addmm(first.bias, wset, first.weight[:, self.feat_dim :].t())
         a = ops.pairs_relu_split(u, v, out=self.h[0])
         n = len(self.lin)
         for k in range(1, n - 1):

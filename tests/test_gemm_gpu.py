@@ -122,11 +122,43 @@ def test_gemm_mn_weight_gradient(cuda, M, gc, hc):
     np.testing.assert_allclose(cs2.cpu().numpy(), G.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5 * float(G.abs().sum(0).max()))
 
 
+@pytest.mark.parametrize("B,W,F,D,H", [(1024, 64, 32, 3, 256), (37, 5, 11, 2, 64), (3, 70, 7, 4, 300), (8, 8, 59, 3, 32)])
+def test_pair_layer1_kernels(cuda, B, W, F, D, H):
+    """Separable first layer on the pair batch: u = feats W1_s^T, v = wset W1_w^T + b1 in one launch, against float64; fp32 FMA
+    chains -> 1e-6 of the magnitude sums."""
+    from morl_baselines_b200 import ops
+
+    g_ = th.Generator(device=cuda).manual_seed(B + 3 * W + F)
+    feats, wset = th.randn(B, F, device=cuda, generator=g_), th.rand(W, D, device=cuda, generator=g_)
+    W1, b1 = th.randn(H, F + D, device=cuda, generator=g_) / 4, th.randn(H, device=cuda, generator=g_)
+    u, v = ops.pair_layer1_uv(feats, wset, W1, b1)
+    ru = feats.double() @ W1[:, :F].double().t()
+    rv = wset.double() @ W1[:, F:].double().t() + b1.double()
+    assert float((u.double() - ru).abs().max()) <= 1e-6 * float((feats.abs().double() @ W1[:, :F].abs().double().t()).max())
+    assert float((v.double() - rv).abs().max()) <= 1e-6 * float((wset.abs().double() @ W1[:, F:].abs().double().t() + b1.abs().double()).max())
+
+
+def test_split_vectorised_path_matches_scalar_path(cuda):
+    """ldp % 8 == 0 takes the 8-columns-per-thread kernel; an unaligned source (ld_src % 4 != 0) and ragged columns must give the same
+    planes as the transposed-input scalar kernel."""
+    from morl_baselines_b200 import ops
+
+    g_ = th.Generator(device=cuda).manual_seed(9)
+    for rows, cols in ((65536, 24), (1000, 250), (77, 13)):
+        x = th.randn(rows, cols, device=cuda, generator=g_)
+        ldp = (cols + 31) // 32 * 32
+        a = ops.split_bf16x3(x, ldp=ldp)  # vectorised
+        b = ops.split_bf16x3(x.t().contiguous(), ldp=ldp, transpose=True)  # scalar kernel on the transposed source
+        assert th.equal(a, b)
+        assert float((a[0].double() + a[1].double() + a[2].double())[:, :cols].sub(x.double()).abs().max()) <= 2.0**-23 * float(x.abs().max())
+        assert float(a[:, :, cols:].abs().max()) == 0.0
+
+
 def test_pairs_grad_reduce(cuda):
     from morl_baselines_b200 import ops
 
     g_ = th.Generator(device=cuda).manual_seed(2)
-    for B, W in ((37, 5), (64, 64)):
+    for B, W in ((37, 5), (64, 64), (300, 33), (5, 70)):
         G = th.randn(B * W, 256, device=cuda, generator=g_)
         Gp = ops.split_bf16x3(G)
         dU, dV = ops.pairs_grad_reduce(Gp, B, W)
