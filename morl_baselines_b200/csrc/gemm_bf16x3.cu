@@ -88,6 +88,24 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// same, with an L2 eviction-priority hint (createpolicy): activations are read once (evict_first), weight planes by every tile (evict_last)
+__device__ __forceinline__ void tma_load_3d_pair_hint(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+            g_smem_u32(dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
@@ -152,6 +170,7 @@ struct GemmArgs {
     const __nv_bfloat16* mask;   // plane 0 of the forward activation [M][ld_mask] for the ReLU-backward mask, or nullptr
     int ld_mask;
     int relu;
+    int l2_hint;                 // L2 eviction hints on the operand loads (MORL_GEMM_L2HINT, default on): A evict_first, B evict_last
     int reverse;                 // walk the row tiles from the last to the first (see morl_gemm_bf16x3_f32: L2 reuse between chained layers)
     unsigned long long* stats;   // diagnostics (MORL_GEMM_STATS=1), else nullptr: [0] MMA wait-on-TMA cycles, [1] MMA wait-on-epilogue,
                                  // [2] MMA loop total, [3] producer wait-on-free-stage, [4] epilogue wait-on-accumulator, [5] epilogue busy
@@ -242,6 +261,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             uint32_t stage = 0, phase = 0;
             long long w_empty = 0;
+            const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
             for (int u = unit; u < n_work; u += n_units) {
                 int tile, n_begin, n_cnt;
                 unit_of(u, tile, n_begin, n_cnt);
@@ -255,9 +275,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         // one expect_tx (leader) covers the four boxes of the pair; every box completes on the leader's barrier
                         if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + 3u * (uint32_t)b_rows * kGemmBK * 2u));
                         const uint32_t lbar = mapa_rank0(g_smem_u32(&full[stage]));
-                        tma_load_3d_pair(smA + stage * a_stage_bytes, &tmA, lbar, kb * kGemmBK, row0, 0);
-                        tma_load_3d_pair(smB + stage * b_stage_stride, n_cnt == BN ? &tmB : &tmBh, lbar, kb * kGemmBK,
-                                         n_begin + (int)cta_rank * b_rows, 0);
+                        if (g.l2_hint) {
+                            tma_load_3d_pair_hint(smA + stage * a_stage_bytes, &tmA, lbar, kb * kGemmBK, row0, 0, pol_a);
+                            tma_load_3d_pair_hint(smB + stage * b_stage_stride, n_cnt == BN ? &tmB : &tmBh, lbar, kb * kGemmBK,
+                                                  n_begin + (int)cta_rank * b_rows, 0, pol_b);
+                        } else {
+                            tma_load_3d_pair(smA + stage * a_stage_bytes, &tmA, lbar, kb * kGemmBK, row0, 0);
+                            tma_load_3d_pair(smB + stage * b_stage_stride, n_cnt == BN ? &tmB : &tmBh, lbar, kb * kGemmBK,
+                                             n_begin + (int)cta_rank * b_rows, 0);
+                        }
                     } else {
                         g_mbar_expect_tx(&full[stage], a_stage_bytes + b_stage_bytes);
                         tma_load_3d(smA + stage * a_stage_bytes, &tmA, &full[stage], kb * kGemmBK, row0, 0);
@@ -1190,6 +1216,8 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     g.c_planes = static_cast<__nv_bfloat16*>(c_planes); g.ldp = ldp; g.plane_stride = c_plane_stride;
     g.mask = static_cast<const __nv_bfloat16*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
     g.reverse = reverse_tiles ? 1 : 0;
+    static const bool want_hint = [] { const char* e = getenv("MORL_GEMM_L2HINT"); return !(e && e[0] == '0'); }();
+    g.l2_hint = want_hint ? 1 : 0;
     static const bool want_stats = [] { const char* e = getenv("MORL_GEMM_STATS"); return e && e[0] == '1'; }();
     g.stats = nullptr;
     if (want_stats) {
