@@ -170,7 +170,7 @@ struct GemmArgs {
     const __nv_bfloat16* mask;   // plane 0 of the forward activation [M][ld_mask] for the ReLU-backward mask, or nullptr
     int ld_mask;
     int relu;
-    int l2_hint;                 // L2 eviction hints on the operand loads (MORL_GEMM_L2HINT, default on): A evict_first, B evict_last
+    int l2_hint;                 // L2 eviction hints on the operand loads (MORL_GEMM_L2HINT=1, default off): A evict_first, B evict_last
     int reverse;                 // walk the row tiles from the last to the first (see morl_gemm_bf16x3_f32: L2 reuse between chained layers)
     unsigned long long* stats;   // diagnostics (MORL_GEMM_STATS=1), else nullptr: [0] MMA wait-on-TMA cycles, [1] MMA wait-on-epilogue,
                                  // [2] MMA loop total, [3] producer wait-on-free-stage, [4] epilogue wait-on-accumulator, [5] epilogue busy
@@ -1216,7 +1216,9 @@ extern "C" int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stri
     g.c_planes = static_cast<__nv_bfloat16*>(c_planes); g.ldp = ldp; g.plane_stride = c_plane_stride;
     g.mask = static_cast<const __nv_bfloat16*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
     g.reverse = reverse_tiles ? 1 : 0;
-    static const bool want_hint = [] { const char* e = getenv("MORL_GEMM_L2HINT"); return !(e && e[0] == '0'); }();
+    // measured on B200 (profiles/r01_s3_l2hint_ab.txt): the hints do not help -- whole step 877 vs 871-876 updates/s, isolated layer on
+    // rotating inputs 47.7 -> 55.0 us -- so they are opt-in (MORL_GEMM_L2HINT=1)
+    static const bool want_hint = [] { const char* e = getenv("MORL_GEMM_L2HINT"); return e && e[0] == '1'; }();
     g.l2_hint = want_hint ? 1 : 0;
     static const bool want_stats = [] { const char* e = getenv("MORL_GEMM_STATS"); return e && e[0] == '1'; }();
     g.stats = nullptr;
