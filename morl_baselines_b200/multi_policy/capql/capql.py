@@ -23,7 +23,6 @@ import numpy as np
 import torch as th
 import torch.nn as nn
 import torch.nn.functional as F
-import torch.optim as optim
 
 from ... import ops
 from ...common.fused_adam import FusedClipAdam
@@ -274,9 +273,6 @@ class CAPQL(MOAgent, MOPolicy):
 
     def _sample_batch_experiences(self):
         return self.replay_buffer.sample(self.batch_size, to_tensor=True, device=self.device)
-
-    def _noise(self, shape):
-        return None if self._noise_hook is None else self._noise_hook(shape)
 
     def _device_update(self, s_obs, s_actions, w, s_rewards, s_next_obs, s_dones, noise):
         """The device side of one gradient update (reference capql.py:323-362) on an already gathered minibatch."""

@@ -24,7 +24,6 @@ from typing import List, Optional, Union
 import numpy as np
 import torch as th
 import torch.nn as nn
-import torch.optim as optim
 
 from ... import ops
 from ...common.fused_adam import FusedClipAdam

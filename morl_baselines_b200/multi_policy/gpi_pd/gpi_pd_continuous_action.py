@@ -30,7 +30,6 @@ import numpy as np
 import torch as th
 import torch.nn as nn
 import torch.nn.functional as F
-import torch.optim as optim
 
 from ... import ops
 from ...common.buffer import ReplayBuffer
@@ -235,9 +234,6 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
     # ------------------------------------------------------------------------------------------ the update
     def _sample_batch_experiences(self):
         return self.replay_buffer.sample(self.batch_size, to_tensor=True, device=self.device)
-
-    def _eps(self, shape):
-        return None if self._noise_hook is None else self._noise_hook(shape)
 
     def _tile_weights(self, weight, picks, B0):
         """Effective-batch weights: ``weight`` for the first B0 rows, support weights ``picks`` for the doubled half (:381-391)."""

@@ -22,7 +22,6 @@ import numpy as np
 import torch as th
 import torch.nn as nn
 import torch.nn.functional as F
-import torch.optim as optim
 
 from ... import ops
 from ...common.buffer import ReplayBuffer
@@ -234,9 +233,6 @@ class MOSAC(MOPolicy):
         with th.no_grad():
             action, _, _ = self.actor.get_action(obs)
         return action[0].detach().cpu().numpy()
-
-    def _noise(self, shape):
-        return None if self._noise_hook is None else self._noise_hook(shape)
 
     def _scal(self, q):
         return self.scalarization(q, self.weights_tensor)
