@@ -451,11 +451,17 @@ __global__ void __launch_bounds__(128) envelope_td_wp_kernel(const float* __rest
                                                              const float* __restrict__ wset, const float* __restrict__ reward,
                                                              const float* __restrict__ done, float gamma, int B, int W, int A,
                                                              int row_order, float* __restrict__ target_out,
-                                                             int32_t* __restrict__ pref_out, int32_t* __restrict__ act_out) {
+                                                             int32_t* __restrict__ pref_out, int32_t* __restrict__ act_out, int pdl) {
     constexpr bool FILTER = (MODE != MORL_DOT_FMA);
     extern __shared__ __align__(16) float smem[];
     const int C = W * A;
     const int CDp = (C * D + 3) & ~3;
+    if (pdl) {
+        // programmatic dependent launch: this grid was allowed to become resident while its predecessor in the stream was still
+        // draining; let OUR successor do the same, then wait until the predecessor's results are visible before any global read
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     float* Qa = smem;                                         // [C*D] AoS Q_on[b]  (bulk async copy)
     float* Qt = Qa + CDp;                                     // [C*D] AoS Q_tg[b]  (bulk async copy)
     float* red_v = Qt + CDp;                                  // [4][64] best group maximum per (candidate quarter, weight)
@@ -786,8 +792,29 @@ extern "C" int morl_envelope_td_f32(const float* q_online, const float* q_target
                             long long gx = (long long)sm_count_cached * occ / gy;
                             if (gx < 1) gx = 1;
                             if (gx > B) gx = B;
-                            kern<<<dim3((unsigned)gx, gy, 1), 128, smem5, st>>>(q_online, q_target, wset, reward, done, gamma, B, W, A, row_order,
-                                                                              target_out, pref_out, act_out);
+                            // measured (profiles/r01_s3_pdl_ab.txt): helps when one CTA per SM is resident (B = 148: 3.8 -> 3.35 us) and in
+                            // launch-bound python loops, hurts at the north-star shape where the next grid's early CTAs compete with the
+                            // 7 resident CTAs per SM of the running grid (9.85 -> 10.65 us); whole step unchanged -> opt-in only
+                            static const bool want_pdl = [] { const char* e = getenv("MORL_ENVELOPE_PDL"); return e && e[0] == '1'; }();
+                            if (want_pdl) {
+                                // programmatic stream serialisation: the grid may start (barrier init, CTA residency) while the previous
+                                // kernel of the stream drains; the kernel's griddepcontrol.wait restores the data dependency
+                                cudaLaunchConfig_t cfg = {};
+                                cfg.gridDim = dim3((unsigned)gx, gy, 1);
+                                cfg.blockDim = dim3(128, 1, 1);
+                                cfg.dynamicSmemBytes = smem5;
+                                cfg.stream = st;
+                                cudaLaunchAttribute attr[1];
+                                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                                cfg.attrs = attr;
+                                cfg.numAttrs = 1;
+                                cudaLaunchKernelEx(&cfg, kern, q_online, q_target, wset, reward, done, gamma, B, W, A, row_order, target_out, pref_out,
+                                                   act_out, 1);
+                            } else {
+                                kern<<<dim3((unsigned)gx, gy, 1), 128, smem5, st>>>(q_online, q_target, wset, reward, done, gamma, B, W, A, row_order,
+                                                                                  target_out, pref_out, act_out, 0);
+                            }
                             launched5 = true;
                         }));
         MORL_REQUIRE(launched5, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: no weight-pair kernel for D=%d mode=%d", D, dot_mode);
