@@ -4,20 +4,18 @@ import numpy as np
 
 
 def weighted_sum(reward: np.ndarray, weights: np.ndarray) -> float:
-    """Linear scalarisation (reference scalarization.py:7-17)."""
+    """Linear scalarisation w . r (reference scalarization.py:7-17); fused into every device kernel of this package."""
     return np.dot(reward, weights)
 
 
 def tchebicheff(tau: float, reward_dim: int):
-    """Adaptive Tchebycheff scalarisation (reference scalarization.py:20-41; the pymoo decomposition is restated:
-    max_r w_r * |f_r - z_r| against the running utopian point)."""
-    best_so_far = [float("-inf") for _ in range(reward_dim)]
+    """Adaptive Tchebycheff scalarisation (reference scalarization.py:20-41).  The reference delegates to pymoo's decomposition; here it
+    is restated directly: the utopian point z tracks max_t (r_t + tau) per objective and the utility is -max_r w_r |r_r - z_r|."""
+    utopia = np.full(reward_dim, -np.inf)
 
-    def thunk(reward: np.ndarray, weights: np.ndarray):
-        for i, r in enumerate(reward):
-            if best_so_far[i] < r + tau:
-                best_so_far[i] = r + tau
-        v = np.abs(np.asarray(reward, dtype=np.float64) - np.asarray(best_so_far)) * np.asarray(weights, dtype=np.float64)
-        return -float(v.max())
+    def scalarize(reward: np.ndarray, weights: np.ndarray) -> float:
+        r = np.asarray(reward, dtype=np.float64)
+        np.maximum(utopia, r + tau, out=utopia)
+        return -float(np.max(np.abs(r - utopia) * np.asarray(weights, dtype=np.float64)))
 
-    return thunk
+    return scalarize

@@ -81,43 +81,16 @@ class QNetwork(nn.Module):
 class GPIPDContinuousAction(MOAgent, MOPolicy):
     """GPI-PD with continuous actions (Alegre et al., AAMAS 2023, appendix): TD3 extended to weight-conditioned vector critics."""
 
-    def __init__(
-        self,
-        env,
-        learning_rate: float = 3e-4,
-        gamma: float = 0.99,
-        tau: float = 0.005,
-        buffer_size: int = 400000,
-        net_arch: List = [256, 256],
-        batch_size: int = 128,
-        num_q_nets: int = 2,
-        delay_policy_update: int = 2,
-        learning_starts: int = 100,
-        gradient_updates: int = 20,
-        use_gpi: bool = False,
-        policy_noise: float = 0.2,
-        noise_clip: float = 0.5,
-        per: bool = True,
-        min_priority: float = 0.1,
-        alpha: float = 0.6,
-        dyna: bool = True,
-        dynamics_net_arch: List = [200, 200, 200, 200],
-        dynamics_train_freq: int = 250,
-        dynamics_rollout_len: int = 5,
-        dynamics_rollout_starts: int = 1000,
-        dynamics_rollout_freq: int = 250,
-        dynamics_rollout_batch_size: int = 50000,
-        dynamics_buffer_size: int = 200000,
-        dynamics_min_uncertainty: float = 2.0,
-        dynamics_real_ratio: float = 0.1,
-        project_name: str = "MORL-Baselines",
-        experiment_name: str = "GPI-PD Continuous Action",
-        wandb_entity: Optional[str] = None,
-        log: bool = True,
-        seed: Optional[int] = None,
-        device: Union[th.device, str] = "auto",
-        use_cuda_graph: bool = True,
-    ):
+    def __init__(self, env, learning_rate: float = 3e-4, gamma: float = 0.99, tau: float = 0.005, buffer_size: int = 400000,
+                 net_arch: List = [256, 256], batch_size: int = 128, num_q_nets: int = 2, delay_policy_update: int = 2,
+                 learning_starts: int = 100, gradient_updates: int = 20, use_gpi: bool = False, policy_noise: float = 0.2,
+                 noise_clip: float = 0.5, per: bool = True, min_priority: float = 0.1, alpha: float = 0.6, dyna: bool = True,
+                 dynamics_net_arch: List = [200, 200, 200, 200], dynamics_train_freq: int = 250, dynamics_rollout_len: int = 5,
+                 dynamics_rollout_starts: int = 1000, dynamics_rollout_freq: int = 250, dynamics_rollout_batch_size: int = 50000,
+                 dynamics_buffer_size: int = 200000, dynamics_min_uncertainty: float = 2.0, dynamics_real_ratio: float = 0.1,
+                 project_name: str = "MORL-Baselines", experiment_name: str = "GPI-PD Continuous Action", wandb_entity: Optional[str] = None,
+                 log: bool = True, seed: Optional[int] = None, device: Union[th.device, str] = "auto", use_cuda_graph: bool = True):
+        """The reference's arguments in the reference's order (gpi_pd_continuous_action.py:86-121) + ``use_cuda_graph``."""
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
         if self.device.type != "cuda":
@@ -127,23 +100,12 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
             raise NotImplementedError("dyna=True (probabilistic ensemble + ModelEnv planning) is outside the accelerated hot path "
                                       "(SURVEY.md section 2, component 20); use dyna=False / GPILSContinuousAction")
         ops._lib.load()
-        self.learning_rate = learning_rate
-        self.tau = tau
-        self.gamma = gamma
-        self.use_gpi = use_gpi
-        self.policy_noise = policy_noise
-        self.noise_clip = noise_clip
-        self.buffer_size = buffer_size
-        self.num_q_nets = num_q_nets
-        self.delay_policy_update = delay_policy_update
-        self.net_arch = net_arch
-        self.dynamics_net_arch = dynamics_net_arch
-        self.learning_starts = learning_starts
-        self.batch_size = batch_size
-        self.gradient_updates = gradient_updates
-        self.per = per
-        self.min_priority = min_priority
-        self.alpha = alpha
+        self.learning_rate, self.tau, self.gamma = learning_rate, tau, gamma
+        self.use_gpi, self.policy_noise, self.noise_clip = use_gpi, policy_noise, noise_clip
+        self.buffer_size, self.batch_size, self.learning_starts, self.gradient_updates = buffer_size, batch_size, learning_starts, gradient_updates
+        self.num_q_nets, self.delay_policy_update = num_q_nets, delay_policy_update
+        self.net_arch, self.dynamics_net_arch = net_arch, dynamics_net_arch
+        self.per, self.min_priority, self.alpha = per, min_priority, alpha
         if self.per:
             self.replay_buffer = PrioritizedReplayBuffer(self.observation_shape, self.action_dim, rew_dim=self.reward_dim, max_size=buffer_size,
                                                          device=self.device)
@@ -168,16 +130,10 @@ class GPIPDContinuousAction(MOAgent, MOPolicy):
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
 
-        self.dyna = False
-        self.dynamics = None
-        self.dynamics_buffer = None
-        self.dynamics_train_freq = dynamics_train_freq
-        self.dynamics_rollout_len = dynamics_rollout_len
-        self.dynamics_rollout_starts = dynamics_rollout_starts
-        self.dynamics_rollout_freq = dynamics_rollout_freq
-        self.dynamics_rollout_batch_size = dynamics_rollout_batch_size
-        self.dynamics_min_uncertainty = dynamics_min_uncertainty
-        self.dynamics_real_ratio = dynamics_real_ratio
+        self.dyna, self.dynamics, self.dynamics_buffer = False, None, None  # Dyna is out of scope; the knobs are kept for get_config()
+        self.dynamics_train_freq, self.dynamics_rollout_len, self.dynamics_rollout_starts = dynamics_train_freq, dynamics_rollout_len, dynamics_rollout_starts
+        self.dynamics_rollout_freq, self.dynamics_rollout_batch_size = dynamics_rollout_freq, dynamics_rollout_batch_size
+        self.dynamics_min_uncertainty, self.dynamics_real_ratio = dynamics_min_uncertainty, dynamics_real_ratio
 
         self.weight_support = []
         self.stacked_weight_support = []

@@ -27,61 +27,29 @@ from ...common.utils import linearly_decaying_value
 class MOQLearning(MOPolicy, MOAgent):
     """One Q-table per objective, actions chosen through a scalarisation function (Van Moffaert et al., ADPRL 2013)."""
 
-    def __init__(
-        self,
-        env,
-        id: Optional[int] = None,
-        weights: np.ndarray = np.array([0.5, 0.5]),
-        scalarization=weighted_sum,
-        learning_rate: float = 0.1,
-        gamma: float = 0.9,
-        initial_epsilon: float = 0.1,
-        final_epsilon: float = 0.1,
-        epsilon_decay_steps: int = None,
-        learning_starts: int = 0,
-        use_gpi_policy: bool = False,
-        dyna: bool = False,
-        dyna_updates: int = 5,
-        model=None,
-        gpi_pd: bool = False,
-        min_priority: float = 0.0001,
-        alpha: float = 0.6,
-        parent=None,
-        project_name: str = "MORL-baselines",
-        experiment_name: str = "MO Q-Learning",
-        wandb_entity: Optional[str] = None,
-        log: bool = True,
-        seed: Optional[int] = None,
-        parent_rng: Optional[np.random.Generator] = None,
-    ):
+    def __init__(self, env, id: Optional[int] = None, weights: np.ndarray = np.array([0.5, 0.5]), scalarization=weighted_sum,
+                 learning_rate: float = 0.1, gamma: float = 0.9, initial_epsilon: float = 0.1, final_epsilon: float = 0.1,
+                 epsilon_decay_steps: int = None, learning_starts: int = 0, use_gpi_policy: bool = False, dyna: bool = False,
+                 dyna_updates: int = 5, model=None, gpi_pd: bool = False, min_priority: float = 0.0001, alpha: float = 0.6, parent=None,
+                 project_name: str = "MORL-baselines", experiment_name: str = "MO Q-Learning", wandb_entity: Optional[str] = None,
+                 log: bool = True, seed: Optional[int] = None, parent_rng: Optional[np.random.Generator] = None):
+        """Same arguments, in the same order, as the reference constructor (mo_q_learning.py:26-52)."""
         MOAgent.__init__(self, env, device="cpu")
         MOPolicy.__init__(self, id, device="cpu")
         if dyna or model is not None:
             raise NotImplementedError("dyna=True (tabular Dyna-Q model) is outside the hot-path scope (SURVEY.md section 2, component 20)")
-        self.learning_rate = learning_rate
-        self.id = id
-        self.seed = seed
-        self.np_random = parent_rng if parent_rng is not None else np.random.default_rng(self.seed)
-        self.idstr = f"_{self.id}" if self.id is not None else ""
-        self.gamma = gamma
-        self.initial_epsilon = initial_epsilon
+        self.id, self.seed, self.parent, self.log = id, seed, parent, log
+        self.idstr = "" if id is None else f"_{id}"
+        self.np_random = np.random.default_rng(seed) if parent_rng is None else parent_rng
+        self.learning_rate, self.gamma = learning_rate, gamma
+        self.initial_epsilon, self.final_epsilon, self.epsilon_decay_steps = initial_epsilon, final_epsilon, epsilon_decay_steps
         self.epsilon = initial_epsilon
-        self.final_epsilon = final_epsilon
-        self.epsilon_decay_steps = epsilon_decay_steps
-        self.learning_starts = learning_starts
-        self.use_gpi_policy = use_gpi_policy
-        self.dyna = False
-        self.dyna_updates = dyna_updates
-        self.gpi_pd = gpi_pd
-        self.min_priority = min_priority
-        self.alpha = alpha
-        self.parent = parent
-        self.weights = weights
-        self.scalarization = scalarization
-        self.q_table = dict()
-        self.model = None
-        self.log = log
-        if self.log and parent_rng is None:
+        self.learning_starts, self.use_gpi_policy = learning_starts, use_gpi_policy
+        self.dyna, self.dyna_updates, self.model = False, dyna_updates, None
+        self.gpi_pd, self.min_priority, self.alpha = gpi_pd, min_priority, alpha
+        self.weights, self.scalarization = weights, scalarization
+        self.q_table = {}  # state tuple -> float64 [|A|, d]
+        if log and parent_rng is None:
             self.setup_wandb(project_name, experiment_name, wandb_entity)
 
     def _act(self, obs) -> int:
