@@ -6,6 +6,8 @@ matrices reproduces the tensor-core arithmetic up to accumulation order.  Report
   fp32        : plain fp32 GEMM (what cuBLAS SGEMM / the reference's MKL path delivers)
   bf16x3 (6)  : A0B0 + A0B1 + A1B0 + A1B1 + A0B2 + A2B0           (today: 6 MMAs, 6 B / element)
   fp16x2 (3)  : A0B0 + A0B1 + A1B0 with per-tensor power-of-two scaling into fp16's normal range   (3 MMAs, 4 B / element)
+  fp16x2 static: the same with FIXED scales (activations 2^6, weights 2^8, gradients 2^22) -- no amax pass, but small values lose bits to
+                 fp16's denormal range
 """
 import numpy as np
 import torch as th
@@ -38,7 +40,7 @@ def pow2_scale(x, target=2.0**10):
     return 2.0 ** np.floor(np.log2(target / m)) if m > 0 else 1.0
 
 
-def report(name, A, B):
+def report(name, A, B, static=None):
     exact = A.double() @ B.double().t()
     bound = A.abs().double() @ B.abs().double().t() + 1e-300
     out = {}
@@ -48,6 +50,9 @@ def report(name, A, B):
     sa, sb = pow2_scale(A), pow2_scale(B)
     a, b = split_fp16(A, 2, sa), split_fp16(B, 2, sb)
     out["fp16x2 (3)"] = (sum((a[i] @ b[j].t()) for i, j in ((1, 0), (0, 1), (0, 0))).double()) / (sa * sb)
+    if static is not None:  # fixed scales chosen without looking at the data (no amax pass): how much accuracy do they cost?
+        a, b = split_fp16(A, 2, static[0]), split_fp16(B, 2, static[1])
+        out["fp16x2 static"] = (sum((a[i] @ b[j].t()) for i, j in ((1, 0), (0, 1), (0, 0))).double()) / (static[0] * static[1])
     row = "  ".join(f"{k}: {float(((v - exact).abs() / bound).max()):.2e}" for k, v in out.items())
     print(f"{name:34s} {row}   (scales 2^{int(np.log2(sa))}, 2^{int(np.log2(sb))})")
 
@@ -70,12 +75,13 @@ for d in range(3):
     g[th.arange(M), act * 3 + d] = 2.0 * th.randn(M) / (65536 * 3)
 print("forward layers  C = H_{k-1} W_k^T")
 for k in (1, 2, 3):
-    report(f"  layer {k + 1} forward", hs[k - 1], lin[k].weight.detach())
-report("  output layer forward", hs[3], lin[4].weight.detach())
+    report(f"  layer {k + 1} forward", hs[k - 1], lin[k].weight.detach(), static=(2.0**6, 2.0**8))
+report("  output layer forward", hs[3], lin[4].weight.detach(), static=(2.0**6, 2.0**8))
 print("backward  dX = G W,  dW = G^T H")
 G = g
 for k in (4, 3, 2):
     W = lin[k].weight.detach()
-    report(f"  dX through layer {k + 1}", G, W.t().contiguous())
-    report(f"  dW of layer {k + 1}", G.t().contiguous(), hs[k - 1].t().contiguous())
+    # static gradient scale 2^22: the seed is 2 delta / (B W d) with |delta| <~ 10, i.e. |g| <~ 1e-4
+    report(f"  dX through layer {k + 1}", G, W.t().contiguous(), static=(2.0**22, 2.0**8))
+    report(f"  dW of layer {k + 1}", G.t().contiguous(), hs[k - 1].t().contiguous(), static=(2.0**22, 2.0**6))
     G = (G @ W) * (hs[k - 1] > 0)
