@@ -107,7 +107,7 @@ def _fill_store(rb, store):
 
 def _make_agent(dev, seed, on_device):
     from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
-    from oracle.ref_harness import FakeEnv  # spaces-only stand-in for a mo-gymnasium env (rollouts are not part of the metric)
+    from morl_baselines_b200.testing import FakeEnv  # spaces-only stand-in for a mo-gymnasium env (rollouts are not part of the metric)
 
     env = FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D)
     return Envelope(env, batch_size=B, num_sample_w=W, per=True, buffer_size=STORE, net_arch=NET, log=False, seed=seed, device=dev,
@@ -251,7 +251,7 @@ def run_b200(args, rank, local_rank, world):
 
     from morl_baselines_b200 import ops
     from morl_baselines_b200.parallel import allgather_fronts
-    from oracle.envelope_update_port import synthetic_store
+    from morl_baselines_b200.testing import synthetic_store
 
     dev = th.device("cuda", local_rank)
     th.cuda.set_device(dev)

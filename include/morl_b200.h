@@ -142,6 +142,8 @@ MORL_API int morl_actor_critic_td_f32(const float* q_nets, int n_nets, const flo
  * MSE, homotopy auxiliary loss) and :329-331 (|w . td| priorities of the first B rows, i.e. weight index 0).
  *   q_values : f32 [W*B, A, D] online net output on the effective batch (row order `row_order`)
  *   action   : int32 [B];  target_q : f32 [W*B, D];  wset : f32 [W, D]
+ *   homotopy_lambda_dev : optional device f32 [1]; when non-NULL the kernels read lambda from it instead of the by-value argument, so a
+ *              captured CUDA graph stays valid while the homotopy schedule (envelope.py:351-358) changes lambda every update
  *   loss_out : f32 [1] = (1-lambda)*mean((q-t)^2) + lambda*mean((w.q - w.t)^2)
  *   grad_q   : f32 [W*B, A, D] = d loss / d q_values (dense; zero off the taken action), or NULL
  *   q_taken  : f32 [W*B, D] the gathered Q(s,a) (optional, NULL to skip)
@@ -150,8 +152,8 @@ MORL_API int morl_actor_critic_td_f32(const float* q_nets, int n_nets, const flo
  */
 MORL_API size_t morl_td_workspace_bytes(int n_rows);
 MORL_API int morl_td_mse_priority_f32(const float* q_values, const int32_t* action, const float* target_q,
-                             const float* wset, float homotopy_lambda, int B, int W, int A, int D, int row_order,
-                             float* loss_out, float* grad_q, float* q_taken, float* prio_out, void* workspace,
+                             const float* wset, float homotopy_lambda, const float* homotopy_lambda_dev, int B, int W, int A,
+                             int D, int row_order, float* loss_out, float* grad_q, float* q_taken, float* prio_out, void* workspace,
                              void* stream);
 
 /* Huber-style TD loss of GPI-PD.  Replaces gpi_pd.py:469-487 per net and :507-520 (priority = | w . max_n |delta_n| |).
@@ -281,6 +283,14 @@ MORL_API int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane_s
  * sgemms and their epilogue kernels).  W1 is the row-major nn.Linear weight [H, F + D]; u [B, H], v [W, H]. */
 MORL_API int morl_pair_layer1_uv_f32(const float* feats, const float* wset, const float* W1, const float* b1, int B, int W, int F, int D, int H,
                                      float* u, float* v, void* stream);
+
+/* Parameter gradients of the separable first layer (backward of morl_pair_layer1_uv_f32; autograd of nn.Linear at envelope.py:316 on the
+ * effective batch, restricted to layer 1):  dW1 [H, F + D] = [dU^T feats | dV^T wset],  db1 [H] = colsum(dV), with dU [B, H] / dV [W, H]
+ * from morl_pairs_grad_reduce_bf16x3.  One launch, deterministic split reduction.  `workspace`: morl_pair_layer1_grad_workspace_bytes(F, D,
+ * H) bytes that must be ZERO before the first call (the kernel leaves its arrival counters zeroed again). */
+MORL_API size_t morl_pair_layer1_grad_workspace_bytes(int F, int D, int H);
+MORL_API int morl_pair_layer1_grad_f32(const float* dU, const float* dV, const float* feats, const float* wset, int B, int W, int F,
+                              int D, int H, float* dW1, float* db1, void* workspace, void* stream);
 
 
 /* Fused gradient clipping + Adam step over a list of tensors (two launches).  Replaces th.nn.utils.clip_grad_norm_ +

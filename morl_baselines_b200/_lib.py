@@ -33,7 +33,7 @@ SIGNATURES = {
     "morl_gpi_envelope_f32": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "morl_actor_critic_td_f32": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _f, _f, _i, _i, _i, _vp, _vp]),
     "morl_td_workspace_bytes": (_sz, [_i]),
-    "morl_td_mse_priority_f32": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "morl_td_mse_priority_f32": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "morl_td_huber_priority_f32": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "morl_host_sumtree_walk": (_i, [_vp, _i, _vp, _i, _vp]),
     "morl_host_sumtree_batch_set": (_i, [_vp, _i, _vp, _vp, _i]),
@@ -54,6 +54,8 @@ SIGNATURES = {
     "morl_colsum_bf16x3": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
     "morl_pairs_grad_reduce_bf16x3": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "morl_pair_layer1_uv_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "morl_pair_layer1_grad_workspace_bytes": (_sz, [_i, _i, _i]),
+    "morl_pair_layer1_grad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "morl_adam_workspace_bytes": (_sz, [_i, _i64]),
     "morl_adam_clip_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _vp, _vp]),
 }

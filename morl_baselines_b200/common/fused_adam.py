@@ -4,8 +4,8 @@
 device scalar), ``exp_avg``, ``exp_avg_sq``), so checkpoints interchange with the reference's optimiser state
 (reference multi_policy/envelope/envelope.py:183, 240-247).  ``step_fused(max_grad_norm)`` performs
 ``clip_grad_norm_(params, max_grad_norm)`` + ``step()`` (reference envelope.py:324-326) with the arithmetic of the reference's
-non-capturable single-tensor Adam.  Parameter gradients must already be populated and keep their storage between steps (they
-do under CUDA-graph replay; in eager mode the pointer table is refreshed when a gradient tensor moves)."""
+non-capturable single-tensor Adam.  Parameter gradients must already be populated; under CUDA-graph replay they keep their storage,
+in eager mode the single pointer table is refreshed in place when a gradient tensor moved (no per-step allocation, nothing retained)."""
 
 from __future__ import annotations
 
@@ -21,7 +21,8 @@ class FusedClipAdam(optim.Adam):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         super().__init__(params, lr=lr, betas=betas, eps=eps, capturable=True)
         self._tables = None
-        self._cache = {}
+        self._cache = {}   # tables referenced by captured CUDA graphs (one per capture)
+        self._eager = None  # the single overwritable table of the eager path
 
     def _ensure_state(self):
         for group in self.param_groups:
@@ -33,13 +34,19 @@ class FusedClipAdam(optim.Adam):
                     st["exp_avg_sq"] = th.zeros_like(p, memory_format=th.preserve_format)
 
     def _build_tables(self, params):
-        """Device-side pointer tables for one set of gradient buffers.  Built through PINNED staging + async copies so that it
-        is legal inside a CUDA-graph capture (the copy becomes a graph node that re-writes the same pointers on every replay);
-        tables are cached per gradient-pointer tuple and never freed, because a captured graph keeps referencing them."""
+        """Device-side pointer tables for one set of gradient buffers, written through PINNED staging + an async copy so that it is legal
+        inside a CUDA-graph capture (the copy becomes a graph node that re-writes the same pointers on every replay).
+
+        Lifetime rules (the per-pointer cache used to grow without bound in eager mode):
+          * while a graph is being CAPTURED the table is cached per gradient-pointer tuple and keeps the gradient tensors alive, because
+            the captured graph keeps referencing both;
+          * in eager mode ONE table (pinned staging, device copy, workspace) is allocated once and overwritten in place whenever a gradient
+            tensor moved (``zero_grad(set_to_none=True)`` callers); nothing is retained, so memory stays flat however long the run is."""
         dev = params[0].device
         grads = [p.grad for p in params]
         key = tuple(g.data_ptr() for g in grads)
-        if key in self._cache:
+        capturing = th.cuda.is_current_stream_capturing()
+        if capturing and key in self._cache:
             self._tables = self._cache[key]
             return
         lists = {
@@ -47,16 +54,31 @@ class FusedClipAdam(optim.Adam):
             "v": [self.state[p]["exp_avg_sq"].data_ptr() for p in params], "s": [self.state[p]["step"].data_ptr() for p in params],
             "n": [p.numel() for p in params],
         }
-        pinned = th.tensor([lists[k] for k in ("p", "g", "m", "v", "s", "n")], dtype=th.int64).pin_memory()
-        table = th.empty_like(pinned, device=dev)
+        rows = th.tensor([lists[k] for k in ("p", "g", "m", "v", "s", "n")], dtype=th.int64)
+        eager = None if capturing else self._eager
+        if eager is not None and eager["pinned"].shape == rows.shape and eager["table"].device == dev:
+            eager["copied"].synchronize()  # the previous refresh of the staging buffer has been consumed
+            pinned, table, ws = eager["pinned"], eager["table"], eager["ws"]
+            pinned.copy_(rows)
+        else:
+            pinned = rows.pin_memory()
+            table = th.empty_like(pinned, device=dev)
+            ws = None
         table.copy_(pinned, non_blocking=True)
         t = {k: table[i] for i, k in enumerate(("p", "g", "m", "v", "s", "n"))}
         t["max"] = max(lists["n"])
-        t["keep"] = (params, grads, pinned, table)
         t["key"] = key
         nbytes = _lib.load().morl_adam_workspace_bytes(len(params), t["max"])
-        t["ws"] = th.empty((nbytes + 3) // 4, dtype=th.float32, device=dev)
-        self._cache[key] = t
+        if ws is None or ws.numel() * 4 < nbytes:
+            ws = th.empty((nbytes + 3) // 4, dtype=th.float32, device=dev)
+        t["ws"] = ws
+        if capturing:
+            t["keep"] = (params, grads, pinned, table)
+            self._cache[key] = t
+        else:
+            ev = eager["copied"] if eager is not None else th.cuda.Event()
+            ev.record()
+            self._eager = {"pinned": pinned, "table": table, "ws": ws, "copied": ev}
         self._tables = t
 
     @th.no_grad()
@@ -69,7 +91,9 @@ class FusedClipAdam(optim.Adam):
         if any(not (p.is_cuda and p.dtype == th.float32 and p.is_contiguous() and p.grad.is_contiguous()) for p in params):
             raise _lib.MorlB200Error("FusedClipAdam: parameters and gradients must be contiguous float32 CUDA tensors")
         self._ensure_state()
-        if self._tables is None or self._tables["key"] != tuple(p.grad.data_ptr() for p in params):
+        # (a table a captured graph will keep reading must be a cached, never-overwritten one -- not the eager scratch table)
+        if (self._tables is None or self._tables["key"] != tuple(p.grad.data_ptr() for p in params)
+                or (th.cuda.is_current_stream_capturing() and "keep" not in self._tables)):
             self._build_tables(params)
         t = self._tables
         b1, b2 = group["betas"]

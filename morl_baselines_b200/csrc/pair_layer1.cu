@@ -6,8 +6,9 @@
 //     u[b, :] = W1_s feats[b]                 (B rows, K = F)
 //     v[j, :] = W1_w wset[j] + b1            (W rows, K = D)
 // are computed (morl_pair_layer1_uv_f32: 6.3 us; the library path was two SIMT sgemms plus their epilogue kernels, ~15 us).  The
-// parameter gradients dW1 = [dU^T feats | dV^T wset], db1 = colsum(dV) stay on the library path: a hand-written chunked reduction was
-// measured at 56 us against ~30 us for the two library GEMMs and was dropped.
+// parameter gradients dW1 = [dU^T feats | dV^T wset], db1 = colsum(dV) are ONE launch as well (morl_pair_layer1_grad_f32: split
+// reduction over the transitions, partial tiles summed in a fixed order by the last block of each column tile), replacing two library
+// sgemms + split-K reduce + cat + sum of the round-1 path.
 // fp32 FMA chains in a fixed order: deterministic, and within the 1e-5 parity bar of the dense layers (tests/test_gemm_gpu.py).
 #include "common.cuh"
 
@@ -73,6 +74,89 @@ __global__ void __launch_bounds__(256) pair_layer1_uv_kernel(const float* __rest
     }
 }
 
+// ---- backward: dW1 [H, F + D] = [dU^T feats | dV^T wset], db1 [H] = colsum(dV) -------------------------------------------------------------
+// grid = (ceil(H / 32), kL1Splits); block 256 = 32 output rows h x 8 column groups.  Split s reduces transitions [s*bs, (s+1)*bs) into the
+// F "u" columns and weight vectors [s*js, (s+1)*js) into the D "v" columns + the bias column; the partial tiles go to
+// workspace[s][H][F + D + 1] and the LAST block of an h-tile to finish (self-resetting arrival counter) adds the kL1Splits partials in
+// split order: deterministic, no float atomics.
+constexpr int kL1Splits = 16;
+constexpr int kL1Chunk = 64;  // reduction rows staged in shared memory per pass
+
+__global__ void __launch_bounds__(256) pair_layer1_grad_kernel(const float* __restrict__ dU, const float* __restrict__ dV, const float* __restrict__ feats,
+                                                               const float* __restrict__ wset, int B, int W, int F, int D, int H, float* __restrict__ dW1,
+                                                               float* __restrict__ db1, float* __restrict__ partial, unsigned int* __restrict__ counters) {
+    extern __shared__ float sm[];          // [kL1Chunk][32] gradient rows, then [kL1Chunk][max(F, D + 1)] input rows
+    __shared__ unsigned int s_last;
+    const int C = F + D + 1;
+    const int h0 = blockIdx.x * 32, s = blockIdx.y;
+    const int hl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int xw = F > D + 1 ? F : D + 1;
+    float* gs = sm;
+    float* xs = sm + kL1Chunk * 32;
+    const int npass = (C + 7) / 8;
+    // ---- u columns: reduction over this split's transitions
+    const int bs = (B + kL1Splits - 1) / kL1Splits;
+    const int b_lo = s * bs, b_hi = min(B, b_lo + bs);
+    const int js = (W + kL1Splits - 1) / kL1Splits;
+    const int j_lo = s * js, j_hi = min(W, j_lo + js);
+    for (int pass = 0; pass < npass; ++pass) {
+        const int c = pass * 8 + grp;
+        const bool is_u = c < F;
+        float acc = 0.f;
+        // (all threads of the block walk the same chunks; a thread's column decides which staged operand it multiplies with)
+        for (int phase = 0; phase < 2; ++phase) {  // 0: transitions (u columns), 1: weight vectors (v + bias columns)
+            const int lo = phase == 0 ? b_lo : j_lo, hi = phase == 0 ? b_hi : j_hi;
+            const float* g = phase == 0 ? dU : dV;
+            for (int r0 = lo; r0 < hi; r0 += kL1Chunk) {
+                const int nr = min(kL1Chunk, hi - r0);
+                __syncthreads();
+                for (int t = threadIdx.x; t < nr * 32; t += blockDim.x) {
+                    const int rr = t >> 5, hh = t & 31;
+                    gs[t] = (h0 + hh < H) ? __ldg(g + (size_t)(r0 + rr) * H + h0 + hh) : 0.f;
+                }
+                for (int t = threadIdx.x; t < nr * xw; t += blockDim.x) {
+                    const int rr = t / xw, k = t - rr * xw;
+                    float x = 0.f;
+                    if (phase == 0) {
+                        if (k < F) x = __ldg(feats + (size_t)(r0 + rr) * F + k);
+                    } else {
+                        if (k < D) x = __ldg(wset + (size_t)(r0 + rr) * D + k);
+                        else if (k == D) x = 1.0f;  // bias column: plain column sum of dV
+                    }
+                    xs[t] = x;
+                }
+                __syncthreads();
+                if (c < C && ((phase == 0) == is_u)) {
+                    const int k = is_u ? c : c - F;
+                    for (int rr = 0; rr < nr; ++rr) acc = __fmaf_rn(gs[rr * 32 + hl], xs[rr * xw + k], acc);
+                }
+            }
+        }
+        if (c < C && h0 + hl < H) partial[((size_t)s * H + h0 + hl) * C + c] = acc;
+    }
+    // ---- last block of this h-tile sums the partial tiles in split order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counters + blockIdx.x, 1u);
+        s_last = (prev == (unsigned int)(kL1Splits - 1));
+        if (s_last) counters[blockIdx.x] = 0u;  // self-resetting: the workspace needs zeroing only once
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int pass = 0; pass < npass; ++pass) {
+        const int c = pass * 8 + grp;
+        if (c >= C || h0 + hl >= H) continue;
+        float acc = 0.f;
+        for (int ss = 0; ss < kL1Splits; ++ss) acc += __ldcg(partial + ((size_t)ss * H + h0 + hl) * C + c);
+        if (c < F + D)
+            dW1[(size_t)(h0 + hl) * (F + D) + c] = acc;
+        else
+            db1[h0 + hl] = acc;
+    }
+}
+
 }  // namespace morl
 
 extern "C" int morl_pair_layer1_uv_f32(const float* feats, const float* wset, const float* W1, const float* b1, int B, int W, int F, int D, int H, float* u,
@@ -86,4 +170,26 @@ extern "C" int morl_pair_layer1_uv_f32(const float* feats, const float* wset, co
     const int blocks = (B + W + kL1Rows - 1) / kL1Rows;
     pair_layer1_uv_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(feats, wset, W1, b1, B, W, F, D, H, u, v);
     return check_launch("morl_pair_layer1_uv_f32");
+}
+
+extern "C" size_t morl_pair_layer1_grad_workspace_bytes(int F, int D, int H) {
+    using namespace morl;
+    if (F <= 0 || D <= 0 || H <= 0) return 0;
+    // [kL1Splits][H][F + D + 1] fp32 partial tiles + one arrival counter per 32-row tile (the counters must be ZERO before the first call)
+    return ((size_t)kL1Splits * H * (F + D + 1) + (size_t)(H + 31) / 32 + 4) * sizeof(float);
+}
+
+extern "C" int morl_pair_layer1_grad_f32(const float* dU, const float* dV, const float* feats, const float* wset, int B, int W, int F, int D, int H,
+                                         float* dW1, float* db1, void* workspace, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(dU && dV && feats && wset && dW1 && db1 && workspace, MORL_ERR_NULL, "morl_pair_layer1_grad_f32: NULL pointer argument");
+    MORL_REQUIRE(B > 0 && W > 0 && F > 0 && D > 0 && H > 0, MORL_ERR_SHAPE, "morl_pair_layer1_grad_f32: bad shape B=%d W=%d F=%d D=%d H=%d", B, W, F, D, H);
+    const int xw = F > D + 1 ? F : D + 1;
+    const size_t smem = (size_t)kL1Chunk * (32 + xw) * sizeof(float);
+    MORL_REQUIRE(smem <= 48 * 1024, MORL_ERR_UNSUPPORTED, "morl_pair_layer1_grad_f32: feature dimension %d too large", xw);
+    float* partial = static_cast<float*>(workspace);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(partial + (size_t)kL1Splits * H * (F + D + 1));
+    dim3 grid((H + 31) / 32, kL1Splits);
+    pair_layer1_grad_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dU, dV, feats, wset, B, W, F, D, H, dW1, db1, partial, counters);
+    return check_launch("morl_pair_layer1_grad_f32");
 }

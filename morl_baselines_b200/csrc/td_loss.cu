@@ -61,10 +61,11 @@ __device__ __forceinline__ void write_grad_row(float* __restrict__ grow, int A, 
 template <int D>
 __global__ void __launch_bounds__(kTdThreads) td_mse_kernel(const float* __restrict__ q_values, const int32_t* __restrict__ action,
                                                             const float* __restrict__ target_q, const float* __restrict__ wset,
-                                                            float lambda, int B, int W, int A, int row_order,
-                                                            float* __restrict__ grad_q, float* __restrict__ q_taken,
+                                                            float lambda_arg, const float* __restrict__ lambda_dev, int B, int W, int A,
+                                                            int row_order, float* __restrict__ grad_q, float* __restrict__ q_taken,
                                                             float* __restrict__ prio_out, float* __restrict__ partials) {
     __shared__ float red[kTdThreads / 32];
+    const float lambda = lambda_dev ? __ldg(lambda_dev) : lambda_arg;  // device-resident schedule value: a captured graph stays valid while it decays
     const long long N = (long long)B * W;
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float sq = 0.f, aux2 = 0.f;
@@ -115,9 +116,11 @@ __global__ void __launch_bounds__(kTdThreads) td_mse_kernel(const float* __restr
     }
 }
 
-__global__ void __launch_bounds__(kTdThreads) td_mse_finalize_kernel(const float* __restrict__ partials, int n_blocks, float lambda,
-                                                                     double inv_nd, double inv_n, float* __restrict__ loss_out) {
+__global__ void __launch_bounds__(kTdThreads) td_mse_finalize_kernel(const float* __restrict__ partials, int n_blocks, float lambda_arg,
+                                                                     const float* __restrict__ lambda_dev, double inv_nd, double inv_n,
+                                                                     float* __restrict__ loss_out) {
     __shared__ double red[2][kTdThreads];
+    const float lambda = lambda_dev ? __ldg(lambda_dev) : lambda_arg;
     double a = 0.0, b = 0.0;
     for (int t = threadIdx.x; t < n_blocks; t += blockDim.x) {
         a += (double)partials[2 * t + 0];
@@ -213,8 +216,8 @@ extern "C" size_t morl_td_workspace_bytes(int n_rows) {
 }
 
 extern "C" int morl_td_mse_priority_f32(const float* q_values, const int32_t* action, const float* target_q, const float* wset,
-                                        float homotopy_lambda, int B, int W, int A, int D, int row_order, float* loss_out,
-                                        float* grad_q, float* q_taken, float* prio_out, void* workspace, void* stream) {
+                                        float homotopy_lambda, const float* homotopy_lambda_dev, int B, int W, int A, int D, int row_order,
+                                        float* loss_out, float* grad_q, float* q_taken, float* prio_out, void* workspace, void* stream) {
     using namespace morl;
     MORL_REQUIRE(q_values && action && target_q && wset && loss_out && workspace, MORL_ERR_NULL,
                  "morl_td_mse_priority_f32: NULL pointer argument");
@@ -229,11 +232,13 @@ extern "C" int morl_td_mse_priority_f32(const float* q_values, const int32_t* ac
     const long long N = (long long)B * W;
     const int blocks = (int)((N + kTdThreads - 1) / kTdThreads);
     float* partials = static_cast<float*>(workspace);
-    MORL_DISPATCH_D(D, (td_mse_kernel<kD><<<blocks, kTdThreads, 0, st>>>(q_values, action, target_q, wset, homotopy_lambda, B, W, A,
-                                                                         row_order, grad_q, q_taken, prio_out, partials)));
+    MORL_DISPATCH_D(D, (td_mse_kernel<kD><<<blocks, kTdThreads, 0, st>>>(q_values, action, target_q, wset, homotopy_lambda,
+                                                                         homotopy_lambda_dev, B, W, A, row_order, grad_q, q_taken, prio_out,
+                                                                         partials)));
     int rc = check_launch("morl_td_mse_priority_f32");
     if (rc) return rc;
-    td_mse_finalize_kernel<<<1, kTdThreads, 0, st>>>(partials, blocks, homotopy_lambda, 1.0 / ((double)N * D), 1.0 / (double)N, loss_out);
+    td_mse_finalize_kernel<<<1, kTdThreads, 0, st>>>(partials, blocks, homotopy_lambda, homotopy_lambda_dev, 1.0 / ((double)N * D),
+                                                     1.0 / (double)N, loss_out);
     return check_launch("morl_td_mse_priority_f32(finalize)");
 }
 

@@ -11,8 +11,13 @@ What changes under the API:
     gather -> MSE -> homotopy loss -> d loss/d q -> PER priorities (envelope.py:301-313, 329-331) is ONE kernel
     (morl_td_mse_priority_f32); the minibatch gather reads a replay store resident in HBM (morl_replay_gather);
     the target sync is one multi-tensor launch (morl_polyak_f32);
-  * the whole gradient update is captured in a CUDA graph and replayed (no host sync inside).
-Dense layers run through cuBLAS FP32 (TF32 disabled) via torch autograd.  Everything requires a CUDA device.
+  * the dense layers (forward on the three passes, hand-written backward) run on the tcgen05 tensor cores with fp32-accurate split
+    operands (tc_mlp.py, csrc/gemm_bf16x3.cu); the update does not go through autograd: the loss kernel emits d loss / d Q, the
+    backward GEMMs write straight into persistent ``.grad`` buffers, clip + Adam is one fused multi-tensor step;
+  * the whole gradient update is captured in a CUDA graph and replayed (no host sync inside, no library kernel in the graph); the
+    homotopy lambda is read from device memory, so the graph stays valid while the schedule decays it.
+``use_tensor_cores=False`` is an explicit validation path (torch autograd + cuBLAS FP32 dense layers around the same fused operators);
+network shapes the tensor-core path does not cover raise instead of silently taking it.  Everything requires a CUDA device.
 """
 
 from __future__ import annotations
@@ -78,16 +83,17 @@ class _FusedTDLoss(th.autograd.Function):
     """critic loss of envelope.py:301-313 as one kernel; backward hands the precomputed d loss / d q_values upstream."""
 
     @staticmethod
-    def forward(ctx, q_values, action, target_q, wset, lam, B, W, workspace, prio_out):
-        loss, grad, _ = ops.td_mse_priority(q_values.detach(), action, target_q, wset, lam, B, W, ops.ROWS_BMAJOR, want_grad=True,
-                                            want_prio=prio_out is not None, workspace=workspace, prio_out=prio_out)
+    def forward(ctx, q_values, action, target_q, wset, lam_dev, B, W, workspace, prio_out, loss_out):
+        loss, grad, _ = ops.td_mse_priority(q_values.detach(), action, target_q, wset, 0.0, B, W, ops.ROWS_BMAJOR, want_grad=True,
+                                            want_prio=prio_out is not None, workspace=workspace, prio_out=prio_out, loss_out=loss_out,
+                                            lambda_dev=lam_dev)
         ctx.save_for_backward(grad)
-        return loss.squeeze(0)
+        return loss.squeeze(0).clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         (grad,) = ctx.saved_tensors
-        return grad * grad_out, None, None, None, None, None, None, None, None
+        return grad * grad_out, None, None, None, None, None, None, None, None, None
 
 
 class Envelope(MOPolicy, MOAgent):
@@ -167,9 +173,17 @@ class Envelope(MOPolicy, MOAgent):
                                      device=self.device if replay_on_device else None)
         self.dot_mode = ops.DOT_UNFUSED
         self.use_cuda_graph = use_cuda_graph
-        # dense layers of the two no-grad target passes on the tcgen05 tensor cores (bf16x3 split, fp32-accurate)
-        self.use_tensor_cores = use_tensor_cores and self.q_net.feature_extractor is None and TCPairMlp.supported(self.q_net.net)
+        # dense layers of all three passes on the tcgen05 tensor cores (split operands, fp32-accurate).  No silent library fallback: a
+        # network the tensor-core path does not cover is an error unless the caller explicitly opts into the validation path.
+        if use_tensor_cores and (self.q_net.feature_extractor is not None or not TCPairMlp.trainable_supported(self.q_net.net, num_sample_w)):
+            raise ops._lib.MorlB200Error(
+                "morl_baselines_b200.Envelope: the tensor-core update path needs a flat observation, equal hidden widths that are multiples "
+                f"of 64 and <= 256, and num_sample_w <= 64 (got obs {self.observation_shape}, net_arch {net_arch}, num_sample_w {num_sample_w}); "
+                "pass use_tensor_cores=False to run the (slow) library-GEMM validation path explicitly")
+        self.use_tensor_cores = bool(use_tensor_cores)
         self._tc_on = self._tc_tg = self._tc_train = None
+        self._dq = self._grad_bufs = None
+        self._last_inds = None
         self._graphs = {}
         self._static = None
         self._last_loss = None
@@ -226,6 +240,7 @@ class Envelope(MOPolicy, MOAgent):
             self.replay_buffer = params["replay_buffer"]
             if hasattr(self.replay_buffer, "to"):
                 self.replay_buffer.to(self.device)
+            self._graphs = {}  # a captured step gathers from the PREVIOUS buffer's device stores: re-capture against the new mirror
 
     def _load_optimizer_inplace(self, sd):
         cur = self.q_optim.state_dict()
@@ -249,7 +264,7 @@ class Envelope(MOPolicy, MOAgent):
     # ------------------------------------------------------------------------------------------ the update
     def _ensure_static(self):
         """Static tensors of the update.  All per-step host inputs live in ONE pinned buffer mirrored by one device buffer:
-            [ replay indices int64 B | weight vectors W x D | obs | next_obs | rewards | dones | actions int32 ]
+            [ replay indices int64 B | homotopy lambda | weight vectors W x D | obs | next_obs | rewards | dones | actions int32 ]
         so a step issues a single host->device copy: indices + weights when the replay store is mirrored in HBM, weights +
         minibatch when it is host-resident (the reference makes six synchronous pageable copies, buffer.py:93-94)."""
         if self._static is not None:
@@ -257,7 +272,7 @@ class Envelope(MOPolicy, MOAgent):
         dev, B, W, D = self.device, self.batch_size, self.num_sample_w, self.reward_dim
         obs_n = int(np.prod(self.observation_shape))
         seg = lambda n: (n + 3) // 4 * 4  # noqa: E731  (16-byte aligned segments)
-        sizes = [("idx", 2 * B), ("wset", W * D), ("obs", B * obs_n), ("nobs", B * obs_n), ("rew", B * D), ("done", B), ("act", B)]
+        sizes = [("idx", 2 * B), ("lam", 4), ("wset", W * D), ("obs", B * obs_n), ("nobs", B * obs_n), ("rew", B * D), ("done", B), ("act", B)]
         off, o = {}, 0
         for k, n in sizes:
             off[k] = (o, n)
@@ -272,6 +287,7 @@ class Envelope(MOPolicy, MOAgent):
         host = {k: cut(pnp, k).reshape(shp[k]) for k in shp if k != "act"}
         host["act"] = cut(pnp, "act").view(np.int32).reshape(B, 1)
         host["idx"] = cut(pnp, "idx").view(np.int64)
+        host["lam"] = cut(pnp, "lam")
         # the captured step reads a PRIVATE copy (`work`, refreshed by the first node of the graph), so the next step's host->device
         # copy may overwrite `pdev` while the backward half of this step is still running
         work = th.zeros(total, dtype=th.float32, device=dev)
@@ -281,13 +297,14 @@ class Envelope(MOPolicy, MOAgent):
         s = {
             "idx": cut(work, "idx").view(th.int64),
             "wset": cut(work, "wset").view(W, D),
+            "lam": cut(work, "lam")[:1],  # device-resident homotopy lambda, refreshed with the per-step pack
             "work": work,
             "result": th.zeros(B + 1, dtype=th.float32, device=dev),  # [priorities (B) | loss]: one device->host copy per step
             "ws": ops.td_workspace(B * W, dev),
             "pack_pin": pin, "pack_dev": pdev, "host": host, "stage": stage,
             # (device slice, pinned slice) of the one copy a step makes
             "copy_device": (pdev[:head_end], pin[:head_end]),
-            "copy_host": (pdev[off["wset"][0] :], pin[off["wset"][0] :]),
+            "copy_host": (pdev[off["lam"][0] :], pin[off["lam"][0] :]),
             "result_pin": th.zeros(B + 1, dtype=th.float32).pin_memory(),
             "h2d_done": th.cuda.Event(),  # guards the pinned staging buffer against being overwritten while a copy is pending
             # recorded INSIDE the captured step right after the fused TD-loss kernel (external event node): the host waits for the
@@ -300,7 +317,10 @@ class Envelope(MOPolicy, MOAgent):
         s["in"] = {"idx": cut(pdev, "idx").view(th.int64), "wset": cut(pdev, "wset").view(W, D)}
         s["in"]["wset"].fill_(1.0 / D)
         s["wset"].fill_(1.0 / D)
-        s["prio"], s["loss"] = s["result"][:B], s["result"][B]
+        for buf in (pdev, work):
+            cut(buf, "lam").fill_(float(self.homotopy_lambda))
+        host["lam"][:] = np.float32(self.homotopy_lambda)
+        s["prio"], s["loss"], s["loss1"] = s["result"][:B], s["result"][B], s["result"][B:]
         s["prio_np"] = s["result_pin"].numpy()[:B]
         s["loss_pin"] = s["result_pin"][B]
         self._static = s
@@ -331,19 +351,35 @@ class Envelope(MOPolicy, MOAgent):
                 target_q, _ = ops.greedy_td(q_on.view(B * W, A, D), q_tg.view(B * W, A, D), wset, rew, done1, self.gamma, self.dot_mode,
                                             ops.MAP_TILE, ops.MAP_BLOCK)
         if self._tc_train is not None and B == self.batch_size and W == self.num_sample_w:
-            # training pass on the tensor cores too: hand-written backward (tc_mlp.TCPairMlpFn); weight planes were refreshed above
-            params = [p for l in self._tc_train.lin for p in (l.weight, l.bias)]
-            q_values = TCPairMlpFn.apply(self._tc_train, obs, wset, *params).view(B * W, A, D)
+            # training pass on the tensor cores, without autograd: forward, fused loss (emits d loss / d Q, the loss and the priorities),
+            # hand-written backward straight into the persistent .grad buffers; weight planes were refreshed above
+            with th.no_grad():
+                q_values = self._tc_train.forward_pairs(obs, wset).view(B * W, A, D)
+                if self._dq is None:
+                    self._dq = th.empty_like(q_values)
+                    self._grad_bufs = []
+                    for l in self._tc_train.lin:
+                        for p in (l.weight, l.bias):
+                            p.grad = th.zeros_like(p)
+                            self._grad_bufs.append(p.grad)
+                ops.td_mse_priority(q_values, act.reshape(-1), target_q, wset, 0.0, B, W, ops.ROWS_BMAJOR, want_grad=True, want_prio=self.per,
+                                    workspace=s["ws"], loss_out=s["loss1"], grad_out=self._dq, prio_out=s["prio"] if self.per else None,
+                                    lambda_dev=s["lam"])
+                # loss and priorities are final here (the loss kernel wrote them): ship them to the host before the backward half starts
+                s["result_pin"].copy_(s["result"], non_blocking=True)
+                s["prio_ready"].record()
+                for l, (gw, gb) in zip(self._tc_train.lin, zip(self._grad_bufs[0::2], self._grad_bufs[1::2])):
+                    if l.weight.grad is not gw or l.bias.grad is not gb:  # (someone called zero_grad(set_to_none=True) in between)
+                        l.weight.grad, l.bias.grad = gw, gb
+                self._tc_train.backward(obs, wset, self._dq.view(B * W, A * D), grads_out=self._grad_bufs)
         else:
+            # explicit validation path (use_tensor_cores=False): torch autograd + library GEMMs around the same fused operators
             q_values = self.q_net.forward_pairs(obs, wset).view(B * W, A, D)
-        loss = _FusedTDLoss.apply(q_values, act.reshape(-1), target_q, wset, float(self.homotopy_lambda), B, W, s["ws"],
-                                  s["prio"] if self.per else None)
-        # loss and priorities are final here (the loss kernel wrote them): ship them to the host before the backward half starts
-        s["loss"].copy_(loss.detach())
-        s["result_pin"].copy_(s["result"], non_blocking=True)
-        s["prio_ready"].record()
-        self.q_optim.zero_grad(set_to_none=True)
-        loss.backward()
+            loss = _FusedTDLoss.apply(q_values, act.reshape(-1), target_q, wset, s["lam"], B, W, s["ws"], s["prio"] if self.per else None, s["loss1"])
+            s["result_pin"].copy_(s["result"], non_blocking=True)
+            s["prio_ready"].record()
+            self.q_optim.zero_grad(set_to_none=True)
+            loss.backward()
         self.q_optim.step_fused(self.max_grad_norm)  # clip_grad_norm_ + Adam.step (envelope.py:324-326) in two launches
 
     def _step(self, mode: str):
@@ -399,9 +435,6 @@ class Envelope(MOPolicy, MOAgent):
         self._graphs[mode] = g
         return g
 
-    def _lambda_is_static(self):
-        return self.homotopy_decay_steps is None
-
     def __sample_indices(self):
         if self.per:
             return self.replay_buffer.tree.sample(self.batch_size)
@@ -425,6 +458,7 @@ class Envelope(MOPolicy, MOAgent):
                 self._stage_host_batch(b_inds)
             w_np = random_weights(dim=self.reward_dim, n=self.num_sample_w, dist="gaussian", rng=self.np_random)
             host["wset"][:] = np.asarray(w_np).reshape(self.num_sample_w, -1)  # float64 -> float32, as th.tensor(w).float() (envelope.py:278)
+            host["lam"][0] = np.float32(self.homotopy_lambda)  # read by the loss kernel from device memory: the graph survives the schedule
             mode = "device" if has_mirror else "host"
             dst, src = s["copy_" + mode]
             # the copy runs on its own stream: the previous step's graph has already consumed `pack_dev` (its first node; the host
@@ -440,14 +474,16 @@ class Envelope(MOPolicy, MOAgent):
                 dst.copy_(src, non_blocking=True)
                 s["h2d_done"].record()
 
-            if self.use_cuda_graph and self._lambda_is_static():
+            if self.use_cuda_graph:
                 g = self._graphs.get(mode) or self._capture(mode)
                 if has_mirror:
                     rb.flush()
                 g.replay()
             else:
                 self._step(mode)
-            critic_losses.append(s["loss"])
+            # (the static loss scalar is overwritten by the next gradient update: keep a copy when several are averaged)
+            critic_losses.append(s["loss"].clone() if self.gradient_updates > 1 else s["loss"])
+            self._last_inds = b_inds
 
             if self.per:
                 s["prio_ready"].synchronize()  # the priorities of THIS step have landed in pinned memory; backward + Adam still run

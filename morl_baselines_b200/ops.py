@@ -158,8 +158,9 @@ def td_workspace(n_rows: int, device) -> th.Tensor:
 
 def td_mse_priority(q_values, action, target_q, wset, homotopy_lambda: float, B: int, W: int, row_order: int = ROWS_REFERENCE,
                     want_grad: bool = True, want_prio: bool = True, workspace: Optional[th.Tensor] = None, loss_out=None, grad_out=None,
-                    prio_out=None, q_taken_out=None):
-    """Fused Envelope TD loss + d loss / d q_values + priorities (reference envelope.py:301-313, 329-331)."""
+                    prio_out=None, q_taken_out=None, lambda_dev=None):
+    """Fused Envelope TD loss + d loss / d q_values + priorities (reference envelope.py:301-313, 329-331).  ``lambda_dev`` (device f32 [1])
+    overrides ``homotopy_lambda`` and is read by the kernels at run time (graph-replay safe)."""
     q_values = _dev(q_values, "q_values")
     N, A, D = q_values.shape
     if N != B * W:
@@ -171,7 +172,7 @@ def td_mse_priority(q_values, action, target_q, wset, homotopy_lambda: float, B:
     grad = (th.empty_like(q_values) if grad_out is None else grad_out) if want_grad else None
     prio = (th.empty(B, device=dev, dtype=th.float32) if prio_out is None else prio_out) if want_prio else None
     ws = td_workspace(N, dev) if workspace is None else workspace
-    rc = _lib.load().morl_td_mse_priority_f32(_ptr(q_values), _ptr(action), _ptr(target_q), _ptr(wset), float(homotopy_lambda), B, W, A, D,
+    rc = _lib.load().morl_td_mse_priority_f32(_ptr(q_values), _ptr(action), _ptr(target_q), _ptr(wset), float(homotopy_lambda), _ptr(lambda_dev), B, W, A, D,
                                               row_order, _ptr(loss), _ptr(grad), _ptr(q_taken_out), _ptr(prio), _ptr(ws), _stream())
     _lib.check(rc, "morl_td_mse_priority_f32")
     _count(2)
@@ -373,6 +374,29 @@ def pair_layer1_uv(feats: th.Tensor, wset: th.Tensor, weight: th.Tensor, bias: t
     return u, v
 
 
+def pair_layer1_grad_workspace(F: int, D: int, H: int, device) -> th.Tensor:
+    nbytes = _lib.load().morl_pair_layer1_grad_workspace_bytes(int(F), int(D), int(H))
+    return th.zeros((nbytes + 3) // 4, device=device, dtype=th.float32)  # arrival counters start at zero (self-resetting afterwards)
+
+
+def pair_layer1_grad(dU: th.Tensor, dV: th.Tensor, feats: th.Tensor, wset: th.Tensor, dW1: Optional[th.Tensor] = None, db1: Optional[th.Tensor] = None,
+                     workspace: Optional[th.Tensor] = None):
+    """dW1 [H, F + D] = [dU^T feats | dV^T wset] and db1 [H] = colsum(dV) in one launch (backward of the separable first layer)."""
+    dU, dV, feats, wset = _dev(dU, "dU"), _dev(dV, "dV"), _dev(feats, "feats"), _dev(wset, "wset")
+    B, H = dU.shape
+    W, D = wset.shape
+    F = feats.shape[1]
+    if dV.shape != (W, H) or feats.shape[0] != B:
+        raise _lib.MorlB200Error(f"pair_layer1_grad: dU {tuple(dU.shape)}, dV {tuple(dV.shape)}, feats {tuple(feats.shape)}, wset {tuple(wset.shape)} disagree")
+    dW1 = th.empty((H, F + D), device=dU.device, dtype=th.float32) if dW1 is None else dW1
+    db1 = th.empty(H, device=dU.device, dtype=th.float32) if db1 is None else db1
+    ws = pair_layer1_grad_workspace(F, D, H, dU.device) if workspace is None else workspace
+    rc = _lib.load().morl_pair_layer1_grad_f32(_ptr(dU), _ptr(dV), _ptr(feats), _ptr(wset), B, W, F, D, H, _ptr(dW1), _ptr(db1), _ptr(ws), _stream())
+    _lib.check(rc, "morl_pair_layer1_grad_f32")
+    _count()
+    return dW1, db1
+
+
 def gemm_mn_workspace(M: int, g_cols: int, h_cols: int, device) -> th.Tensor:
     nbytes = _lib.load().morl_gemm_mn_workspace_bytes(int(M), int(g_cols), int(h_cols))
     return th.empty((nbytes + 3) // 4, device=device, dtype=th.float32)
@@ -409,12 +433,13 @@ def colsum_bf16x3(planes: th.Tensor, n_cols: int, out: Optional[th.Tensor] = Non
     return out
 
 
-def pairs_grad_reduce(planes: th.Tensor, B: int, W: int, workspace: Optional[th.Tensor] = None):
+def pairs_grad_reduce(planes: th.Tensor, B: int, W: int, workspace: Optional[th.Tensor] = None, dU: Optional[th.Tensor] = None,
+                      dV: Optional[th.Tensor] = None):
     """dU [B, H] and dV [W, H] from the planes of dL/dh1 [3, B*W, H] (gradient of relu(u[b] + v[j]) w.r.t. u and v)."""
     _, M, H = planes.shape
     dev = planes.device
-    dU = th.empty((B, H), device=dev, dtype=th.float32)
-    dV = th.empty((W, H), device=dev, dtype=th.float32)
+    dU = th.empty((B, H), device=dev, dtype=th.float32) if dU is None else dU
+    dV = th.empty((W, H), device=dev, dtype=th.float32) if dV is None else dV
     ws = th.empty(296 * W * H, device=dev, dtype=th.float32) if workspace is None else workspace
     rc = _lib.load().morl_pairs_grad_reduce_bf16x3(_ptr(planes), planes.stride(0), B, W, H, _ptr(dU), _ptr(dV), _ptr(ws), _stream())
     _lib.check(rc, "morl_pairs_grad_reduce_bf16x3")

@@ -3,7 +3,7 @@
 ``TCPairMlp`` runs the reference's ``mlp`` stack (common/networks.py:10-48: Linear -> ReLU ... -> Linear) for every
 (observation b, weight vector j) pair of a minibatch without ever materialising fp32 activations in HBM:
 
-    layer 1   : u = feats @ W1[:, :F]^T (B rows), v = wset @ W1[:, F:]^T + b1 (W rows)  -- two small library GEMMs --
+    layer 1   : u = feats @ W1[:, :F]^T (B rows), v = wset @ W1[:, F:]^T + b1 (W rows)  -- one launch (morl_pair_layer1_uv_f32) --
                 h1[b*W + j] = relu(u[b] + v[j]) written straight into bf16x3 planes (morl_pairs_relu_split_bf16x3);
     layers 2..: morl_gemm_bf16x3_f32 (TMA -> tcgen05.mma -> TMEM -> epilogue) with the activation re-split fused in the
                 epilogue; the last layer writes fp32 Q-values.
@@ -12,7 +12,9 @@
 ``TCPairMlpFn`` wraps forward + a hand-written backward for the training pass:
     G_L = dL/dQ;  dW_l = G_l^T H_{l-1} (MN-major split-K GEMM);  db_l = colsum(G_l);
     G_{l-1} = (G_l W_l) * [H_{l-1} > 0] (K-major GEMM with the ReLU mask fused in the epilogue);
-    layer 1: dU = sum_j G_1, dV = sum_b G_1, dW1 = [dU^T feats | dV^T wset], db1 = sum_j dV.
+    layer 1: dU = sum_j G_1, dV = sum_b G_1 (morl_pairs_grad_reduce_bf16x3), dW1 = [dU^T feats | dV^T wset], db1 = sum_j dV
+             (morl_pair_layer1_grad_f32).
+No library (ATen / cuBLAS) kernel runs anywhere in forward or backward.
 """
 
 from __future__ import annotations
@@ -29,7 +31,6 @@ import os
 
 _SNAKE = os.environ.get("MORL_TC_SNAKE", "1") == "1"          # alternate the GEMM tile order between chained layers
 _MULTI_SPLIT = os.environ.get("MORL_TC_MULTI_SPLIT", "1") == "1"  # one launch for all weight splits of a step
-_FUSED_L1 = os.environ.get("MORL_TC_FUSED_L1", "1") == "1"        # separable first layer as custom launches instead of library sgemms
 
 
 def _pad32(n: int) -> int:
@@ -88,6 +89,10 @@ class TCPairMlp:
                 self.wtp.append(th.empty((3, _pad32(l.in_features), kdim), device=dev, dtype=th.bfloat16))
             self.ws_mn = ops.gemm_mn_workspace(M, 256, 256, dev)
             self.ws_red = th.empty(296 * max(n_w * hid, 256), device=dev, dtype=th.float32)
+            first = self.lin[0]
+            self.ws_l1 = ops.pair_layer1_grad_workspace(feat_dim, first.in_features - feat_dim, first.out_features, dev)
+            self.dU = th.empty((n_obs, first.out_features), device=dev, dtype=th.float32)
+            self.dV = th.empty((n_w, first.out_features), device=dev, dtype=th.float32)
 
     def refresh_weights(self):
         """Re-split the (fp32) weights of layers 2.. into bf16x3 planes; call after every optimiser step / target sync."""
@@ -122,11 +127,9 @@ class TCPairMlp:
     def forward_pairs(self, feats: th.Tensor, wset: th.Tensor) -> th.Tensor:
         """feats [B, F], wset [W, D] -> Q [B*W, out] (fp32, row b*W + j).  Uses the planes of the last refresh_weights()."""
         first = self.lin[0]
-        if _FUSED_L1 and feats.shape[1] == self.feat_dim and first.in_features == self.feat_dim + wset.shape[1]:
-            u, v = ops.pair_layer1_uv(feats, wset, first.weight.detach(), first.bias.detach())  # one launch (csrc/pair_layer1.cu)
-        else:
-            u = feats @ first.weight[:, : self.feat_dim].t()
-            v = th.addmm(first.bias, wset, first.weight[:, self.feat_dim :].t())
+        if feats.shape[1] != self.feat_dim or first.in_features != self.feat_dim + wset.shape[1]:
+            raise ops._lib.MorlB200Error(f"TCPairMlp: feats {tuple(feats.shape)} / wset {tuple(wset.shape)} do not match the first layer ({first.in_features} inputs)")
+        u, v = ops.pair_layer1_uv(feats, wset, first.weight.detach(), first.bias.detach())  # one launch (csrc/pair_layer1.cu)
         a = ops.pairs_relu_split(u, v, out=self.h[0])
         n = len(self.lin)
         for k in range(1, n - 1):
@@ -143,10 +146,11 @@ class TCPairMlp:
         ops.split_bf16x3_multi(self._transposed_jobs())
 
     @th.no_grad()
-    def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor):
-        """Gradients of all Linear parameters given dL/dQ [B*W, out]; uses the activations of the last forward_pairs()."""
+    def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor, grads_out: Optional[List[th.Tensor]] = None):
+        """Gradients of all Linear parameters given dL/dQ [B*W, out]; uses the activations of the last forward_pairs().
+        ``grads_out`` (weight, bias per Linear, in order) receives them in place -- the persistent ``.grad`` buffers of the update."""
         n = len(self.lin)
-        grads = [None] * (2 * n)
+        grads = [None] * (2 * n) if grads_out is None else list(grads_out)
         if getattr(self, "_wt_fresh", False):
             self._wt_fresh = False  # refreshed together with the forward planes of this step (refresh_many)
         else:
@@ -155,14 +159,15 @@ class TCPairMlp:
         for k in range(n - 1, 0, -1):
             l = self.lin[k]
             # dW_k = G_k^T H_{k-1} and db_k = colsum(G_k) in one pass over the G planes
-            grads[2 * k + 1] = th.empty(l.out_features, device=dq.device, dtype=th.float32)
-            grads[2 * k] = ops.gemm_bf16x3_mn(G, l.out_features, self.h[k - 1], l.in_features, workspace=self.ws_mn, colsum=grads[2 * k + 1])
+            if grads[2 * k + 1] is None:
+                grads[2 * k + 1] = th.empty(l.out_features, device=dq.device, dtype=th.float32)
+            grads[2 * k] = ops.gemm_bf16x3_mn(G, l.out_features, self.h[k - 1], l.in_features, out=grads[2 * k], workspace=self.ws_mn,
+                                              colsum=grads[2 * k + 1])
             # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1})
             _, G = ops.gemm_bf16x3(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
                                    c_planes=self.g[k & 1], reverse_tiles=_SNAKE and bool(k & 1))
-        dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red)
-        grads[0] = th.cat([dU.t() @ feats, dV.t() @ wset], dim=1)
-        grads[1] = dV.sum(0)
+        dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV)
+        grads[0], grads[1] = ops.pair_layer1_grad(dU, dV, feats, wset, dW1=grads[0], db1=grads[1], workspace=self.ws_l1)
         return grads
 
 

@@ -87,13 +87,4 @@ class EnvelopeUpdatePort:
         return float(loss.item()), prio.numpy()
 
 
-def synthetic_store(n, obs_dim=32, n_actions=8, rew_dim=3, seed=0):
-    """The synthetic replay contents of BASELINE.md section 3 / SURVEY.md 8(d)."""
-    rng = np.random.default_rng(seed)
-    return dict(
-        obs=rng.standard_normal((n, obs_dim)).astype(np.float32),
-        next_obs=rng.standard_normal((n, obs_dim)).astype(np.float32),
-        actions=rng.integers(0, n_actions, size=(n, 1)).astype(np.uint8),
-        rewards=rng.standard_normal((n, rew_dim)).astype(np.float32),
-        dones=(rng.random((n, 1)) < 0.02).astype(np.float32),
-    )
+from morl_baselines_b200.testing import synthetic_store  # noqa: E402,F401  (kept importable from here for the tests)

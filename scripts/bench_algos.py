@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch as th
 
-from oracle.ref_harness import FakeEnv  # spaces-only stand-in for a mo-gymnasium env
+from morl_baselines_b200.testing import FakeEnv  # spaces-only stand-in for a mo-gymnasium env
 
 dev = th.device("cuda:0")
 out = {}

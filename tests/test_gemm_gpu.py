@@ -138,6 +138,25 @@ def test_pair_layer1_kernels(cuda, B, W, F, D, H):
     assert float((v.double() - rv).abs().max()) <= 1e-6 * float((wset.abs().double() @ W1[:, F:].abs().double().t() + b1.abs().double()).max())
 
 
+@pytest.mark.parametrize("B,W,F,D,H", [(1024, 64, 32, 3, 256), (256, 32, 7, 3, 256), (37, 5, 11, 2, 64), (3, 70, 7, 4, 300), (8, 8, 59, 3, 32)])
+def test_pair_layer1_grad(cuda, B, W, F, D, H):
+    """dW1 = [dU^T feats | dV^T wset], db1 = colsum(dV) in one launch (split reduction, fixed summation order), against float64;
+    run twice on the same workspace: the arrival counters must reset themselves and the result must be bit-identical."""
+    from morl_baselines_b200 import ops
+
+    g_ = th.Generator(device=cuda).manual_seed(B + 3 * W + F)
+    feats, wset = th.randn(B, F, device=cuda, generator=g_), th.rand(W, D, device=cuda, generator=g_)
+    dU, dV = th.randn(B, H, device=cuda, generator=g_), th.randn(W, H, device=cuda, generator=g_)
+    ws = ops.pair_layer1_grad_workspace(F, D, H, cuda)
+    dW1, db1 = ops.pair_layer1_grad(dU, dV, feats, wset, workspace=ws)
+    ref_w = th.cat([dU.double().t() @ feats.double(), dV.double().t() @ wset.double()], dim=1)
+    mag_w = th.cat([dU.abs().double().t() @ feats.abs().double(), dV.abs().double().t() @ wset.abs().double()], dim=1)
+    assert float((dW1.double() - ref_w).abs().max()) <= 2e-6 * float(mag_w.max())
+    assert float((db1.double() - dV.double().sum(0)).abs().max()) <= 2e-6 * float(dV.abs().double().sum(0).max())
+    dW1b, db1b = ops.pair_layer1_grad(dU, dV, feats, wset, workspace=ws)
+    assert th.equal(dW1, dW1b) and th.equal(db1, db1b)
+
+
 def test_split_vectorised_path_matches_scalar_path(cuda):
     """ldp % 8 == 0 takes the 8-columns-per-thread kernel; an unaligned source (ld_src % 4 != 0) and ragged columns must give the same
     planes as the transposed-input scalar kernel."""

@@ -455,3 +455,28 @@ def test_fused_clip_adam_matches_torch(cuda, max_norm):
         np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().numpy(), rtol=2e-6, atol=2e-6)
     sd = o_mine.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 3.0
+
+
+def test_fused_clip_adam_eager_steps_do_not_grow(cuda):
+    """with ``zero_grad(set_to_none=True)`` callers every eager step presents NEW gradient storage; the optimiser
+    must refresh ONE pointer table in place -- no per-step cache entry, no retained gradients, flat device memory over 100 steps."""
+    from morl_baselines_b200.common.fused_adam import FusedClipAdam
+
+    th.manual_seed(0)
+    ps = [th.nn.Parameter(th.randn(256, 256, device=cuda)), th.nn.Parameter(th.randn(256, device=cuda))]
+    opt = FusedClipAdam(ps, lr=1e-3)
+    held = []
+    mem = []
+    for step in range(120):
+        for p in ps:
+            p.grad = th.randn_like(p)  # fresh storage every step
+        if step < 4:
+            held.extend(p.grad for p in ps)  # (keeps early grads alive so later ones really land at new addresses)
+        opt.step_fused(1.0)
+        opt.zero_grad(set_to_none=True)
+        if step >= 20:
+            th.cuda.synchronize()
+            mem.append(th.cuda.memory_allocated())
+    assert len(opt._cache) == 0
+    assert max(mem) == min(mem), (min(mem), max(mem))
+    assert float(opt.state[ps[0]]["step"]) == 120.0
