@@ -216,67 +216,78 @@ MORL_API int morl_polyak_f32(const float* const* params, float* const* targets, 
 /* ------------------------------------------------------------------------------------------------
  * FP32-accurate dense layers on the tcgen05 tensor cores.  Replace the fp32 GEMMs behind the reference's nn.Linear layers
  * (common/networks.py:10-48; called from envelope.py:59-77 / :300, :420, :429 on the 65,536-row effective batch).
- * Every fp32 operand is carried as three bf16 planes x = x0 + x1 + x2 ("bf16x3", [3][rows][ld] with `plane_stride`
- * elements between planes); a product is six bf16 MMAs with fp32 accumulation in tensor memory (see csrc/gemm_bf16x3.cu).
+ * Every fp32 operand is carried as P 16-bit planes [P][rows][ld] (`plane_stride` elements between planes) whose sum reproduces it;
+ * a product is the sum of the significant plane-by-plane MMAs with fp32 accumulation in tensor memory (csrc/gemm_planes.cu):
+ *   MORL_FMT_F16X2  : P = 2 fp16 planes of  scale * x  (scale: a power of two held in a DEVICE float, NULL = 1), 3 MMAs, exact to
+ *                     2^-22; |scale * x| must stay below 65,504 -- beyond it the planes hold Inf/NaN (propagating to every output)
+ *                     and morl_plane_overflow_count() becomes non-zero.  4 bytes / element.
+ *   MORL_FMT_BF16X3 : P = 3 bf16 planes of x (fp32 exponent range, scale pointers normally NULL), 6 MMAs, exact to 2^-24.  6 bytes / element.
+ * All scale arguments are device pointers so that a captured CUDA graph stays valid when the scales change.
  *
- * morl_split_bf16x3 : fp32 [rows, cols] (row stride ld_src; transposed read if `transpose`) -> planes [3][rows_pad][ldp],
+ * morl_amax_scale_f32 : *scale_out = 2^(target_exp - e) with max|src| < 2^e, i.e. scale * max|src| in [2^(target_exp-1), 2^target_exp)
+ *                     (1 if src is all zero).  workspace: 8 bytes, ZERO before the first call (left zero again).
+ * morl_split_planes : fp32 [rows, cols] (row stride ld_src; transposed read if `transpose`) -> planes [P][rows_pad][ldp] of scale * x,
  *                     zero padded.
- * morl_gemm_bf16x3_f32 : C = act(A . B^T + bias),  A planes [3][M][K] (K-major), B planes [3][N_pad][K] (K-major weights);
- *                     K % 32 == 0, N_pad % 32 == 0, N_pad <= 256.  Outputs: c_f32 [M, ldc] and/or c_planes [3][M][ldp]
- *                     (the operand format of the next layer).  relu != 0 applies max(x, 0); relu_mask_plane0 (plane 0 of a
- *                     forward activation, [M][ld_mask] bf16) zeroes the outputs where that activation was <= 0 (ReLU backward).
+ * morl_split_planes_multi : up to MORL_SPLIT_MAX_JOBS independent splits (all weight matrices of a network, plain and transposed) in
+ *                     one launch; a job with auto_scale != 0 derives its scale from the largest magnitude of its own matrix
+ *                     (scale * amax in [2^(target_exp-1), 2^target_exp)) and stores it in *scale.
+ * morl_gemm_planes_f32 : C = act(A . B^T + bias),  A planes [P][M][K] (K-major), B planes [P][N_pad][K] (K-major weights);
+ *                     K % 64 == 0 (f16x2) / K % 32 == 0 (bf16x3), N_pad % 32 == 0, N_pad <= 256.  The accumulator is multiplied by
+ *                     1 / (a_scale * b_scale) before the bias.  Outputs: c_f32 [M, ldc] and/or c_planes [P][M][ldp] holding
+ *                     c_scale * C (the operand format of the next layer).  relu != 0 applies max(x, 0); relu_mask_plane0 (plane 0 of
+ *                     a forward activation, [M][ld_mask] 16-bit) zeroes the outputs where that activation was <= 0 (ReLU backward).
  *                     reverse_tiles != 0 walks the 128-row tiles from the last to the first: alternate it between the layers of
  *                     a chain so that a layer starts on the rows its producer wrote last (still in the 126 MB L2).
- * morl_split_bf16x3_multi : up to MORL_SPLIT_MAX_JOBS independent splits (all weight matrices of a network, plain and
- *                     transposed) in one launch.
  */
+#define MORL_FMT_BF16X3 0
+#define MORL_FMT_F16X2 1
 #define MORL_SPLIT_MAX_JOBS 16
 typedef struct MorlSplitJob {
     const float* src;       /* fp32 [rows, cols], row stride ld_src */
-    void* dst_planes;       /* bf16 [3][rows_pad][ldp] */
+    void* dst_planes;       /* 16-bit [P][rows_pad][ldp] */
     long long plane_stride; /* elements between planes */
+    float* scale;           /* device float: read (auto_scale == 0; NULL = 1) or written (auto_scale != 0; NULL = not published) */
     int rows, cols, ld_src, transpose, rows_pad, ldp;
+    int auto_scale, target_exp;
 } MorlSplitJob;
-MORL_API int morl_split_bf16x3_multi(const MorlSplitJob* jobs, int n_jobs, void* stream);
-MORL_API int morl_split_bf16x3(const float* src, int rows, int cols, int ld_src, int transpose, void* dst_planes, int rows_pad,
-                               int ldp, long long plane_stride, void* stream);
-MORL_API int morl_gemm_bf16x3_f32(const void* a_planes, long long a_plane_stride, const void* b_planes, long long b_plane_stride,
-                                  int M, int N, int N_pad, int K, const float* bias, int relu, const void* relu_mask_plane0,
-                                  int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp, long long c_plane_stride,
-                                  int reverse_tiles, void* stream);
-/* Diagnostics (not part of the reference surface): per-role cycle counters of morl_gemm_bf16x3_f32, summed over CTAs and launches
+MORL_API int morl_plane_overflow_count(int reset); /* >= 0: f16x2 range violations seen since the last reset (synchronises the device) */
+MORL_API int morl_amax_scale_f32(const float* src, long long n, int target_exp, float* scale_out, void* workspace, void* stream);
+MORL_API int morl_split_planes_multi(int fmt, const MorlSplitJob* jobs, int n_jobs, void* stream);
+MORL_API int morl_split_planes(int fmt, const float* src, int rows, int cols, int ld_src, int transpose, void* dst_planes, int rows_pad,
+                               int ldp, long long plane_stride, const float* scale, void* stream);
+MORL_API int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* b_planes,
+                                  long long b_plane_stride, const float* b_scale, int M, int N, int N_pad, int K, const float* bias,
+                                  int relu, const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp,
+                                  long long c_plane_stride, const float* c_scale, int reverse_tiles, void* stream);
+/* Diagnostics (not part of the reference surface): per-role cycle counters of morl_gemm_planes_f32, summed over CTAs and launches
  * since the last reset; collected only when the environment variable MORL_GEMM_STATS=1 is set before the first GEMM call.
  * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,
  * [3] TMA thread waiting for a free stage, [4] epilogue waiting for an accumulator, [5] epilogue busy; [6], [7] reserved. */
 MORL_API int morl_debug_gemm_stats(unsigned long long* out8, int reset);
-/* Diagnostics of the tensor-core envelope kernel (MORL_ENVELOPE_STATS=1 before the first call): cycles summed over CTAs and launches,
- * one thread per role: [0] converter waiting, [1] converter busy, [2] MMA thread waiting, [3] scanner waiting, [4] scanner busy,
- * [5] finisher waiting, [6] finisher busy, [7] kernel start -> last finisher iteration. */
-MORL_API int morl_debug_envelope_stats(unsigned long long* out8, int reset);
-/* h[b*W + j, :] = relu(u[b, :] + v[j, :]) written directly as bf16x3 planes [3][B*W][H] (separable first layer of the
+/* h[b*W + j, :] = relu(u[b, :] + v[j, :]) written directly as planes [P][B*W][H] of scale * h (separable first layer of the
  * weight-conditioned Q-network: W1 [s || w] + b1 = W1_s s + (W1_w w + b1); reference envelope.py:75 builds the concat). */
-MORL_API int morl_pairs_relu_split_bf16x3(const float* u, const float* v, int B, int W, int H, void* dst_planes,
-                                          long long plane_stride, void* stream);
+MORL_API int morl_pairs_relu_split_planes(int fmt, const float* u, const float* v, int B, int W, int H, void* dst_planes,
+                                          long long plane_stride, const float* scale, void* stream);
 
 
 /* Weight-gradient GEMM (reduction over the batch rows), split-K, deterministic:
- *   out[n, k] = sum_m G[m, n] * H[m, k]      G planes [3][M][ldg] (n < g_cols), H planes [3][M][ldh] (k < h_cols), bf16x3;
- *   ldg, ldh multiples of 64, ldh <= 256;  transpose_out != 0 stores out[k, n] instead.  Replaces the dW = dY^T X products that
- *   torch autograd issues for the nn.Linear layers of the reference networks (loss.backward(), envelope.py:316).
+ *   out[n, k] = sum_m G[m, n] * H[m, k]      G planes [P][M][ldg] (n < g_cols, scaled by *g_scale), H planes [P][M][ldh] (k < h_cols,
+ *   scaled by *h_scale);  ldg, ldh multiples of 64, ldh <= 256;  transpose_out != 0 stores out[k, n] instead.  Replaces the
+ *   dW = dY^T X products that torch autograd issues for the nn.Linear layers of the reference networks (loss.backward(), envelope.py:316).
  *   colsum_out (nullable, [g_cols]): out_b[n] = sum_m G[m, n], the bias gradient db = colsum(dY), evaluated in the same pass as
- *   G^T . ones on the tensor cores (replaces a separate 100 MB sweep of the G planes).
+ *   G^T . ones on the tensor cores (replaces a separate sweep of the G planes).
  *   workspace: morl_gemm_mn_workspace_bytes(M, g_cols, h_cols) bytes. */
 MORL_API size_t morl_gemm_mn_workspace_bytes(int M, int a_cols, int b_cols);
-MORL_API int morl_gemm_bf16x3_mn_f32(const void* g_planes, long long g_plane_stride, int ldg, int g_cols, const void* h_planes,
-                                     long long h_plane_stride, int ldh, int h_cols, int M, int transpose_out, float* out,
-                                     int ld_out, float* colsum_out, void* workspace, void* stream);
-/* out[n] = sum_m sum_p planes[p][m][n]  (bias gradients); workspace: 296 * N floats */
-MORL_API int morl_colsum_bf16x3(const void* planes, long long plane_stride, int M, int ld, int N, float* out, void* workspace,
-                                void* stream);
-/* gradients of the separable first layer: dU[b,:] = sum_j G[b*W+j,:], dV[j,:] = sum_b G[b*W+j,:]  (G planes [3][B*W][H], W <= 64);
- * workspace: 296 * W * H floats */
-MORL_API int morl_pairs_grad_reduce_bf16x3(const void* planes, long long plane_stride, int B, int W, int H, float* dU, float* dV,
-                                           void* workspace, void* stream);
+MORL_API int morl_gemm_planes_mn_f32(int fmt, const void* g_planes, long long g_plane_stride, int ldg, int g_cols, const float* g_scale,
+                                     const void* h_planes, long long h_plane_stride, int ldh, int h_cols, const float* h_scale, int M,
+                                     int transpose_out, float* out, int ld_out, float* colsum_out, void* workspace, void* stream);
+/* out[n] = (1 / *scale) sum_m sum_p planes[p][m][n]  (bias gradients); workspace: 296 * N floats */
+MORL_API int morl_colsum_planes(int fmt, const void* planes, long long plane_stride, const float* scale, int M, int ld, int N, float* out,
+                                void* workspace, void* stream);
+/* gradients of the separable first layer: dU[b,:] = sum_j G[b*W+j,:], dV[j,:] = sum_b G[b*W+j,:]  (G planes [P][B*W][H] scaled by
+ * *scale, W <= 64 for the one-pass kernel); workspace: 296 * W * H floats */
+MORL_API int morl_pairs_grad_reduce_planes(int fmt, const void* planes, long long plane_stride, const float* scale, int B, int W, int H,
+                                           float* dU, float* dV, void* workspace, void* stream);
 
 /* Separable first layer of the weight-conditioned Q-network on the pair batch (reference envelope.py:59-77 builds [s || w] rows for
  * nn.Linear):  u[b, :] = W1[:, :F] feats[b],  v[j, :] = W1[:, F:] wset[j] + b1  in ONE launch (replaces two library
@@ -286,7 +297,7 @@ MORL_API int morl_pair_layer1_uv_f32(const float* feats, const float* wset, cons
 
 /* Parameter gradients of the separable first layer (backward of morl_pair_layer1_uv_f32; autograd of nn.Linear at envelope.py:316 on the
  * effective batch, restricted to layer 1):  dW1 [H, F + D] = [dU^T feats | dV^T wset],  db1 [H] = colsum(dV), with dU [B, H] / dV [W, H]
- * from morl_pairs_grad_reduce_bf16x3.  One launch, deterministic split reduction.  `workspace`: morl_pair_layer1_grad_workspace_bytes(F, D,
+ * from morl_pairs_grad_reduce_planes.  One launch, deterministic split reduction.  `workspace`: morl_pair_layer1_grad_workspace_bytes(F, D,
  * H) bytes that must be ZERO before the first call (the kernel leaves its arrival counters zeroed again). */
 MORL_API size_t morl_pair_layer1_grad_workspace_bytes(int F, int D, int H);
 MORL_API int morl_pair_layer1_grad_f32(const float* dU, const float* dV, const float* feats, const float* wset, int B, int W, int F,

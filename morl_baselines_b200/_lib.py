@@ -19,6 +19,7 @@ MAP_TILE, MAP_BLOCK = 0, 1
 ROWS_REFERENCE, ROWS_BMAJOR = 0, 1
 AC_ELEMENTWISE_MIN, AC_SCALAR_MIN, AC_ARGMIN_GATHER = 0, 1, 2
 MAX_D = 8
+FMT_BF16X3, FMT_F16X2 = 0, 1
 
 _vp, _i, _f, _d, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64, C.c_size_t
 
@@ -43,16 +44,18 @@ SIGNATURES = {
     "morl_pareto_mask_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_pareto_mask_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_polyak_f32": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),
-    "morl_split_bf16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, C.c_longlong, _vp]),
-    "morl_gemm_bf16x3_f32": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_longlong, _i, _vp]),
-    "morl_split_bf16x3_multi": (_i, [_vp, _i, _vp]),
+    "morl_plane_overflow_count": (_i, [_i]),
+    "morl_amax_scale_f32": (_i, [_vp, C.c_longlong, _i, _vp, _vp, _vp]),
+    "morl_split_planes_multi": (_i, [_i, _vp, _i, _vp]),
+    "morl_split_planes": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _i, _i, C.c_longlong, _vp, _vp]),
+    "morl_gemm_planes_f32": (_i, [_i, _vp, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_longlong,
+                                  _vp, _i, _vp]),
     "morl_debug_gemm_stats": (_i, [_vp, _i]),
-    "morl_debug_envelope_stats": (_i, [_vp, _i]),
-    "morl_pairs_relu_split_bf16x3": (_i, [_vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
+    "morl_pairs_relu_split_planes": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp, _vp]),
     "morl_gemm_mn_workspace_bytes": (_sz, [_i, _i, _i]),
-    "morl_gemm_bf16x3_mn_f32": (_i, [_vp, C.c_longlong, _i, _i, _vp, C.c_longlong, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
-    "morl_colsum_bf16x3": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
-    "morl_pairs_grad_reduce_bf16x3": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "morl_gemm_planes_mn_f32": (_i, [_i, _vp, C.c_longlong, _i, _i, _vp, _vp, C.c_longlong, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "morl_colsum_planes": (_i, [_i, _vp, C.c_longlong, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "morl_pairs_grad_reduce_planes": (_i, [_i, _vp, C.c_longlong, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "morl_pair_layer1_uv_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "morl_pair_layer1_grad_workspace_bytes": (_sz, [_i, _i, _i]),
     "morl_pair_layer1_grad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -66,8 +69,8 @@ SPLIT_MAX_JOBS = 16
 class SplitJob(C.Structure):
     """MorlSplitJob of include/morl_b200.h"""
 
-    _fields_ = [("src", _vp), ("dst_planes", _vp), ("plane_stride", C.c_longlong), ("rows", _i), ("cols", _i), ("ld_src", _i), ("transpose", _i),
-                ("rows_pad", _i), ("ldp", _i)]
+    _fields_ = [("src", _vp), ("dst_planes", _vp), ("plane_stride", C.c_longlong), ("scale", _vp), ("rows", _i), ("cols", _i), ("ld_src", _i),
+                ("transpose", _i), ("rows_pad", _i), ("ldp", _i), ("auto_scale", _i), ("target_exp", _i)]
 
 
 _lib = None

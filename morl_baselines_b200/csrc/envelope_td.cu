@@ -721,23 +721,19 @@ static EnvelopePlan plan_envelope(int B, int W, int A, int D) {
 }
 
 // Path selection, read on every call: MORL_ENVELOPE_PATH = "v1" (generic kernel), "v3" (CUDA-core fast path), "wp" (v5, weight-pair
-// re-blocking of v3; the default whenever the shape fits, then v3, then v1), "tc" (tensor-core filter, envelope_td_tc.cu: opt-in -- bit-identical, but measured SLOWER on B200 because reading the
-// 128 KB score tile back from tensor memory is limited to 64 B/clk per SM).  MORL_ENVELOPE_FORCE_V1 is the older
-// spelling of "v1".
+// re-blocking of v3; the default whenever the shape fits, then v3, then v1).  (A tensor-core scoring path existed in round 1; it was
+// bit-identical but measured SLOWER on B200 -- reading the 128 KB score tile back from tensor memory is limited to 64 B/clk per SM,
+// profiles/r01_s3_envelope_tc_ncu.txt -- and has been removed from the library)  MORL_ENVELOPE_FORCE_V1 is the
+// older spelling of "v1".
 static int envelope_path_override() {
     if (getenv("MORL_ENVELOPE_FORCE_V1") != nullptr) return 1;
     const char* e = getenv("MORL_ENVELOPE_PATH");
     if (!e) return 0;
     if (e[0] == 'v' && e[1] == '1') return 1;
     if (e[0] == 'v' && e[1] == '3') return 3;
-    if (e[0] == 't' && e[1] == 'c') return 4;
     if (e[0] == 'w' && e[1] == 'p') return 5;
     return 0;
 }
-
-int envelope_td_tc_try_launch(const float* q_online, const float* q_target, const float* wset, const float* reward, const float* done,
-                              float gamma, int B, int W, int A, int D, int dot_mode, int row_order, float* target_out, int32_t* pref_out,
-                              int32_t* act_out, cudaStream_t st, int sm_count);
 
 }  // namespace morl
 
@@ -769,12 +765,6 @@ extern "C" int morl_envelope_td_f32(const float* q_online, const float* q_target
         }
     }
     const int path = envelope_path_override();
-    if (path == 4) {
-        if (envelope_td_tc_try_launch(q_online, q_target, wset, reward, done, gamma, B, W, A, D, dot_mode, row_order, target_out, pref_out,
-                                      act_out, st, sm_count_cached))
-            return check_launch("morl_envelope_td_f32(tc)");
-        MORL_REQUIRE(false, MORL_ERR_UNSUPPORTED, "morl_envelope_td_f32: MORL_ENVELOPE_PATH=tc but the shape W=%d A=%d D=%d is outside the tensor-core path", W, A, D);
-    }
     // v5 (weight pairs): the default fast path when the shape fits; "wp" forces it, "v3" / "v1" skip it
     const long long Cw = (long long)W * A;
     const bool wp_ok = W > 32 && (Cw % 16) == 0 && ((Cw * D) % 4) == 0 && (2 * ((Cw * D + 3) & ~3LL) + 3 * 256 + 16) * 4 <= 96 * 1024;

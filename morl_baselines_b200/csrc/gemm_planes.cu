@@ -1,0 +1,1544 @@
+// gemm_planes.cu -- FP32-accurate dense layers on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces the cuBLAS SIMT sgemm calls behind the reference's nn.Linear layers (common/networks.py:10-48, called from
+// multi_policy/envelope/envelope.py:59-77, 300, 420, 429) on the 65,536-row effective batch.  The 1e-5 parity bar rules out
+// plain TF32/BF16/FP16, so every fp32 operand is carried as a small number of 16-bit PLANES whose sum reproduces it, and a product
+// A.B^T is the sum of the significant plane-by-plane tensor-core MMAs, accumulated in fp32 in tensor memory.  Two operand formats:
+//
+//   MORL_FMT_F16X2  (default of the update path)   s x = h0 + h1: two fp16 planes (11 + 11 significand bits) of the operand scaled
+//       by a power of two s (device-resident, per tensor) -- exact to 2^-22 relative; THREE MMAs  A1B0 + A0B1 + A0B0  per product
+//       (the dropped A1B1 term is O(2^-22)), 4 bytes per element.  Each fp16 x fp16 product is exact in fp32.  fp16 has 5 exponent
+//       bits: |s x| must stay below 65,504 (an overflow becomes Inf/NaN downstream AND raises a device flag, morl_plane_overflow_count),
+//       elements below 2^-14 / s lose relative (not absolute) accuracy -- the scales are chosen so that this floor sits >= 2^-26 below
+//       the typical magnitude.
+//   MORL_FMT_BF16X3 (wide-range format)            x = x0 + x1 + x2: three bf16 planes (8 + 8 + 8 bits, fp32 exponent range, no scale),
+//       exact to 2^-24; SIX MMAs  A2B0 + A0B2 + A1B1 + A1B0 + A0B1 + A0B0, 6 bytes per element.
+// Either way the result differs from an fp32 GEMM only at the level of its own accumulation-order noise (tests/test_gemm_gpu.py).
+//
+// K-major kernel anatomy (persistent, one CTA per SM -- or one CTA PAIR per TPC with tcgen05 cta_group::2 --, 320 threads):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor.3d of a [P planes x 128 rows x BK] A box and a [P x BN x BK] B box per stage
+//              (f16x2: BK = 64, 128-byte swizzle, 3 x 64 KB stages; bf16x3: BK = 32, 64-byte swizzle, 3 x 48 KB stages), mbarrier ring;
+//   warp 1   : MMA issuer     -- one elected thread issues NPROD x BK/16 tcgen05.mma.kind::f16 (M=128/256, N=BN, K=16) per stage and
+//              commits the stage back to the producer; accumulators live in TMEM (2 x BN columns, double buffered);
+//   warps 2-9: epilogue       -- tcgen05.ld (32 lanes x 32 columns per warp-instruction), x 2^-(sA+sB), + bias, ReLU / ReLU-mask, then
+//              an fp32 row-major store and/or a re-split into planes (the operand format of the next layer) through a TMA store, so
+//              intermediate activations never exist in fp32 in HBM.
+// Operands: A [P][M][K] (K-major), B [P][N_pad][K] (K-major), K % BK == 0, N_pad % 32 == 0, N_pad <= 256.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace morl {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quadrant)
+
+__device__ unsigned int g_plane_overflow;  // number of kernel launches (approx.) that saw an f16x2 element out of fp16 range
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug becomes a trap (launch error) instead of a hung GPU.
+__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(g_smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(g_smem_u32(dst)),
+        "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// ---- CTA-pair (cta_group::2) flavours: the pair's TMA loads signal the LEADER's (cluster rank 0) mbarrier, the leader's MMA
+// commit is multicast to the same barrier offset in both CTAs, the peer's epilogue releases the accumulator remotely ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t smem_addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_addr));
+    return r;
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            g_smem_u32(dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// same, with an L2 eviction-priority hint (createpolicy): activations are read once (evict_first), weight planes by every tile (evict_last)
+__device__ __forceinline__ void tma_load_3d_pair_hint(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+            g_smem_u32(dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(g_smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- operand formats ------------------------------------------------------------------------------------------------------
+template <int FMT>
+struct PlaneFmt;
+
+template <>
+struct PlaneFmt<MORL_FMT_BF16X3> {
+    static constexpr int P = 3, NPROD = 6;
+    static constexpr int BK = 32;                                  // 16-bit elements per K-major stage row (64-byte swizzle)
+    static constexpr uint32_t kIdescAB = (1u << 7) | (1u << 10);   // instruction descriptor: a_format = b_format = BF16
+    static constexpr uint32_t kOnes2 = 0x3F803F80u;                // two packed 1.0
+    static constexpr int kStages1 = 2, kStages2 = 3, kStagesMn = 3;
+    // small terms first: A2B0, A0B2, A1B1, A1B0, A0B1, A0B0
+    __device__ static constexpr int pa(int t) { return t == 0 ? 2 : (t == 2 || t == 3) ? 1 : 0; }
+    __device__ static constexpr int pb(int t) { return t == 1 ? 2 : (t == 2 || t == 4) ? 1 : 0; }
+    // (a, b) -> P words, word p = plane p of a (low half) and b (high half)
+    __device__ __forceinline__ static void split2(float a, float b, uint32_t (&w)[3], float&) {
+        const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
+        const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
+        const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
+        const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
+        const __nv_bfloat16 a2 = __float2bfloat16_rn(sa), b2 = __float2bfloat16_rn(sb);
+        w[0] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+        w[1] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+        w[2] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+    }
+    __device__ __forceinline__ static void split1(float a, uint16_t (&h)[3], float&) {
+        const __nv_bfloat16 a0 = __float2bfloat16_rn(a);
+        const float ra = a - __bfloat162float(a0);
+        const __nv_bfloat16 a1 = __float2bfloat16_rn(ra);
+        const __nv_bfloat16 a2 = __float2bfloat16_rn(ra - __bfloat162float(a1));
+        h[0] = __bfloat16_as_ushort(a0); h[1] = __bfloat16_as_ushort(a1); h[2] = __bfloat16_as_ushort(a2);
+    }
+    __device__ __forceinline__ static void add8(float (&acc)[8], const uint4 v) {  // += eight packed elements of one plane
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            acc[2 * q] += __uint_as_float(w[q] << 16);
+            acc[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+        }
+    }
+};
+
+template <>
+struct PlaneFmt<MORL_FMT_F16X2> {
+    static constexpr int P = 2, NPROD = 3;
+    static constexpr int BK = 64;                                  // 128-byte swizzle rows
+    static constexpr uint32_t kIdescAB = 0u;                       // a_format = b_format = F16
+    static constexpr uint32_t kOnes2 = 0x3C003C00u;
+    static constexpr int kStages1 = 2, kStages2 = 3, kStagesMn = 4;
+    // small terms first: A1B0, A0B1, A0B0
+    __device__ static constexpr int pa(int t) { return t == 0 ? 1 : 0; }
+    __device__ static constexpr int pb(int t) { return t == 1 ? 1 : 0; }
+    // `amax` tracks max |a| of the (already scaled) values, for the fp16-range check
+    __device__ __forceinline__ static void split2(float a, float b, uint32_t (&w)[2], float& amax) {
+        amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+        const __half2 h0 = __floats2half2_rn(a, b);
+        const float2 f0 = __half22float2(h0);
+        const __half2 h1 = __floats2half2_rn(a - f0.x, b - f0.y);
+        w[0] = *reinterpret_cast<const uint32_t*>(&h0);
+        w[1] = *reinterpret_cast<const uint32_t*>(&h1);
+    }
+    __device__ __forceinline__ static void split1(float a, uint16_t (&h)[2], float& amax) {
+        amax = fmaxf(amax, fabsf(a));
+        const __half h0 = __float2half_rn(a);
+        const __half h1 = __float2half_rn(a - __half2float(h0));
+        h[0] = __half_as_ushort(h0); h[1] = __half_as_ushort(h1);
+    }
+    __device__ __forceinline__ static void add8(float (&acc)[8], const uint4 v) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+            acc[2 * q] += f.x;
+            acc[2 * q + 1] += f.y;
+        }
+    }
+};
+
+// |scaled value| beyond the largest finite fp16: the planes hold Inf / NaN from here on (they propagate to the loss) and the flag says why
+__device__ __forceinline__ void note_overflow(float amax) {
+    if (amax > 65504.f) atomicAdd(&g_plane_overflow, 1u);
+}
+__device__ __forceinline__ float ld_scale(const float* p) { return p ? __ldg(p) : 1.0f; }
+
+#define MORL_DISPATCH_FMT(F_, ...)                                                         \
+    switch (F_) {                                                                          \
+        case MORL_FMT_BF16X3: { constexpr int kFmt = MORL_FMT_BF16X3; __VA_ARGS__; } break; \
+        case MORL_FMT_F16X2: { constexpr int kFmt = MORL_FMT_F16X2; __VA_ARGS__; } break;   \
+        default: break;                                                                    \
+    }
+
+// Shared-memory matrix descriptor, K-major canonical layout (cute::UMMA::SmemDescriptor, version 1) with ROWB-byte rows = the swizzle
+// span (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B); 8-row groups are contiguous: SBO = 8 * ROWB; LBO unused (1).  A K step of 16
+// elements inside the swizzle span is a +32 B advance of the start address.
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
+    static_assert(ROWB == 64 || ROWB == 128, "swizzle span");
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major), 16-byte units
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;            // stride byte offset: 8 rows x ROWB
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)(ROWB == 64 ? 4 : 2) << 61;         // layout type: SWIZZLE_64B = 4, SWIZZLE_128B = 2
+    return d;
+}
+
+struct GemmArgs {
+    int M, N, N_pad, K;          // N_pad = B rows covered by the tensor map box (multiple of 16, <= 256)
+    const float* bias;           // [N] or nullptr
+    float* c_f32;                // [M, ldc] or nullptr
+    int ldc;
+    void* c_planes;              // [P][M][ldp] or nullptr (re-split output: operand of the next layer)
+    int ldp;                     // columns of a plane row (>= N, multiple of 32; columns [N, ldp) are written as zero)
+    long long plane_stride;      // elements between planes
+    const uint16_t* mask;        // plane 0 of the forward activation [M][ld_mask] for the ReLU-backward mask, or nullptr
+    int ld_mask;
+    int relu;
+    const float* a_scale;        // device scalars (powers of two) the A / B planes were scaled by; nullptr = 1
+    const float* b_scale;
+    const float* c_scale;        // scale applied to the output before it is re-split into c_planes; nullptr = 1
+    int l2_hint;                 // L2 eviction hints on the operand loads (MORL_GEMM_L2HINT=1, default off): A evict_first, B evict_last
+    int reverse;                 // walk the row tiles from the last to the first (see morl_gemm_planes_f32: L2 reuse between chained layers)
+    unsigned long long* stats;   // diagnostics (MORL_GEMM_STATS=1), else nullptr: [0] MMA wait-on-TMA cycles, [1] MMA wait-on-epilogue,
+                                 // [2] MMA loop total, [3] producer wait-on-free-stage, [4] epilogue wait-on-accumulator, [5] epilogue busy
+};
+
+__device__ unsigned long long g_gemm_stats[8];
+
+// shared-memory plan of the K-major kernel (host and device agree through these)
+template <int NCTA, int FMT>
+struct KPlan {
+    using F = PlaneFmt<FMT>;
+    static constexpr int kStages = NCTA == 2 ? F::kStages2 : F::kStages1;
+    static constexpr uint32_t kRowB = F::BK * 2;                                  // bytes per staged row = swizzle span
+    static constexpr uint32_t kAStage = F::P * kGemmBM * kRowB;                   // A box bytes
+    static constexpr uint32_t kBStage = F::P * (256 / NCTA) * kRowB;              // B box bytes at N_pad = 256
+    static constexpr uint32_t kStageC = F::P * 2048;                              // per-epilogue-warp TMA-store tile: P x 32 rows x 64 B
+    static constexpr uint32_t kOffB = kStages * kAStage;
+    static constexpr uint32_t kOffC = kOffB + kStages * kBStage;                  // 1024-aligned (all stage sizes are multiples of 1 KB)
+    static constexpr uint32_t kOffBar = kOffC + 8 * kStageC;
+    static constexpr uint32_t kOffBias = kOffBar + 256;
+    static constexpr uint32_t kBytes = kOffBias + 1024 + 1024;                    // + alignment slack of the dynamic segment
+};
+
+// NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2 on one TPC) per 256-row tile, tcgen05 cta_group::2 --
+// each CTA stages its own 128 A rows and HALF of the B (weight) rows, the pair's tensor cores read both halves, so the L2 -> smem
+// traffic of the weight planes is halved.
+// SPLIT = 1 ("split accumulators"): the tensor cores accumulate in fp32 with TRUNCATION (round toward zero) at every MMA, a bias of
+// about -0.5 ulp of the running sum per instruction; with all NPROD x K/16 products in one accumulator that is ~2e-6 (f16x2) to ~4e-6
+// (bf16x3) of systematic shrinkage per layer at K = 256 (measured: scripts/gemm_error_probe.py).  In split mode the LEADING products
+// A0B0 go to accumulator 0 and the correction products (2^-11 / 2^-8 of the magnitude) to accumulator 1, so only K/16 truncations happen
+// at full magnitude; the epilogue adds the two with one correctly rounded fp32 add.  Cost: the two TMEM buffers no longer double-buffer
+// the accumulator, so the epilogue of a tile does not overlap the MMAs of the next one (the TMA ring still runs ahead).
+template <int NCTA, int FMT, int SPLIT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
+                   const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+    using F = PlaneFmt<FMT>;
+    using L = KPlan<NCTA, FMT>;
+    constexpr int P = F::P;
+    constexpr int BK = F::BK;
+    constexpr int kStages = L::kStages;
+    constexpr uint32_t ROWB = L::kRowB;
+    extern __shared__ uint8_t gsmem_raw[];
+    uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
+    const int BN = g.N_pad;
+    constexpr uint32_t a_stage_bytes = L::kAStage;
+    constexpr uint32_t b_stage_stride = L::kBStage;
+    uint8_t* smA = gsmem;
+    uint8_t* smB = gsmem + L::kOffB;
+    uint8_t* stage_c = gsmem + L::kOffC;  // per-epilogue-warp staging tiles for the TMA store of the re-split activations
+    uint64_t* full = reinterpret_cast<uint64_t*>(gsmem + L::kOffBar);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_s = reinterpret_cast<float*>(gsmem + L::kOffBias);  // [256]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+    const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;  // a unit = one CTA (NCTA = 1) or one CTA pair
+    const int n_tiles = (g.M + kGemmBM * NCTA - 1) / (kGemmBM * NCTA);
+    const int n_kblk = g.K / BK;
+    // Work units.  A static round-robin over `n_units` workers leaves a tail of L = n_tiles % n_units tiles that costs a whole
+    // extra round (65,536 rows: 256 pair tiles on 74 pairs = 3.46 -> 4 rounds).  When 2L <= n_units the tail tiles are split into
+    // two half-width (N/2) units each, so the tail costs half a round.  All three roles enumerate the same sequence.
+    const int full_units = (n_tiles / n_units) * n_units;
+    const int tail = n_tiles - full_units;
+    const bool split_tail = NCTA == 2 && tail > 0 && 2 * tail <= n_units && (BN % 64) == 0;
+    const int n_work = split_tail ? full_units + 2 * tail : n_tiles;
+    auto unit_of = [&](int u, int& tile, int& n_begin, int& n_cnt) {
+        if (!split_tail || u < full_units) {
+            tile = u; n_begin = 0; n_cnt = BN;
+        } else {
+            const int r = u - full_units;
+            tile = full_units + (r >> 1); n_cnt = BN >> 1; n_begin = (r & 1) * n_cnt;
+        }
+        if (g.reverse) tile = n_tiles - 1 - tile;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            g_mbar_init(&full[s], 1);
+            g_mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            g_mbar_init(&tfull[s], 1);
+            g_mbar_init(&tempty[s], 8 * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's barrier)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) bias_s[t] = (g.bias && t < g.N) ? g.bias[t] : 0.f;
+    if (warp == 1) {  // TMEM: 512 columns (two BN-column accumulators); in a pair both CTAs' warp 1 execute the paired allocation
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            uint32_t stage = 0, phase = 0;
+            long long w_empty = 0;
+            const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
+            for (int u = unit; u < n_work; u += n_units) {
+                int tile, n_begin, n_cnt;
+                unit_of(u, tile, n_begin, n_cnt);
+                const int row0 = (tile * NCTA + (int)cta_rank) * kGemmBM;
+                const int b_rows = n_cnt / NCTA;  // B rows this CTA stages for the unit
+                for (int kb = 0; kb < n_kblk; ++kb) {
+                    const long long c0 = g.stats ? clock64() : 0;
+                    g_mbar_wait(&empty[stage], phase ^ 1u);
+                    if (g.stats) w_empty += clock64() - c0;
+                    if (NCTA == 2) {
+                        // one expect_tx (leader) covers the four boxes of the pair; every box completes on the leader's barrier
+                        if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + (uint32_t)P * (uint32_t)b_rows * ROWB));
+                        const uint32_t lbar = mapa_rank0(g_smem_u32(&full[stage]));
+                        if (g.l2_hint) {
+                            tma_load_3d_pair_hint(smA + stage * a_stage_bytes, &tmA, lbar, kb * BK, row0, 0, pol_a);
+                            tma_load_3d_pair_hint(smB + stage * b_stage_stride, n_cnt == BN ? &tmB : &tmBh, lbar, kb * BK,
+                                                  n_begin + (int)cta_rank * b_rows, 0, pol_b);
+                        } else {
+                            tma_load_3d_pair(smA + stage * a_stage_bytes, &tmA, lbar, kb * BK, row0, 0);
+                            tma_load_3d_pair(smB + stage * b_stage_stride, n_cnt == BN ? &tmB : &tmBh, lbar, kb * BK,
+                                             n_begin + (int)cta_rank * b_rows, 0);
+                        }
+                    } else {
+                        g_mbar_expect_tx(&full[stage], a_stage_bytes + (uint32_t)P * (uint32_t)BN * ROWB);
+                        tma_load_3d(smA + stage * a_stage_bytes, &tmA, &full[stage], kb * BK, row0, 0);
+                        tma_load_3d(smB + stage * b_stage_stride, &tmB, &full[stage], kb * BK, 0, 0);
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+            if (g.stats) atomicAdd(&g.stats[3], (unsigned long long)w_empty);
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0 && cta_rank == 0) {  // in a pair only the leader issues; its MMAs drive both CTAs' tensor cores
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B format of the plane type, K-major both, N, M=128 (256 per pair)
+            constexpr uint32_t a_plane = kGemmBM * ROWB;
+            uint32_t stage = 0, phase = 0, it = 0;
+            long long w_full = 0, w_tempty = 0;
+            const long long t_begin = g.stats ? clock64() : 0;
+            for (int u = unit; u < n_work; u += n_units, ++it) {
+                int tile, n_begin, n_cnt;
+                unit_of(u, tile, n_begin, n_cnt);
+                const uint32_t idesc = (1u << 4) | F::kIdescAB | ((uint32_t)(n_cnt >> 3) << 17) | ((uint32_t)((kGemmBM * NCTA) >> 4) << 24);
+                const uint32_t b_plane = (uint32_t)(n_cnt / NCTA) * ROWB;
+                const uint32_t as = SPLIT ? 0u : (it & 1u);
+                long long c0 = g.stats ? clock64() : 0;
+                g_mbar_wait(&tempty[as], SPLIT ? ((it & 1u) ^ 1u) : (((it >> 1) & 1u) ^ 1u));
+                if (g.stats) w_tempty += clock64() - c0;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256u;
+                for (int kb = 0; kb < n_kblk; ++kb) {
+                    c0 = g.stats ? clock64() : 0;
+                    g_mbar_wait(&full[stage], phase);
+                    if (g.stats) w_full += clock64() - c0;
+                    tc_fence_after();
+                    const uint32_t a0 = g_smem_u32(smA + stage * a_stage_bytes);
+                    const uint32_t b0 = g_smem_u32(smB + stage * b_stage_stride);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+#pragma unroll
+                        for (int t = 0; t < F::NPROD; ++t) {
+                            const uint64_t ad = make_desc_k<ROWB>(a0 + F::pa(t) * a_plane + ks * 32);
+                            const uint64_t bd = make_desc_k<ROWB>(b0 + F::pb(t) * b_plane + ks * 32);
+                            // split mode: the last product of the list is the leading one (A0B0) -> accumulator 0, the rest -> accumulator 1
+                            const bool lead = t == F::NPROD - 1;
+                            const uint32_t d = SPLIT ? (lead ? d_tmem : d_tmem + 256u) : d_tmem;
+                            const uint32_t acc = SPLIT ? ((lead ? (kb | ks) : (kb | ks | t)) != 0 ? 1u : 0u) : ((kb | ks | t) != 0 ? 1u : 0u);
+                            if (NCTA == 2)
+                                tc_mma_bf16_pair(d, ad, bd, idesc, acc);
+                            else
+                                tc_mma_bf16(d, ad, bd, idesc, acc);
+                        }
+                    }
+                    // frees the smem stage (in both CTAs of a pair) when the MMAs above have read it
+                    if (NCTA == 2) tc_commit_pair(&empty[stage]); else tc_commit(&empty[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (NCTA == 2) tc_commit_pair(&tfull[as]); else tc_commit(&tfull[as]);  // accumulator complete
+            }
+            if (g.stats) {
+                atomicAdd(&g.stats[0], (unsigned long long)w_full);
+                atomicAdd(&g.stats[1], (unsigned long long)w_tempty);
+                atomicAdd(&g.stats[2], (unsigned long long)(clock64() - t_begin));
+            }
+        }
+    } else {
+        // ================= epilogue warps (2..9) =================
+        // warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a quadrant take alternating 32-column chunks
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        uint8_t* my_stage = stage_c + (warp - 2) * L::kStageC;
+        const float inv_ab = 1.0f / (ld_scale(g.a_scale) * ld_scale(g.b_scale));  // exact: the scales are powers of two
+        const float c_mul = ld_scale(g.c_scale);
+        float amax = 0.f;
+        auto process = [&](const uint32_t (&v)[32], int n0, int row, bool row_ok) {
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float f = __fmaf_rn(__uint_as_float(v[j]), inv_ab, bias_s[n0 + j]);
+                if (g.relu) f = fmaxf(f, 0.f);
+                x[j] = f;
+            }
+            if (g.mask && row_ok) {
+                const uint4* mrow = reinterpret_cast<const uint4*>(g.mask + (size_t)row * g.ld_mask + n0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 mm = __ldg(mrow + q);
+                    const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t bits = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xFFFFu);
+                        // (bf16 or fp16) > 0  <=>  sign bit clear and magnitude non-zero (NaN never occurs in a ReLU output)
+                        if ((bits & 0x8000u) || (bits & 0x7FFFu) == 0u) x[8 * q + e] = 0.f;
+                    }
+                }
+            }
+            if (row_ok && g.c_f32) {
+                float* crow = g.c_f32 + (size_t)row * g.ldc + n0;
+                if (n0 + 32 <= g.N && (g.ldc % 4 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < g.N) crow[j] = x[j];
+                }
+            }
+            if (g.c_planes && n0 < g.ldp) {
+                // re-split (c_scale x) into P planes, two columns per word
+                uint32_t pw[P][16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float a = (n0 + j < g.N) ? x[j] * c_mul : 0.f, b = (n0 + j + 1 < g.N) ? x[j + 1] * c_mul : 0.f;
+                    uint32_t w[P];
+                    F::split2(a, b, w, amax);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) pw[p][j / 2] = w[p];
+                }
+                // stage the warp's [32 rows x 32 cols] x P planes in shared memory (TMA SWIZZLE_64B pattern: 16-byte chunk index
+                // XOR ((row >> 1) & 3), bank-conflict free), then ONE bulk tensor store writes it out coalesced and asynchronously
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has read the staging tile
+                __syncwarp();
+                uint8_t* st = my_stage + lane * 64;
+                const int sw = (lane >> 1) & 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int off = ((q ^ sw) << 4);
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        *reinterpret_cast<uint4*>(st + p * 2048 + off) = make_uint4(pw[p][4 * q], pw[p][4 * q + 1], pw[p][4 * q + 2], pw[p][4 * q + 3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmC), "r"(g_smem_u32(my_stage)),
+                                 "r"(n0), "r"(row - lane), "r"(0)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        };
+        uint32_t it = 0;
+        long long w_tfull = 0, busy = 0;
+        for (int u = unit; u < n_work; u += n_units, ++it) {
+            int tile, n_begin, n_cnt;
+            unit_of(u, tile, n_begin, n_cnt);
+            const uint32_t as = SPLIT ? 0u : (it & 1u);
+            const long long c0 = g.stats ? clock64() : 0;
+            g_mbar_wait(&tfull[as], SPLIT ? (it & 1u) : ((it >> 1) & 1u));
+            const long long c1 = g.stats ? clock64() : 0;
+            w_tfull += c1 - c0;
+            tc_fence_after();
+            const int row = (tile * NCTA + (int)cta_rank) * kGemmBM + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            const uint32_t t_row = tmem_base + as * 256u + ((uint32_t)(quad * 32) << 16);
+            uint32_t va[32], vb[32];
+            int n0 = 32 * half;  // accumulator column of the unit; the output column is n_begin + n0
+            if constexpr (SPLIT) {
+                // leading + correction accumulators: two TMEM loads per chunk, one correctly rounded add
+                while (n0 < n_cnt) {
+                    tc_ld32(t_row + (uint32_t)n0, va);
+                    tc_ld32(t_row + 256u + (uint32_t)n0, vb);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) va[j] = __float_as_uint(__fadd_rn(__uint_as_float(va[j]), __uint_as_float(vb[j])));
+                    process(va, n_begin + n0, row, row_ok);
+                    n0 += 64;
+                }
+            } else {
+                // software pipeline over this warp's chunks n0 = 32*half, 32*half + 64, ...: the TMEM load of the next chunk is in
+                // flight while the current one is converted and stored
+                if (n0 < n_cnt) {
+                    tc_ld32(t_row + (uint32_t)n0, va);
+                    tc_ld_wait();
+                }
+                while (n0 < n_cnt) {
+                    const int n1 = n0 + 64;
+                    if (n1 < n_cnt) tc_ld32(t_row + (uint32_t)n1, vb);
+                    process(va, n_begin + n0, row, row_ok);
+                    tc_ld_wait();
+                    if (n1 >= n_cnt) break;
+                    const int n2 = n1 + 64;
+                    if (n2 < n_cnt) tc_ld32(t_row + (uint32_t)n2, va);
+                    process(vb, n_begin + n1, row, row_ok);
+                    tc_ld_wait();
+                    n0 = n2;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (NCTA == 2) mbar_arrive_remote(mapa_rank0(g_smem_u32(&tempty[as]))); else g_mbar_arrive(&tempty[as]);
+            }
+            if (g.stats) busy += clock64() - c1;
+        }
+        if (g.stats && warp == 2 && lane == 0) {
+            atomicAdd(&g.stats[4], (unsigned long long)w_tfull);
+            atomicAdd(&g.stats[5], (unsigned long long)busy);
+        }
+        if (FMT == MORL_FMT_F16X2) note_overflow(amax);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp have completed
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();  // no CTA of a pair exits (or frees TMEM) while its peer can still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        if (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// =================================================================================================================
+// MN-major split-K variant: weight gradients  dW[n, k] = sum_m G[m, n] * H[m, k]  (reduction over the 65,536 batch rows).
+// Both operands are the row-major plane tensors the forward/backward GEMMs already produced, read "MN-major" (the MMA's M / N
+// index is the contiguous one), 128-byte swizzle:  A = G^T (M_mma = n, 128 per CTA), B = H^T (N_mma = k <= 256), K_mma = m.
+// One CTA per (128-row block of n, split s of the m range); fp32 partial tiles are summed by reduce_partials_kernel
+// (deterministic, no atomics), which also removes the operand scales.
+// =================================================================================================================
+constexpr int kMnKT = 32;  // batch rows (K_mma direction) per pipeline stage
+
+// canonical MN-major layout, SWIZZLE_128B: 64 contiguous MN elements (128 B) x 8 K-rows per 1 KB atom;
+// SBO = 1024 B (next 8 K-rows), LBO = distance between 64-element MN chunks.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+struct GemmMnArgs {
+    int M;            // reduction length (batch rows)
+    int n_tiles;      // ceil(A columns / 128)
+    int NB;           // N_mma = B columns covered (multiple of 64, <= 256)
+    int rows_per_split;
+    float* partial;   // [S][n_tiles*128][NB]
+    float* colsum_partial;  // [S][n_tiles*128] or nullptr: per-split column sums of G (bias gradient), fused as G^T . ones
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(192, 1)
+gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmMnArgs g) {
+    using F = PlaneFmt<FMT>;
+    constexpr int P = F::P;
+    constexpr int kStages = F::kStagesMn;
+    extern __shared__ uint8_t gsmem_raw[];
+    uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t chunk_bytes = (uint32_t)P * kMnKT * 128u;   // one 64-element MN chunk, P planes
+    constexpr uint32_t a_stage = 2u * chunk_bytes;
+    constexpr uint32_t b_stage = 4u * chunk_bytes;                 // (allocated for NB = 256)
+    const int nb_chunks = g.NB / 64;
+    uint8_t* smA = gsmem;
+    uint8_t* smB = gsmem + kStages * a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kStages * b_stage);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    // 4 KB of 1.0: the B operand of the fused bias-gradient product  colsum(G) = G^T . ones  (N = 16; every element is 1,
+    // so the swizzle pattern is irrelevant)
+    uint32_t* ones = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+    for (int t = threadIdx.x; t < 1024; t += blockDim.x) ones[t] = F::kOnes2;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x % g.n_tiles;
+    const int split = blockIdx.x / g.n_tiles;
+    const int m_begin = split * g.rows_per_split;
+    const int m_end = min(g.M, m_begin + g.rows_per_split);
+    const int n_kblk = (m_end - m_begin + kMnKT - 1) / kMnKT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            g_mbar_init(&full[s], 1);
+            g_mbar_init(&empty[s], 1);
+        }
+        g_mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // 256 accumulator columns + 16 for the fused column sums (allocation granularity: power of two)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                g_mbar_wait(&empty[stage], phase ^ 1u);
+                g_mbar_expect_tx(&full[stage], (2u + (uint32_t)nb_chunks) * chunk_bytes);
+                const int m0 = m_begin + kb * kMnKT;
+                for (int c = 0; c < 2; ++c) tma_load_3d(smA + stage * a_stage + c * chunk_bytes, &tmA, &full[stage], nt * 128 + c * 64, m0, 0);
+                for (int c = 0; c < nb_chunks; ++c) tma_load_3d(smB + stage * b_stage + c * chunk_bytes, &tmB, &full[stage], c * 64, m0, 0);
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A/B of the plane type, both MN-major, N = NB, M = 128
+            const uint32_t idesc = (1u << 4) | F::kIdescAB | (1u << 15) | (1u << 16) | ((uint32_t)(g.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_ones = (1u << 4) | F::kIdescAB | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t ones_desc = make_desc_mn_sw128(g_smem_u32(ones), chunk_bytes);
+            constexpr uint32_t plane = kMnKT * 128u;  // 4 KB: one plane of one chunk
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                g_mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a0 = g_smem_u32(smA + stage * a_stage);
+                const uint32_t b0 = g_smem_u32(smB + stage * b_stage);
+#pragma unroll
+                for (int ks = 0; ks < kMnKT / 16; ++ks) {
+#pragma unroll
+                    for (int t = 0; t < F::NPROD; ++t) {
+                        const uint64_t ad = make_desc_mn_sw128(a0 + F::pa(t) * plane + ks * 2048u, chunk_bytes);
+                        const uint64_t bd = make_desc_mn_sw128(b0 + F::pb(t) * plane + ks * 2048u, chunk_bytes);
+                        tc_mma_bf16(tmem_base, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
+                    }
+                    if (g.colsum_partial) {  // (G_{P-1} + ... + G_0)^T . ones -> 16 identical columns at TMEM column 256
+#pragma unroll
+                        for (int pl = P - 1; pl >= 0; --pl)
+                            tc_mma_bf16(tmem_base + 256u, make_desc_mn_sw128(a0 + pl * plane + ks * 2048u, chunk_bytes), ones_desc, idesc_ones,
+                                        (kb | ks | (P - 1 - pl)) != 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty[stage]);
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            tc_commit(tfull);
+        }
+    } else {
+        const int quad = warp & 3;
+        g_mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int row = nt * 128 + quad * 32 + lane;  // output row (n)
+        float* prow = g.partial + ((size_t)split * g.n_tiles * 128 + row) * g.NB;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int n0 = 0; n0 < g.NB; n0 += 32) {
+            uint32_t v[32];
+            tc_ld32(t_row + (uint32_t)n0, v);
+            tc_ld_wait();
+            if (n_kblk > 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(prow + n0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(prow + n0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (g.colsum_partial) {
+            uint32_t v[32];
+            tc_ld32(t_row + 256u, v);
+            tc_ld_wait();
+            g.colsum_partial[(size_t)split * g.n_tiles * 128 + row] = n_kblk > 0 ? __uint_as_float(v[0]) : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// out[r][c] (or out[c][r] if transpose) = mul * sum_s partial[s][r][c] for r < rows, c < cols, mul = 1 / (scale_a * scale_b).
+// blockDim = (32, 8): 32 consecutive output elements per block, the S partials are strided over threadIdx.y (fixed order:
+// deterministic), then combined through shared memory.
+// Blocks beyond the matrix (blockIdx.x >= main_blocks) reduce the fused column-sum partials vec_partial[s][prow] into vec_out[rows]
+// (mul = 1 / scale_a).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int S, int prow, int pcol, int rows, int cols,
+                                                              int transpose, float* __restrict__ out, int ld_out, int main_blocks,
+                                                              const float* __restrict__ vec_partial, float* __restrict__ vec_out,
+                                                              const float* __restrict__ scale_a, const float* __restrict__ scale_b) {
+    __shared__ float red[8][33];
+    float mul = 1.0f / (ld_scale(scale_a) * ld_scale(scale_b));
+    if ((int)blockIdx.x >= main_blocks) {  // uniform per block
+        partial = vec_partial;
+        out = vec_out;
+        pcol = 1; cols = 1; transpose = 0; ld_out = 1;
+        mul = 1.0f / ld_scale(scale_a);
+    }
+    const int e = ((int)blockIdx.x >= main_blocks ? (int)blockIdx.x - main_blocks : (int)blockIdx.x) * 32 + threadIdx.x;
+    const int total = rows * cols;
+    float acc = 0.f;
+    int r = 0, c = 0;
+    if (e < total) {
+        r = e / cols;
+        c = e - r * cols;
+        const float* p = partial + (size_t)r * pcol + c;
+        const size_t stride = (size_t)prow * pcol;
+        float a0 = 0.f, a1 = 0.f;
+        int s = threadIdx.y;
+        for (; s + 8 < S; s += 16) {
+            a0 += p[(size_t)s * stride];
+            a1 += p[(size_t)(s + 8) * stride];
+        }
+        if (s < S) a0 += p[(size_t)s * stride];
+        acc = a0 + a1;
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < total) {
+        float t = red[0][threadIdx.x];
+#pragma unroll
+        for (int y = 1; y < 8; ++y) t += red[y][threadIdx.x];
+        t *= mul;
+        if (transpose)
+            out[(size_t)c * ld_out + r] = t;
+        else
+            out[(size_t)r * ld_out + c] = t;
+    }
+}
+
+// column sums of a plane tensor: part[chunk][n] = sum over the chunk's rows and the P planes of G[p][m][n] (still scaled).
+// blockDim = (32, 8): a thread owns 8 consecutive columns (one 16-byte load per plane per row) and every 8th row.
+template <int FMT>
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const uint16_t* __restrict__ planes, long long plane_stride, int M, int ld, int N,
+                                                            int rows_per_chunk, float* __restrict__ part) {
+    using F = PlaneFmt<FMT>;
+    __shared__ float red[8][32][9];
+    const int n0 = (blockIdx.y * 32 + threadIdx.x) * 8;
+    const int m0 = blockIdx.x * rows_per_chunk, m1 = min(M, m0 + rows_per_chunk);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (n0 < ld) {
+        for (int m = m0 + threadIdx.y; m < m1; m += 8) {
+            const size_t o = (size_t)m * ld + n0;
+#pragma unroll
+            for (int p = 0; p < F::P; ++p) F::add8(acc, __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][j];
+            if (n0 + j < N) part[(size_t)blockIdx.x * N + n0 + j] = t;
+        }
+    }
+}
+
+// dU[b][h] = (1/scale) sum_j sum_p G[p][b*W + j][h]   (one block per b; blockDim = (32, 8), 8 columns per thread, j strided over y)
+template <int FMT>
+__global__ void __launch_bounds__(256) pairs_rowblock_sum_kernel(const uint16_t* __restrict__ planes, long long plane_stride, int W, int H,
+                                                                 float* __restrict__ dU, const float* __restrict__ scale) {
+    using F = PlaneFmt<FMT>;
+    __shared__ float red[8][32][9];
+    const int b = blockIdx.x;
+    const int h0 = (blockIdx.y * 32 + threadIdx.x) * 8;
+    const float inv = 1.0f / ld_scale(scale);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (h0 < H) {
+        for (int j = threadIdx.y; j < W; j += 8) {
+            const size_t o = ((size_t)b * W + j) * H + h0;
+#pragma unroll
+            for (int p = 0; p < F::P; ++p) F::add8(acc, __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && h0 < H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][j];
+            dU[(size_t)b * H + h0 + j] = t * inv;
+        }
+    }
+}
+
+// dU and the per-chunk partials of dV in ONE pass over the planes of dL/dh1 (|W| <= 64): block = (chunk of <= kPgrMaxB transitions, 256
+// columns), thread (x, y) owns 8 columns and the weights j = y, y + 8, ...; the 8 y-partials of dU of every transition of the chunk are
+// parked in shared memory and reduced after ONE barrier (same order as pairs_rowblock_sum_kernel), dV[j] accumulates over the
+// transitions of the chunk in registers (its scale is removed by the final reduce_partials_kernel).
+constexpr int kPgrMaxB = 8;
+template <int FMT>
+__global__ void __launch_bounds__(256) pairs_grad_reduce_fused_kernel(const uint16_t* __restrict__ planes, long long plane_stride, int B, int W,
+                                                                      int H, int b_per_chunk, float* __restrict__ dU, float* __restrict__ partV,
+                                                                      const float* __restrict__ scale) {
+    using F = PlaneFmt<FMT>;
+    extern __shared__ float red_dyn[];  // [kPgrMaxB][8][32][9]
+    const int h0 = (blockIdx.y * 32 + threadIdx.x) * 8;
+    const int b0 = blockIdx.x * b_per_chunk, b1 = min(B, b0 + b_per_chunk);
+    const float inv = 1.0f / ld_scale(scale);
+    float accV[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) accV[k][c] = 0.f;
+    for (int b = b0; b < b1; ++b) {
+        float accU[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) accU[c] = 0.f;
+        if (h0 < H) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int j = threadIdx.y + 8 * k;
+                if (j < W) {
+                    const size_t o = ((size_t)b * W + j) * H + h0;
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+#pragma unroll
+                    for (int p = 0; p < F::P; ++p) F::add8(v, __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        accU[c] += v[c];
+                        accV[k][c] += v[c];
+                    }
+                }
+            }
+        }
+        float* r = red_dyn + (((size_t)(b - b0) * 8 + threadIdx.y) * 32 + threadIdx.x) * 9;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) r[c] = accU[c];
+    }
+    __syncthreads();
+    if (h0 < H) {
+        for (int bl = threadIdx.y; bl < b1 - b0; bl += 8) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float t = 0.f;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) t += red_dyn[(((size_t)bl * 8 + y) * 32 + threadIdx.x) * 9 + c];
+                dU[(size_t)(b0 + bl) * H + h0 + c] = t * inv;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = threadIdx.y + 8 * k;
+            if (j < W) {
+                float* dst = partV + ((size_t)blockIdx.x * W + j) * H + h0;
+                *reinterpret_cast<float4*>(dst) = make_float4(accV[k][0], accV[k][1], accV[k][2], accV[k][3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(accV[k][4], accV[k][5], accV[k][6], accV[k][7]);
+            }
+        }
+    }
+}
+
+// ---- power-of-two scale of a tensor from its largest magnitude ----------------------------------------------------------------
+// scale = 2^(target_exp - e) with amax < 2^e, so that  2^(target_exp-1) <= scale * amax < 2^target_exp  (1 if the tensor is all zero).
+__device__ __forceinline__ float scale_from_amax(float amax, int target_exp) {
+    if (!(amax > 0.f) || !isfinite(amax)) return 1.0f;
+    int e;
+    (void)frexpf(amax, &e);
+    int k = target_exp - e;
+    k = k < -60 ? -60 : (k > 60 ? 60 : k);
+    return ldexpf(1.0f, k);
+}
+
+// ws[0] = running max (bit pattern of a non-negative float), ws[1] = arrival counter; both zero on entry and zero again on exit
+__global__ void __launch_bounds__(256) amax_scale_kernel(const float* __restrict__ src, long long n, int target_exp, float* __restrict__ scale_out,
+                                                         unsigned int* __restrict__ ws) {
+    __shared__ float red[8];
+    float m = 0.f;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) ? (n >> 2) : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(src + i)));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        atomicMax(&ws[0], __float_as_uint(m));  // non-negative floats order like their bit patterns; max is order independent
+        __threadfence();
+        if (atomicAdd(&ws[1], 1u) == gridDim.x - 1) {
+            __threadfence();
+            const float amax = __uint_as_float(atomicExch(&ws[0], 0u));
+            *scale_out = scale_from_amax(amax, target_exp);
+            ws[1] = 0u;
+        }
+    }
+}
+
+// ---- fp32 -> planes (operands produced outside the GEMM epilogue: network inputs, weights, gradients) ---------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, int transpose,
+                                                           uint16_t* __restrict__ dst, int rows_pad, int ldp, long long plane_stride,
+                                                           const float* __restrict__ scale) {
+    using F = PlaneFmt<FMT>;
+    // dst[p][r][c] for r < rows_pad, c < ldp; source element (r, c) = transpose ? src[c * ld_src + r] : src[r * ld_src + c]
+    const long long total = (long long)rows_pad * ldp;
+    const float s = ld_scale(scale);
+    float amax = 0.f;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / ldp), c = (int)(e - (long long)r * ldp);
+        float x = 0.f;
+        if (r < rows && c < cols) x = (transpose ? src[(size_t)c * ld_src + r] : src[(size_t)r * ld_src + c]) * s;
+        uint16_t h[F::P];
+        F::split1(x, h, amax);
+#pragma unroll
+        for (int p = 0; p < F::P; ++p) dst[p * plane_stride + e] = h[p];
+    }
+    if (FMT == MORL_FMT_F16X2) note_overflow(amax);
+}
+
+// non-transposed, ldp % 8 == 0: one thread converts 8 consecutive columns (two 128-bit loads when the source row allows it) and writes one
+// 128-bit store per plane -- the gradient seed dL/dQ [65,536 x 24] of every step goes through here
+template <int FMT>
+__global__ void __launch_bounds__(256) split_planes_vec8_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
+                                                                uint16_t* __restrict__ dst, int rows_pad, int ldp, long long plane_stride,
+                                                                const float* __restrict__ scale) {
+    using F = PlaneFmt<FMT>;
+    const int cpr = ldp >> 3;  // 8-column chunks per row
+    const long long total = (long long)rows_pad * cpr;
+    const bool vec_ok = (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const float s = ld_scale(scale);
+    float amax = 0.f;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(t / cpr), c0 = (int)(t - (long long)r * cpr) << 3;
+        float x[8];
+        if (r < rows && c0 + 8 <= cols && vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c0 + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = (r < rows && c0 + k < cols) ? __ldg(src + (size_t)r * ld_src + c0 + k) : 0.f;
+        }
+        uint32_t pw[F::P][4];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            uint32_t w[F::P];
+            F::split2(x[k] * s, x[k + 1] * s, w, amax);
+#pragma unroll
+            for (int p = 0; p < F::P; ++p) pw[p][k >> 1] = w[p];
+        }
+        const size_t e = (size_t)r * ldp + c0;
+#pragma unroll
+        for (int p = 0; p < F::P; ++p) *reinterpret_cast<uint4*>(dst + p * plane_stride + e) = make_uint4(pw[p][0], pw[p][1], pw[p][2], pw[p][3]);
+    }
+    if (FMT == MORL_FMT_F16X2) note_overflow(amax);
+}
+
+// several small matrices (the weight matrices of a network, plain and transposed) in ONE launch: blockIdx.y selects the job.  A job with
+// auto_scale != 0 derives its power-of-two scale from the largest |element| of ITS matrix: every block of the job reduces the whole (small)
+// matrix itself -- no inter-block dependency, every block arrives at the same value -- and block 0 publishes it in *scale.
+struct SplitJobs {
+    MorlSplitJob job[MORL_SPLIT_MAX_JOBS];
+};
+template <int FMT>
+__global__ void __launch_bounds__(256) split_planes_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+    using F = PlaneFmt<FMT>;
+    __shared__ float red[8];
+    const MorlSplitJob& j = jobs.job[blockIdx.y];
+    const float* __restrict__ src = j.src;
+    uint16_t* __restrict__ dst = static_cast<uint16_t*>(j.dst_planes);
+    float s = 1.0f;
+    if (j.auto_scale) {
+        float m = 0.f;
+        const int n_src = j.transpose ? j.cols : j.rows, k_src = j.transpose ? j.rows : j.cols;  // source matrix [n_src, k_src]
+        const long long tot = (long long)n_src * k_src;
+        for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
+            const int r = (int)(e / k_src), c = (int)(e - (long long)r * k_src);
+            m = fmaxf(m, fabsf(__ldg(src + (size_t)r * j.ld_src + c)));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+        s = scale_from_amax(m, j.target_exp);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && j.scale) *j.scale = s;
+    } else if (j.scale) {
+        s = *j.scale;
+    }
+    const long long total = (long long)j.rows_pad * j.ldp;
+    float amax = 0.f;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / j.ldp), c = (int)(e - (long long)r * j.ldp);
+        float x = 0.f;
+        if (r < j.rows && c < j.cols) x = (j.transpose ? src[(size_t)c * j.ld_src + r] : src[(size_t)r * j.ld_src + c]) * s;
+        uint16_t h[F::P];
+        F::split1(x, h, amax);
+#pragma unroll
+        for (int p = 0; p < F::P; ++p) dst[p * j.plane_stride + e] = h[p];
+    }
+    if (FMT == MORL_FMT_F16X2) note_overflow(amax);
+}
+
+// ---- separable first layer: h[b*W + j] = relu(u[b] + v[j]) straight into planes ------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) pairs_relu_split_kernel(const float* __restrict__ u, const float* __restrict__ v, int B, int W, int H,
+                                                               uint16_t* __restrict__ dst, long long plane_stride, const float* __restrict__ scale) {
+    using F = PlaneFmt<FMT>;
+    const int hv = H / 8;  // 8 columns per thread: two float4 loads per operand, one 16-byte store per plane
+    const long long total = (long long)B * W * hv;
+    const float s = ld_scale(scale);
+    float amax = 0.f;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int h8 = (int)(e % hv);
+        const long long row = e / hv;
+        const int b = (int)(row / W), j = (int)(row - (long long)b * W);
+        const float4* up = reinterpret_cast<const float4*>(u + (size_t)b * H + 8 * h8);
+        const float4* vp = reinterpret_cast<const float4*>(v + (size_t)j * H + 8 * h8);
+        const float4 u0 = __ldg(up), u1 = __ldg(up + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
+        const float x[8] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w};
+        uint32_t o[F::P][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t w[F::P];
+            F::split2(fmaxf(x[2 * q], 0.f) * s, fmaxf(x[2 * q + 1], 0.f) * s, w, amax);
+#pragma unroll
+            for (int p = 0; p < F::P; ++p) o[p][q] = w[p];
+        }
+        const long long off = row * H + 8 * h8;
+#pragma unroll
+        for (int p = 0; p < F::P; ++p) *reinterpret_cast<uint4*>(dst + p * plane_stride + off) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+    }
+    if (FMT == MORL_FMT_F16X2) note_overflow(amax);
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) ----------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+static inline int fmt_planes(int fmt) { return fmt == MORL_FMT_F16X2 ? 2 : 3; }
+static inline CUtensorMapDataType fmt_tm_type(int fmt) { return fmt == MORL_FMT_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
+
+// [P][rows][K] plane tensor, box = P x box_rows x box_k elements, swizzle span = box_k * 2 bytes (64 or 128)
+static int make_plane_map(CUtensorMap* map, int fmt, const void* base, int rows, int K, long long plane_stride_elems, int box_rows, int box_k) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return -1;
+    const cuuint32_t P = (cuuint32_t)fmt_planes(fmt);
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, P};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_stride_elems * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, P};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, fmt_tm_type(fmt), 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int make_plane_map_mn(CUtensorMap* map, int fmt, const void* base, int rows, int ld, long long plane_stride_elems) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return -1;
+    const cuuint32_t P = (cuuint32_t)fmt_planes(fmt);
+    const cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, P};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride_elems * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)kMnKT, P};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, fmt_tm_type(fmt), 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static inline bool fmt_ok(int fmt) { return fmt == MORL_FMT_BF16X3 || fmt == MORL_FMT_F16X2; }
+
+}  // namespace morl
+
+extern "C" int morl_plane_overflow_count(int reset) {
+    using namespace morl;
+    unsigned int v = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(&v, g_plane_overflow, sizeof(v)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("morl_plane_overflow_count: no CUDA device");
+        return MORL_ERR_NO_DEVICE;
+    }
+    if (reset) {
+        const unsigned int z = 0;
+        cudaMemcpyToSymbol(g_plane_overflow, &z, sizeof(z));
+    }
+    return (int)(v > 0x7fffffffu ? 0x7fffffffu : v);
+}
+
+extern "C" int morl_amax_scale_f32(const float* src, long long n, int target_exp, float* scale_out, void* workspace, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(src && scale_out && workspace, MORL_ERR_NULL, "morl_amax_scale_f32: NULL pointer argument");
+    MORL_REQUIRE(n > 0 && target_exp >= -14 && target_exp <= 15, MORL_ERR_SHAPE, "morl_amax_scale_f32: bad n=%lld / target_exp=%d", n, target_exp);
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148) blocks = 148;
+    if (blocks < 1) blocks = 1;
+    amax_scale_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, target_exp, scale_out, static_cast<unsigned int*>(workspace));
+    return check_launch("morl_amax_scale_f32");
+}
+
+extern "C" size_t morl_gemm_mn_workspace_bytes(int M, int a_cols, int b_cols) {
+    if (M <= 0 || a_cols <= 0 || b_cols <= 0) return 0;
+    const int n_tiles = (a_cols + 127) / 128;
+    int S = 148 / n_tiles;
+    if (S < 1) S = 1;
+    int rps = ((M + S - 1) / S + 31) / 32 * 32;
+    S = (M + rps - 1) / rps;
+    const int NB = (b_cols + 63) / 64 * 64;
+    return (size_t)S * n_tiles * 128 * NB * sizeof(float) + (size_t)256 * 256 * sizeof(float);  // tail: [S][n_tiles*128] column-sum partials
+}
+
+extern "C" int morl_gemm_planes_mn_f32(int fmt, const void* g_planes, long long g_plane_stride, int ldg, int g_cols, const float* g_scale,
+                                       const void* h_planes, long long h_plane_stride, int ldh, int h_cols, const float* h_scale, int M,
+                                       int transpose_out, float* out, int ld_out, float* colsum_out, void* workspace, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_gemm_planes_mn_f32: unknown plane format %d", fmt);
+    MORL_REQUIRE(g_planes && h_planes && out && workspace, MORL_ERR_NULL, "morl_gemm_planes_mn_f32: NULL pointer argument");
+    MORL_REQUIRE(M > 0 && g_cols > 0 && h_cols > 0, MORL_ERR_SHAPE, "morl_gemm_planes_mn_f32: bad shape M=%d g_cols=%d h_cols=%d", M, g_cols, h_cols);
+    MORL_REQUIRE(ldg % 64 == 0 && ldh % 64 == 0 && ldh <= 256 && g_cols <= ldg && h_cols <= ldh, MORL_ERR_UNSUPPORTED,
+                 "morl_gemm_planes_mn_f32: plane row lengths must be multiples of 64 (ldg=%d ldh=%d), ldh <= 256", ldg, ldh);
+    const int n_tiles = (g_cols + 127) / 128;
+    MORL_REQUIRE(n_tiles * 128 <= ldg || ldg % 128 == 0 || n_tiles * 128 - ldg <= 64, MORL_ERR_UNSUPPORTED, "morl_gemm_planes_mn_f32: ldg=%d", ldg);
+    int S = 148 / n_tiles;
+    if (S < 1) S = 1;
+    const int rps = ((M + S - 1) / S + 31) / 32 * 32;
+    S = (M + rps - 1) / rps;
+    const int NB = (h_cols + 63) / 64 * 64;
+    CUtensorMap tmA, tmB;
+    int rc = make_plane_map_mn(&tmA, fmt, g_planes, M, ldg, g_plane_stride);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_planes_mn_f32: cuTensorMapEncodeTiled(G) failed (%d)", rc);
+    rc = make_plane_map_mn(&tmB, fmt, h_planes, M, ldh, h_plane_stride);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_planes_mn_f32: cuTensorMapEncodeTiled(H) failed (%d)", rc);
+    GemmMnArgs g;
+    g.M = M; g.n_tiles = n_tiles; g.NB = NB; g.rows_per_split = rps; g.partial = static_cast<float*>(workspace);
+    g.colsum_partial = colsum_out ? g.partial + (size_t)S * n_tiles * 128 * NB : nullptr;  // S * n_tiles * 128 <= 148 * 128 floats < 256 KB tail
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MORL_DISPATCH_FMT(fmt, {
+        using F = PlaneFmt<kFmt>;
+        const size_t smem = (size_t)F::kStagesMn * (6u * F::P * kMnKT * 128u) + 256 + 1024 + 64 + 1024 + 4096;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(gemm_planes_mn_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        gemm_planes_mn_kernel<kFmt><<<n_tiles * S, 192, smem, st>>>(tmA, tmB, g);
+    });
+    rc = check_launch("morl_gemm_planes_mn_f32");
+    if (rc) return rc;
+    const int total = g_cols * h_cols;
+    const int main_blocks = (total + 31) / 32, vec_blocks = colsum_out ? (g_cols + 31) / 32 : 0;
+    reduce_partials_kernel<<<main_blocks + vec_blocks, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out,
+                                                                             main_blocks, g.colsum_partial, colsum_out, g_scale, h_scale);
+    return check_launch("morl_gemm_planes_mn_f32(reduce)");
+}
+
+extern "C" int morl_colsum_planes(int fmt, const void* planes, long long plane_stride, const float* scale, int M, int ld, int N, float* out,
+                                  void* workspace, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_colsum_planes: unknown plane format %d", fmt);
+    MORL_REQUIRE(planes && out && workspace, MORL_ERR_NULL, "morl_colsum_planes: NULL pointer argument");
+    MORL_REQUIRE(M > 0 && N > 0 && ld >= N && ld % 8 == 0 && plane_stride % 8 == 0, MORL_ERR_SHAPE, "morl_colsum_planes: bad shape M=%d N=%d ld=%d", M, N, ld);
+    const int chunks = 296;
+    const int rpc = (M + chunks - 1) / chunks;
+    const int nch = (M + rpc - 1) / rpc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* part = static_cast<float*>(workspace);
+    MORL_DISPATCH_FMT(fmt, (colsum_planes_kernel<kFmt><<<dim3((unsigned)nch, (unsigned)((ld + 255) / 256)), dim3(32, 8), 0, st>>>(
+                               static_cast<const uint16_t*>(planes), plane_stride, M, ld, N, rpc, part)));
+    int rc = check_launch("morl_colsum_planes");
+    if (rc) return rc;
+    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, out, N, 1 << 30, nullptr, nullptr, scale, nullptr);
+    return check_launch("morl_colsum_planes(reduce)");
+}
+
+extern "C" int morl_pairs_grad_reduce_planes(int fmt, const void* planes, long long plane_stride, const float* scale, int B, int W, int H, float* dU,
+                                             float* dV, void* workspace, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_pairs_grad_reduce_planes: unknown plane format %d", fmt);
+    MORL_REQUIRE(planes && dU && dV && workspace, MORL_ERR_NULL, "morl_pairs_grad_reduce_planes: NULL pointer argument");
+    MORL_REQUIRE(B > 0 && W > 0 && H > 0 && H % 8 == 0 && plane_stride % 8 == 0, MORL_ERR_SHAPE, "morl_pairs_grad_reduce_planes: bad shape B=%d W=%d H=%d", B, W, H);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint16_t* pl = static_cast<const uint16_t*>(planes);
+    if (W <= 64) {
+        // one pass: dU directly, dV as per-chunk partials [chunks][W*H] reduced in a fixed order
+        int bpc = (B + 295) / 296;  // <= 296 chunks (the documented workspace size), at most kPgrMaxB transitions per chunk
+        if (bpc > kPgrMaxB) bpc = kPgrMaxB;
+        const int nchf = (B + bpc - 1) / bpc;
+        if (nchf <= 296) {
+            const int Nf = W * H;
+            float* partf = static_cast<float*>(workspace);
+            const size_t smemf = (size_t)kPgrMaxB * 8 * 32 * 9 * sizeof(float);  // 73,728 B
+            MORL_DISPATCH_FMT(fmt, {
+                static bool configured = false;
+                if (!configured) {
+                    cudaFuncSetAttribute(pairs_grad_reduce_fused_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf);
+                    configured = true;
+                }
+                pairs_grad_reduce_fused_kernel<kFmt><<<dim3((unsigned)nchf, (unsigned)((H + 255) / 256)), dim3(32, 8), smemf, st>>>(pl, plane_stride, B, W,
+                                                                                                                                     H, bpc, dU, partf, scale);
+            });
+            int rcf = check_launch("morl_pairs_grad_reduce_planes(fused)");
+            if (rcf) return rcf;
+            reduce_partials_kernel<<<(Nf + 31) / 32, dim3(32, 8), 0, st>>>(partf, nchf, 1, Nf, 1, Nf, 0, dV, Nf, 1 << 30, nullptr, nullptr, scale, nullptr);
+            return check_launch("morl_pairs_grad_reduce_planes(reduce)");
+        }
+    }
+    // dU[b] = sum over the W rows of transition b
+    MORL_DISPATCH_FMT(fmt, (pairs_rowblock_sum_kernel<kFmt><<<dim3((unsigned)B, (unsigned)((H + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, W, H,
+                                                                                                                                     dU, scale)));
+    int rc = check_launch("morl_pairs_grad_reduce_planes(dU)");
+    if (rc) return rc;
+    // dV[j] = sum over b: column sums of the [B, W*H] view
+    const int N = W * H;
+    const int chunks = 74;
+    const int rpc = (B + chunks - 1) / chunks;
+    const int nch = (B + rpc - 1) / rpc;
+    float* part = static_cast<float*>(workspace);
+    MORL_DISPATCH_FMT(fmt, (colsum_planes_kernel<kFmt><<<dim3((unsigned)nch, (unsigned)((N + 255) / 256)), dim3(32, 8), 0, st>>>(pl, plane_stride, B, N, N,
+                                                                                                                                  rpc, part)));
+    rc = check_launch("morl_pairs_grad_reduce_planes(dV)");
+    if (rc) return rc;
+    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, dV, N, 1 << 30, nullptr, nullptr, scale, nullptr);
+    return check_launch("morl_pairs_grad_reduce_planes(reduce)");
+}
+
+extern "C" int morl_split_planes(int fmt, const float* src, int rows, int cols, int ld_src, int transpose, void* dst_planes, int rows_pad, int ldp,
+                                 long long plane_stride, const float* scale, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_split_planes: unknown plane format %d", fmt);
+    MORL_REQUIRE(src && dst_planes, MORL_ERR_NULL, "morl_split_planes: NULL pointer argument");
+    MORL_REQUIRE(rows > 0 && cols > 0 && rows_pad >= rows && ldp >= cols && ld_src > 0, MORL_ERR_SHAPE,
+                 "morl_split_planes: bad shape rows=%d cols=%d rows_pad=%d ldp=%d", rows, cols, rows_pad, ldp);
+    MORL_REQUIRE(plane_stride >= (long long)rows_pad * ldp, MORL_ERR_SHAPE, "morl_split_planes: plane_stride too small");
+    const long long total = (long long)rows_pad * ldp;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint16_t* dst = static_cast<uint16_t*>(dst_planes);
+    if (!transpose && (ldp & 7) == 0 && (plane_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(dst_planes) & 15u) == 0) {
+        const long long chunks = total >> 3;
+        long long vb = (chunks + 255) / 256;
+        if (vb > 148 * 8) vb = 148 * 8;
+        MORL_DISPATCH_FMT(fmt, (split_planes_vec8_kernel<kFmt><<<(int)vb, 256, 0, st>>>(src, rows, cols, ld_src, dst, rows_pad, ldp, plane_stride, scale)));
+        return check_launch("morl_split_planes(vec8)");
+    }
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    MORL_DISPATCH_FMT(fmt, (split_planes_kernel<kFmt><<<(int)blocks, 256, 0, st>>>(src, rows, cols, ld_src, transpose, dst, rows_pad, ldp, plane_stride, scale)));
+    return check_launch("morl_split_planes");
+}
+
+extern "C" int morl_split_planes_multi(int fmt, const MorlSplitJob* jobs, int n_jobs, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_split_planes_multi: unknown plane format %d", fmt);
+    MORL_REQUIRE(jobs, MORL_ERR_NULL, "morl_split_planes_multi: NULL pointer argument");
+    MORL_REQUIRE(n_jobs > 0 && n_jobs <= MORL_SPLIT_MAX_JOBS, MORL_ERR_SHAPE, "morl_split_planes_multi: n_jobs=%d out of range", n_jobs);
+    SplitJobs sj;
+    memset(&sj, 0, sizeof(sj));
+    long long max_total = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        const MorlSplitJob& j = jobs[i];
+        MORL_REQUIRE(j.src && j.dst_planes, MORL_ERR_NULL, "morl_split_planes_multi: job %d has a NULL pointer", i);
+        MORL_REQUIRE(j.rows > 0 && j.cols > 0 && j.rows_pad >= j.rows && j.ldp >= j.cols && j.ld_src > 0 &&
+                         j.plane_stride >= (long long)j.rows_pad * j.ldp,
+                     MORL_ERR_SHAPE, "morl_split_planes_multi: job %d bad shape rows=%d cols=%d rows_pad=%d ldp=%d", i, j.rows, j.cols, j.rows_pad, j.ldp);
+        MORL_REQUIRE(!j.auto_scale || (j.target_exp >= -14 && j.target_exp <= 15), MORL_ERR_SHAPE, "morl_split_planes_multi: job %d target_exp=%d", i,
+                     j.target_exp);
+        sj.job[i] = j;
+        const long long t = (long long)j.rows_pad * j.ldp;
+        if (t > max_total) max_total = t;
+    }
+    long long bx = (max_total + 255) / 256;
+    if (bx > 148) bx = 148;
+    MORL_DISPATCH_FMT(fmt, (split_planes_multi_kernel<kFmt><<<dim3((unsigned)bx, (unsigned)n_jobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(sj)));
+    return check_launch("morl_split_planes_multi");
+}
+
+extern "C" int morl_pairs_relu_split_planes(int fmt, const float* u, const float* v, int B, int W, int H, void* dst_planes, long long plane_stride,
+                                            const float* scale, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_pairs_relu_split_planes: unknown plane format %d", fmt);
+    MORL_REQUIRE(u && v && dst_planes, MORL_ERR_NULL, "morl_pairs_relu_split_planes: NULL pointer argument");
+    MORL_REQUIRE(B > 0 && W > 0 && H > 0 && H % 8 == 0 && plane_stride % 8 == 0 && plane_stride >= (long long)B * W * H, MORL_ERR_SHAPE,
+                 "morl_pairs_relu_split_planes: bad shape B=%d W=%d H=%d", B, W, H);
+    const long long total = (long long)B * W * (H / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    MORL_DISPATCH_FMT(fmt, (pairs_relu_split_kernel<kFmt><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                               u, v, B, W, H, static_cast<uint16_t*>(dst_planes), plane_stride, scale)));
+    return check_launch("morl_pairs_relu_split_planes");
+}
+
+// Diagnostics: cycle counters of the K-major GEMM roles, accumulated over all CTAs and launches since the last reset
+// (only when MORL_GEMM_STATS=1 was set before the first GEMM call).
+extern "C" int morl_debug_gemm_stats(unsigned long long* out8, int reset) {
+    using namespace morl;
+    MORL_REQUIRE(out8, MORL_ERR_NULL, "morl_debug_gemm_stats: NULL pointer argument");
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_gemm_stats, 8 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_gemm_stats, z, sizeof(z));
+    }
+    return check_launch("morl_debug_gemm_stats");
+}
+
+namespace morl {
+template <int FMT, int SPLIT>
+static int launch_gemm_planes(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& tmC, const GemmArgs& g, bool pair,
+                              int sms, cudaStream_t st) {
+    constexpr size_t smem1 = KPlan<1, FMT>::kBytes, smem2 = KPlan<2, FMT>::kBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gemm_planes_kernel<1, FMT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        cudaFuncSetAttribute(gemm_planes_kernel<2, FMT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        attr_set = true;
+    }
+    if (pair) {
+        const int n_tiles = (g.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+        const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem2;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, gemm_planes_kernel<2, FMT, SPLIT>, tmA, tmB, tmBh, tmC, g);
+    } else {
+        const int n_tiles = (g.M + kGemmBM - 1) / kGemmBM;
+        const int grid = n_tiles < sms ? n_tiles : sms;
+        gemm_planes_kernel<1, FMT, SPLIT><<<grid, kGemmThreads, smem1, st>>>(tmA, tmB, tmBh, tmC, g);
+    }
+    return check_launch("morl_gemm_planes_f32");
+}
+}  // namespace morl
+
+extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* b_planes,
+                                    long long b_plane_stride, const float* b_scale, int M, int N, int N_pad, int K, const float* bias, int relu,
+                                    const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp, long long c_plane_stride,
+                                    const float* c_scale, int reverse_tiles, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_gemm_planes_f32: unknown plane format %d", fmt);
+    MORL_REQUIRE(a_planes && b_planes && (c_f32 || c_planes), MORL_ERR_NULL, "morl_gemm_planes_f32: NULL pointer argument");
+    MORL_REQUIRE(M > 0 && N > 0 && K > 0 && N_pad >= N, MORL_ERR_SHAPE, "morl_gemm_planes_f32: bad shape M=%d N=%d N_pad=%d K=%d", M, N, N_pad, K);
+    const int BK = fmt == MORL_FMT_F16X2 ? PlaneFmt<MORL_FMT_F16X2>::BK : PlaneFmt<MORL_FMT_BF16X3>::BK;
+    MORL_REQUIRE(K % BK == 0 && N_pad % 32 == 0 && N_pad <= 256, MORL_ERR_UNSUPPORTED,
+                 "morl_gemm_planes_f32: need K %% %d == 0, N_pad %% 32 == 0, N_pad <= 256 (K=%d N_pad=%d)", BK, K, N_pad);
+    MORL_REQUIRE(aligned16(a_planes) && aligned16(b_planes), MORL_ERR_ALIGN, "morl_gemm_planes_f32: operand planes must be 16-byte aligned");
+    if (c_planes)
+        MORL_REQUIRE(ldp % 32 == 0 && ldp >= N && ldp <= N_pad && aligned16(c_planes) && c_plane_stride % 8 == 0, MORL_ERR_SHAPE,
+                     "morl_gemm_planes_f32: ldp=%d must be a multiple of 32 with N <= ldp <= N_pad", ldp);
+    int sms = morl_device_sm_count();
+    if (sms <= 0) sms = 148;
+    // CTA pairs (tcgen05 cta_group::2) whenever there are at least two 128-row tiles; MORL_GEMM_FORCE_1CTA=1 keeps the 1-CTA kernel
+    static const bool force_1cta = [] { const char* e = getenv("MORL_GEMM_FORCE_1CTA"); return e && e[0] == '1'; }();
+    const bool pair = !force_1cta && M > kGemmBM && sms >= 2;
+    const int ncta = pair ? 2 : 1;
+    CUtensorMap tmA, tmB;
+    int rc = make_plane_map(&tmA, fmt, a_planes, M, K, a_plane_stride, kGemmBM, BK);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_planes_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
+    rc = make_plane_map(&tmB, fmt, b_planes, N_pad, K, b_plane_stride, N_pad / ncta, BK);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_planes_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+    CUtensorMap tmBh = tmB;  // half-width units of the tail split: boxes of N_pad / 4 rows
+    if (pair && N_pad % 64 == 0) {
+        rc = make_plane_map(&tmBh, fmt, b_planes, N_pad, K, b_plane_stride, N_pad / 4, BK);
+        MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_planes_f32: cuTensorMapEncodeTiled(B half) failed (%d)", rc);
+    }
+    CUtensorMap tmC;
+    memset(&tmC, 0, sizeof(tmC));
+    if (c_planes) {  // store map of the re-split output: [P][M][ldp], box 32 cols x 32 rows x P planes (64-byte swizzle)
+        rc = make_plane_map(&tmC, fmt, c_planes, M, ldp, c_plane_stride, 32, 32);
+        MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_planes_f32: cuTensorMapEncodeTiled(C) failed (%d)", rc);
+    }
+    GemmArgs g;
+    g.M = M; g.N = N; g.N_pad = N_pad; g.K = K;
+    g.bias = bias; g.c_f32 = c_f32; g.ldc = ldc;
+    g.c_planes = c_planes; g.ldp = ldp; g.plane_stride = c_plane_stride;
+    g.mask = static_cast<const uint16_t*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
+    g.a_scale = a_scale; g.b_scale = b_scale; g.c_scale = c_scale;
+    g.reverse = reverse_tiles ? 1 : 0;
+    // measured on B200 (profiles/r01_s3_l2hint_ab.txt): the hints do not help, so they are opt-in (MORL_GEMM_L2HINT=1)
+    static const bool want_hint = [] { const char* e = getenv("MORL_GEMM_L2HINT"); return e && e[0] == '1'; }();
+    g.l2_hint = want_hint ? 1 : 0;
+    static const bool want_stats = [] { const char* e = getenv("MORL_GEMM_STATS"); return e && e[0] == '1'; }();
+    g.stats = nullptr;
+    if (want_stats) {
+        void* sp = nullptr;
+        cudaGetSymbolAddress(&sp, g_gemm_stats);
+        g.stats = static_cast<unsigned long long*>(sp);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // split accumulators (see gemm_planes_kernel) are the default; MORL_GEMM_SPLIT_ACC=0 selects the single double-buffered accumulator
+    static const bool split_acc = [] { const char* e = getenv("MORL_GEMM_SPLIT_ACC"); return !(e && e[0] == '0'); }();
+    if (fmt == MORL_FMT_F16X2)
+        return split_acc ? launch_gemm_planes<MORL_FMT_F16X2, 1>(tmA, tmB, tmBh, tmC, g, pair, sms, st)
+                         : launch_gemm_planes<MORL_FMT_F16X2, 0>(tmA, tmB, tmBh, tmC, g, pair, sms, st);
+    return split_acc ? launch_gemm_planes<MORL_FMT_BF16X3, 1>(tmA, tmB, tmBh, tmC, g, pair, sms, st)
+                     : launch_gemm_planes<MORL_FMT_BF16X3, 0>(tmA, tmB, tmBh, tmC, g, pair, sms, st);
+}

@@ -132,6 +132,7 @@ class Envelope(MOPolicy, MOAgent):
         use_cuda_graph: bool = True,
         replay_on_device: bool = True,
         use_tensor_cores: bool = True,
+        tensor_core_format: Optional[str] = None,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
@@ -175,7 +176,15 @@ class Envelope(MOPolicy, MOAgent):
         self.use_cuda_graph = use_cuda_graph
         # dense layers of all three passes on the tcgen05 tensor cores (split operands, fp32-accurate).  No silent library fallback: a
         # network the tensor-core path does not cover is an error unless the caller explicitly opts into the validation path.
-        if use_tensor_cores and (self.q_net.feature_extractor is not None or not TCPairMlp.trainable_supported(self.q_net.net, num_sample_w)):
+        # operand format of the tensor-core dense layers: "f16x2" (default: 3 MMAs / 4 B per element, fp16 exponent range with device-resident
+        # power-of-two scales) or "bf16x3" (6 MMAs / 6 B per element, fp32 exponent range) -- tc_mlp.py
+        fmt_name = tensor_core_format or os.environ.get("MORL_TC_FMT", "f16x2")
+        if fmt_name not in ("f16x2", "bf16x3"):
+            raise ValueError(f"tensor_core_format must be 'f16x2' or 'bf16x3', got {fmt_name!r}")
+        self.tensor_core_format = fmt_name
+        self._tc_fmt = ops.FMT_F16X2 if fmt_name == "f16x2" else ops.FMT_BF16X3
+        if use_tensor_cores and (self.q_net.feature_extractor is not None
+                                 or not TCPairMlp.trainable_supported(self.q_net.net, num_sample_w, self._tc_fmt)):
             raise ops._lib.MorlB200Error(
                 "morl_baselines_b200.Envelope: the tensor-core update path needs a flat observation, equal hidden widths that are multiples "
                 f"of 64 and <= 256, and num_sample_w <= 64 (got obs {self.observation_shape}, net_arch {net_arch}, num_sample_w {num_sample_w}); "
@@ -333,9 +342,9 @@ class Envelope(MOPolicy, MOAgent):
         with th.no_grad():
             if self.use_tensor_cores and B == self.batch_size and W == self.num_sample_w:
                 if self._tc_on is None:
-                    self._tc_on = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W)
-                    self._tc_tg = TCPairMlp(self.target_q_net.net, self.target_q_net.feat_dim, B, W)
-                    if TCPairMlp.trainable_supported(self.q_net.net, W):
+                    self._tc_on = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W, fmt=self._tc_fmt)
+                    self._tc_tg = TCPairMlp(self.target_q_net.net, self.target_q_net.feat_dim, B, W, fmt=self._tc_fmt)
+                    if TCPairMlp.trainable_supported(self.q_net.net, W, self._tc_fmt):
                         self._tc_train = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W, share_weights_with=self._tc_on, trainable=True)
                 # every weight plane this step needs (online, target, transposed-for-backward) in one launch
                 TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
@@ -487,6 +496,8 @@ class Envelope(MOPolicy, MOAgent):
 
             if self.per:
                 s["prio_ready"].synchronize()  # the priorities of THIS step have landed in pinned memory; backward + Adam still run
+                if not np.isfinite(s["prio_np"]).all():
+                    self._raise_non_finite()
                 priority = (s["prio_np"] + rb.min_priority) ** self.per_alpha  # envelope.py:333 (float32, as the reference's tensor math)
                 rb.update_priorities(b_inds, priority)
 
@@ -508,6 +519,16 @@ class Envelope(MOPolicy, MOAgent):
             wandb.log({"losses/grad_norm": get_grad_norm(self.q_net.parameters()).item(), "global_step": self.global_step})
             if self.per:
                 wandb.log({"metrics/mean_priority": np.mean(priority)})
+
+    def _raise_non_finite(self):
+        """The priorities of an update came back Inf / NaN: say why (the reference would silently write NaN priorities into its sum-tree)."""
+        n = ops.plane_overflow_count() if self.use_tensor_cores and self._tc_fmt == ops.FMT_F16X2 else 0
+        if n:
+            raise ops._lib.MorlB200Error(
+                f"Envelope.update: non-finite TD errors; {n} kernel(s) saw an activation / weight / gradient outside the fp16 range of the "
+                "'f16x2' tensor-core operand format (|activation| >= 8188, see tc_mlp.py) -- construct the agent with "
+                "tensor_core_format='bf16x3' (fp32 exponent range) for this problem")
+        raise FloatingPointError("Envelope.update: non-finite TD errors (diverged Q-network or non-finite rewards / observations in the replay buffer)")
 
     def last_loss_host(self, wait: bool = True) -> float:
         """Critic loss of the most recent gradient update as a python float (the reference reads ``critic_loss.item()`` every update,

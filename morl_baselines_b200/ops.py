@@ -284,75 +284,126 @@ def _pad(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
-def split_bf16x3(x: th.Tensor, rows_pad: Optional[int] = None, ldp: Optional[int] = None, transpose: bool = False,
-                 out: Optional[th.Tensor] = None) -> th.Tensor:
-    """fp32 [rows, cols] -> bf16x3 planes [3, rows_pad, ldp] (zero padded); with ``transpose`` the planes hold x^T."""
+FMT_BF16X3, FMT_F16X2 = _lib.FMT_BF16X3, _lib.FMT_F16X2
+_FMT_DTYPE = {FMT_BF16X3: th.bfloat16, FMT_F16X2: th.float16}
+_FMT_PLANES = {FMT_BF16X3: 3, FMT_F16X2: 2}
+
+
+def fmt_of(planes: th.Tensor) -> int:
+    """Plane format of a plane tensor: bf16 [3, rows, ld] = bf16x3, fp16 [2, rows, ld] = f16x2."""
+    if planes.dtype == th.bfloat16 and planes.shape[0] == 3:
+        return FMT_BF16X3
+    if planes.dtype == th.float16 and planes.shape[0] == 2:
+        return FMT_F16X2
+    raise _lib.MorlB200Error(f"not a plane tensor: dtype {planes.dtype}, leading dimension {planes.shape[0]}")
+
+
+def empty_planes(fmt: int, rows: int, ld: int, device) -> th.Tensor:
+    return th.empty((_FMT_PLANES[fmt], rows, ld), device=device, dtype=_FMT_DTYPE[fmt])
+
+
+def scale_tensor(value: float, device) -> th.Tensor:
+    """A device-resident power-of-two scale (float32 [1])."""
+    return th.full((1,), float(value), device=device, dtype=th.float32)
+
+
+def plane_overflow_count(reset: bool = False) -> int:
+    """Number of f16x2 range violations (|scale * x| > 65504) the plane-producing kernels saw since the last reset (synchronises)."""
+    n = _lib.load().morl_plane_overflow_count(int(reset))
+    if n < 0:
+        _lib.check(n, "morl_plane_overflow_count")
+    return n
+
+
+def amax_scale(x: th.Tensor, target_exp: int, scale_out: th.Tensor, workspace: th.Tensor) -> th.Tensor:
+    """scale_out[0] = 2^(target_exp - e) with max|x| < 2^e (one launch; workspace: 2 zeroed int32, left zeroed)."""
+    x = _dev(x, "x")
+    rc = _lib.load().morl_amax_scale_f32(_ptr(x), x.numel(), int(target_exp), _ptr(scale_out), _ptr(workspace), _stream())
+    _lib.check(rc, "morl_amax_scale_f32")
+    _count()
+    return scale_out
+
+
+def split_planes(x: th.Tensor, fmt: int = FMT_F16X2, rows_pad: Optional[int] = None, ldp: Optional[int] = None, transpose: bool = False,
+                 out: Optional[th.Tensor] = None, scale: Optional[th.Tensor] = None) -> th.Tensor:
+    """fp32 [rows, cols] -> planes [P, rows_pad, ldp] of scale * x (zero padded); with ``transpose`` the planes hold x^T."""
     x = _dev(x, "x")
     r, c = (x.shape[1], x.shape[0]) if transpose else (x.shape[0], x.shape[1])
     rows_pad = r if rows_pad is None else rows_pad
-    ldp = _pad(c, 32) if ldp is None else ldp
+    ldp = _pad(c, 64 if fmt == FMT_F16X2 else 32) if ldp is None else ldp
     if out is None:
-        out = th.empty((3, rows_pad, ldp), device=x.device, dtype=th.bfloat16)
-    rc = _lib.load().morl_split_bf16x3(_ptr(x), r, c, x.shape[1], int(transpose), _ptr(out), rows_pad, ldp, out.stride(0), _stream())
-    _lib.check(rc, "morl_split_bf16x3")
+        out = empty_planes(fmt, rows_pad, ldp, x.device)
+    rc = _lib.load().morl_split_planes(fmt, _ptr(x), r, c, x.shape[1], int(transpose), _ptr(out), rows_pad, ldp, out.stride(0), _ptr(scale), _stream())
+    _lib.check(rc, "morl_split_planes")
     _count()
     return out
 
 
-def split_bf16x3_multi(jobs) -> None:
-    """One launch for several splits.  jobs: iterable of (src [rows, cols] fp32 CUDA, out [3, rows_pad, ldp] bf16, transpose)."""
+def split_planes_multi(jobs, fmt: int = FMT_F16X2) -> None:
+    """One launch for several splits.  jobs: iterable of (src [rows, cols] fp32 CUDA, out planes [P, rows_pad, ldp], transpose, scale, target_exp):
+    ``scale`` is a device float [1] or None; ``target_exp`` None = use the scale as given, an int = derive it from the matrix's amax and store it."""
     jobs = list(jobs)
     if not jobs:
         return
     if len(jobs) > _lib.SPLIT_MAX_JOBS:
-        raise _lib.MorlB200Error(f"split_bf16x3_multi: at most {_lib.SPLIT_MAX_JOBS} jobs per call")
+        raise _lib.MorlB200Error(f"split_planes_multi: at most {_lib.SPLIT_MAX_JOBS} jobs per call")
     arr = (_lib.SplitJob * len(jobs))()
-    for k, (src, out, transpose) in enumerate(jobs):
+    for k, job in enumerate(jobs):
+        src, out, transpose = job[0], job[1], job[2]
+        scale = job[3] if len(job) > 3 else None
+        target_exp = job[4] if len(job) > 4 else None
         src = _dev(src, "src")
         rows, cols = (src.shape[1], src.shape[0]) if transpose else (src.shape[0], src.shape[1])
         arr[k].src, arr[k].dst_planes, arr[k].plane_stride = src.data_ptr(), out.data_ptr(), out.stride(0)
+        arr[k].scale = None if scale is None else scale.data_ptr()
         arr[k].rows, arr[k].cols, arr[k].ld_src, arr[k].transpose = rows, cols, src.stride(0), int(bool(transpose))
         arr[k].rows_pad, arr[k].ldp = out.shape[1], out.shape[2]
-    rc = _lib.load().morl_split_bf16x3_multi(arr, len(jobs), _stream())
-    _lib.check(rc, "morl_split_bf16x3_multi")
+        arr[k].auto_scale, arr[k].target_exp = (0, 0) if target_exp is None else (1, int(target_exp))
+    rc = _lib.load().morl_split_planes_multi(fmt, arr, len(jobs), _stream())
+    _lib.check(rc, "morl_split_planes_multi")
     _count()
 
 
-def gemm_bf16x3(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Optional[th.Tensor] = None, relu: bool = False,
+def gemm_planes(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Optional[th.Tensor] = None, relu: bool = False,
                 relu_mask: Optional[th.Tensor] = None, out_f32: bool = True, out_planes: bool = False, c_f32: Optional[th.Tensor] = None,
-                c_planes: Optional[th.Tensor] = None, reverse_tiles: bool = False):
-    """C = act(A . B^T + bias) on the tcgen05 tensor cores with bf16x3 split operands (fp32-accurate).
-    a_planes [3, M, K], b_planes [3, N_pad, K] (bf16); returns (c_f32 [M, n_out] or None, c_planes [3, M, ldp] or None)."""
-    if a_planes.dtype != th.bfloat16 or b_planes.dtype != th.bfloat16 or not a_planes.is_cuda:
-        raise _lib.MorlB200Error("gemm_bf16x3: operands must be CUDA bfloat16 plane tensors")
+                c_planes: Optional[th.Tensor] = None, reverse_tiles: bool = False, a_scale: Optional[th.Tensor] = None,
+                b_scale: Optional[th.Tensor] = None, c_scale: Optional[th.Tensor] = None):
+    """C = act(A . B^T + bias) on the tcgen05 tensor cores with split operands (fp32-accurate).
+    a_planes [P, M, K], b_planes [P, N_pad, K]; the scales are device floats the planes were multiplied by (None = 1);
+    returns (c_f32 [M, n_out] or None, c_planes [P, M, ldp] holding c_scale * C, or None)."""
+    fmt = fmt_of(a_planes)
+    if fmt_of(b_planes) != fmt or not a_planes.is_cuda:
+        raise _lib.MorlB200Error("gemm_planes: operands must be CUDA plane tensors of the same format")
     _, M, K = a_planes.shape
     _, n_pad, Kb = b_planes.shape
     if Kb != K or a_planes.stride(1) != K or b_planes.stride(1) != K:
-        raise _lib.MorlB200Error("gemm_bf16x3: operand planes must be K-major with equal K")
+        raise _lib.MorlB200Error("gemm_planes: operand planes must be K-major with equal K")
     dev = a_planes.device
     if out_f32 and c_f32 is None:
         c_f32 = th.empty((M, n_out), device=dev, dtype=th.float32)
     if out_planes and c_planes is None:
-        c_planes = th.empty((3, M, _pad(n_out, 32)), device=dev, dtype=th.bfloat16)
+        c_planes = empty_planes(fmt, M, _pad(n_out, 32), dev)
     mask0 = None if relu_mask is None else relu_mask[0]
-    rc = _lib.load().morl_gemm_bf16x3_f32(_ptr(a_planes), a_planes.stride(0), _ptr(b_planes), b_planes.stride(0), M, n_out, n_pad, K, _ptr(bias),
-                                          int(relu), _ptr(mask0), 0 if mask0 is None else mask0.stride(0), _ptr(c_f32),
+    rc = _lib.load().morl_gemm_planes_f32(fmt, _ptr(a_planes), a_planes.stride(0), _ptr(a_scale), _ptr(b_planes), b_planes.stride(0), _ptr(b_scale), M,
+                                          n_out, n_pad, K, _ptr(bias), int(relu), _ptr(mask0), 0 if mask0 is None else mask0.stride(0), _ptr(c_f32),
                                           0 if c_f32 is None else c_f32.stride(0), _ptr(c_planes), 0 if c_planes is None else c_planes.shape[2],
-                                          0 if c_planes is None else c_planes.stride(0), int(reverse_tiles), _stream())
-    _lib.check(rc, "morl_gemm_bf16x3_f32")
+                                          0 if c_planes is None else c_planes.stride(0), _ptr(c_scale), int(reverse_tiles), _stream())
+    _lib.check(rc, "morl_gemm_planes_f32")
     _count()
     return c_f32, c_planes
 
 
-def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None) -> th.Tensor:
-    """relu(u[b] + v[j]) for every pair, written as bf16x3 planes [3, B*W, H] (row b*W + j)."""
+def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None, fmt: int = FMT_F16X2, scale: Optional[th.Tensor] = None) -> th.Tensor:
+    """relu(u[b] + v[j]) for every pair, written as planes [P, B*W, H] of scale * h (row b*W + j)."""
     u, v = _dev(u, "u"), _dev(v, "v")
     B, H = u.shape
     W = v.shape[0]
     if out is None:
-        out = th.empty((3, B * W, H), device=u.device, dtype=th.bfloat16)
-    rc = _lib.load().morl_pairs_relu_split_bf16x3(_ptr(u), _ptr(v), B, W, H, _ptr(out), out.stride(0), _stream())
-    _lib.check(rc, "morl_pairs_relu_split_bf16x3")
+        out = empty_planes(fmt, B * W, H, u.device)
+    else:
+        fmt = fmt_of(out)
+    rc = _lib.load().morl_pairs_relu_split_planes(fmt, _ptr(u), _ptr(v), B, W, H, _ptr(out), out.stride(0), _ptr(scale), _stream())
+    _lib.check(rc, "morl_pairs_relu_split_planes")
     _count()
     return out
 
@@ -402,46 +453,51 @@ def gemm_mn_workspace(M: int, g_cols: int, h_cols: int, device) -> th.Tensor:
     return th.empty((nbytes + 3) // 4, device=device, dtype=th.float32)
 
 
-def gemm_bf16x3_mn(g_planes: th.Tensor, g_cols: int, h_planes: th.Tensor, h_cols: int, transpose_out: bool = False,
-                   out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None, colsum: Optional[th.Tensor] = None) -> th.Tensor:
-    """out[n, k] = sum_m G[m, n] H[m, k] (weight gradient; reduction over the rows) from bf16x3 plane tensors [3, M, ld].
+def gemm_planes_mn(g_planes: th.Tensor, g_cols: int, h_planes: th.Tensor, h_cols: int, transpose_out: bool = False,
+                   out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None, colsum: Optional[th.Tensor] = None,
+                   g_scale: Optional[th.Tensor] = None, h_scale: Optional[th.Tensor] = None) -> th.Tensor:
+    """out[n, k] = sum_m G[m, n] H[m, k] (weight gradient; reduction over the rows) from plane tensors [P, M, ld] (scales removed).
     ``colsum`` ([g_cols] fp32, optional) additionally receives sum_m G[m, n] (the bias gradient) from the same pass."""
+    fmt = fmt_of(g_planes)
     _, M, ldg = g_planes.shape
     _, M2, ldh = h_planes.shape
-    if M != M2 or g_planes.dtype != th.bfloat16 or h_planes.dtype != th.bfloat16:
-        raise _lib.MorlB200Error("gemm_bf16x3_mn: plane tensors must be bfloat16 with the same number of rows")
+    if M != M2 or fmt_of(h_planes) != fmt:
+        raise _lib.MorlB200Error("gemm_planes_mn: plane tensors must share format and number of rows")
     dev = g_planes.device
     if out is None:
         out = th.empty((h_cols, g_cols) if transpose_out else (g_cols, h_cols), device=dev, dtype=th.float32)
     ws = gemm_mn_workspace(M, g_cols, h_cols, dev) if workspace is None else workspace
-    rc = _lib.load().morl_gemm_bf16x3_mn_f32(_ptr(g_planes), g_planes.stride(0), ldg, g_cols, _ptr(h_planes), h_planes.stride(0), ldh, h_cols, M,
-                                             int(transpose_out), _ptr(out), out.stride(0), _ptr(colsum), _ptr(ws), _stream())
-    _lib.check(rc, "morl_gemm_bf16x3_mn_f32")
+    rc = _lib.load().morl_gemm_planes_mn_f32(fmt, _ptr(g_planes), g_planes.stride(0), ldg, g_cols, _ptr(g_scale), _ptr(h_planes), h_planes.stride(0), ldh,
+                                             h_cols, _ptr(h_scale), M, int(transpose_out), _ptr(out), out.stride(0), _ptr(colsum), _ptr(ws), _stream())
+    _lib.check(rc, "morl_gemm_planes_mn_f32")
     _count(2)
     return out
 
 
-def colsum_bf16x3(planes: th.Tensor, n_cols: int, out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None) -> th.Tensor:
-    """Column sums over the rows and the three planes (bias gradients)."""
+def colsum_planes(planes: th.Tensor, n_cols: int, out: Optional[th.Tensor] = None, workspace: Optional[th.Tensor] = None,
+                  scale: Optional[th.Tensor] = None) -> th.Tensor:
+    """Column sums over the rows and the planes, scale removed (bias gradients)."""
+    fmt = fmt_of(planes)
     _, M, ld = planes.shape
     dev = planes.device
     out = th.empty(n_cols, device=dev, dtype=th.float32) if out is None else out
     ws = th.empty(296 * n_cols, device=dev, dtype=th.float32) if workspace is None else workspace
-    rc = _lib.load().morl_colsum_bf16x3(_ptr(planes), planes.stride(0), M, ld, n_cols, _ptr(out), _ptr(ws), _stream())
-    _lib.check(rc, "morl_colsum_bf16x3")
+    rc = _lib.load().morl_colsum_planes(fmt, _ptr(planes), planes.stride(0), _ptr(scale), M, ld, n_cols, _ptr(out), _ptr(ws), _stream())
+    _lib.check(rc, "morl_colsum_planes")
     _count(2)
     return out
 
 
 def pairs_grad_reduce(planes: th.Tensor, B: int, W: int, workspace: Optional[th.Tensor] = None, dU: Optional[th.Tensor] = None,
-                      dV: Optional[th.Tensor] = None):
-    """dU [B, H] and dV [W, H] from the planes of dL/dh1 [3, B*W, H] (gradient of relu(u[b] + v[j]) w.r.t. u and v)."""
+                      dV: Optional[th.Tensor] = None, scale: Optional[th.Tensor] = None):
+    """dU [B, H] and dV [W, H] from the planes of dL/dh1 [P, B*W, H] (gradient of relu(u[b] + v[j]) w.r.t. u and v), scale removed."""
+    fmt = fmt_of(planes)
     _, M, H = planes.shape
     dev = planes.device
     dU = th.empty((B, H), device=dev, dtype=th.float32) if dU is None else dU
     dV = th.empty((W, H), device=dev, dtype=th.float32) if dV is None else dV
     ws = th.empty(296 * W * H, device=dev, dtype=th.float32) if workspace is None else workspace
-    rc = _lib.load().morl_pairs_grad_reduce_bf16x3(_ptr(planes), planes.stride(0), B, W, H, _ptr(dU), _ptr(dV), _ptr(ws), _stream())
-    _lib.check(rc, "morl_pairs_grad_reduce_bf16x3")
+    rc = _lib.load().morl_pairs_grad_reduce_planes(fmt, _ptr(planes), planes.stride(0), _ptr(scale), B, W, H, _ptr(dU), _ptr(dV), _ptr(ws), _stream())
+    _lib.check(rc, "morl_pairs_grad_reduce_planes")
     _count(2)
     return dU, dV

@@ -1,47 +1,59 @@
-"""Weight-conditioned MLP evaluated on the tcgen05 tensor cores (bf16x3 split operands, fp32-accurate).
+"""Dense layers of the weight-conditioned Q-network on the tcgen05 tensor cores (csrc/gemm_planes.cu).
 
 ``TCPairMlp`` runs the reference's ``mlp`` stack (common/networks.py:10-48: Linear -> ReLU ... -> Linear) for every
 (observation b, weight vector j) pair of a minibatch without ever materialising fp32 activations in HBM:
 
     layer 1   : u = feats @ W1[:, :F]^T (B rows), v = wset @ W1[:, F:]^T + b1 (W rows)  -- one launch (morl_pair_layer1_uv_f32) --
-                h1[b*W + j] = relu(u[b] + v[j]) written straight into bf16x3 planes (morl_pairs_relu_split_bf16x3);
-    layers 2..: morl_gemm_bf16x3_f32 (TMA -> tcgen05.mma -> TMEM -> epilogue) with the activation re-split fused in the
-                epilogue; the last layer writes fp32 Q-values.
+                 h1[b*W + j] = relu(u[b] + v[j]) written straight into operand planes (morl_pairs_relu_split_planes);
+    layers 2..: morl_gemm_planes_f32 (TMA -> tcgen05.mma -> TMEM -> epilogue) with the activation re-split fused in the
+                 epilogue; the last layer writes fp32 Q-values.
 
-``forward_pairs`` alone serves the two no-grad passes of the envelope target (online + target net on s');
-``TCPairMlpFn`` wraps forward + a hand-written backward for the training pass:
+Operand formats (``fmt``): ``ops.FMT_F16X2`` (default; two fp16 planes of a power-of-two-scaled operand, three MMAs per product, 4 B per
+element) or ``ops.FMT_BF16X3`` (three bf16 planes, six MMAs, 6 B per element, fp32 exponent range).  Scales of the f16x2 format, all
+device-resident so a captured CUDA graph survives their changes:
+    activations : fixed 2^3   (|h| < 8,188 representable; absolute resolution 2^-28)
+    weights     : per matrix, from its own largest magnitude at every refresh (amax * s in [2^13, 2^14))
+    gradients   : one per update, from the largest magnitude of dL/dQ (amax * s in [2^8, 2^9): 2^7 of growth head-room through the
+                  backward chain, whose operators W_l^T have spectral norm ~1)
+A value outside the fp16 range becomes Inf/NaN in the planes -- it reaches the loss -- and raises ``ops.plane_overflow_count()``.
+
+The weight planes are refreshed with ``refresh_weights()`` after every optimiser step (one small launch per 16 matrices).
+
+Hand-written backward for the training pass:
     G_L = dL/dQ;  dW_l = G_l^T H_{l-1} (MN-major split-K GEMM);  db_l = colsum(G_l);
     G_{l-1} = (G_l W_l) * [H_{l-1} > 0] (K-major GEMM with the ReLU mask fused in the epilogue);
-    layer 1: dU = sum_j G_1, dV = sum_b G_1 (morl_pairs_grad_reduce_bf16x3), dW1 = [dU^T feats | dV^T wset], db1 = sum_j dV
+    layer 1: dU = sum_j G_1, dV = sum_b G_1 (morl_pairs_grad_reduce_planes), dW1 = [dU^T feats | dV^T wset], db1 = sum_j dV
              (morl_pair_layer1_grad_f32).
 No library (ATen / cuBLAS) kernel runs anywhere in forward or backward.
 """
 
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch as th
-import torch.nn as nn
+from torch import nn
 
 from . import ops
 
-
-import os
-
 _SNAKE = os.environ.get("MORL_TC_SNAKE", "1") == "1"          # alternate the GEMM tile order between chained layers
-_MULTI_SPLIT = os.environ.get("MORL_TC_MULTI_SPLIT", "1") == "1"  # one launch for all weight splits of a step
+_DEFAULT_FMT = ops.FMT_BF16X3 if os.environ.get("MORL_TC_FMT", "f16x2") == "bf16x3" else ops.FMT_F16X2
+
+ACT_SCALE = 8.0        # f16x2 activations
+W_TARGET_EXP = 14      # f16x2 weights: amax * scale in [2^13, 2^14)
+G_TARGET_EXP = 9       # f16x2 gradients: amax(dL/dQ) * scale in [2^8, 2^9)
 
 
-def _pad32(n: int) -> int:
-    return (n + 31) // 32 * 32
+def _pad(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
 
 
 class TCPairMlp:
     """Static plan (buffers + weight planes) for one nn.Sequential MLP and a fixed number of pair rows."""
 
     @staticmethod
-    def supported(net: nn.Sequential) -> bool:
+    def supported(net: nn.Sequential, fmt: int = _DEFAULT_FMT) -> bool:
         mods = list(net)
         lin = [m for m in mods if isinstance(m, nn.Linear)]
         if len(lin) < 2 or any(not isinstance(m, (nn.Linear, nn.ReLU)) for m in mods):
@@ -49,44 +61,56 @@ class TCPairMlp:
         if not all(isinstance(mods[2 * i], nn.Linear) for i in range(len(lin))):
             return False
         hidden = [l.out_features for l in lin[:-1]]
-        return all(h % 32 == 0 and h <= 256 for h in hidden) and lin[-1].out_features <= 256
+        kmul = 64 if fmt == ops.FMT_F16X2 else 32  # K extent of one pipeline stage
+        return all(h % kmul == 0 and h <= 256 for h in hidden) and lin[-1].out_features <= 256
 
     @staticmethod
-    def trainable_supported(net: nn.Sequential, n_w: int) -> bool:
+    def trainable_supported(net: nn.Sequential, n_w: int, fmt: int = _DEFAULT_FMT) -> bool:
         """The hand-written backward additionally needs equal hidden widths (multiples of 64) and at most 64 weight vectors."""
-        if not TCPairMlp.supported(net):
+        if not TCPairMlp.supported(net, fmt):
             return False
         hidden = {m.out_features for m in list(net)[:-1] if isinstance(m, nn.Linear)}
         return len(hidden) == 1 and next(iter(hidden)) % 64 == 0 and n_w <= 64
 
     def __init__(self, net: nn.Sequential, feat_dim: int, n_obs: int, n_w: int, share_weights_with: Optional["TCPairMlp"] = None,
-                 trainable: bool = False):
+                 trainable: bool = False, fmt: Optional[int] = None):
         self.net = net
         self.lin: List[nn.Linear] = [m for m in net if isinstance(m, nn.Linear)]
         self.feat_dim = feat_dim
         self.B, self.W = n_obs, n_w
+        self.fmt = fmt = (share_weights_with.fmt if share_weights_with is not None else _DEFAULT_FMT) if fmt is None else fmt
+        if not TCPairMlp.supported(net, fmt):
+            raise ops._lib.MorlB200Error("TCPairMlp: unsupported network (Linear/ReLU stack with hidden widths that are multiples of 64 (f16x2) or "
+                                         "32 (bf16x3) and <= 256)")
         dev = self.lin[0].weight.device
         M = n_obs * n_w
-        self.h = [th.empty((3, M, l.out_features), device=dev, dtype=th.bfloat16) for l in self.lin[:-1]]
+        scaled = fmt == ops.FMT_F16X2
+        self.h = [ops.empty_planes(fmt, M, l.out_features, dev) for l in self.lin[:-1]]
+        self.s_act = ops.scale_tensor(ACT_SCALE, dev) if scaled else None
         if share_weights_with is not None:
-            self.wp = share_weights_with.wp  # same network: one set of weight planes, refreshed once per step
+            if share_weights_with.fmt != fmt:
+                raise ops._lib.MorlB200Error("TCPairMlp: plans sharing weight planes must use the same operand format")
+            self.wp, self.s_w = share_weights_with.wp, share_weights_with.s_w  # same network: one set of weight planes, refreshed once per step
         else:
-            self.wp = [th.empty((3, _pad32(l.out_features), l.in_features), device=dev, dtype=th.bfloat16) for l in self.lin[1:]]
+            self.wp = [ops.empty_planes(fmt, _pad(l.out_features, 32), l.in_features, dev) for l in self.lin[1:]]
+            self.s_w = [ops.scale_tensor(1.0, dev) if scaled else None for _ in self.lin[1:]]
         self.q = th.empty((M, self.lin[-1].out_features), device=dev, dtype=th.float32)
         self.trainable = trainable
         if trainable:
             if n_w > 64:
                 raise ops._lib.MorlB200Error("TCPairMlp backward supports at most 64 weight vectors per minibatch")
             out = self.lin[-1].out_features
-            self.ld_last = (out + 63) // 64 * 64
+            self.ld_last = _pad(out, 64)
             hid = max(l.out_features for l in self.lin[:-1])
-            self.g_last = th.empty((3, M, self.ld_last), device=dev, dtype=th.bfloat16)
-            self.g = [th.empty((3, M, hid), device=dev, dtype=th.bfloat16) for _ in range(2)]
-            # transposed weight planes W_l^T [3, in_l, K = padded out_l] for the dX products
+            self.g_last = ops.empty_planes(fmt, M, self.ld_last, dev)
+            self.g = [ops.empty_planes(fmt, M, hid, dev) for _ in range(2)]
+            self.s_g = ops.scale_tensor(1.0, dev) if scaled else None
+            self.ws_amax = th.zeros(2, device=dev, dtype=th.int32)
+            # transposed weight planes W_l^T [P, in_l, K = padded out_l] for the dX products
             self.wtp = []
             for k, l in enumerate(self.lin[1:], start=1):
                 kdim = self.ld_last if k == len(self.lin) - 1 else l.out_features
-                self.wtp.append(th.empty((3, _pad32(l.in_features), kdim), device=dev, dtype=th.bfloat16))
+                self.wtp.append(ops.empty_planes(fmt, _pad(l.in_features, 32), kdim, dev))
             self.ws_mn = ops.gemm_mn_workspace(M, 256, 256, dev)
             self.ws_red = th.empty(296 * max(n_w * hid, 256), device=dev, dtype=th.float32)
             first = self.lin[0]
@@ -94,35 +118,43 @@ class TCPairMlp:
             self.dU = th.empty((n_obs, first.out_features), device=dev, dtype=th.float32)
             self.dV = th.empty((n_w, first.out_features), device=dev, dtype=th.float32)
 
-    def refresh_weights(self):
-        """Re-split the (fp32) weights of layers 2.. into bf16x3 planes; call after every optimiser step / target sync."""
-        ops.split_bf16x3_multi(self._weight_jobs())
+    # ------------------------------------------------------------------------------------------------ weight planes
+    def _texp(self):
+        return W_TARGET_EXP if self.fmt == ops.FMT_F16X2 else None
 
     def _weight_jobs(self):
-        return [(l.weight.detach(), wp, False) for l, wp in zip(self.lin[1:], self.wp)]
+        return [(l.weight.detach(), wp, False, s, self._texp()) for l, wp, s in zip(self.lin[1:], self.wp, self.s_w)]
 
     def _transposed_jobs(self):
-        return [(l.weight.detach(), wt, True) for l, wt in zip(self.lin[1:], self.wtp)]
+        # same matrix, same amax, same scale: the transposed job re-derives (and re-publishes) the value of the plain one
+        return [(l.weight.detach(), wt, True, s, self._texp()) for l, wt, s in zip(self.lin[1:], self.wtp, self.s_w)]
+
+    def refresh_weights(self):
+        """Re-split the (fp32) weights of layers 2.. into operand planes; call after every optimiser step / target sync."""
+        ops.split_planes_multi(self._weight_jobs(), self.fmt)
+
+    def refresh_transposed_weights(self):
+        ops.split_planes_multi(self._transposed_jobs(), self.fmt)
 
     @staticmethod
     def refresh_many(plans, transposed_of=()):
         """All weight planes of several plans (and the transposed planes of the trainable ones) in a single launch per 16 matrices.
         Plans sharing their planes (``share_weights_with``) are split once."""
         jobs, seen = [], set()
+        fmt = plans[0].fmt
         for p in plans:
+            if p.fmt != fmt:
+                raise ops._lib.MorlB200Error("TCPairMlp.refresh_many: mixed operand formats")
             if id(p.wp) not in seen:
                 seen.add(id(p.wp))
                 jobs += p._weight_jobs()
         for p in transposed_of:
             jobs += p._transposed_jobs()
             p._wt_fresh = True
-        if not _MULTI_SPLIT:
-            for src, out, tr in jobs:
-                ops.split_bf16x3(src, rows_pad=out.shape[1], ldp=out.shape[2], transpose=tr, out=out)
-            return
         for i in range(0, len(jobs), 16):
-            ops.split_bf16x3_multi(jobs[i:i + 16])
+            ops.split_planes_multi(jobs[i:i + 16], fmt)
 
+    # ------------------------------------------------------------------------------------------------ forward / backward
     @th.no_grad()
     def forward_pairs(self, feats: th.Tensor, wset: th.Tensor) -> th.Tensor:
         """feats [B, F], wset [W, D] -> Q [B*W, out] (fp32, row b*W + j).  Uses the planes of the last refresh_weights()."""
@@ -130,20 +162,17 @@ class TCPairMlp:
         if feats.shape[1] != self.feat_dim or first.in_features != self.feat_dim + wset.shape[1]:
             raise ops._lib.MorlB200Error(f"TCPairMlp: feats {tuple(feats.shape)} / wset {tuple(wset.shape)} do not match the first layer ({first.in_features} inputs)")
         u, v = ops.pair_layer1_uv(feats, wset, first.weight.detach(), first.bias.detach())  # one launch (csrc/pair_layer1.cu)
-        a = ops.pairs_relu_split(u, v, out=self.h[0])
+        a = ops.pairs_relu_split(u, v, out=self.h[0], scale=self.s_act)
         n = len(self.lin)
         for k in range(1, n - 1):
             l = self.lin[k]
             # alternate the tile order: a layer starts on the rows its producer wrote last (L2-resident)
-            _, a = ops.gemm_bf16x3(a, self.wp[k - 1], l.out_features, bias=l.bias, relu=True, out_f32=False, out_planes=True, c_planes=self.h[k],
-                                   reverse_tiles=_SNAKE and bool(k & 1))
+            _, a = ops.gemm_planes(a, self.wp[k - 1], l.out_features, bias=l.bias, relu=True, out_f32=False, out_planes=True, c_planes=self.h[k],
+                                   reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_act, b_scale=self.s_w[k - 1], c_scale=self.s_act)
         last = self.lin[-1]
-        q, _ = ops.gemm_bf16x3(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
-                               reverse_tiles=_SNAKE and bool((n - 1) & 1))
+        q, _ = ops.gemm_planes(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
+                               reverse_tiles=_SNAKE and bool((n - 1) & 1), a_scale=self.s_act, b_scale=self.s_w[n - 2])
         return q
-
-    def refresh_transposed_weights(self):
-        ops.split_bf16x3_multi(self._transposed_jobs())
 
     @th.no_grad()
     def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor, grads_out: Optional[List[th.Tensor]] = None):
@@ -155,18 +184,21 @@ class TCPairMlp:
             self._wt_fresh = False  # refreshed together with the forward planes of this step (refresh_many)
         else:
             self.refresh_transposed_weights()
-        G = ops.split_bf16x3(dq, rows_pad=dq.shape[0], ldp=self.ld_last, out=self.g_last)
+        if self.s_g is not None:
+            ops.amax_scale(dq, G_TARGET_EXP, self.s_g, self.ws_amax)  # this update's gradient scale
+        G = ops.split_planes(dq, self.fmt, rows_pad=dq.shape[0], ldp=self.ld_last, out=self.g_last, scale=self.s_g)
         for k in range(n - 1, 0, -1):
             l = self.lin[k]
             # dW_k = G_k^T H_{k-1} and db_k = colsum(G_k) in one pass over the G planes
             if grads[2 * k + 1] is None:
                 grads[2 * k + 1] = th.empty(l.out_features, device=dq.device, dtype=th.float32)
-            grads[2 * k] = ops.gemm_bf16x3_mn(G, l.out_features, self.h[k - 1], l.in_features, out=grads[2 * k], workspace=self.ws_mn,
-                                              colsum=grads[2 * k + 1])
-            # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1})
-            _, G = ops.gemm_bf16x3(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
-                                   c_planes=self.g[k & 1], reverse_tiles=_SNAKE and bool(k & 1))
-        dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV)
+            grads[2 * k] = ops.gemm_planes_mn(G, l.out_features, self.h[k - 1], l.in_features, out=grads[2 * k], workspace=self.ws_mn,
+                                              colsum=grads[2 * k + 1], g_scale=self.s_g, h_scale=self.s_act)
+            # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1}), kept at the gradient scale
+            _, G = ops.gemm_planes(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
+                                   c_planes=self.g[k & 1], reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_g, b_scale=self.s_w[k - 1],
+                                   c_scale=self.s_g)
+        dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV, scale=self.s_g)
         grads[0], grads[1] = ops.pair_layer1_grad(dU, dV, feats, wset, dW1=grads[0], db1=grads[1], workspace=self.ws_l1)
         return grads
 

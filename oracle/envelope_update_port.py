@@ -62,14 +62,28 @@ class EnvelopeUpdatePort:
         picked = nqt.gather(2, ac.unsqueeze(2).unsqueeze(3).expand(-1, -1, 1, self.D)).squeeze(2)
         return picked.gather(1, pref.reshape(-1, 1, 1).expand(-1, 1, self.D)).squeeze(1)
 
-    def update(self, obs, actions, rewards, next_obs, dones, sampled_w, homotopy_lambda=0.0):
+    @th.no_grad()
+    def envelope_target_dedup(self, next_obs, sampled_w):
+        """NOT the reference's code path: the same target (envelope.py:404-440) with Q evaluated once per DISTINCT (s'_b, w_j) pair
+        (B*|W| rows instead of B*|W|^2) and a joint first-occurrence argmax over (j, a) -- the "de-duplicated CPU restatement" BASELINE.md
+        section 2 quotes for context.  Returns rows in the reference's order k = i*B + b."""
+        B, n_w = next_obs.size(0), sampled_w.size(0)
+        w_rep = sampled_w.repeat(B, 1)
+        nobs = next_obs.repeat_interleave(n_w, 0)
+        nq = self._q(self.q_net, nobs, w_rep).view(B, n_w * self.A, self.D)
+        nqt = self._q(self.target_q_net, nobs, w_rep).view(B, n_w * self.A, self.D)
+        scal = th.einsum("id,bkd->ibk", sampled_w, nq)          # [W, B, W*A]
+        best = th.argmax(scal, dim=2)                            # first occurrence over (j, a) row-major == two-stage max / argmax
+        return nqt.gather(1, best.t().unsqueeze(2).expand(-1, -1, self.D)).transpose(0, 1).reshape(n_w * B, self.D)
+
+    def update(self, obs, actions, rewards, next_obs, dones, sampled_w, homotopy_lambda=0.0, dedup=False):
         """One gradient step on a host minibatch; returns (loss, priorities of the first B rows)."""
         B, n_w = obs.size(0), sampled_w.size(0)
         w = sampled_w.repeat_interleave(B, 0)  # first tiling (envelope.py:284-291)
         obs_t, nobs_t = obs.repeat(n_w, 1), next_obs.repeat(n_w, 1)
         act_t, rew_t, done_t = actions.repeat(n_w, 1), rewards.repeat(n_w, 1), dones.repeat(n_w, 1)
         with th.no_grad():
-            target = self.envelope_target(nobs_t, w, sampled_w)
+            target = self.envelope_target_dedup(next_obs, sampled_w) if dedup else self.envelope_target(nobs_t, w, sampled_w)
             target_q = rew_t + (1 - done_t) * self.gamma * target
         q_values = self._q(self.q_net, obs_t, w)
         q_value = q_values.gather(1, act_t.long().reshape(-1, 1, 1).expand(-1, 1, self.D)).reshape(-1, self.D)

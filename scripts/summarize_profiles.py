@@ -74,7 +74,7 @@ for rep in glob.glob(os.path.join(OUT, "prof_*.ncu-rep")):
         json.dump({"kernel": traffic[0][0], "dram_bytes_per_launch": traffic[0][1], "source": f"profiles/{tag}_{name}_ncu.txt"},
                   open(os.path.join(ROOT, "profiles", "envelope_td_traffic.json"), "w"))
     if name == "gemm" and traffic:
-        k = [t for t in traffic if "gemm_bf16x3_kernel" in t[0]] or traffic
+        k = [t for t in traffic if "gemm_planes_kernel" in t[0]] or traffic
         json.dump({"kernel": k[0][0], "dram_bytes_per_launch": k[0][1], "source": f"profiles/{tag}_{name}_ncu.txt"},
                   open(os.path.join(ROOT, "profiles", "gemm_traffic.json"), "w"))
     print("wrote", name)

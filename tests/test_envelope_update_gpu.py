@@ -88,7 +88,7 @@ def test_envelope_api_surface(cuda):
     from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
 
     env = FakeEnv(obs_dim=6, n_actions=3, reward_dim=2)
-    agent = Envelope(env, batch_size=16, num_sample_w=4, buffer_size=256, net_arch=[32, 32], log=False, seed=0, device=cuda)
+    agent = Envelope(env, batch_size=16, num_sample_w=4, buffer_size=256, net_arch=[64, 64], log=False, seed=0, device=cuda)
     obs, _ = env.reset(seed=0)
     w = np.array([0.3, 0.7], dtype=np.float32)
     a = agent.eval(obs, w)

@@ -1,14 +1,17 @@
-"""GPU tests of the tcgen05 bf16x3 GEMM (csrc/gemm_bf16x3.cu) against a float64 reference.
+"""GPU tests of the tcgen05 split-operand GEMMs (csrc/gemm_planes.cu) against a float64 reference, for both operand formats:
+f16x2 (two fp16 planes of a power-of-two-scaled operand, three MMAs) and bf16x3 (three bf16 planes, six MMAs).
 
-Tolerance: the six-term bf16x3 expansion is exact to ~2^-24 per product and accumulates in fp32, so the result must agree
+Tolerance: the expansions are exact to ~2^-22 (f16x2) / 2^-24 (bf16x3) per product and accumulate in fp32, so the result must agree
 with the float64 product to fp32-GEMM accuracy: |err| <= 2e-6 * (|A| . |B|^T) elementwise (2e-6 ~ 32 ulp of headroom for the
-K = 256 accumulation; a plain BF16 or TF32 GEMM misses this bound by two to three orders of magnitude)."""
+K = 256 accumulation; a plain FP16 / BF16 / TF32 GEMM misses this bound by two to three orders of magnitude)."""
 
 import numpy as np
 import pytest
 import torch as th
 
 pytestmark = pytest.mark.gpu
+
+FMTS = [pytest.param(1, id="f16x2"), pytest.param(0, id="bf16x3")]
 
 
 def _ref(a, b, bias):
@@ -22,31 +25,81 @@ def _bound(a, b):
     return 2e-6 * (a.abs().double() @ b.abs().double().t()) + 1e-30
 
 
-def test_split_planes_are_exact_to_2pow24(cuda):
+def _scale(fmt, value, dev):
+    from morl_baselines_b200 import ops
+
+    return ops.scale_tensor(value, dev) if fmt == ops.FMT_F16X2 else None
+
+
+def _sum(p):
+    return sum(p[i].double() for i in range(p.shape[0]))
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_split_planes_reproduce_the_operand(cuda, fmt):
     from morl_baselines_b200 import ops
 
     g = th.Generator(device=cuda).manual_seed(0)
-    x = th.randn(300, 70, device=cuda, generator=g) * th.exp(3 * th.randn(300, 70, device=cuda, generator=g))
-    p = ops.split_bf16x3(x, rows_pad=320, ldp=96)
-    s = p[0].double() + p[1].double() + p[2].double()
+    if fmt == ops.FMT_F16X2:  # fp16 exponent range: moderate dynamic range, power-of-two scale
+        x = th.randn(300, 70, device=cuda, generator=g) * th.exp(th.randn(300, 70, device=cuda, generator=g))
+        sc, rel = ops.scale_tensor(64.0, cuda), 2.0**-21
+    else:
+        x = th.randn(300, 70, device=cuda, generator=g) * th.exp(3 * th.randn(300, 70, device=cuda, generator=g))
+        sc, rel = None, 2.0**-23
+    p = ops.split_planes(x, fmt, rows_pad=320, ldp=128, scale=sc)
+    s = _sum(p) / (64.0 if sc is not None else 1.0)
     assert th.all(s[300:] == 0) and th.all(s[:, 70:] == 0)
-    assert float(((s[:300, :70] - x.double()).abs() / x.abs().double()).max()) <= 2.0**-23
-    pt = ops.split_bf16x3(x, transpose=True)
+    big = x.abs() > 1e-3  # (f16x2: elements below 2^-14 / scale keep absolute, not relative, accuracy)
+    assert float(((s[:300, :70] - x.double()).abs() / x.abs().double())[big].max()) <= rel
+    assert float((s[:300, :70] - x.double()).abs().max()) <= rel * float(x.abs().max())
+    pt = ops.split_planes(x, fmt, transpose=True, scale=sc)
     assert th.equal(pt[0][:70, :300], p[0][:300, :70].t())
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1000, 256, 256), (65536, 256, 256), (4096, 24, 256), (777, 256, 32), (513, 64, 64)])
+def test_f16x2_overflow_is_flagged(cuda):
+    from morl_baselines_b200 import ops
+
+    ops.plane_overflow_count(reset=True)
+    x = th.ones(64, 64, device=cuda)
+    ops.split_planes(x, ops.FMT_F16X2, scale=ops.scale_tensor(1024.0, cuda))
+    assert ops.plane_overflow_count() == 0
+    x[3, 5] = 100.0  # 100 * 1024 > 65504
+    p = ops.split_planes(x, ops.FMT_F16X2, scale=ops.scale_tensor(1024.0, cuda))
+    assert ops.plane_overflow_count(reset=True) > 0 and not bool(th.isfinite(p.float()).all())
+    assert ops.plane_overflow_count() == 0
+
+
+def test_amax_scale(cuda):
+    from morl_baselines_b200 import ops
+
+    ws = th.zeros(2, device=cuda, dtype=th.int32)
+    out = th.zeros(1, device=cuda)
+    g = th.Generator(device=cuda).manual_seed(4)
+    for n, mag in ((65536 * 24, 3e-5), (1000, 7.0), (13, 1e-9), (5, 0.0)):
+        x = th.randn(n, device=cuda, generator=g) * mag
+        ops.amax_scale(x, 9, out, ws)
+        amax, s = float(x.abs().max()), float(out)
+        assert int(ws.abs().sum()) == 0  # workspace left zeroed
+        if amax == 0:
+            assert s == 1.0
+        else:
+            assert np.log2(s) == round(np.log2(s)) and 2.0**8 <= amax * s < 2.0**9, (amax, s)
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1000, 256, 256), (65536, 256, 256), (4096, 24, 256), (777, 256, 64), (513, 64, 64)])
 @pytest.mark.parametrize("relu", [False, True])
-def test_gemm_bf16x3_matches_float64(cuda, M, N, K, relu):
+def test_gemm_planes_matches_float64(cuda, fmt, M, N, K, relu):
     from morl_baselines_b200 import ops
 
     g = th.Generator(device=cuda).manual_seed(M + N + K)
     a = th.randn(M, K, device=cuda, generator=g)
     b = th.randn(N, K, device=cuda, generator=g) / np.sqrt(K)
     bias = th.randn(N, device=cuda, generator=g)
-    ap = ops.split_bf16x3(a)
-    bp = ops.split_bf16x3(b, rows_pad=(N + 31) // 32 * 32)
-    c, cp = ops.gemm_bf16x3(ap, bp, N, bias=bias, relu=relu, out_f32=True, out_planes=(N % 32 == 0))
+    sa, sb, sc = _scale(fmt, 8.0, cuda), _scale(fmt, 4096.0, cuda), _scale(fmt, 16.0, cuda)
+    ap = ops.split_planes(a, fmt, scale=sa)
+    bp = ops.split_planes(b, fmt, rows_pad=(N + 31) // 32 * 32, scale=sb)
+    c, cp = ops.gemm_planes(ap, bp, N, bias=bias, relu=relu, out_f32=True, out_planes=(N % 32 == 0), a_scale=sa, b_scale=sb, c_scale=sc)
     ref = _ref(a, b, bias)
     if relu:
         ref = ref.clamp_min(0)
@@ -58,11 +111,13 @@ def test_gemm_bf16x3_matches_float64(cuda, M, N, K, relu):
     c32 = c32.clamp_min(0) if relu else c32
     assert bool(((c32.double() - ref).abs() <= bound).all())
     if cp is not None:
-        s = cp[0].double() + cp[1].double() + cp[2].double()
-        assert float((s - c.double()).abs().max()) <= 2.0**-22 * float(c.abs().max())
+        s = _sum(cp) / (16.0 if sc is not None else 1.0)
+        assert float((s - c.double()).abs().max()) <= 2.0**-21 * float(c.abs().max())
+    assert ops.plane_overflow_count() == 0
 
 
-def test_gemm_relu_mask_and_chaining(cuda):
+@pytest.mark.parametrize("fmt", FMTS)
+def test_gemm_relu_mask_and_chaining(cuda, fmt):
     """Two chained layers through the plane format (no fp32 round trip) and the ReLU-backward mask."""
     from morl_baselines_b200 import ops
 
@@ -72,52 +127,59 @@ def test_gemm_relu_mask_and_chaining(cuda):
     w1 = th.randn(H, H, device=cuda, generator=g) / 16
     w2 = th.randn(H, H, device=cuda, generator=g) / 16
     b1 = th.randn(H, device=cuda, generator=g) * 0.1
-    xp = ops.split_bf16x3(x)
-    _, h1p = ops.gemm_bf16x3(xp, ops.split_bf16x3(w1), H, bias=b1, relu=True, out_f32=False, out_planes=True)
-    y, _ = ops.gemm_bf16x3(h1p, ops.split_bf16x3(w2), H)
+    sx, sw, sg = _scale(fmt, 8.0, cuda), _scale(fmt, 1024.0, cuda), _scale(fmt, 64.0, cuda)
+    xp = ops.split_planes(x, fmt, scale=sx)
+    _, h1p = ops.gemm_planes(xp, ops.split_planes(w1, fmt, scale=sw), H, bias=b1, relu=True, out_f32=False, out_planes=True, a_scale=sx, b_scale=sw,
+                             c_scale=sx)
+    y, _ = ops.gemm_planes(h1p, ops.split_planes(w2, fmt, scale=sw), H, a_scale=sx, b_scale=sw)
     h1 = (x.double() @ w1.double().t() + b1.double()).clamp_min(0)
     ref = h1 @ w2.double().t()
     assert float((y.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
     # backward of layer 2 w.r.t. h1, masked by relu'(h1):  dH = (dY . W2) * [h1 > 0]
     dy = th.randn(M, H, device=cuda, generator=g)
-    dh, _ = ops.gemm_bf16x3(ops.split_bf16x3(dy), ops.split_bf16x3(w2, transpose=True), H, relu_mask=h1p)
+    dh, _ = ops.gemm_planes(ops.split_planes(dy, fmt, scale=sg), ops.split_planes(w2, fmt, transpose=True, scale=sw), H, relu_mask=h1p, a_scale=sg,
+                            b_scale=sw)
     ref_dh = (dy.double() @ w2.double()) * (h1 > 0)
     assert float((dh.double() - ref_dh).abs().max()) <= 1e-5 * float(ref_dh.abs().max())
 
 
-def test_pairs_relu_split(cuda):
+@pytest.mark.parametrize("fmt", FMTS)
+def test_pairs_relu_split(cuda, fmt):
     from morl_baselines_b200 import ops
 
     g = th.Generator(device=cuda).manual_seed(1)
     u, v = th.randn(37, 256, device=cuda, generator=g), th.randn(5, 256, device=cuda, generator=g)
-    p = ops.pairs_relu_split(u, v)
+    sc = _scale(fmt, 8.0, cuda)
+    p = ops.pairs_relu_split(u, v, fmt=fmt, scale=sc)
     ref = (u.unsqueeze(1) + v.unsqueeze(0)).clamp_min(0).view(-1, 256)
-    s = p[0].double() + p[1].double() + p[2].double()
-    assert float((s - ref.double()).abs().max()) <= 2.0**-22 * float(ref.abs().max())
+    s = _sum(p) / (8.0 if sc is not None else 1.0)
+    assert float((s - ref.double()).abs().max()) <= 2.0**-21 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("fmt", FMTS)
 @pytest.mark.parametrize("M,gc,hc", [(65536, 256, 256), (5000, 256, 256), (4096, 24, 256), (1000, 128, 64), (333, 256, 192)])
-def test_gemm_mn_weight_gradient(cuda, M, gc, hc):
+def test_gemm_mn_weight_gradient(cuda, fmt, M, gc, hc):
     """dW[n, k] = sum_m G[m, n] H[m, k] (MN-major operands, split-K) against float64."""
     from morl_baselines_b200 import ops
 
     g_ = th.Generator(device=cuda).manual_seed(M + gc)
-    G = th.randn(M, gc, device=cuda, generator=g_)
+    G = th.randn(M, gc, device=cuda, generator=g_) * 1e-4
     H = th.randn(M, hc, device=cuda, generator=g_).clamp_min(0)
-    Gp = ops.split_bf16x3(G, ldp=(gc + 63) // 64 * 64)
-    Hp = ops.split_bf16x3(H, ldp=(hc + 63) // 64 * 64)
-    dW = ops.gemm_bf16x3_mn(Gp, gc, Hp, hc)
+    sg, sh = _scale(fmt, 2.0**20, cuda), _scale(fmt, 8.0, cuda)
+    Gp = ops.split_planes(G, fmt, ldp=(gc + 63) // 64 * 64, scale=sg)
+    Hp = ops.split_planes(H, fmt, ldp=(hc + 63) // 64 * 64, scale=sh)
+    dW = ops.gemm_planes_mn(Gp, gc, Hp, hc, g_scale=sg, h_scale=sh)
     ref = G.double().t() @ H.double()
     bound = 2e-6 * (G.abs().double().t() @ H.abs().double()) * max(1.0, np.sqrt(M / 4096)) + 1e-30
     err = (dW.double() - ref).abs()
     assert bool((err <= bound).all()), float((err / bound).max())
-    dWt = ops.gemm_bf16x3_mn(Gp, gc, Hp, hc, transpose_out=True)
+    dWt = ops.gemm_planes_mn(Gp, gc, Hp, hc, transpose_out=True, g_scale=sg, h_scale=sh)
     assert th.equal(dWt, dW.t().contiguous())
-    cs = ops.colsum_bf16x3(Gp, gc)
+    cs = ops.colsum_planes(Gp, gc, scale=sg)
     np.testing.assert_allclose(cs.cpu().numpy(), G.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5 * float(G.abs().sum(0).max()))
     # bias gradient fused into the same pass (G^T . ones on the tensor cores); the weight gradient must be unchanged by it
     cs2 = th.full((gc,), float("nan"), device=cuda)
-    dW2 = ops.gemm_bf16x3_mn(Gp, gc, Hp, hc, colsum=cs2)
+    dW2 = ops.gemm_planes_mn(Gp, gc, Hp, hc, colsum=cs2, g_scale=sg, h_scale=sh)
     assert th.equal(dW2, dW)
     np.testing.assert_allclose(cs2.cpu().numpy(), G.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5 * float(G.abs().sum(0).max()))
 
@@ -157,38 +219,45 @@ def test_pair_layer1_grad(cuda, B, W, F, D, H):
     assert th.equal(dW1, dW1b) and th.equal(db1, db1b)
 
 
-def test_split_vectorised_path_matches_scalar_path(cuda):
+@pytest.mark.parametrize("fmt", FMTS)
+def test_split_vectorised_path_matches_scalar_path(cuda, fmt):
     """ldp % 8 == 0 takes the 8-columns-per-thread kernel; an unaligned source (ld_src % 4 != 0) and ragged columns must give the same
     planes as the transposed-input scalar kernel."""
     from morl_baselines_b200 import ops
 
     g_ = th.Generator(device=cuda).manual_seed(9)
+    sc = _scale(fmt, 32.0, cuda)
     for rows, cols in ((65536, 24), (1000, 250), (77, 13)):
         x = th.randn(rows, cols, device=cuda, generator=g_)
         ldp = (cols + 31) // 32 * 32
-        a = ops.split_bf16x3(x, ldp=ldp)  # vectorised
-        b = ops.split_bf16x3(x.t().contiguous(), ldp=ldp, transpose=True)  # scalar kernel on the transposed source
+        a = ops.split_planes(x, fmt, ldp=ldp, scale=sc)  # vectorised
+        b = ops.split_planes(x.t().contiguous(), fmt, ldp=ldp, transpose=True, scale=sc)  # scalar kernel on the transposed source
         assert th.equal(a, b)
-        assert float((a[0].double() + a[1].double() + a[2].double())[:, :cols].sub(x.double()).abs().max()) <= 2.0**-23 * float(x.abs().max())
-        assert float(a[:, :, cols:].abs().max()) == 0.0
+        s = _sum(a) / (32.0 if sc is not None else 1.0)
+        assert float(s[:, :cols].sub(x.double()).abs().max()) <= 2.0**-21 * float(x.abs().max())
+        assert float(a[:, :, cols:].float().abs().max()) == 0.0
 
 
-def test_pairs_grad_reduce(cuda):
+@pytest.mark.parametrize("fmt", FMTS)
+def test_pairs_grad_reduce(cuda, fmt):
     from morl_baselines_b200 import ops
 
     g_ = th.Generator(device=cuda).manual_seed(2)
+    sc = _scale(fmt, 16.0, cuda)
     for B, W in ((37, 5), (64, 64), (300, 33), (5, 70)):
         G = th.randn(B * W, 256, device=cuda, generator=g_)
-        Gp = ops.split_bf16x3(G)
-        dU, dV = ops.pairs_grad_reduce(Gp, B, W)
+        Gp = ops.split_planes(G, fmt, scale=sc)
+        dU, dV = ops.pairs_grad_reduce(Gp, B, W, scale=sc)
         ref = G.double().view(B, W, 256)
         np.testing.assert_allclose(dU.cpu().numpy(), ref.sum(1).cpu().numpy(), rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(dV.cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
-def test_gemm_single_cta_kernel_still_correct(cuda):
-    """Large shapes use the CTA-pair (cta_group::2) kernel; MORL_GEMM_FORCE_1CTA=1 keeps the one-CTA kernel alive as a cross-check.
-    The switch is read once per process, hence the subprocess."""
+@pytest.mark.parametrize("env_flags", [{"MORL_GEMM_FORCE_1CTA": "1"}, {"MORL_GEMM_SPLIT_ACC": "0"}, {"MORL_GEMM_FORCE_1CTA": "1", "MORL_GEMM_SPLIT_ACC": "0"}])
+def test_gemm_alternative_kernels_still_correct(cuda, env_flags):
+    """Large shapes use the CTA-pair (cta_group::2) kernel with split accumulators; MORL_GEMM_FORCE_1CTA=1 keeps the one-CTA kernel and
+    MORL_GEMM_SPLIT_ACC=0 the single double-buffered accumulator alive as cross-checks.  The switches are read once per process, hence
+    the subprocess."""
     import os
     import subprocess
     import sys
@@ -198,32 +267,57 @@ def test_gemm_single_cta_kernel_still_correct(cuda):
         "from morl_baselines_b200 import ops\n"
         "g = th.Generator(device='cuda').manual_seed(3)\n"
         "a = th.randn(5000, 256, device='cuda', generator=g); b = th.randn(256, 256, device='cuda', generator=g) / 16\n"
-        "c, _ = ops.gemm_bf16x3(ops.split_bf16x3(a), ops.split_bf16x3(b), 256)\n"
         "ref = a.double() @ b.double().t()\n"
-        "err = float((c.double() - ref).abs().max()); print('ERR', err); assert err < 2e-5\n"
+        "for fmt in (ops.FMT_F16X2, ops.FMT_BF16X3):\n"
+        "    sa = ops.scale_tensor(8.0, 'cuda') if fmt == ops.FMT_F16X2 else None\n"
+        "    sb = ops.scale_tensor(1024.0, 'cuda') if fmt == ops.FMT_F16X2 else None\n"
+        "    c, _ = ops.gemm_planes(ops.split_planes(a, fmt, scale=sa), ops.split_planes(b, fmt, scale=sb), 256, a_scale=sa, b_scale=sb)\n"
+        "    err = float((c.double() - ref).abs().max()); print('ERR', fmt, err); assert err < 2e-5\n"
     )
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = {}
-    for flag in ("1", "0"):
-        env = dict(os.environ, MORL_GEMM_FORCE_1CTA=flag, PYTHONPATH=root)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stdout + r.stderr
-        outs[flag] = r.stdout
-    assert "ERR" in outs["1"] and "ERR" in outs["0"]
+    env = dict(os.environ, PYTHONPATH=root, **env_flags)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ERR") == 2
 
 
-def test_reverse_tile_order_and_multi_split_are_bit_identical(cuda):
+@pytest.mark.parametrize("fmt", FMTS)
+def test_reverse_tile_order_and_multi_split_are_bit_identical(cuda, fmt):
     from morl_baselines_b200 import ops
 
     g = th.Generator(device=cuda).manual_seed(11)
     a = th.randn(40000, 256, device=cuda, generator=g)
     ws = [th.randn(256, 256, device=cuda, generator=g) / 16, th.randn(24, 256, device=cuda, generator=g), th.randn(256, 64, device=cuda, generator=g)]
-    ap = ops.split_bf16x3(a)
-    singles = [ops.split_bf16x3(ws[0]), ops.split_bf16x3(ws[1], rows_pad=32), ops.split_bf16x3(ws[2], rows_pad=64, ldp=256, transpose=True)]
+    sa, sw = _scale(fmt, 8.0, cuda), _scale(fmt, 512.0, cuda)
+    ap = ops.split_planes(a, fmt, scale=sa)
+    singles = [ops.split_planes(ws[0], fmt, scale=sw), ops.split_planes(ws[1], fmt, rows_pad=32, scale=sw),
+               ops.split_planes(ws[2], fmt, rows_pad=64, ldp=256, transpose=True, scale=sw)]
     multi = [th.empty_like(s) for s in singles]
-    ops.split_bf16x3_multi([(ws[0], multi[0], False), (ws[1], multi[1], False), (ws[2], multi[2], True)])
+    ops.split_planes_multi([(ws[0], multi[0], False, sw), (ws[1], multi[1], False, sw), (ws[2], multi[2], True, sw)], fmt)
     for s, m in zip(singles, multi):
         assert th.equal(s, m)
-    c0, p0 = ops.gemm_bf16x3(ap, singles[0], 256, relu=True, out_f32=True, out_planes=True)
-    c1, p1 = ops.gemm_bf16x3(ap, singles[0], 256, relu=True, out_f32=True, out_planes=True, reverse_tiles=True)
+    c0, p0 = ops.gemm_planes(ap, singles[0], 256, relu=True, out_f32=True, out_planes=True, a_scale=sa, b_scale=sw, c_scale=sa)
+    c1, p1 = ops.gemm_planes(ap, singles[0], 256, relu=True, out_f32=True, out_planes=True, reverse_tiles=True, a_scale=sa, b_scale=sw, c_scale=sa)
     assert th.equal(c0, c1) and th.equal(p0, p1)
+
+
+def test_multi_split_auto_scale(cuda):
+    """auto_scale jobs derive a power-of-two scale from their own matrix (amax * s in [2^13, 2^14)), publish it, and the plain and the
+    transposed job of the same matrix agree on it."""
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(12)
+    w = th.randn(256, 256, device=cuda, generator=g) * 0.07
+    w2 = th.randn(24, 256, device=cuda, generator=g) * 3.0
+    s1, s2 = ops.scale_tensor(1.0, cuda), ops.scale_tensor(1.0, cuda)
+    outs = [ops.empty_planes(ops.FMT_F16X2, 256, 256, cuda), ops.empty_planes(ops.FMT_F16X2, 256, 256, cuda), ops.empty_planes(ops.FMT_F16X2, 32, 256, cuda)]
+    ops.split_planes_multi([(w, outs[0], False, s1, 14), (w, outs[1], True, s1, 14), (w2, outs[2], False, s2, 14)], ops.FMT_F16X2)
+    for s, m in ((s1, w), (s2, w2)):
+        v = float(s) * float(m.abs().max())
+        assert 2.0**13 <= v < 2.0**14 and np.log2(float(s)) == round(np.log2(float(s)))
+    assert th.equal(outs[1], outs[0].transpose(1, 2).contiguous())
+    rec = _sum(outs[0]) / float(s1)
+    assert float((rec - w.double()).abs().max()) <= 2.0**-21 * float(w.abs().max())
+    rec2 = _sum(outs[2])[:24] / float(s2)
+    assert float((rec2 - w2.double()).abs().max()) <= 2.0**-21 * float(w2.abs().max())
+    assert ops.plane_overflow_count() == 0

@@ -147,7 +147,7 @@ def _env_path(path, *a, **k):
 @pytest.mark.parametrize("kind", ["plain", "ties", "neartie", "signed", "special"])
 def test_envelope_td_kernel_families_agree_bitwise(cuda, shape, kind):
     """The kernel families of morl_envelope_td_f32 -- generic (v1), CUDA-core fast paths (v3: FMA-chain filter + exact re-check; wp: its
-    weight-pair re-blocking, the default at |W| > 32), tensor-core filter (tc: bf16x3 scores from tcgen05.mma, exact re-check) -- return bit-identical targets and indices, in every
+    weight-pair re-blocking, the default at |W| > 32) -- return bit-identical targets and indices, in every
     arithmetic mode and row order, on continuous data, exact ties, candidates a few ulps apart, mixed-sign weights / large values,
     and NaN / +-inf / all-zero / huge / tiny blocks.  v1 is pinned to the oracle and the reference's golden vectors above."""
     from morl_baselines_b200 import ops
@@ -182,19 +182,10 @@ def test_envelope_td_kernel_families_agree_bitwise(cuda, shape, kind):
         combos += [(ops.DOT_UNFUSED, ops.ROWS_REFERENCE), (ops.DOT_FMA, ops.ROWS_BMAJOR), (ops.DOT_PAIRFMA, ops.ROWS_REFERENCE)]
     for mode, order in combos:
         ref = _env_path("v1", q_on, q_tg, wset, rew, done, 0.99, mode, order)
-        for path in (("v3", "wp", "tc") if W > 32 else ("v3", "tc")):
+        for path in (("v3", "wp") if W > 32 else ("v3",)):
             got = _env_path(path, q_on, q_tg, wset, rew, done, 0.99, mode, order)
             assert th.equal(ref[0].view(th.int32), got[0].view(th.int32)), (path, mode, order)  # bit pattern (NaN-safe)
             assert th.equal(ref[1], got[1]) and th.equal(ref[2], got[2]), (path, mode, order)
-
-
-def test_envelope_td_tc_path_rejects_unsupported_shapes(cuda):
-    from morl_baselines_b200 import _lib, ops
-
-    B, W, A, D = 4, 70, 9, 4  # |W| > 64, D > 3
-    z = th.zeros(B, W, A, D, device=cuda)
-    with pytest.raises(_lib.MorlB200Error):
-        _env_path("tc", z, z, th.ones(W, D, device=cuda), th.zeros(B, D, device=cuda), th.zeros(B, device=cuda), 0.99)
 
 
 # ------------------------------------------------------------------------------------------------ per-row targets
