@@ -204,6 +204,18 @@ MORL_API int morl_replay_gather(const float* obs_store, const float* next_obs_st
 MORL_API int morl_pareto_mask_f32(const float* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream);
 MORL_API int morl_pareto_mask_f64(const double* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream);
 
+/* Fixed-shape records for the ONE all-gather of per-rank non-dominated fronts per evaluation round (BASELINE.json north_star; the
+ * reference has no multi-GPU path -- the call it replaces is the single-process archive update of multi_policy/morld/morld.py:306-335).
+ *   record (float64) = [ count | cap x d rows | n_extra extras ]
+ * morl_front_pack_f64   : rows of pts [n, d] with keep[i] != 0 (keep NULL = all), in input order; count is NOT clipped to cap (overflow is
+ *                         visible to every rank after the gather); unused rows are -inf (dominated by any real point).  One block.
+ * morl_front_unpack_f64 : gathered [world][1 + cap*d + n_extra] -> pts_out [world*cap, d] (input of the global prune) and
+ *                         meta_out [world][1 + n_extra] (every rank's count and extras, contiguous).
+ * No host synchronisation, no allocation: the whole exchange is stream-ordered. */
+MORL_API int morl_front_pack_f64(const double* pts, const uint8_t* keep, int n, int d, int cap, const double* extras, int n_extra, double* rec,
+                                 void* stream);
+MORL_API int morl_front_unpack_f64(const double* gathered, int world, int d, int cap, int n_extra, double* pts_out, double* meta_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Multi-tensor target-network sync.  Replaces polyak_update (common/networks.py:121-139):
  *   tau == 1 : target <- param;  else target <- fma(tau, param, fl((1 - tau) * target))   (mul_ then ATen's fused add(alpha))
@@ -238,6 +250,11 @@ MORL_API int morl_polyak_f32(const float* const* params, float* const* targets, 
  *                     a forward activation, [M][ld_mask] 16-bit) zeroes the outputs where that activation was <= 0 (ReLU backward).
  *                     reverse_tiles != 0 walks the 128-row tiles from the last to the first: alternate it between the layers of
  *                     a chain so that a layer starts on the rows its producer wrote last (still in the 126 MB L2).
+ *                     split_accumulators != 0: the leading products A0.B0 and the correction products accumulate in separate TMEM
+ *                     buffers and are added once, correctly rounded, in the epilogue -- the tensor cores TRUNCATE their fp32
+ *                     accumulation at every MMA, which costs ~2e-6 (f16x2) / ~4e-6 (bf16x3) of systematic relative shrinkage per
+ *                     K = 256 layer in one accumulator and ~2.5x less in split mode (profiles/r02_gemm_error.txt); the price is that
+ *                     the epilogue of a tile no longer overlaps the MMAs of the next one.
  */
 #define MORL_FMT_BF16X3 0
 #define MORL_FMT_F16X2 1
@@ -246,7 +263,7 @@ typedef struct MorlSplitJob {
     const float* src;       /* fp32 [rows, cols], row stride ld_src */
     void* dst_planes;       /* 16-bit [P][rows_pad][ldp] */
     long long plane_stride; /* elements between planes */
-    float* scale;           /* device float: read (auto_scale == 0; NULL = 1) or written (auto_scale != 0; NULL = not published) */
+    float* scale;           /* device float: read (auto_scale == 0; NULL = 1) or written first, then used (auto_scale != 0; must not be NULL) */
     int rows, cols, ld_src, transpose, rows_pad, ldp;
     int auto_scale, target_exp;
 } MorlSplitJob;
@@ -258,7 +275,7 @@ MORL_API int morl_split_planes(int fmt, const float* src, int rows, int cols, in
 MORL_API int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* b_planes,
                                   long long b_plane_stride, const float* b_scale, int M, int N, int N_pad, int K, const float* bias,
                                   int relu, const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp,
-                                  long long c_plane_stride, const float* c_scale, int reverse_tiles, void* stream);
+                                  long long c_plane_stride, const float* c_scale, int reverse_tiles, int split_accumulators, void* stream);
 /* Diagnostics (not part of the reference surface): per-role cycle counters of morl_gemm_planes_f32, summed over CTAs and launches
  * since the last reset; collected only when the environment variable MORL_GEMM_STATS=1 is set before the first GEMM call.
  * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,

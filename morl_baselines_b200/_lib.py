@@ -43,13 +43,15 @@ SIGNATURES = {
     "morl_replay_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "morl_pareto_mask_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_pareto_mask_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "morl_front_pack_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "morl_front_unpack_f64": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "morl_polyak_f32": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),
     "morl_plane_overflow_count": (_i, [_i]),
     "morl_amax_scale_f32": (_i, [_vp, C.c_longlong, _i, _vp, _vp, _vp]),
     "morl_split_planes_multi": (_i, [_i, _vp, _i, _vp]),
     "morl_split_planes": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _i, _i, C.c_longlong, _vp, _vp]),
     "morl_gemm_planes_f32": (_i, [_i, _vp, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_longlong,
-                                  _vp, _i, _vp]),
+                                  _vp, _i, _i, _vp]),
     "morl_debug_gemm_stats": (_i, [_vp, _i]),
     "morl_pairs_relu_split_planes": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp, _vp]),
     "morl_gemm_mn_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -487,14 +487,21 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         uint8_t* my_stage = stage_c + (warp - 2) * L::kStageC;
-        const float inv_ab = 1.0f / (ld_scale(g.a_scale) * ld_scale(g.b_scale));  // exact: the scales are powers of two
+        // x = acc / (sA sB) + bias; when only planes are written (the hidden layers) the output scale is FOLDED into the two constants:
+        // fold * x = acc * (fold / (sA sB)) + fold * bias (exact, powers of two), and max / mask commute with a positive factor
         const float c_mul = ld_scale(g.c_scale);
+        const bool folded = g.c_f32 == nullptr;
+        const float fold = folded ? c_mul : 1.0f;
+        const float k_acc = fold / (ld_scale(g.a_scale) * ld_scale(g.b_scale));
+        if (warp == 2 && folded)  // (bias_s was filled before the CTA barrier; one warp rescales it)
+            for (int t = lane; t < 256; t += 32) bias_s[t] *= fold;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
         float amax = 0.f;
         auto process = [&](const uint32_t (&v)[32], int n0, int row, bool row_ok) {
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float f = __fmaf_rn(__uint_as_float(v[j]), inv_ab, bias_s[n0 + j]);
+                float f = __fmaf_rn(__uint_as_float(v[j]), k_acc, bias_s[n0 + j]);
                 if (g.relu) f = fmaxf(f, 0.f);
                 x[j] = f;
             }
@@ -524,15 +531,29 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
             if (g.c_planes && n0 < g.ldp) {
+                if (n0 + 32 > g.N) {  // ragged last chunk: columns [N, ldp) are written as zero
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j >= g.N) x[j] = 0.f;
+                }
                 // re-split (c_scale x) into P planes, two columns per word
                 uint32_t pw[P][16];
+                if (folded) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float a = (n0 + j < g.N) ? x[j] * c_mul : 0.f, b = (n0 + j + 1 < g.N) ? x[j + 1] * c_mul : 0.f;
-                    uint32_t w[P];
-                    F::split2(a, b, w, amax);
+                    for (int j = 0; j < 32; j += 2) {
+                        uint32_t w[P];
+                        F::split2(x[j], x[j + 1], w, amax);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) pw[p][j / 2] = w[p];
+                        for (int p = 0; p < P; ++p) pw[p][j / 2] = w[p];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        uint32_t w[P];
+                        F::split2(x[j] * c_mul, x[j + 1] * c_mul, w, amax);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) pw[p][j / 2] = w[p];
+                    }
                 }
                 // stage the warp's [32 rows x 32 cols] x P planes in shared memory (TMA SWIZZLE_64B pattern: 16-byte chunk index
                 // XOR ((row >> 1) & 3), bank-conflict free), then ONE bulk tensor store writes it out coalesced and asynchronously
@@ -1080,39 +1101,48 @@ __global__ void __launch_bounds__(256) split_planes_vec8_kernel(const float* __r
     if (FMT == MORL_FMT_F16X2) note_overflow(amax);
 }
 
-// several small matrices (the weight matrices of a network, plain and transposed) in ONE launch: blockIdx.y selects the job.  A job with
-// auto_scale != 0 derives its power-of-two scale from the largest |element| of ITS matrix: every block of the job reduces the whole (small)
-// matrix itself -- no inter-block dependency, every block arrives at the same value -- and block 0 publishes it in *scale.
+// several small matrices (the weight matrices of a network, plain and transposed) in ONE launch: blockIdx.y selects the job.  Jobs with
+// auto_scale != 0 derive their power-of-two scale from the largest |element| of their matrix in a one-block-per-job pre-pass
+// (split_amax_multi_kernel, launched right before by the same entry point), which publishes it in *scale.
 struct SplitJobs {
     MorlSplitJob job[MORL_SPLIT_MAX_JOBS];
 };
+__global__ void __launch_bounds__(1024) split_amax_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+    __shared__ float red[32];
+    const MorlSplitJob& j = jobs.job[blockIdx.x];
+    if (!j.auto_scale || !j.scale) return;  // uniform per block
+    const float* __restrict__ src = j.src;
+    const int n_src = j.transpose ? j.cols : j.rows, k_src = j.transpose ? j.rows : j.cols;  // source matrix [n_src, k_src], row stride ld_src
+    float m = 0.f;
+    if (j.ld_src == k_src && (k_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {  // dense: 128-bit loads
+        const int n4 = (n_src * k_src) >> 2;
+        for (int e = threadIdx.x; e < n4; e += blockDim.x) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + e);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+    } else {
+        for (int r = threadIdx.x / 32; r < n_src; r += blockDim.x / 32)
+            for (int c = threadIdx.x & 31; c < k_src; c += 32) m = fmaxf(m, fabsf(__ldg(src + (size_t)r * j.ld_src + c)));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if (threadIdx.x == 0) *j.scale = scale_from_amax(m, j.target_exp);
+    }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(256) split_planes_multi_kernel(const __grid_constant__ SplitJobs jobs) {
     using F = PlaneFmt<FMT>;
-    __shared__ float red[8];
     const MorlSplitJob& j = jobs.job[blockIdx.y];
     const float* __restrict__ src = j.src;
     uint16_t* __restrict__ dst = static_cast<uint16_t*>(j.dst_planes);
-    float s = 1.0f;
-    if (j.auto_scale) {
-        float m = 0.f;
-        const int n_src = j.transpose ? j.cols : j.rows, k_src = j.transpose ? j.rows : j.cols;  // source matrix [n_src, k_src]
-        const long long tot = (long long)n_src * k_src;
-        for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
-            const int r = (int)(e / k_src), c = (int)(e - (long long)r * k_src);
-            m = fmaxf(m, fabsf(__ldg(src + (size_t)r * j.ld_src + c)));
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
-        s = scale_from_amax(m, j.target_exp);
-        if (blockIdx.x == 0 && threadIdx.x == 0 && j.scale) *j.scale = s;
-    } else if (j.scale) {
-        s = *j.scale;
-    }
+    const float s = j.scale ? *j.scale : 1.0f;  // (auto-scaled jobs: written by the pre-pass)
     const long long total = (long long)j.rows_pad * j.ldp;
     float amax = 0.f;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -1401,14 +1431,21 @@ extern "C" int morl_split_planes_multi(int fmt, const MorlSplitJob* jobs, int n_
         MORL_REQUIRE(j.rows > 0 && j.cols > 0 && j.rows_pad >= j.rows && j.ldp >= j.cols && j.ld_src > 0 &&
                          j.plane_stride >= (long long)j.rows_pad * j.ldp,
                      MORL_ERR_SHAPE, "morl_split_planes_multi: job %d bad shape rows=%d cols=%d rows_pad=%d ldp=%d", i, j.rows, j.cols, j.rows_pad, j.ldp);
-        MORL_REQUIRE(!j.auto_scale || (j.target_exp >= -14 && j.target_exp <= 15), MORL_ERR_SHAPE, "morl_split_planes_multi: job %d target_exp=%d", i,
-                     j.target_exp);
+        MORL_REQUIRE(!j.auto_scale || (j.scale && j.target_exp >= -14 && j.target_exp <= 15), MORL_ERR_SHAPE,
+                     "morl_split_planes_multi: job %d auto_scale needs a scale pointer and -14 <= target_exp <= 15 (got %d)", i, j.target_exp);
         sj.job[i] = j;
         const long long t = (long long)j.rows_pad * j.ldp;
         if (t > max_total) max_total = t;
     }
     long long bx = (max_total + 255) / 256;
     if (bx > 148) bx = 148;
+    bool any_auto = false;
+    for (int i = 0; i < n_jobs; ++i) any_auto = any_auto || (jobs[i].auto_scale && jobs[i].scale);
+    if (any_auto) {
+        split_amax_multi_kernel<<<n_jobs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(sj);
+        int rca = check_launch("morl_split_planes_multi(amax)");
+        if (rca) return rca;
+    }
     MORL_DISPATCH_FMT(fmt, (split_planes_multi_kernel<kFmt><<<dim3((unsigned)bx, (unsigned)n_jobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(sj)));
     return check_launch("morl_split_planes_multi");
 }
@@ -1482,7 +1519,7 @@ static int launch_gemm_planes(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* b_planes,
                                     long long b_plane_stride, const float* b_scale, int M, int N, int N_pad, int K, const float* bias, int relu,
                                     const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp, long long c_plane_stride,
-                                    const float* c_scale, int reverse_tiles, void* stream) {
+                                    const float* c_scale, int reverse_tiles, int split_accumulators, void* stream) {
     using namespace morl;
     MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_gemm_planes_f32: unknown plane format %d", fmt);
     MORL_REQUIRE(a_planes && b_planes && (c_f32 || c_planes), MORL_ERR_NULL, "morl_gemm_planes_f32: NULL pointer argument");
@@ -1534,8 +1571,9 @@ extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_p
         g.stats = static_cast<unsigned long long*>(sp);
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // split accumulators (see gemm_planes_kernel) are the default; MORL_GEMM_SPLIT_ACC=0 selects the single double-buffered accumulator
-    static const bool split_acc = [] { const char* e = getenv("MORL_GEMM_SPLIT_ACC"); return !(e && e[0] == '0'); }();
+    // accumulator mode (see gemm_planes_kernel): per call; MORL_GEMM_SPLIT_ACC=0 / 1 overrides every call (A/B measurements)
+    static const int split_env = [] { const char* e = getenv("MORL_GEMM_SPLIT_ACC"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    const bool split_acc = split_env >= 0 ? split_env != 0 : split_accumulators != 0;
     if (fmt == MORL_FMT_F16X2)
         return split_acc ? launch_gemm_planes<MORL_FMT_F16X2, 1>(tmA, tmB, tmBh, tmC, g, pair, sms, st)
                          : launch_gemm_planes<MORL_FMT_F16X2, 0>(tmA, tmB, tmBh, tmC, g, pair, sms, st);

@@ -75,64 +75,69 @@ __global__ void __launch_bounds__(256) pair_layer1_uv_kernel(const float* __rest
 }
 
 // ---- backward: dW1 [H, F + D] = [dU^T feats | dV^T wset], db1 [H] = colsum(dV) -------------------------------------------------------------
-// grid = (ceil(H / 32), kL1Splits); block 256 = 32 output rows h x 8 column groups.  Split s reduces transitions [s*bs, (s+1)*bs) into the
-// F "u" columns and weight vectors [s*js, (s+1)*js) into the D "v" columns + the bias column; the partial tiles go to
-// workspace[s][H][F + D + 1] and the LAST block of an h-tile to finish (self-resetting arrival counter) adds the kL1Splits partials in
-// split order: deterministic, no float atomics.
-constexpr int kL1Splits = 16;
-constexpr int kL1Chunk = 64;  // reduction rows staged in shared memory per pass
+// grid = (ceil(H / 32), kL1Splits); block 256 = 32 output rows h (lane) x 8 column groups (warp).  Split s reduces transitions
+// [s*bs, (s+1)*bs) into the F "u" columns and weight vectors [s*js, (s+1)*js) into the D "v" columns + the bias column.  A chunk of
+// reduction rows is staged ONCE in shared memory and every thread accumulates all of its columns (c = warp, warp + 8, ...) from it in
+// registers; the partial tiles go to workspace[s][H][F + D + 1] and the LAST block of an h-tile to finish (self-resetting arrival counter)
+// adds the kL1Splits partials in split order: deterministic, no float atomics.
+constexpr int kL1Splits = 32;
+constexpr int kL1Chunk = 32;   // reduction rows staged per pass
+constexpr int kL1ColsPerThread = 8;  // columns per thread per column block (8 groups x 8 = 64 columns per block of columns)
 
 __global__ void __launch_bounds__(256) pair_layer1_grad_kernel(const float* __restrict__ dU, const float* __restrict__ dV, const float* __restrict__ feats,
                                                                const float* __restrict__ wset, int B, int W, int F, int D, int H, float* __restrict__ dW1,
                                                                float* __restrict__ db1, float* __restrict__ partial, unsigned int* __restrict__ counters) {
-    extern __shared__ float sm[];          // [kL1Chunk][32] gradient rows, then [kL1Chunk][max(F, D + 1)] input rows
+    __shared__ float gs[kL1Chunk][33];                          // gradient rows (dU or dV) of the chunk, this block's 32 h columns
+    __shared__ float xs[kL1Chunk][8 * kL1ColsPerThread + 1];    // input rows of the chunk, the current block of <= 64 columns
     __shared__ unsigned int s_last;
     const int C = F + D + 1;
     const int h0 = blockIdx.x * 32, s = blockIdx.y;
     const int hl = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int xw = F > D + 1 ? F : D + 1;
-    float* gs = sm;
-    float* xs = sm + kL1Chunk * 32;
-    const int npass = (C + 7) / 8;
-    // ---- u columns: reduction over this split's transitions
-    const int bs = (B + kL1Splits - 1) / kL1Splits;
-    const int b_lo = s * bs, b_hi = min(B, b_lo + bs);
-    const int js = (W + kL1Splits - 1) / kL1Splits;
-    const int j_lo = s * js, j_hi = min(W, j_lo + js);
-    for (int pass = 0; pass < npass; ++pass) {
-        const int c = pass * 8 + grp;
-        const bool is_u = c < F;
-        float acc = 0.f;
-        // (all threads of the block walk the same chunks; a thread's column decides which staged operand it multiplies with)
-        for (int phase = 0; phase < 2; ++phase) {  // 0: transitions (u columns), 1: weight vectors (v + bias columns)
-            const int lo = phase == 0 ? b_lo : j_lo, hi = phase == 0 ? b_hi : j_hi;
+    const int bs = (B + kL1Splits - 1) / kL1Splits, js = (W + kL1Splits - 1) / kL1Splits;
+    for (int cb = 0; cb < C; cb += 8 * kL1ColsPerThread) {  // column blocks of 64 (one for the usual F + D + 1 <= 64)
+        const int ncol = min(8 * kL1ColsPerThread, C - cb);
+        float acc[kL1ColsPerThread];
+#pragma unroll
+        for (int k = 0; k < kL1ColsPerThread; ++k) acc[k] = 0.f;
+        for (int phase = 0; phase < 2; ++phase) {  // 0: transitions (u columns [0, F)), 1: weight vectors (v columns [F, F + D) + bias column)
+            const int lo = phase == 0 ? s * bs : s * js, hi = phase == 0 ? min(B, lo + bs) : min(W, lo + js);
+            const int c_lo = phase == 0 ? 0 : F, c_hi = phase == 0 ? F : C;   // global column range this phase contributes to
+            if (cb >= c_hi || cb + ncol <= c_lo) continue;                   // (uniform) nothing of this column block in this phase
             const float* g = phase == 0 ? dU : dV;
             for (int r0 = lo; r0 < hi; r0 += kL1Chunk) {
                 const int nr = min(kL1Chunk, hi - r0);
                 __syncthreads();
-                for (int t = threadIdx.x; t < nr * 32; t += blockDim.x) {
+                for (int t = threadIdx.x; t < nr * 32; t += 256) {
                     const int rr = t >> 5, hh = t & 31;
-                    gs[t] = (h0 + hh < H) ? __ldg(g + (size_t)(r0 + rr) * H + h0 + hh) : 0.f;
+                    gs[rr][hh] = (h0 + hh < H) ? __ldg(g + (size_t)(r0 + rr) * H + h0 + hh) : 0.f;
                 }
-                for (int t = threadIdx.x; t < nr * xw; t += blockDim.x) {
-                    const int rr = t / xw, k = t - rr * xw;
-                    float x = 0.f;
-                    if (phase == 0) {
-                        if (k < F) x = __ldg(feats + (size_t)(r0 + rr) * F + k);
+                for (int t = threadIdx.x; t < nr * 64; t += 256) {
+                    const int rr = t >> 6, cl = t & 63, c = cb + cl;
+                    float x = 0.f;  // columns of the other phase (and beyond the last column) contribute nothing here
+                    if (cl >= ncol) {
+                    } else if (phase == 0) {
+                        if (c < F) x = __ldg(feats + (size_t)(r0 + rr) * F + c);
                     } else {
-                        if (k < D) x = __ldg(wset + (size_t)(r0 + rr) * D + k);
-                        else if (k == D) x = 1.0f;  // bias column: plain column sum of dV
+                        if (c >= F && c < F + D) x = __ldg(wset + (size_t)(r0 + rr) * D + (c - F));
+                        else if (c == F + D) x = 1.0f;  // bias column: plain column sum of dV
                     }
-                    xs[t] = x;
+                    xs[rr][cl] = x;
                 }
                 __syncthreads();
-                if (c < C && ((phase == 0) == is_u)) {
-                    const int k = is_u ? c : c - F;
-                    for (int rr = 0; rr < nr; ++rr) acc = __fmaf_rn(gs[rr * 32 + hl], xs[rr * xw + k], acc);
+                for (int rr = 0; rr < nr; ++rr) {
+                    const float gv = gs[rr][hl];
+#pragma unroll
+                    for (int k = 0; k < kL1ColsPerThread; ++k) acc[k] = __fmaf_rn(gv, xs[rr][grp + 8 * k], acc[k]);
                 }
             }
         }
-        if (c < C && h0 + hl < H) partial[((size_t)s * H + h0 + hl) * C + c] = acc;
+        if (h0 + hl < H) {
+#pragma unroll
+            for (int k = 0; k < kL1ColsPerThread; ++k) {
+                const int c = cb + grp + 8 * k;
+                if (grp + 8 * k < ncol) partial[((size_t)s * H + h0 + hl) * C + c] = acc[k];
+            }
+        }
     }
     // ---- last block of this h-tile sums the partial tiles in split order
     __threadfence();
@@ -145,11 +150,16 @@ __global__ void __launch_bounds__(256) pair_layer1_grad_kernel(const float* __re
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int pass = 0; pass < npass; ++pass) {
-        const int c = pass * 8 + grp;
-        if (c >= C || h0 + hl >= H) continue;
-        float acc = 0.f;
-        for (int ss = 0; ss < kL1Splits; ++ss) acc += __ldcg(partial + ((size_t)ss * H + h0 + hl) * C + c);
+    for (int c = grp; c < C; c += 8) {
+        if (h0 + hl >= H) continue;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four interleaved chains (fixed order: deterministic)
+        for (int ss = 0; ss < kL1Splits; ss += 4) {
+            a0 += __ldcg(partial + ((size_t)(ss + 0) * H + h0 + hl) * C + c);
+            a1 += __ldcg(partial + ((size_t)(ss + 1) * H + h0 + hl) * C + c);
+            a2 += __ldcg(partial + ((size_t)(ss + 2) * H + h0 + hl) * C + c);
+            a3 += __ldcg(partial + ((size_t)(ss + 3) * H + h0 + hl) * C + c);
+        }
+        const float acc = (a0 + a1) + (a2 + a3);
         if (c < F + D)
             dW1[(size_t)(h0 + hl) * (F + D) + c] = acc;
         else
@@ -184,12 +194,9 @@ extern "C" int morl_pair_layer1_grad_f32(const float* dU, const float* dV, const
     using namespace morl;
     MORL_REQUIRE(dU && dV && feats && wset && dW1 && db1 && workspace, MORL_ERR_NULL, "morl_pair_layer1_grad_f32: NULL pointer argument");
     MORL_REQUIRE(B > 0 && W > 0 && F > 0 && D > 0 && H > 0, MORL_ERR_SHAPE, "morl_pair_layer1_grad_f32: bad shape B=%d W=%d F=%d D=%d H=%d", B, W, F, D, H);
-    const int xw = F > D + 1 ? F : D + 1;
-    const size_t smem = (size_t)kL1Chunk * (32 + xw) * sizeof(float);
-    MORL_REQUIRE(smem <= 48 * 1024, MORL_ERR_UNSUPPORTED, "morl_pair_layer1_grad_f32: feature dimension %d too large", xw);
     float* partial = static_cast<float*>(workspace);
     unsigned int* counters = reinterpret_cast<unsigned int*>(partial + (size_t)kL1Splits * H * (F + D + 1));
     dim3 grid((H + 31) / 32, kL1Splits);
-    pair_layer1_grad_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dU, dV, feats, wset, B, W, F, D, H, dW1, db1, partial, counters);
+    pair_layer1_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dU, dV, feats, wset, B, W, F, D, H, dW1, db1, partial, counters);
     return check_launch("morl_pair_layer1_grad_f32");
 }

@@ -95,6 +95,63 @@ static int pareto_launch(const char* fn, const T* pts, int N, int D, int remove_
     return check_launch(fn);
 }
 
+// ---- front records for the one-collective exchange of non-dominated fronts ----------------------------------------------
+// record = [ count | cap x d rows | n_extra extras ] (float64).  Everything stays on the device and on one stream: no host-visible count,
+// fixed shapes, so the evaluation round is  prune -> pack -> ONE all-gather -> unpack -> prune -> pack -> one device->host copy.
+constexpr int kPackThreads = 1024;
+
+// count = number of rows with keep != 0 (NOT clipped to cap, so overflow is visible to every rank); the first `cap` kept rows follow in
+// input order; unused rows are -inf in every coordinate (dominated by any real point: harmless in the global prune).
+__global__ void __launch_bounds__(kPackThreads) front_pack_kernel(const double* __restrict__ pts, const uint8_t* __restrict__ keep, int n, int d, int cap,
+                                                                  const double* __restrict__ extras, int n_extra, double* __restrict__ rec) {
+    __shared__ int warp_cnt[kPackThreads / 32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += kPackThreads) {
+        const int i = i0 + threadIdx.x;
+        const bool k = i < n && (keep == nullptr || keep[i] != 0);
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int before = base_s;
+        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+        const int pos = before + __popc(m & ((1u << lane) - 1u));
+        if (k && pos < cap)
+            for (int r = 0; r < d; ++r) rec[1 + (size_t)pos * d + r] = pts[(size_t)i * d + r];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < kPackThreads / 32; ++w) tot += warp_cnt[w];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+    const int count = base_s;
+    const double ninf = -__longlong_as_double(0x7FF0000000000000LL);
+    for (long long e = (long long)min(count, cap) * d + threadIdx.x; e < (long long)cap * d; e += kPackThreads) rec[1 + e] = ninf;
+    for (int e = threadIdx.x; e < n_extra; e += kPackThreads) rec[1 + (size_t)cap * d + e] = extras[e];
+    if (threadIdx.x == 0) rec[0] = (double)count;
+}
+
+// gathered [world][rec_len] -> pts_out [world * cap, d] (rows as packed, -inf padding included) and meta_out [world][1 + n_extra]
+// (count and extras of every rank, contiguous)
+__global__ void __launch_bounds__(256) front_unpack_kernel(const double* __restrict__ gathered, int world, int rec_len, int d, int cap, int n_extra,
+                                                           double* __restrict__ pts_out, double* __restrict__ meta_out) {
+    const long long per = (long long)cap * d;
+    const long long total = (long long)world * per;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / per);
+        pts_out[e] = gathered[(size_t)r * rec_len + 1 + (e - (long long)r * per)];
+    }
+    const int m = world * (1 + n_extra);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
+        const int r = e / (1 + n_extra), k = e - r * (1 + n_extra);
+        meta_out[e] = k == 0 ? gathered[(size_t)r * rec_len] : gathered[(size_t)r * rec_len + 1 + per + (k - 1)];
+    }
+}
+
 }  // namespace morl
 
 extern "C" int morl_pareto_mask_f32(const float* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream) {
@@ -103,4 +160,25 @@ extern "C" int morl_pareto_mask_f32(const float* pts, int N, int D, int remove_d
 
 extern "C" int morl_pareto_mask_f64(const double* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream) {
     return morl::pareto_launch<double>("morl_pareto_mask_f64", pts, N, D, remove_duplicates, keep, stream);
+}
+
+extern "C" int morl_front_pack_f64(const double* pts, const uint8_t* keep, int n, int d, int cap, const double* extras, int n_extra, double* rec,
+                                   void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(rec && (pts || n == 0) && (extras || n_extra == 0), MORL_ERR_NULL, "morl_front_pack_f64: NULL pointer argument");
+    MORL_REQUIRE(n >= 0 && d > 0 && cap > 0 && n_extra >= 0, MORL_ERR_SHAPE, "morl_front_pack_f64: bad shape n=%d d=%d cap=%d n_extra=%d", n, d, cap, n_extra);
+    front_pack_kernel<<<1, kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(pts, keep, n, d, cap, extras, n_extra, rec);
+    return check_launch("morl_front_pack_f64");
+}
+
+extern "C" int morl_front_unpack_f64(const double* gathered, int world, int d, int cap, int n_extra, double* pts_out, double* meta_out, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(gathered && pts_out && meta_out, MORL_ERR_NULL, "morl_front_unpack_f64: NULL pointer argument");
+    MORL_REQUIRE(world > 0 && d > 0 && cap > 0 && n_extra >= 0, MORL_ERR_SHAPE, "morl_front_unpack_f64: bad shape world=%d d=%d cap=%d n_extra=%d", world, d,
+                 cap, n_extra);
+    const int rec_len = 1 + cap * d + n_extra;
+    long long blocks = ((long long)world * cap * d + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    front_unpack_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, rec_len, d, cap, n_extra, pts_out, meta_out);
+    return check_launch("morl_front_unpack_f64");
 }

@@ -106,7 +106,7 @@ class GPIPD(MOPolicy, MOAgent):
         gamma: float = 0.99,
         max_grad_norm: Optional[float] = None,
         use_gpi: bool = True,
-        dyna: bool = False,
+        dyna: bool = True,
         per: bool = True,
         gpi_pd: bool = True,
         alpha_per: float = 0.6,
@@ -127,8 +127,11 @@ class GPIPD(MOPolicy, MOAgent):
         if self.device.type != "cuda":
             raise ops._lib.MorlB200Error("morl_baselines_b200.GPIPD needs a CUDA device: the update path is CUDA-only (no CPU fallback)")
         if dyna:
-            raise NotImplementedError("dyna=True (model-based GPI-PD: probabilistic ensemble + ModelEnv) is outside the accelerated hot "
-                                      "path (SURVEY.md section 2, component 20); use dyna=False")
+            # `dyna=True` is the reference's DEFAULT (gpi_pd.py:106): keep the default and fail loudly rather than silently run model-free
+            # under the GPI-PD name.  Pass dyna=False explicitly (or use GPILS) for the model-free algorithm this class accelerates.
+            raise NotImplementedError("GPIPD(dyna=True) -- the reference's default: model-based GPI-PD with a probabilistic ensemble + ModelEnv -- "
+                                      "is outside the accelerated hot path (SURVEY.md section 8(f)3); construct with dyna=False (model-free "
+                                      "GPI-PD / GPI-LS) explicitly")
         ops._lib.load()
         self.learning_rate = learning_rate
         self.initial_epsilon = initial_epsilon

@@ -145,6 +145,7 @@ class MORLD(MOAgent):
         ]
         self.archive = ParetoArchive()
         self.global_front = None
+        self._front_prune = None  # dominance test of the front exchange: None = the CUDA kernel (tests on CPU/gloo inject one)
         if self.log:
             self.setup_wandb(project_name=self.project_name, experiment_name=self.experiment_name, entity=wandb_entity)
         if self.shared_buffer:
@@ -208,21 +209,18 @@ class MORLD(MOAgent):
             disc = self._eval_policy(agent, eval_env, num_eval_episodes_for_front)
             evals[agent.id] = disc
             self.archive.add(agent, disc)
-        if self.world > 1:
-            # every rank needs the evaluation of every policy for weight adaptation: tiny all-gather of pop_size x d floats
-            mine = th.full((self.pop_size, self.reward_dim), float("nan"), dtype=th.float64, device=self.device)
-            for p in self.local_policies():
-                mine[p.id] = th.from_numpy(np.asarray(evals[p.id], dtype=np.float64)).to(self.device)
-            gathered = [th.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(gathered, mine)
-            for r, g in enumerate(gathered):
-                g = g.cpu().numpy()
-                for pid in range(self.pop_size):
-                    if self.owner(pid) == r:
-                        evals[pid] = g[pid]
+        # ONE collective per round: the record of a rank carries its local non-dominated front AND the evaluations of the policies it owns
+        # (every rank needs all of them for the weight adaptation); NaN marks the slots of policies other ranks own
+        mine = np.full((self.pop_size, self.reward_dim), np.nan, dtype=np.float64)
+        for p in self.local_policies():
+            mine[p.id] = np.asarray(evals[p.id], dtype=np.float64)
         local = np.array(self.archive.evaluations, dtype=np.float64).reshape(-1, self.reward_dim)
-        front = allgather_fronts(th.from_numpy(local).to(self.device), cap=max(64, 2 * self.pop_size))
-        self.global_front = front.cpu().numpy()
+        front, gathered = allgather_fronts(th.from_numpy(local).to(self.device), cap=max(64, 2 * self.pop_size), prune=self._front_prune,
+                                           extras=th.from_numpy(mine.reshape(-1)).to(self.device))
+        gathered = gathered.numpy().reshape(self.world, self.pop_size, self.reward_dim)
+        for pid in range(self.pop_size):
+            evals[pid] = gathered[self.owner(pid), pid]
+        self.global_front = front.numpy()
         if self.log and self.rank == 0:
             from ...common.evaluation import log_all_multi_policy_metrics
 

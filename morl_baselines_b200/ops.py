@@ -230,22 +230,44 @@ def replay_gather(obs_store, next_obs_store, act_store, rew_store, done_store, i
     return obs, act, rew, nobs, done
 
 
-def pareto_mask(points: th.Tensor, remove_duplicates: bool = True) -> th.Tensor:
-    """Non-dominated mask (reference pareto.py:34-57) of an [N, D] fp32 / fp64 CUDA tensor -> bool [N]."""
+def pareto_mask(points: th.Tensor, remove_duplicates: bool = True, raw: bool = False, out: Optional[th.Tensor] = None) -> th.Tensor:
+    """Non-dominated mask (reference pareto.py:34-57) of an [N, D] fp32 / fp64 CUDA tensor -> bool [N] (``raw``: the kernel's uint8 [N],
+    optionally written into ``out``: no further launch)."""
     if not points.is_cuda:
         raise _lib.MorlB200Error("points must be a CUDA tensor (morl_baselines_b200 has no CPU fallback)")
     if points.dtype not in (th.float32, th.float64):
         raise _lib.MorlB200Error(f"points must be float32 or float64, got {points.dtype}")
     points = points.contiguous()
     N, D = points.shape
-    keep = th.empty(N, device=points.device, dtype=th.uint8)
+    keep = th.empty(N, device=points.device, dtype=th.uint8) if out is None else out
     if N == 0:
-        return keep.bool()
+        return keep if raw else keep.bool()
     fn = _lib.load().morl_pareto_mask_f32 if points.dtype == th.float32 else _lib.load().morl_pareto_mask_f64
     rc = fn(_ptr(points), N, D, int(bool(remove_duplicates)), _ptr(keep), _stream())
     _lib.check(rc, "morl_pareto_mask")
     _count(2)
-    return keep.bool()
+    return keep if raw else keep.bool()
+
+
+def front_pack(points: th.Tensor, keep: Optional[th.Tensor], cap: int, rec: th.Tensor, extras: Optional[th.Tensor] = None) -> th.Tensor:
+    """rec (float64 [1 + cap*d + n_extra]) = [count | first cap kept rows of points [n, d] (float64), -inf padded | extras]; one launch,
+    no host sync (the count stays on the device)."""
+    n, d = points.shape
+    n_extra = 0 if extras is None else extras.numel()
+    if points.dtype != th.float64 or not points.is_contiguous() or rec.numel() != 1 + cap * d + n_extra:
+        raise _lib.MorlB200Error("front_pack: points must be contiguous float64 [n, d] and rec float64 [1 + cap*d + n_extra]")
+    rc = _lib.load().morl_front_pack_f64(_ptr(points), _ptr(keep), n, d, cap, _ptr(extras), n_extra, _ptr(rec), _stream())
+    _lib.check(rc, "morl_front_pack_f64")
+    _count()
+    return rec
+
+
+def front_unpack(gathered: th.Tensor, world: int, d: int, cap: int, n_extra: int, pts_out: th.Tensor, meta_out: th.Tensor):
+    """gathered records [world, 1 + cap*d + n_extra] -> pts_out [world*cap, d], meta_out [world, 1 + n_extra] (count, extras); one launch."""
+    rc = _lib.load().morl_front_unpack_f64(_ptr(gathered), world, d, cap, n_extra, _ptr(pts_out), _ptr(meta_out), _stream())
+    _lib.check(rc, "morl_front_unpack_f64")
+    _count()
+    return pts_out, meta_out
 
 
 class PolyakPlan:
@@ -361,15 +383,17 @@ def split_planes_multi(jobs, fmt: int = FMT_F16X2) -> None:
         arr[k].auto_scale, arr[k].target_exp = (0, 0) if target_exp is None else (1, int(target_exp))
     rc = _lib.load().morl_split_planes_multi(fmt, arr, len(jobs), _stream())
     _lib.check(rc, "morl_split_planes_multi")
-    _count()
+    _count(2 if any(a.auto_scale for a in arr) else 1)
 
 
 def gemm_planes(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Optional[th.Tensor] = None, relu: bool = False,
                 relu_mask: Optional[th.Tensor] = None, out_f32: bool = True, out_planes: bool = False, c_f32: Optional[th.Tensor] = None,
                 c_planes: Optional[th.Tensor] = None, reverse_tiles: bool = False, a_scale: Optional[th.Tensor] = None,
-                b_scale: Optional[th.Tensor] = None, c_scale: Optional[th.Tensor] = None):
+                b_scale: Optional[th.Tensor] = None, c_scale: Optional[th.Tensor] = None, split_acc: bool = True):
     """C = act(A . B^T + bias) on the tcgen05 tensor cores with split operands (fp32-accurate).
     a_planes [P, M, K], b_planes [P, N_pad, K]; the scales are device floats the planes were multiplied by (None = 1);
+    ``split_acc``: leading and correction products in separate accumulators (the tensor cores truncate their fp32 accumulation; ~2.5x
+    smaller systematic error, a little slower) -- the choice of the accuracy-critical forward passes; False: one double-buffered accumulator.
     returns (c_f32 [M, n_out] or None, c_planes [P, M, ldp] holding c_scale * C, or None)."""
     fmt = fmt_of(a_planes)
     if fmt_of(b_planes) != fmt or not a_planes.is_cuda:
@@ -387,7 +411,7 @@ def gemm_planes(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Opti
     rc = _lib.load().morl_gemm_planes_f32(fmt, _ptr(a_planes), a_planes.stride(0), _ptr(a_scale), _ptr(b_planes), b_planes.stride(0), _ptr(b_scale), M,
                                           n_out, n_pad, K, _ptr(bias), int(relu), _ptr(mask0), 0 if mask0 is None else mask0.stride(0), _ptr(c_f32),
                                           0 if c_f32 is None else c_f32.stride(0), _ptr(c_planes), 0 if c_planes is None else c_planes.shape[2],
-                                          0 if c_planes is None else c_planes.stride(0), _ptr(c_scale), int(reverse_tiles), _stream())
+                                          0 if c_planes is None else c_planes.stride(0), _ptr(c_scale), int(reverse_tiles), int(bool(split_acc)), _stream())
     _lib.check(rc, "morl_gemm_planes_f32")
     _count()
     return c_f32, c_planes

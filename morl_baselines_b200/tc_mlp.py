@@ -197,7 +197,7 @@ class TCPairMlp:
             # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1}), kept at the gradient scale
             _, G = ops.gemm_planes(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
                                    c_planes=self.g[k & 1], reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_g, b_scale=self.s_w[k - 1],
-                                   c_scale=self.s_g)
+                                   c_scale=self.s_g, split_acc=False)  # gradients: Adam is invariant to the ~2e-6 uniform shrinkage
         dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV, scale=self.s_g)
         grads[0], grads[1] = ops.pair_layer1_grad(dU, dV, feats, wset, dW1=grads[0], db1=grads[1], workspace=self.ws_l1)
         return grads

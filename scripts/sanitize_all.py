@@ -1,0 +1,132 @@
+"""Small launches of EVERY kernel of libmorl_b200.so for compute-sanitizer:
+
+    compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python scripts/sanitize_all.py [group ...]
+
+groups: envelope td gemm optim pareto replay layer1 (default: all).  Shapes are small (sanitizer slows kernels 10-100x) but exercise
+every code path: all envelope kernel families, both GEMM operand formats x CTA modes x accumulator modes, MN split-K GEMM with the fused
+column sums, every split / reduction helper, the loss kernels, Adam, polyak, Pareto + front records, replay gather."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch as th
+
+from morl_baselines_b200 import ops
+
+dev = th.device("cuda:0")
+g = th.Generator(device=dev).manual_seed(0)
+groups = set(sys.argv[1:]) or {"envelope", "td", "gemm", "optim", "pareto", "replay", "layer1"}
+
+
+def rn(*s, scale=1.0):
+    return th.randn(*s, device=dev, generator=g) * scale
+
+
+if "envelope" in groups:
+    for (B, W, A, D) in [(40, 64, 8, 3), (9, 48, 4, 2)]:
+        q_on, q_tg, wset, rew, done = rn(B, W, A, D), rn(B, W, A, D), th.rand(W, D, device=dev, generator=g), rn(B, D), th.zeros(B, device=dev)
+        ref = None
+        for path in ("v1", "v3", "wp"):
+            if path == "wp" and W <= 32:
+                continue
+            os.environ["MORL_ENVELOPE_PATH"] = path
+            out = ops.envelope_td(q_on, q_tg, wset, rew, done, 0.99)
+            th.cuda.synchronize()
+            ref = ref or out
+            assert all(th.equal(a, b) for a, b in zip(ref, out)), path
+        os.environ.pop("MORL_ENVELOPE_PATH", None)
+    print("envelope ok")
+
+if "td" in groups:
+    B, W, A, D = 24, 8, 4, 3
+    q = rn(B * W, A, D)
+    ops.greedy_td(q, rn(B * W, A, D), th.rand(W, D, device=dev, generator=g), rn(B, D), th.zeros(B, device=dev), 0.99, ops.DOT_UNFUSED, ops.MAP_TILE, ops.MAP_BLOCK)
+    act = th.randint(0, A, (B,), device=dev, generator=g, dtype=th.int32)
+    lam = th.full((1,), 0.3, device=dev)
+    ops.td_mse_priority(q, act, rn(B * W, D), th.rand(W, D, device=dev, generator=g), 0.0, B, W, ops.ROWS_BMAJOR, lambda_dev=lam)
+    qn = rn(2, B, A, D)
+    ops.critic_min_td(qn, th.rand(B, D, device=dev, generator=g), rn(B, D), th.zeros(B, device=dev), 0.99)
+    ops.gpi_envelope(rn(2, B, 5, A, D), th.rand(B, D, device=dev, generator=g))
+    act2 = th.randint(0, A, (B // 2,), device=dev, generator=g, dtype=th.int32)
+    ops.td_huber_priority(rn(2, B, A, D, scale=0.02), act2, rn(B, D, scale=0.02), rn(B, D, scale=0.02), th.rand(B, D, device=dev, generator=g), 0.01, B // 2)
+    ops.actor_critic_td(rn(2, B, D), th.rand(D, device=dev, generator=g), rn(B, D), th.zeros(B, 1, device=dev), rn(B, 1), 0.2, 0.99, ops.AC_SCALAR_MIN)
+    th.cuda.synchronize()
+    print("td ok")
+
+if "gemm" in groups:
+    for fmt in (ops.FMT_F16X2, ops.FMT_BF16X3):
+        sa = ops.scale_tensor(8.0, dev) if fmt == ops.FMT_F16X2 else None
+        sw = ops.scale_tensor(512.0, dev) if fmt == ops.FMT_F16X2 else None
+        for M in (100, 700):  # 1-CTA kernel / CTA-pair kernel with a ragged last tile
+            a, b, bias = rn(M, 128), rn(64, 128, scale=1 / 8), rn(64)
+            ap, bp = ops.split_planes(a, fmt, scale=sa), ops.split_planes(b, fmt, scale=sw)
+            for split in (True, False):
+                c, cp = ops.gemm_planes(ap, bp, 64, bias=bias, relu=True, out_f32=True, out_planes=True, a_scale=sa, b_scale=sw, c_scale=sa, split_acc=split)
+                ops.gemm_planes(ap, bp, 64, relu_mask=cp, out_f32=True, a_scale=sa, b_scale=sw, split_acc=split, reverse_tiles=True)
+                ref = (a.double() @ b.double().t() + bias.double()).clamp_min(0)
+                assert float((c.double() - ref).abs().max()) < 1e-4
+        G, H = rn(600, 24, scale=1e-3), rn(600, 128).relu_()
+        sg = ops.scale_tensor(2.0**16, dev) if fmt == ops.FMT_F16X2 else None
+        Gp, Hp = ops.split_planes(G, fmt, ldp=64, scale=sg), ops.split_planes(H, fmt, scale=sa)
+        cs = th.empty(24, device=dev)
+        dW = ops.gemm_planes_mn(Gp, 24, Hp, 128, colsum=cs, g_scale=sg, h_scale=sa)
+        assert float((dW.double() - G.double().t() @ H.double()).abs().max()) < 1e-4
+        ops.colsum_planes(Gp, 24, scale=sg)
+        ops.pairs_grad_reduce(ops.split_planes(rn(6 * 5, 64), fmt, scale=sa), 6, 5, scale=sa)
+        ops.pairs_grad_reduce(ops.split_planes(rn(3 * 70, 64), fmt, scale=sa), 3, 70, scale=sa)
+        ops.pairs_relu_split(rn(6, 64), rn(5, 64), fmt=fmt, scale=sa)
+        w1, w2 = rn(64, 64, scale=0.1), rn(24, 64)
+        o = [ops.empty_planes(fmt, 64, 64, dev), ops.empty_planes(fmt, 64, 64, dev), ops.empty_planes(fmt, 32, 64, dev)]
+        s1, s2 = ops.scale_tensor(1.0, dev), ops.scale_tensor(1.0, dev)
+        te = 14 if fmt == ops.FMT_F16X2 else None
+        ops.split_planes_multi([(w1, o[0], False, s1, te), (w1, o[1], True, s1, te), (w2, o[2], False, s2, te)], fmt)
+        ops.split_planes(rn(50, 13), fmt, ldp=32, scale=sa)
+    out, ws = th.zeros(1, device=dev), th.zeros(2, device=dev, dtype=th.int32)
+    ops.amax_scale(rn(5000, scale=1e-5), 9, out, ws)
+    th.cuda.synchronize()
+    assert ops.plane_overflow_count() == 0
+    print("gemm ok")
+
+if "layer1" in groups:
+    feats, wset, W1, b1 = rn(37, 11), th.rand(5, 2, device=dev, generator=g), rn(64, 13), rn(64)
+    u, v = ops.pair_layer1_uv(feats, wset, W1, b1)
+    ops.pair_layer1_grad(rn(37, 64), rn(5, 64), feats, wset)
+    th.cuda.synchronize()
+    print("layer1 ok")
+
+if "optim" in groups:
+    from morl_baselines_b200.common.fused_adam import FusedClipAdam
+
+    ps = [th.nn.Parameter(rn(64, 35)), th.nn.Parameter(rn(64))]
+    opt = FusedClipAdam(ps, lr=1e-3)
+    for _ in range(2):
+        for p in ps:
+            p.grad = th.randn_like(p)
+        opt.step_fused(1.0)
+    ts = [rn(64, 35), rn(64)]
+    ops.PolyakPlan([p.data for p in ps], ts).run(0.5)
+    th.cuda.synchronize()
+    print("optim ok")
+
+if "pareto" in groups:
+    pts = th.randn(700, 3, device=dev, generator=g, dtype=th.float64)
+    keep = ops.pareto_mask(pts, True, raw=True)
+    ops.pareto_mask(pts.float(), False)
+    rec = th.empty(1 + 64 * 3 + 2, dtype=th.float64, device=dev)
+    ops.front_pack(pts, keep, 64, rec, th.ones(2, dtype=th.float64, device=dev))
+    gathered = th.stack([rec, rec]).contiguous()
+    ops.front_unpack(gathered, 2, 3, 64, 2, th.empty(128, 3, dtype=th.float64, device=dev), th.empty(2, 3, dtype=th.float64, device=dev))
+    th.cuda.synchronize()
+    print("pareto ok")
+
+if "replay" in groups:
+    N, B = 300, 32
+    obs, nobs = rn(N, 7), rn(N, 7)
+    act = th.randint(0, 4, (N, 1), device=dev, generator=g, dtype=th.uint8)
+    rew, done = rn(N, 3), th.zeros(N, 1, device=dev)
+    idx = th.randint(0, N, (B,), device=dev, generator=g)
+    ops.replay_gather(obs, nobs, act, rew, done, idx)
+    th.cuda.synchronize()
+    print("replay ok")
+print("sanitize run ok")

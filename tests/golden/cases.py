@@ -124,3 +124,15 @@ PARETO_CASES = [
     "random_f64_d3",
     "single_dim",
 ]
+
+
+def archive_sequence():
+    """Evaluations fed one by one to ParetoArchive.add (reference common/pareto.py:149-175): a coarse integer grid, so later points
+    duplicate or dominate earlier ones and the archive shrinks as well as grows."""
+    rng = np.random.default_rng(77)
+    seq = []
+    while len(seq) < 120:
+        p = rng.integers(0, 10, size=3)
+        if p.sum() <= 14:  # a budget: the non-dominated set is the sum ~ 14 band, not a single corner
+            seq.append(p.astype(np.float64))
+    return seq

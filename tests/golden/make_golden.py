@@ -183,6 +183,17 @@ def gen_pareto(out):
         arch.add(i, np.array(e, dtype=np.float64))
     out["archive_a5_evals"] = np.array(arch.evaluations)
     out["archive_a5_inds"] = np.array(arch.individuals)
+    # a longer sequence: 80 three-objective evaluations on a coarse grid (many duplicates and dominated points), individuals = insertion index
+    arch = pm.ParetoArchive()
+    seq = cases.archive_sequence()
+    sizes = []
+    for i, e in enumerate(seq):
+        arch.add(i, e)
+        sizes.append(len(arch.evaluations))
+    out["archive_seq_sizes"] = np.array(sizes, np.int32)
+    out["archive_seq_evals"] = np.array(arch.evaluations)
+    out["archive_seq_inds"] = np.array(arch.individuals)
+    print(f"archive: {len(seq)} adds -> {len(arch.evaluations)} kept")
 
 
 def gen_sumtree(out):

@@ -139,9 +139,12 @@ def test_shard_range_and_front_records():
     spans = [shard_range(10, r, 4) for r in range(4)]
     assert [b - a for a, b in spans] == [3, 3, 2, 2] and spans[-1][1] == 10
     pts = th.arange(12, dtype=th.float64).view(4, 3)
-    rec = pack_front(pts, cap=8)
-    allp, counts = unpack_fronts(th.stack([rec, pack_front(pts[:1], 8)]), 2, 8, 3)
-    assert counts.tolist() == [4, 1] and allp.shape == (5, 3)
+    rec = pack_front(pts, cap=8, extras=th.tensor([7.0, 9.0]))
+    allp, counts, ex = unpack_fronts(th.stack([rec, pack_front(pts[:1], 8, extras=th.tensor([1.0, 2.0]))]), 2, 8, 3, n_extra=2)
+    assert counts.tolist() == [4, 1] and allp.shape == (16, 3) and int(th.isfinite(allp).all(dim=1).sum()) == 5
+    assert ex.tolist() == [[7.0, 9.0], [1.0, 2.0]]
+    rec = pack_front(pts, cap=2)  # overflow: the count is NOT clipped, only the rows are
+    assert float(rec[0]) == 4 and rec.numel() == 1 + 2 * 3
 
 
 def _gloo_worker(rank, world, port, q):
@@ -187,6 +190,83 @@ def test_allgather_fronts_gloo_world2():
     allpts = allpts / np.linalg.norm(allpts, axis=1, keepdims=True)
     expect = allpts[orc.pareto_mask(allpts, True)]
     assert {tuple(r) for r in f0} == {tuple(r) for r in expect}
+
+
+def _morld_eval_worker(rank, world, port, q):
+    """Rank `rank` of a 2-rank MORL/D evaluation round on CPU / gloo: stub learners with fixed evaluations, the oracle as dominance test
+    (the CUDA prune is not available on this host), the REAL MORLD._eval_all_policies / owner / local_policies / ParetoArchive logic."""
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import morl_baselines_b200.common.pareto as pareto_mod
+    from morl_baselines_b200.multi_policy.morld.morld import MORLD
+    from oracle import oracle as orc_
+
+    pareto_mod.get_non_pareto_dominated_inds = lambda c, remove_duplicates=True: orc_.pareto_mask(np.asarray(c, dtype=np.float64), remove_duplicates)
+    calls = {"n": 0}
+    real_gather, real_gather_list = dist.all_gather_into_tensor, dist.all_gather
+
+    def counting(fn):
+        def wrapped(*a, **k):
+            calls["n"] += 1
+            return fn(*a, **k)
+        return wrapped
+
+    dist.all_gather_into_tensor, dist.all_gather = counting(real_gather), counting(real_gather_list)
+
+    class _Learner:
+        def __init__(self, pid):
+            self.pid = pid
+
+        def policy_eval(self, eval_env, weights=None, scalarization=None, log=False):
+            return None, None, None, _MORLD_EVALS[self.pid].copy()
+
+    class _Pol:
+        def __init__(self, pid):
+            self.id, self.weights, self.wrapped = pid, np.array([0.5, 0.5]), _Learner(pid)
+
+    algo = object.__new__(MORLD)
+    algo.pop_size, algo.reward_dim, algo.rank, algo.world = len(_MORLD_EVALS), 2, rank, world
+    algo.device, algo.log, algo.evaluation_mode, algo.scalarization = th.device("cpu"), False, "ser", None
+    algo.population = [_Pol(i) for i in range(algo.pop_size)]
+    algo.archive = pareto_mod.ParetoArchive()
+    algo.global_front = None
+    algo._front_prune = lambda p: th.from_numpy(orc_.pareto_mask(p.numpy(), True))
+    evals = algo._eval_all_policies(None, 1, 5, np.zeros(2))
+    q.put((rank, np.array(evals), algo.global_front, calls["n"], [p.id for p in algo.local_policies()], [int(i.id) for i in algo.archive.individuals]))
+    dist.destroy_process_group()
+
+
+_MORLD_EVALS = np.array([[1.0, 9.0], [2.0, 8.0], [2.0, 7.0], [5.0, 5.0], [4.0, 4.0], [9.0, 1.0], [8.0, 0.5]])
+
+
+def test_morld_eval_round_gloo_world2():
+    """MORLD._eval_all_policies on 2 ranks (reference morld.py:306-335 is the single-process form): policy p is evaluated by rank p % 2,
+    every rank ends up with ALL evaluations and the SAME global front, and the round issues exactly ONE collective."""
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_morld_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect_front = _MORLD_EVALS[orc.pareto_mask(_MORLD_EVALS, True)]
+    for rank, evals, front, n_coll, local_ids, arch_ids in res:
+        assert np.array_equal(evals, _MORLD_EVALS)                       # everyone holds every policy's evaluation
+        assert {tuple(r) for r in front} == {tuple(r) for r in expect_front}
+        assert n_coll == 1                                               # one collective per evaluation round
+        assert local_ids == [i for i in range(len(_MORLD_EVALS)) if i % 2 == rank]
+        assert set(arch_ids) <= set(local_ids)                           # the local archive only holds the rank's own policies
+    assert np.array_equal(res[0][2], res[1][2])                          # identical front on both ranks
 
 
 class _NumpySumTree:

@@ -471,3 +471,25 @@ def test_fused_clip_adam_eager_steps_do_not_grow(cuda):
     assert len(opt._cache) == 0
     assert max(mem) == min(mem), (min(mem), max(mem))
     assert float(opt.state[ps[0]]["step"]) == 120.0
+
+
+def test_pareto_archive_matches_reference(cuda, golden):
+    """``ParetoArchive.add`` (reference common/pareto.py:149-175) on top of the device prune: the Appendix A.5 sequence and a 120-add
+    sequence with duplicates / dominated / dominating arrivals -- same kept evaluations, in the same order, with the same individuals,
+    and the same archive size after EVERY add (goldens from the unmodified reference, tests/golden/make_golden.py)."""
+    from morl_baselines_b200.common.pareto import ParetoArchive
+    from tests.golden import cases
+
+    arch = ParetoArchive()
+    for i, e in enumerate([[1, 2], [2, 1], [1, 2], [3, 3], [0, 5]]):
+        arch.add(i, np.array(e, dtype=np.float64))
+    assert np.array_equal(np.array(arch.evaluations), golden["archive_a5_evals"])
+    assert np.array_equal(np.array(arch.individuals), golden["archive_a5_inds"])
+    arch = ParetoArchive()
+    sizes = []
+    for i, e in enumerate(cases.archive_sequence()):
+        arch.add(i, e)
+        sizes.append(len(arch.evaluations))
+    assert np.array_equal(np.array(sizes, np.int32), golden["archive_seq_sizes"])
+    assert np.array_equal(np.array(arch.evaluations), golden["archive_seq_evals"])
+    assert np.array_equal(np.array(arch.individuals), golden["archive_seq_inds"])
