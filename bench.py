@@ -8,16 +8,17 @@ obs_dim=32, |A|=8, d_obj=3, |W|=64, batch=1024, net 4x256: replay gather -> Q on
 target, no grad) -> fused envelope-TD target -> online forward on 65,536 rows -> fused TD loss/priorities -> backward ->
 grad clip -> Adam (+ target sync every 200 steps).
 
-  value  : updates/s with the replay store, the per-step indices and weight sets already resident in HBM (CUDA-graph replay).
-  e2e    : updates/s through the public API (Envelope.update()) with a HOST-resident replay buffer + PER sum-tree: per step the
-           minibatch (pinned) crosses host->device and the priorities + loss come back device->host.
+  value  : updates/s of the FULL update (PER sample, targets, forward/backward, optimiser, priority write-back) through
+           Envelope.update() with the replay store resident in HBM (per step 9 KB of indices + weights in, 4 KB of priorities + loss out).
+  e2e    : updates/s through the same call with a HOST-resident replay buffer: per step the gathered minibatch (pinned, 283 KB) crosses
+           host->device and the priorities + loss come back device->host; the loss is read as a python float every update.
   roofline     : the dominant kernel of the step (bf16x3 tcgen05 GEMM of one hidden layer) against the measured dense bf16 peak.
   roofline_envelope : the fused envelope-TD kernel (the one north_star names) against the measured HBM bandwidth, timed alone in a
                  CUDA graph on rotating buffer sets larger than L2.
   cpu_baseline : the reference's CPU implementation (oracle port, or the unmodified reference when mounted) at the SAME full config,
                  a bounded NUMBER of updates (not a bounded batch); cpu_dedup_restatement: the de-duplicated CPU restatement for context.
-N > 1: every rank runs an independent update stream (weak scaling, no data-path collective) and the ranks exchange their
-non-dominated fronts with ONE NCCL all-gather per evaluation round (one round inside the timed region).
+N > 1: every rank runs an independent update stream (weak scaling, no data-path collective); the ranks exchange their non-dominated
+fronts with ONE NCCL all-gather per evaluation round, which is timed separately (config.ms_eval_round_*), not inside the updates.
 """
 
 from __future__ import annotations
@@ -354,38 +355,34 @@ def run_b200(args, rank, local_rank, world):
     store = synthetic_store(STORE, OBS, A, D, seed=0)
     np.random.seed(1000 + rank)
 
-    # ---------------- device-resident arm (`value`) ------------------------------------------------------------
+    # ---------------- `value`: the full update of SURVEY 8(d) -- PER sample + targets + forward/backward + optimiser + priority write-back --
+    # through the public API with the replay store RESIDENT IN HBM: per step the host walks the sum-tree, 9 KB of indices + weights go
+    # host->device, one graph replay, 4 KB of priorities + loss come back and are written into the tree (overlapped with backward + Adam)
     agent = _make_agent(dev, seed=rank, on_device=True)
     _fill_store(agent.replay_buffer, store)
     agent.replay_buffer.flush()
+    agent.global_step = 1
     s = agent._ensure_static()
-    rng = np.random.default_rng(rank)
-    total = K + Wm
-    idx_all = th.from_numpy(rng.integers(0, STORE, size=(total, B))).to(dev)
-    w_np = np.abs(rng.standard_normal((total, W, D)))
-    w_all = th.from_numpy((w_np / w_np.sum(2, keepdims=True)).astype(np.float32)).to(dev)
-    graph = agent._capture("device")
+    for _ in range(max(Wm, 3)):
+        agent.update()
     launches_per_step = agent.launches_per_step
-    from morl_baselines_b200.common.networks import polyak_update
 
-    def dev_step(t):
-        s["in"]["idx"].copy_(idx_all[t])
-        s["in"]["wset"].copy_(w_all[t])
-        graph.replay()
-        if (t + 1) % agent.target_net_update_freq == 0:
-            polyak_update(agent.q_net.parameters(), agent.target_q_net.parameters(), 1.0)
+    # one evaluation round: local non-dominated front of this rank's policy set -> ONE all-gather -> global prune, all stream-ordered
+    from morl_baselines_b200.tc_mlp import TCPairMlp
+
+    ev_plan = TCPairMlp(agent.q_net.net, agent.q_net.feat_dim, 256, W, share_weights_with=agent._tc_on)
+    ev_w = s["wset"].repeat(256, 1)
+    ev_vals64 = th.empty((256 * W, D), dtype=th.float64, device=dev)
 
     def eval_round():
-        # one evaluation round: local non-dominated front of this rank's policy set -> ONE all-gather -> global prune
         with th.no_grad():
             ev = agent.replay_buffer.device_stores()[0][:256]
-            q = agent.q_net.forward_pairs(ev, s["wset"])  # [256, W, A, D]
-            vals, _, _ = ops.gpi_envelope(q.reshape(1, 256 * W, 1, A, D), s["wset"].repeat(256, 1))
-        return allgather_fronts(vals.double(), cap=512)
+            q = ev_plan.forward_pairs(ev, s["wset"])  # [256 * W, A * D] on the tensor cores (weight planes of the last update)
+            vals, _, _ = ops.gpi_envelope(q.view(1, 256 * W, 1, A, D), ev_w)
+            ev_vals64.copy_(vals)
+        return allgather_fronts(ev_vals64, cap=512)
 
-    for t in range(Wm):
-        dev_step(t)
-    eval_round()  # untimed warm-up of the evaluation round (module loading, cuBLAS heuristics for its shapes)
+    eval_round()  # untimed warm-up of the evaluation round
     if world > 1:
         dist.barrier()
     th.cuda.synchronize()
@@ -394,27 +391,32 @@ def run_b200(args, rank, local_rank, world):
     launches0 = ops.launch_count
     e0, em, e1 = (th.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    for t in range(Wm, total):
-        dev_step(t)
+    for _ in range(K):
+        agent.update()
     em.record()
-    global_front = eval_round()
-    e1.record()
     if world > 1:
         dist.barrier()
     th.cuda.synchronize()
-    ms_steps, ms_eval = e0.elapsed_time(em), em.elapsed_time(e1)
-    ms = e0.elapsed_time(e1)
+    ms_steps = e0.elapsed_time(em)
     clocks = sampler.result()
     gpu_launches = (ops.launch_count - launches0) + launches_per_step * K
-    t_ms = th.tensor([ms], device=dev)
+    # the evaluation round, timed on its own (it is NOT part of an update): 3 rounds, the last one reported
+    for _ in range(3):
+        em.record()
+        global_front = eval_round()
+        e1.record()
+        th.cuda.synchronize()
+    ms_eval = em.elapsed_time(e1)
+    t_ms = th.tensor([ms_steps, ms_eval], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
+    ms, ms_eval_max = float(t_ms[0]), float(t_ms[1])
     value = world * K / (ms * 1e-3)
-    loss_dev = float(s["loss"])
+    loss_dev = agent.last_loss_host()
+    h2d_value = B * 8 + 16 + W * D * 4
+    del ev_plan
 
     # ---------------- end-to-end arm (`e2e`): public API, host replay + host PER tree ------------------------------
-    del graph
     agent_h = _make_agent(dev, seed=rank, on_device=False)
     _fill_store(agent_h.replay_buffer, store)
     agent_h.global_step = 1
@@ -465,10 +467,14 @@ def run_b200(args, rank, local_rank, world):
         "config": {
             "workload": f"Envelope-Q gradient update obs={OBS} |A|={A} d={D} |W|={W} batch={B} net=4x256 per=True, store {STORE} transitions",
             "parallelism": f"replicas x{world} + 1 front all-gather per evaluation round" if world > 1 else "single GPU",
-            "l2": "no explicit flush: each step streams ~1 GB of activations (65,536 x 256 fp32 per layer), far above the 126 MB L2",
-            "per_writeback": "host sum-tree write-back is timed in e2e; `value` keeps indices/weights pre-staged in HBM",
+            "l2": "no explicit flush: each step streams ~0.7 GB of activation planes (65,536 x 256 x 4 B per layer), far above the 126 MB L2",
+            "value_definition": "Envelope.update() with the replay store resident in HBM: PER sum-tree walk, H2D of indices + weights "
+                                f"({h2d_value} B), one CUDA-graph replay, D2H of priorities + loss ({B * 4 + 4} B), priority write-back -- all inside the timed region",
+            "e2e_definition": "the same call with a HOST-resident replay buffer: the gathered minibatch crosses PCIe every update",
+            "eval_round": "NOT inside the timed updates: local front -> one all-gather of fixed-shape records -> global prune, stream-ordered; "
+                          "timed separately, max over ranks",
             "front_points_after_allgather": int(global_front.shape[0]),
-            "ms_steps_rank0": ms_steps, "ms_eval_round_rank0": ms_eval,
+            "ms_steps_rank0": ms_steps, "ms_eval_round_rank0": ms_eval, "ms_eval_round_max": ms_eval_max,
         },
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(gpu_launches),
@@ -514,12 +520,103 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_morld(args, rank, local_rank, world):
+    """`--workload morld` (BASELINE.json configs[4]): MORL/D with 64 MOSAC subproblems at mo-hopper-v4 dimensions (obs 11, 3 actions, 3
+    objectives; 2 x 256 nets, batch 128), policy p owned by rank p % world.  A step = one improvement pass of ``__update_others``
+    (reference morld.py:423-433: every policy but the current one gets one SAC update, strictly serially) over the rank's shard, replayed
+    as ONE multi-branch CUDA graph per rank; no data-path collective.  Metric: policy updates / s, whole job.  One evaluation-round
+    exchange (fronts + evaluations in ONE all-gather) is timed separately."""
+    import torch as th
+    import torch.distributed as dist
+
+    from morl_baselines_b200 import ops
+    from morl_baselines_b200.multi_policy.morld.morld import MORLD
+    from morl_baselines_b200.testing import FakeEnv
+
+    dev = th.device("cuda", local_rank)
+    th.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    POP, OBS_H, ACT_H, D_H, N_BUF = 64, 11, 3, 3, 16384
+    env = FakeEnv(obs_dim=OBS_H, continuous_action_dim=ACT_H, reward_dim=D_H)
+    algo = MORLD(env, pop_size=POP, update_passes=1, log=False, device=dev, seed=0, weight_init_method="random", shared_buffer=True,
+                 neighborhood_size=1, policy_args={"learning_starts": 0, "buffer_size": N_BUF})
+    algo.population_graph = os.environ.get("MORL_POPULATION_GRAPH", "1") != "0"
+    rng = np.random.default_rng(0)
+    buf = algo.population[0].wrapped.get_buffer()
+    buf.obs[:], buf.next_obs[:] = rng.standard_normal((N_BUF, OBS_H)).astype(np.float32), rng.standard_normal((N_BUF, OBS_H)).astype(np.float32)
+    buf.actions[:] = rng.uniform(-1, 1, (N_BUF, ACT_H)).astype(np.float32)
+    buf.rewards[:], buf.dones[:] = rng.standard_normal((N_BUF, D_H)).astype(np.float32), (rng.random((N_BUF, 1)) < 0.02).astype(np.float32)
+    buf.size, buf.ptr = N_BUF, 0
+    buf.mark_all_dirty()
+    np.random.seed(1000 + rank)
+    local = algo.local_policies()
+    current = algo.population[0]
+    n_upd = len([p for p in local if p != current])
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def one_pass(t):
+        for p in algo.population:
+            p.wrapped.global_step = 2 * t  # actor + target updates every pass (policy_freq = 2, target_net_freq = 1)
+        algo._update_others(current)
+
+    for t in range(Wm):
+        one_pass(t)
+    if world > 1:
+        dist.barrier()
+    th.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launch_count
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(K):
+        one_pass(Wm + t)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    th.cuda.synchronize()
+    clocks = sampler.result()
+    # evaluation round exchange (stub evaluations: the rollouts are host work and not part of this measurement)
+    evs = {p.id: rng.standard_normal(D_H) for p in algo.population}
+    algo._eval_policy = lambda agent, eval_env, n: evs[agent.id]
+    algo.archive.individuals, algo.archive.evaluations = [], []
+    algo._eval_all_policies(None, 1, 5, np.zeros(D_H))
+    th.cuda.synchronize()
+    t0 = time.perf_counter()
+    algo._eval_all_policies(None, 1, 5, np.zeros(D_H))
+    ms_eval = (time.perf_counter() - t0) * 1e3
+    t_ms = th.tensor([e0.elapsed_time(e1)], device=dev)
+    n_all = th.tensor([float(n_upd)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_all, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms = float(t_ms.item())
+        line = {"metric": "morld_policy_updates_per_sec", "value": float(n_all.item()) * K / (ms * 1e-3), "unit": "policy updates/s", "n_gpus": world,
+                "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"MORL/D __update_others pass: {POP} MOSAC subproblems (obs {OBS_H}, act {ACT_H}, d {D_H}, 2x256, batch 128), "
+                                       f"policy p on rank p % {world}, shared replay buffer of {N_BUF} transitions",
+                           "parallelism": f"population sharded over {world} rank(s), one multi-branch CUDA graph per rank"
+                                          if algo.population_graph else "one graph replay per policy (serial)",
+                           "policies_updated_per_pass": int(n_all.item()), "ms_eval_exchange_rank0": ms_eval,
+                           "front_points": int(algo.global_front.shape[0]),
+                           "note": "dense layers of the 2x256 actor / critics are library (cuBLAS) kernels inside the graph; the TD target, Adam, "
+                                   "polyak and replay gather are repo kernels"},
+                "gpu_launches": int(ops.launch_count - l0), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="envelope", choices=["envelope", "morld"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -527,6 +624,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+    elif args.workload == "morld":
+        run_morld(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 

@@ -216,6 +216,12 @@ MORL_API int morl_front_pack_f64(const double* pts, const uint8_t* keep, int n, 
                                  void* stream);
 MORL_API int morl_front_unpack_f64(const double* gathered, int world, int d, int cap, int n_extra, double* pts_out, double* meta_out, void* stream);
 
+/* Exact hypervolume (maximisation) of the points with keep[i] != 0 (keep NULL = all) above the reference point `ref` [d], 1 <= d <= 3,
+ * n <= 2048, float64, one launch, result in *out (device): replaces `hypervolume(ref_point, points)` of the reference
+ * (common/performance_indicators.py:15-25; pymoo's exact HV) for fronts that already live on the device.  Points that do not exceed
+ * `ref` in every objective contribute nothing; dominated points are harmless (the volume is that of the union of boxes). */
+MORL_API int morl_hypervolume_f64(const double* pts, const uint8_t* keep, int n, int d, const double* ref, double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Multi-tensor target-network sync.  Replaces polyak_update (common/networks.py:121-139):
  *   tau == 1 : target <- param;  else target <- fma(tau, param, fl((1 - tau) * target))   (mul_ then ATen's fused add(alpha))
@@ -224,6 +230,29 @@ MORL_API int morl_front_unpack_f64(const double* gathered, int world, int d, int
 MORL_API int morl_polyak_f32(const float* const* params, float* const* targets, const int64_t* sizes, int n_tensors,
                     int64_t max_size, double tau, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident prioritised-replay sum tree, bit-identical to the reference's numpy tree (common/prioritized_buffer.py:
+ * 12-82): float64, level l (2^l nodes) at element 2^l - 1 of `tree`, root first -- the layout of morl_host_sumtree_*.
+ *   morl_sumtree_walk_f64       : SumTree.sample without the RNG (:40-54): query_i = scale_by_root ? tree[0] * u[i] : u[i]  (the host draws
+ *                                 u with np.random.random_sample, the same stream np.random.uniform(0, root) consumes), level walk with
+ *                                 strict '>' going right; out_index int64 [n].
+ *   morl_sumtree_batch_set_f64  : SumTree.batch_set (:66-82): np.unique first-occurrence semantics, diff = new - leaf, then the per-level
+ *                                 additions of np.add.at in sorted-leaf order; n <= 2048 indices per call.  *err_flag (device int) is set
+ *                                 to 1 if an index is out of range.
+ *   morl_sumtree_set_f64        : SumTree.set (:56-64; replay_buffer.add): one leaf, scalar arguments; use_min_priority != 0 takes the new
+ *                                 priority from the buffer's current min_priority (device float64: the reference's python float until the first ratchet) instead
+ *                                 of `priority`.
+ *   morl_per_priority_f32       : p = fl32(fl32(raw + fl32(min_p)) ** alpha) (envelope.py:333; gpi_pd.py:523-525 callers pass their own raw),
+ *                                 prio64 = (double) p for the tree, optional float32 copy, then *min_priority = max(*min_priority, max p)
+ *                                 (prioritized_buffer.py:194).
+ * All of them are single stream-ordered launches without host synchronisation: sample -> gather -> update -> priorities -> tree is one CUDA graph. */
+MORL_API int morl_sumtree_walk_f64(const double* tree, int n_levels, const double* u, int n, int scale_by_root, long long* out_index, void* stream);
+MORL_API int morl_sumtree_batch_set_f64(double* tree, int n_levels, const long long* index, const double* priority, int n, int* err_flag,
+                                        void* stream);
+MORL_API int morl_sumtree_set_f64(double* tree, int n_levels, long long index, double priority, int use_min_priority, const double* min_priority,
+                                  int* err_flag, void* stream);
+MORL_API int morl_per_priority_f32(const float* raw, int n, float alpha, double* min_priority, double* prio64, float* prio32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FP32-accurate dense layers on the tcgen05 tensor cores.  Replace the fp32 GEMMs behind the reference's nn.Linear layers

@@ -40,11 +40,16 @@ SIGNATURES = {
     "morl_host_sumtree_batch_set": (_i, [_vp, _i, _vp, _vp, _i]),
     "morl_host_gather_rows": (_i, [_vp, C.c_longlong, _vp, _i, _vp]),
     "morl_host_gather_u8_to_i32": (_i, [_vp, C.c_longlong, _vp, _i, _vp]),
+    "morl_sumtree_walk_f64": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
+    "morl_sumtree_batch_set_f64": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "morl_sumtree_set_f64": (_i, [_vp, _i, C.c_longlong, _d, _i, _vp, _vp, _vp]),
+    "morl_per_priority_f32": (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),
     "morl_replay_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "morl_pareto_mask_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_pareto_mask_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "morl_front_pack_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "morl_front_unpack_f64": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "morl_hypervolume_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "morl_polyak_f32": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),
     "morl_plane_overflow_count": (_i, [_i]),
     "morl_amax_scale_f32": (_i, [_vp, C.c_longlong, _i, _vp, _vp, _vp]),

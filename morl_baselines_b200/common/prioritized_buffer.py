@@ -64,20 +64,146 @@ class SumTree:
                    "morl_host_sumtree_batch_set")
 
 
+class DeviceSumTree:
+    """The same tree resident in HBM (csrc/sumtree.cu): same layout, same float64 operations in the same order as the
+    reference's numpy tree, so walks and updates are bit-identical to ``SumTree`` -- but stream-ordered, so that sampling, the minibatch
+    gather, the update and the priority write-back can be captured in ONE CUDA graph with no device->host->device round trip.
+
+    Host-facing methods (``sample``, ``walk``, ``set``, ``batch_set``, ``nodes``) keep the reference's signatures and synchronise;
+    ``walk_into`` / ``batch_set_dev`` are the in-graph forms on device tensors."""
+
+    MAX_BATCH = 2048
+
+    def __init__(self, max_size, device):
+        self.n_levels = int(np.ceil(np.log2(max_size))) + 1
+        self.device = th.device(device)
+        self._lib = _lib.load()
+        self.flat = th.zeros((1 << self.n_levels) - 1, dtype=th.float64, device=self.device)
+        self.err = th.zeros(1, dtype=th.int32, device=self.device)
+
+    # ---- host-facing (reference signatures)
+    @property
+    def nodes(self):
+        """The reference's list of per-level arrays (root first), as numpy views of a host copy (synchronises)."""
+        flat = self.flat.cpu().numpy()
+        return [flat[(1 << l) - 1 : (1 << (l + 1)) - 1] for l in range(self.n_levels)]
+
+    def __getstate__(self):
+        return {"n_levels": self.n_levels, "flat": self.flat.cpu().numpy(), "device": str(self.device)}
+
+    def __setstate__(self, state):
+        self.n_levels, self.device = state["n_levels"], th.device(state["device"])
+        self._lib = _lib.load()
+        self.flat = th.from_numpy(np.ascontiguousarray(state["flat"], dtype=np.float64)).to(self.device)
+        self.err = th.zeros(1, dtype=th.int32, device=self.device)
+
+    def _stream(self):
+        return th.cuda.current_stream().cuda_stream
+
+    def sample(self, batch_size):
+        u = np.random.random_sample(batch_size)  # the stream np.random.uniform(0, root, n) consumes (:40); query = root * u on the device
+        return self._walk_host(u, scale_by_root=True)
+
+    def walk(self, query):
+        return self._walk_host(np.asarray(query, dtype=np.float64), scale_by_root=False)
+
+    def _walk_host(self, u, scale_by_root):
+        u_dev = th.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).to(self.device)
+        out = th.empty(u_dev.shape[0], dtype=th.int64, device=self.device)
+        self.walk_into(u_dev, out, scale_by_root)
+        return out.cpu().numpy()
+
+    def set(self, node_index, new_priority=None, min_priority_dev=None):
+        """One leaf (``replay_buffer.add``); ``new_priority=None`` takes the buffer's current (device-resident) min_priority."""
+        use_min = new_priority is None
+        _lib.check(self._lib.morl_sumtree_set_f64(self.flat.data_ptr(), self.n_levels, int(node_index), 0.0 if use_min else float(new_priority),
+                                                  int(use_min), None if min_priority_dev is None else min_priority_dev.data_ptr(),
+                                                  self.err.data_ptr(), self._stream()), "morl_sumtree_set_f64")
+
+    def batch_set(self, node_index, new_priority):
+        """np.unique first-occurrence semantics + per-level np.add.at order (:66-82).  Batches beyond MAX_BATCH are made unique and sorted
+        on the host and applied in consecutive chunks -- the same additions in the same order."""
+        idx = np.ascontiguousarray(node_index, dtype=np.int64).reshape(-1)
+        pr = np.ascontiguousarray(new_priority, dtype=np.float64).reshape(-1)
+        if pr.shape[0] != idx.shape[0]:
+            raise ValueError("batch_set: node_index and new_priority must have the same length")
+        if idx.shape[0] > self.MAX_BATCH:
+            idx, first = np.unique(idx, return_index=True)
+            pr = pr[first]
+        for i in range(0, idx.shape[0], self.MAX_BATCH):
+            self.batch_set_dev(th.from_numpy(idx[i:i + self.MAX_BATCH]).to(self.device), th.from_numpy(pr[i:i + self.MAX_BATCH]).to(self.device))
+        self.check()
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            self.err.zero_()
+            raise _lib.MorlB200Error("DeviceSumTree: leaf index out of range")
+
+    # ---- in-graph forms (device tensors, no synchronisation)
+    def walk_into(self, u_dev, out_idx_dev, scale_by_root=True):
+        _lib.check(self._lib.morl_sumtree_walk_f64(self.flat.data_ptr(), self.n_levels, u_dev.data_ptr(), u_dev.shape[0], int(scale_by_root),
+                                                   out_idx_dev.data_ptr(), self._stream()), "morl_sumtree_walk_f64")
+
+    def batch_set_dev(self, idx_dev, prio64_dev):
+        _lib.check(self._lib.morl_sumtree_batch_set_f64(self.flat.data_ptr(), self.n_levels, idx_dev.data_ptr(), prio64_dev.data_ptr(),
+                                                        idx_dev.shape[0], self.err.data_ptr(), self._stream()), "morl_sumtree_batch_set_f64")
+
+
 class PrioritizedReplayBuffer(ReplayBuffer):
-    """Prioritised replay buffer (same constructor and methods as reference prioritized_buffer.py:85-226)."""
+    """Prioritised replay buffer (same constructor and methods as reference prioritized_buffer.py:85-226).  With ``tree_on_device`` (needs
+    ``device``) the sum tree and ``min_priority`` live in HBM next to the transition mirror (DeviceSumTree)."""
 
     def __init__(self, obs_shape, action_dim, rew_dim=1, max_size=100000, obs_dtype=np.float32, action_dtype=np.float32,
-                 min_priority=1e-5, device=None):
+                 min_priority=1e-5, device=None, tree_on_device=False):
         super().__init__(obs_shape, action_dim, rew_dim=rew_dim, max_size=max_size, obs_dtype=obs_dtype, action_dtype=action_dtype,
                          device=device)
-        self.tree = SumTree(max_size)
-        self.min_priority = min_priority
+        self.tree_on_device = bool(tree_on_device and device is not None)
+        if self.tree_on_device:
+            self.tree = DeviceSumTree(max_size, device)
+            self._min_p_dev = th.full((1,), float(min_priority), dtype=th.float64, device=device)  # (a python float in the reference until the first ratchet)
+        else:
+            self.tree = SumTree(max_size)
+            self._min_p_host = min_priority
+
+    # -- pickling / checkpoints: a device tree is saved as the (bit-identical) host tree and re-created by ``to(device)``
+    def __getstate__(self):
+        d = dict(super().__getstate__())
+        if self.tree_on_device:
+            host = SumTree.__new__(SumTree)
+            host.n_levels = self.tree.n_levels
+            host._alloc(self.tree.flat.cpu().numpy())
+            d.pop("_min_p_dev", None)
+            d.update(tree=host, _min_p_host=self.min_priority, tree_on_device=False, _want_device_tree=True)
+        return d
+
+    def to(self, device):
+        super().to(device)
+        if getattr(self, "_want_device_tree", False) and not self.tree_on_device and th.device(device).type == "cuda":
+            t = DeviceSumTree(self.max_size, device)
+            t.flat.copy_(th.from_numpy(self.tree._flat))
+            self._min_p_dev = th.full((1,), float(self._min_p_host), dtype=th.float64, device=device)
+            self.tree, self.tree_on_device = t, True
+        return self
+
+    @property
+    def min_priority(self):
+        """Largest priority ever written (starts at the constructor's value).  Device trees keep it on the device: reading synchronises."""
+        return float(self._min_p_dev.item()) if self.tree_on_device else self._min_p_host
+
+    @min_priority.setter
+    def min_priority(self, value):
+        if self.tree_on_device:
+            self._min_p_dev.fill_(float(value))
+        else:
+            self._min_p_host = value
 
     def add(self, obs, action, reward, next_obs, done, priority=None):
         p = self.ptr
         super().add(obs, action, reward, next_obs, done)
-        self.tree.set(p, self.min_priority if priority is None else priority)
+        if self.tree_on_device:
+            self.tree.set(p, priority, self._min_p_dev)  # one tiny launch, no synchronisation (min_priority is read on the device)
+        else:
+            self.tree.set(p, self.min_priority if priority is None else priority)
 
     def sample(self, batch_size, to_tensor=False, device=None):
         idxes = self.tree.sample(batch_size)
@@ -96,6 +222,17 @@ class PrioritizedReplayBuffer(ReplayBuffer):
     def update_priorities(self, idxes, priorities):
         self.min_priority = max(self.min_priority, priorities.max())
         self.tree.batch_set(np.asarray(idxes), priorities)
+
+    def update_priorities_dev(self, idx_dev, raw_dev, alpha: float, prio64_dev, prio32_dev=None):
+        """In-graph form of  p = (raw + min_priority) ** alpha; update_priorities(idx, p)  (envelope.py:333-334 + :186-195 here) on device
+        tensors: two launches, no synchronisation.  ``raw_dev`` float32 [n] (e.g. |w . td|), ``prio64_dev`` float64 [n] scratch."""
+        if not self.tree_on_device:
+            raise _lib.MorlB200Error("update_priorities_dev needs tree_on_device=True")
+        lib = _lib.load()
+        st = th.cuda.current_stream().cuda_stream
+        _lib.check(lib.morl_per_priority_f32(raw_dev.data_ptr(), raw_dev.shape[0], float(alpha), self._min_p_dev.data_ptr(), prio64_dev.data_ptr(),
+                                             None if prio32_dev is None else prio32_dev.data_ptr(), st), "morl_per_priority_f32")
+        self.tree.batch_set_dev(idx_dev, prio64_dev)
 
     def get_all_data(self, max_samples=None, to_tensor=False, device=None):
         if max_samples is not None and max_samples < self.size:

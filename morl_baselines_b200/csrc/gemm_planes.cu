@@ -317,7 +317,9 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int kStages = L::kStages;
     constexpr uint32_t ROWB = L::kRowB;
     extern __shared__ uint8_t gsmem_raw[];
-    uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment by pointer arithmetic ON the shared array (not through an integer cast), so that the compiler keeps every derived
+    // pointer in the shared address space: through the cast the bias / staging accesses were generic LD.E / ST.E (long-scoreboard stalls)
+    uint8_t* gsmem = gsmem_raw + ((1024u - (g_smem_u32(gsmem_raw) & 1023u)) & 1023u);
     const int BN = g.N_pad;
     constexpr uint32_t a_stage_bytes = L::kAStage;
     constexpr uint32_t b_stage_stride = L::kBStage;
@@ -502,7 +504,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float f = __fmaf_rn(__uint_as_float(v[j]), k_acc, bias_s[n0 + j]);
-                if (g.relu) f = fmaxf(f, 0.f);
+                if (g.relu) f = (f < 0.f) ? 0.f : f;  // (NaN stays NaN, like torch.relu: an overflow upstream must reach the loss)
                 x[j] = f;
             }
             if (g.mask && row_ok) {
@@ -689,7 +691,9 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     constexpr int P = F::P;
     constexpr int kStages = F::kStagesMn;
     extern __shared__ uint8_t gsmem_raw[];
-    uint8_t* gsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsmem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment by pointer arithmetic ON the shared array (not through an integer cast), so that the compiler keeps every derived
+    // pointer in the shared address space: through the cast the bias / staging accesses were generic LD.E / ST.E (long-scoreboard stalls)
+    uint8_t* gsmem = gsmem_raw + ((1024u - (g_smem_u32(gsmem_raw) & 1023u)) & 1023u);
     constexpr uint32_t chunk_bytes = (uint32_t)P * kMnKT * 128u;   // one 64-element MN chunk, P planes
     constexpr uint32_t a_stage = 2u * chunk_bytes;
     constexpr uint32_t b_stage = 4u * chunk_bytes;                 // (allocated for NB = 256)
@@ -702,7 +706,8 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
     // 4 KB of 1.0: the B operand of the fused bias-gradient product  colsum(G) = G^T . ones  (N = 16; every element is 1,
     // so the swizzle pattern is irrelevant)
-    uint32_t* ones = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ones_b = reinterpret_cast<uint8_t*>(tmem_slot + 4);
+    uint32_t* ones = reinterpret_cast<uint32_t*>(ones_b + ((1024u - (g_smem_u32(ones_b) & 1023u)) & 1023u));
     for (int t = threadIdx.x; t < 1024; t += blockDim.x) ones[t] = F::kOnes2;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
@@ -1178,7 +1183,8 @@ __global__ void __launch_bounds__(256) pairs_relu_split_kernel(const float* __re
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t w[F::P];
-            F::split2(fmaxf(x[2 * q], 0.f) * s, fmaxf(x[2 * q + 1], 0.f) * s, w, amax);
+            const float r0 = x[2 * q] < 0.f ? 0.f : x[2 * q], r1 = x[2 * q + 1] < 0.f ? 0.f : x[2 * q + 1];  // NaN-propagating ReLU
+            F::split2(r0 * s, r1 * s, w, amax);
 #pragma unroll
             for (int p = 0; p < F::P; ++p) o[p][q] = w[p];
         }

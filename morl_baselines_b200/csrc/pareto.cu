@@ -152,6 +152,76 @@ __global__ void __launch_bounds__(256) front_unpack_kernel(const double* __restr
     }
 }
 
+// ---- exact hypervolume (maximisation) of <= kHvMaxN points in d <= 3 objectives w.r.t. a reference point, one block ---------------------
+// Replaces the host-side exact sweep behind `hypervolume(ref_point, points)` (reference common/performance_indicators.py:15-25, which
+// delegates to pymoo's exact HV) for fronts that already live on the device (the output of the global prune of an evaluation round).
+// q_i = p_i - ref clipped at 0 (a point that does not exceed ref in some objective spans no volume); volume of the union of the boxes
+// [0, q_i]:  d = 1: max q.   d = 2: sum over points in x-descending order of (x_(i) - x_(i+1)) * max_{j <= i} y_(j).   d = 3: slabs in
+// z-descending order: thread k integrates the 2-D staircase of the points with z-rank <= k over the x-descending order (an O(n) loop
+// per thread, n threads' worth of work in parallel -- n^2 total, no scans, no atomics) and multiplies by the slab height z_(k) - z_(k+1);
+// the n slab volumes are added by a fixed-shape tree reduction (deterministic).  Ranks come from counting (ties by index).
+constexpr int kHvMaxN = 2048;
+constexpr int kHvThreads = 1024;
+
+__global__ void __launch_bounds__(kHvThreads) hypervolume_kernel(const double* __restrict__ pts, const uint8_t* __restrict__ keep, int n, int d,
+                                                                 const double* __restrict__ ref, double* __restrict__ out) {
+    extern __shared__ double hv_smem[];  // (everything dynamic: 7 n + 1 + 1024 doubles + n shorts -- up to ~127 KB at n = 2048)
+    double* red = hv_smem;                       // [kHvThreads] tree reduction
+    double* rx = red + kHvThreads;               // [3][n] staging (x, y, z of point i, input order)
+    double* ry = rx + n;
+    double* rz = ry + n;
+    double* qx = rz + n;                         // shifted, clipped coordinates in x-descending order
+    double* qy = qx + n;
+    double* qz = qy + n;
+    double* zs = qz + n;                         // [n + 1] z values in z-descending order, then 0
+    short* zr = reinterpret_cast<short*>(zs + n + 1);  // z-rank (0 = largest z) of the point at x-position i
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const bool k = keep == nullptr || keep[i] != 0;
+        double c[3] = {0.0, 1.0, 1.0};  // missing objectives: unit extent (the product then is the lower-dimensional volume)
+        bool ok = k;
+        for (int r = 0; r < d; ++r) {
+            const double v = pts[(size_t)i * d + r] - ref[r];
+            c[r] = v > 0.0 ? v : 0.0;  // (NaN fails the comparison: contributes nothing)
+            ok = ok && (v > 0.0);
+        }
+        rx[i] = ok ? c[0] : 0.0; ry[i] = ok ? c[1] : 0.0; rz[i] = ok ? c[2] : 0.0;
+    }
+    __syncthreads();
+    // rank by counting: position of point i in x-descending order (ties by index), and its z-descending rank
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double xi = rx[i], zi = rz[i];
+        int px = 0, pz = 0;
+        for (int j = 0; j < n; ++j) {
+            px += (rx[j] > xi || (rx[j] == xi && j < i)) ? 1 : 0;
+            pz += (rz[j] > zi || (rz[j] == zi && j < i)) ? 1 : 0;
+        }
+        qx[px] = xi; qy[px] = ry[i]; qz[px] = zi; zr[px] = (short)pz;
+        zs[pz] = zi;
+    }
+    if (threadIdx.x == 0) zs[n] = 0.0;
+    __syncthreads();
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double height = zs[k] - zs[k + 1];  // slab between the k-th and (k+1)-th largest z
+        if (height > 0.0) {
+            double m = 0.0, area = 0.0;
+            for (int i = 0; i < n; ++i) {
+                if ((int)zr[i] <= k) m = fmax(m, qy[i]);
+                const double xn = i + 1 < n ? qx[i + 1] : 0.0;
+                area += (qx[i] - xn) * m;
+            }
+            acc += area * height;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = kHvThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
 }  // namespace morl
 
 extern "C" int morl_pareto_mask_f32(const float* pts, int N, int D, int remove_duplicates, uint8_t* keep, void* stream) {
@@ -181,4 +251,20 @@ extern "C" int morl_front_unpack_f64(const double* gathered, int world, int d, i
     if (blocks > 148 * 4) blocks = 148 * 4;
     front_unpack_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, rec_len, d, cap, n_extra, pts_out, meta_out);
     return check_launch("morl_front_unpack_f64");
+}
+
+extern "C" int morl_hypervolume_f64(const double* pts, const uint8_t* keep, int n, int d, const double* ref, double* out, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(ref && out && (pts || n == 0), MORL_ERR_NULL, "morl_hypervolume_f64: NULL pointer argument");
+    MORL_REQUIRE(n >= 0 && d >= 1 && d <= 3, MORL_ERR_UNSUPPORTED, "morl_hypervolume_f64: exact device hypervolume supports 1 <= d <= 3 (got d=%d)", d);
+    MORL_REQUIRE(n <= kHvMaxN, MORL_ERR_UNSUPPORTED, "morl_hypervolume_f64: at most %d points (got %d): prune the set first", kHvMaxN, n);
+    const size_t smem = ((size_t)kHvThreads + 7 * (size_t)n + 1) * sizeof(double) + (size_t)n * sizeof(short) + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(hypervolume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(((size_t)kHvThreads + 7 * (size_t)kHvMaxN + 1) * sizeof(double) + (size_t)kHvMaxN * sizeof(short) + 16));
+        configured = true;
+    }
+    hypervolume_kernel<<<1, kHvThreads, smem, static_cast<cudaStream_t>(stream)>>>(pts, keep, n, d, ref, out);
+    return check_launch("morl_hypervolume_f64");
 }

@@ -133,6 +133,7 @@ class Envelope(MOPolicy, MOAgent):
         replay_on_device: bool = True,
         use_tensor_cores: bool = True,
         tensor_core_format: Optional[str] = None,
+        per_on_device: bool = True,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
@@ -169,9 +170,15 @@ class Envelope(MOPolicy, MOAgent):
         self.envelope = envelope
         self.num_sample_w = num_sample_w
         self.homotopy_lambda = self.initial_homotopy_lambda
-        buf_cls = PrioritizedReplayBuffer if self.per else ReplayBuffer
-        self.replay_buffer = buf_cls(self.observation_shape, 1, rew_dim=self.reward_dim, max_size=buffer_size, action_dtype=np.uint8,
-                                     device=self.device if replay_on_device else None)
+        if self.per:
+            # with the transitions mirrored in HBM the sum tree lives there too (common/prioritized_buffer.DeviceSumTree, bit-identical to the
+            # reference's numpy tree): sample -> gather -> update -> priorities -> tree is then ONE CUDA graph with no host round trip
+            self.replay_buffer = PrioritizedReplayBuffer(self.observation_shape, 1, rew_dim=self.reward_dim, max_size=buffer_size, action_dtype=np.uint8,
+                                                         device=self.device if replay_on_device else None,
+                                                         tree_on_device=bool(replay_on_device and per_on_device and use_cuda_graph))
+        else:
+            self.replay_buffer = ReplayBuffer(self.observation_shape, 1, rew_dim=self.reward_dim, max_size=buffer_size, action_dtype=np.uint8,
+                                              device=self.device if replay_on_device else None)
         self.dot_mode = ops.DOT_UNFUSED
         self.use_cuda_graph = use_cuda_graph
         # dense layers of all three passes on the tcgen05 tensor cores (split operands, fp32-accurate).  No silent library fallback: a
@@ -192,11 +199,11 @@ class Envelope(MOPolicy, MOAgent):
         self.use_tensor_cores = bool(use_tensor_cores)
         self._tc_on = self._tc_tg = self._tc_train = None
         self._dq = self._grad_bufs = None
-        self._last_inds = None
+        self._last_lazy, self._last_inds_v, self._last_priority_v, self._updates_done = False, None, None, 0
+        self._side_pending = False
         self._graphs = {}
         self._static = None
         self._last_loss = None
-        self._last_priority = None
         self.log = log
         if log:
             self.setup_wandb(project_name, experiment_name, wandb_entity, group)
@@ -308,18 +315,20 @@ class Envelope(MOPolicy, MOAgent):
             "wset": cut(work, "wset").view(W, D),
             "lam": cut(work, "lam")[:1],  # device-resident homotopy lambda, refreshed with the per-step pack
             "work": work,
-            "result": th.zeros(B + 1, dtype=th.float32, device=dev),  # [priorities (B) | loss]: one device->host copy per step
+            # [priorities (B) | loss | pad | sampled indices as int64 (2 B floats)]: one device->host copy per step
+            "result": th.zeros(seg(B + 1) + 2 * B, dtype=th.float32, device=dev),
             "ws": ops.td_workspace(B * W, dev),
             "pack_pin": pin, "pack_dev": pdev, "host": host, "stage": stage,
             # (device slice, pinned slice) of the one copy a step makes
             "copy_device": (pdev[:head_end], pin[:head_end]),
             "copy_host": (pdev[off["lam"][0] :], pin[off["lam"][0] :]),
-            "result_pin": th.zeros(B + 1, dtype=th.float32).pin_memory(),
+            "result_pin": th.zeros(seg(B + 1) + 2 * B, dtype=th.float32).pin_memory(),
             "h2d_done": th.cuda.Event(),  # guards the pinned staging buffer against being overwritten while a copy is pending
             # recorded INSIDE the captured step right after the fused TD-loss kernel (external event node): the host waits for the
             # priorities only, writes them back to the sum-tree and prepares the next minibatch while the GPU runs backward + Adam
             "prio_ready": th.cuda.Event(external=True),
             "copy_stream": th.cuda.Stream(device=dev),
+            "side_stream": th.cuda.Stream(device=dev),
         }
         # where a caller that stages inputs on the device itself (bench.py's `value` arm) must write them: the staging buffer, not the
         # private copy the graph refreshes from it
@@ -329,13 +338,22 @@ class Envelope(MOPolicy, MOAgent):
         for buf in (pdev, work):
             cut(buf, "lam").fill_(float(self.homotopy_lambda))
         host["lam"][:] = np.float32(self.homotopy_lambda)
-        s["prio"], s["loss"], s["loss1"] = s["result"][:B], s["result"][B], s["result"][B:]
+        s["prio"], s["loss"], s["loss1"] = s["result"][:B], s["result"][B], s["result"][B : B + 1]
         s["prio_np"] = s["result_pin"].numpy()[:B]
         s["loss_pin"] = s["result_pin"][B]
+        # device-resident PER (mode "device_per"): the idx segment of the pack carries B uniform doubles instead of B int64 indices
+        s["u"] = cut(work, "idx").view(th.float64)
+        s["idx_out"] = s["result"][seg(B + 1) :].view(th.int64)  # the walk writes the sampled indices straight into the result record
+        s["inds_np"] = s["result_pin"].numpy()[seg(B + 1) :].view(np.int64)
+        s["host"]["u"] = cut(pnp, "idx").view(np.float64)
+        s["raw_prio"] = th.zeros(B, dtype=th.float32, device=dev)
+        s["prio64"] = th.zeros(B, dtype=th.float64, device=dev)
+        # recorded INSIDE the captured step right after its first node: the staging buffer may be overwritten by the next step's copy
+        s["consumed"] = th.cuda.Event(external=True)
         self._static = s
         return s
 
-    def _gradient_step(self, obs, act, rew, nobs, done, wset):
+    def _gradient_step(self, obs, act, rew, nobs, done, wset, device_per: bool = False):
         """One gradient update on device tensors (everything between sampling and the priority write-back)."""
         s = self._static
         B, W, A, D = obs.shape[0], wset.shape[0], self.action_dim, self.reward_dim
@@ -371,12 +389,10 @@ class Envelope(MOPolicy, MOAgent):
                         for p in (l.weight, l.bias):
                             p.grad = th.zeros_like(p)
                             self._grad_bufs.append(p.grad)
+                raw = (s["raw_prio"] if device_per else s["prio"]) if self.per else None
                 ops.td_mse_priority(q_values, act.reshape(-1), target_q, wset, 0.0, B, W, ops.ROWS_BMAJOR, want_grad=True, want_prio=self.per,
-                                    workspace=s["ws"], loss_out=s["loss1"], grad_out=self._dq, prio_out=s["prio"] if self.per else None,
-                                    lambda_dev=s["lam"])
-                # loss and priorities are final here (the loss kernel wrote them): ship them to the host before the backward half starts
-                s["result_pin"].copy_(s["result"], non_blocking=True)
-                s["prio_ready"].record()
+                                    workspace=s["ws"], loss_out=s["loss1"], grad_out=self._dq, prio_out=raw, lambda_dev=s["lam"])
+                self._ship_results(raw, device_per)
                 for l, (gw, gb) in zip(self._tc_train.lin, zip(self._grad_bufs[0::2], self._grad_bufs[1::2])):
                     if l.weight.grad is not gw or l.bias.grad is not gb:  # (someone called zero_grad(set_to_none=True) in between)
                         l.weight.grad, l.bias.grad = gw, gb
@@ -384,32 +400,63 @@ class Envelope(MOPolicy, MOAgent):
         else:
             # explicit validation path (use_tensor_cores=False): torch autograd + library GEMMs around the same fused operators
             q_values = self.q_net.forward_pairs(obs, wset).view(B * W, A, D)
-            loss = _FusedTDLoss.apply(q_values, act.reshape(-1), target_q, wset, s["lam"], B, W, s["ws"], s["prio"] if self.per else None, s["loss1"])
-            s["result_pin"].copy_(s["result"], non_blocking=True)
-            s["prio_ready"].record()
+            raw = (s["raw_prio"] if device_per else s["prio"]) if self.per else None
+            loss = _FusedTDLoss.apply(q_values, act.reshape(-1), target_q, wset, s["lam"], B, W, s["ws"], raw, s["loss1"])
+            self._ship_results(raw, device_per)
             self.q_optim.zero_grad(set_to_none=True)
             loss.backward()
         self.q_optim.step_fused(self.max_grad_norm)  # clip_grad_norm_ + Adam.step (envelope.py:324-326) in two launches
+
+    def _ship_results(self, raw, device_per: bool):
+        """Loss and priorities are final (the loss kernel wrote them): ship them to the host before the backward half starts.  With
+        device-resident PER the priority power, the min_priority ratchet and SumTree.batch_set (envelope.py:329-334, prioritized_buffer.py:
+        186-195) run here too, on a side stream -- a parallel branch of the captured graph, off the critical path of backward + Adam; it is
+        joined again at the end of the step, so the tree is up to date for the next step's walk."""
+        s = self._static
+        if not device_per:
+            s["result_pin"].copy_(s["result"], non_blocking=True)
+            s["prio_ready"].record()
+            return
+        main, side = th.cuda.current_stream(), s["side_stream"]
+        side.wait_stream(main)
+        with th.cuda.stream(side):
+            self.replay_buffer.update_priorities_dev(s["idx_out"], raw, self.per_alpha, s["prio64"], prio32_dev=s["prio"])
+            s["result_pin"].copy_(s["result"], non_blocking=True)
+            s["prio_ready"].record()
+        self._side_pending = True
 
     def _step(self, mode: str):
         """What one CUDA graph captures.  mode "device": gather from the HBM-resident store by the static index buffer, then
         the gradient step; mode "host": the gradient step on the static staging tensors the host minibatch was copied into."""
         s = self._static
-        src = s["copy_" + mode][0]  # the segment of the staging buffer this mode's host->device copy fills
+        src = s["copy_" + ("device" if mode == "device_per" else mode)][0]  # the segment of the staging buffer this mode's host->device copy fills
         s["work"][src.storage_offset() : src.storage_offset() + src.numel()].copy_(src)
-        if mode == "device":
+        s["consumed"].record()  # the staging buffer may now be refilled for the next step
+        if mode == "device_per":
+            # SumTree.sample on the device (prioritized_buffer.py:30-54): the host only supplied B uniform doubles from the numpy stream
+            self.replay_buffer.tree.walk_into(s["u"], s["idx_out"], scale_by_root=True)
+            obs_s, nobs_s, act_s, rew_s, done_s = self.replay_buffer.device_stores()
+            obs, act, rew, nobs, done = ops.replay_gather(obs_s, nobs_s, act_s, rew_s, done_s, s["idx_out"])
+        elif mode == "device":
             obs_s, nobs_s, act_s, rew_s, done_s = self.replay_buffer.device_stores()
             obs, act, rew, nobs, done = ops.replay_gather(obs_s, nobs_s, act_s, rew_s, done_s, s["idx"])
+            s["idx_out"].copy_(s["idx"])
         else:
             st = s["stage"]
             obs, act, rew, nobs, done = st["obs"], st["act"], st["rew"], st["nobs"], st["done"]
-        self._gradient_step(obs, act, rew, nobs, done, s["wset"])
+        self._gradient_step(obs, act, rew, nobs, done, s["wset"], device_per=(mode == "device_per"))
+        if self._side_pending:  # join the priority / tree branch
+            th.cuda.current_stream().wait_stream(s["side_stream"])
+            self._side_pending = False
 
     def _snapshot(self):
         snap = {"p": [p.detach().clone() for p in self.q_net.parameters()], "o": []}
         for p in self.q_net.parameters():
             st = self.q_optim.state.get(p, None)
             snap["o"].append(None if not st else {k: (v.clone() if th.is_tensor(v) else v) for k, v in st.items()})
+        rb = self.replay_buffer
+        if getattr(rb, "tree_on_device", False):  # the captured step also writes the device sum tree and min_priority
+            snap["tree"] = (rb.tree.flat.clone(), rb._min_p_dev.clone())
         return snap
 
     def _restore(self, snap):
@@ -421,6 +468,9 @@ class Envelope(MOPolicy, MOAgent):
                     for k, v in st.items():
                         if th.is_tensor(v):
                             v.copy_(st_saved[k]) if st_saved is not None else v.zero_()
+            if "tree" in snap:
+                self.replay_buffer.tree.flat.copy_(snap["tree"][0])
+                self.replay_buffer._min_p_dev.copy_(snap["tree"][1])
 
     def _capture(self, mode: str):
         """Warm up on a side stream, capture one step into a CUDA graph, then restore parameters and optimiser state IN
@@ -454,28 +504,35 @@ class Envelope(MOPolicy, MOAgent):
         s = self._ensure_static()
         rb = self.replay_buffer
         has_mirror = getattr(rb, "_dev", None) is not None
+        # device-resident PER: the host's share of a step is B uniform doubles (the numpy stream SumTree.sample consumes) and the weight set;
+        # walk, gather, update, priorities and the tree write-back are one graph replay and the host never waits for the GPU
+        dev_per = bool(self.per and has_mirror and getattr(rb, "tree_on_device", False) and self.use_cuda_graph)
         critic_losses = []
         priority = None
         for _ in range(self.gradient_updates):
             # RNG consumption order of the reference: replay indices (global numpy RNG) first, then the weights (self.np_random)
             s["h2d_done"].synchronize()
-            b_inds = self.__sample_indices()
             host = s["host"]
-            if has_mirror:
-                host["idx"][:] = b_inds
-            else:  # host-resident buffer: the minibatch crosses PCIe every update, packed into the pinned staging buffer
-                self._stage_host_batch(b_inds)
+            b_inds = None
+            if dev_per:
+                host["u"][:] = np.random.random_sample(self.batch_size)  # np.random.uniform(0, root, B) = root * these, formed on the device
+            else:
+                b_inds = self.__sample_indices()
+                if has_mirror:
+                    host["idx"][:] = b_inds
+                else:  # host-resident buffer: the minibatch crosses PCIe every update, packed into the pinned staging buffer
+                    self._stage_host_batch(b_inds)
             w_np = random_weights(dim=self.reward_dim, n=self.num_sample_w, dist="gaussian", rng=self.np_random)
             host["wset"][:] = np.asarray(w_np).reshape(self.num_sample_w, -1)  # float64 -> float32, as th.tensor(w).float() (envelope.py:278)
             host["lam"][0] = np.float32(self.homotopy_lambda)  # read by the loss kernel from device memory: the graph survives the schedule
-            mode = "device" if has_mirror else "host"
-            dst, src = s["copy_" + mode]
-            # the copy runs on its own stream: the previous step's graph has already consumed `pack_dev` (its first node; the host
-            # waited for that step's priorities, which come later in the graph), so the copy overlaps that step's backward half
-            # (only with PER -- without it the host never waits on the GPU, so the copy simply stays in stream order)
+            mode = "device_per" if dev_per else ("device" if has_mirror else "host")
+            dst, src = s["copy_" + ("device" if has_mirror else "host")]
+            # the copy runs on its own stream and waits (on the device) until the previous step's graph has consumed the staging buffer
+            # (`consumed`, recorded right after the graph's first node), so it overlaps that step's forward / backward
             if self.per:
                 cs = s["copy_stream"]
                 with th.cuda.stream(cs):
+                    cs.wait_event(s["consumed"])
                     dst.copy_(src, non_blocking=True)
                     s["h2d_done"].record(cs)
                 th.cuda.current_stream().wait_event(s["h2d_done"])
@@ -492,14 +549,20 @@ class Envelope(MOPolicy, MOAgent):
                 self._step(mode)
             # (the static loss scalar is overwritten by the next gradient update: keep a copy when several are averaged)
             critic_losses.append(s["loss"].clone() if self.gradient_updates > 1 else s["loss"])
-            self._last_inds = b_inds
+            self._updates_done += 1
 
-            if self.per:
+            if dev_per:
+                self._last_lazy = True  # indices / priorities of this step sit in the pinned result record: fetched on demand
+                if self._updates_done % 256 == 0:
+                    self._fetch_last()  # periodic health check: non-finite priorities must not poison the tree silently
+            elif self.per:
                 s["prio_ready"].synchronize()  # the priorities of THIS step have landed in pinned memory; backward + Adam still run
                 if not np.isfinite(s["prio_np"]).all():
                     self._raise_non_finite()
                 priority = (s["prio_np"] + rb.min_priority) ** self.per_alpha  # envelope.py:333 (float32, as the reference's tensor math)
                 rb.update_priorities(b_inds, priority)
+            if not dev_per:
+                self._last_lazy, self._last_inds_v, self._last_priority_v = False, b_inds, priority
 
         if self.tau != 1 or self.global_step % self.target_net_update_freq == 0:
             polyak_update(self.q_net.parameters(), self.target_q_net.parameters(), self.tau)
@@ -510,7 +573,6 @@ class Envelope(MOPolicy, MOAgent):
             self.homotopy_lambda = linearly_decaying_value(self.initial_homotopy_lambda, self.homotopy_decay_steps, self.global_step,
                                                            self.learning_starts, self.final_homotopy_lambda)
         self._last_loss = critic_losses[-1] if critic_losses else None
-        self._last_priority = priority
         if self.log and self.global_step % 100 == 0:
             import wandb
 
@@ -518,16 +580,40 @@ class Envelope(MOPolicy, MOAgent):
                        "metrics/homotopy_lambda": self.homotopy_lambda, "global_step": self.global_step})
             wandb.log({"losses/grad_norm": get_grad_norm(self.q_net.parameters()).item(), "global_step": self.global_step})
             if self.per:
-                wandb.log({"metrics/mean_priority": np.mean(priority)})
+                wandb.log({"metrics/mean_priority": np.mean(self._last_priority)})
+
+    def _fetch_last(self):
+        """Device PER: wait for the last step's result record (sampled indices, powered priorities, loss) and check it."""
+        s = self._static
+        s["prio_ready"].synchronize()
+        self._last_inds_v, self._last_priority_v = s["inds_np"].copy(), s["prio_np"].copy()
+        self._last_lazy = False
+        if not np.isfinite(self._last_priority_v).all():
+            self._raise_non_finite()
+        self.replay_buffer.tree.check()
+
+    @property
+    def _last_inds(self):
+        """Replay indices of the most recent gradient update (numpy int64 [B])."""
+        if self._last_lazy:
+            self._fetch_last()
+        return self._last_inds_v
+
+    @property
+    def _last_priority(self):
+        """Priorities (|w . td| + min_priority) ** alpha written by the most recent gradient update (numpy float32 [B]); None without PER."""
+        if self._last_lazy:
+            self._fetch_last()
+        return self._last_priority_v
 
     def _raise_non_finite(self):
         """The priorities of an update came back Inf / NaN: say why (the reference would silently write NaN priorities into its sum-tree)."""
         n = ops.plane_overflow_count() if self.use_tensor_cores and self._tc_fmt == ops.FMT_F16X2 else 0
         if n:
             raise ops._lib.MorlB200Error(
-                f"Envelope.update: non-finite TD errors; {n} kernel(s) saw an activation / weight / gradient outside the fp16 range of the "
-                "'f16x2' tensor-core operand format (|activation| >= 8188, see tc_mlp.py) -- construct the agent with "
-                "tensor_core_format='bf16x3' (fp32 exponent range) for this problem")
+                f"Envelope.update: non-finite TD errors; {n} kernel launch(es) saw an activation or a back-propagated gradient outside the fp16 "
+                "range of the 'f16x2' tensor-core operand format (|activation| >= 32752, or a backward gain beyond 2^13; see tc_mlp.py) -- "
+                "construct the agent with tensor_core_format='bf16x3' (fp32 exponent range) for this problem")
         raise FloatingPointError("Envelope.update: non-finite TD errors (diverged Q-network or non-finite rewards / observations in the replay buffer)")
 
     def last_loss_host(self, wait: bool = True) -> float:

@@ -145,6 +145,8 @@ class MORLD(MOAgent):
         ]
         self.archive = ParetoArchive()
         self.global_front = None
+        self.population_graph = True  # replay a rank's learners as one multi-branch CUDA graph in _update_others
+        self._pop_graphs = {}
         self._front_prune = None  # dominance test of the front exchange: None = the CUDA kernel (tests on CPU/gloo inject one)
         if self.log:
             self.setup_wandb(project_name=self.project_name, experiment_name=self.experiment_name, entity=wandb_entity)
@@ -271,12 +273,28 @@ class MORLD(MOAgent):
             p.weights = normalized
 
     def _update_others(self, current: Policy):
-        """``update_passes`` improvement passes over every policy except ``current`` (reference morld.py:423-433), restricted
-        to the policies this rank owns -- the population is embarrassingly parallel across GPUs."""
+        """``update_passes`` improvement passes over every policy except ``current`` (reference morld.py:423-433), restricted to the policies
+        this rank owns -- the population is embarrassingly parallel across GPUs -- and, within a rank, replayed as ONE CUDA graph with
+        parallel branches (common/graphed.PopulationGraph) instead of one graph replay per policy.  The host halves (replay-index draws
+        from the global numpy RNG) run in the reference's policy order, so RNG consumption is unchanged."""
+        pols = [p for p in self.local_policies() if len(p.wrapped.get_buffer()) > 0 and p != current]
+        if not pols:
+            return
+        batched = self.population_graph and len(pols) > 1 and all(getattr(p.wrapped, "graph_update_ready", lambda: False)() for p in pols)
         for _ in range(self.update_passes):
-            for p in self.local_policies():
-                if len(p.wrapped.get_buffer()) > 0 and p != current:
+            if not batched:
+                for p in pols:
                     p.wrapped.update()
+                continue
+            states = [p.wrapped._prepare_graph_update() for p in pols]
+            key = tuple((p.id, st["key"]) for p, st in zip(pols, states))
+            pg = self._pop_graphs.get(key)
+            if pg is None:
+                from ...common.graphed import PopulationGraph
+
+                pg = self._pop_graphs[key] = PopulationGraph([st["step"] for st in states],
+                                                             lambda pols=pols: [t for p in pols for t in p.wrapped._mutated_tensors()])
+            pg()
 
     def save(self, save_dir="weights/", filename=None, save_replay_buffer=True):
         """Save population and archive with the reference's keys (morld.py:435-457)."""

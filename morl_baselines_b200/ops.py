@@ -270,6 +270,20 @@ def front_unpack(gathered: th.Tensor, world: int, d: int, cap: int, n_extra: int
     return pts_out, meta_out
 
 
+def hypervolume(points: th.Tensor, ref_point: th.Tensor, keep: Optional[th.Tensor] = None, out: Optional[th.Tensor] = None) -> th.Tensor:
+    """Exact hypervolume (maximisation, d <= 3, n <= 2048) of float64 CUDA points [n, d] above ``ref_point`` [d]; returns a device float64
+    scalar tensor [1] (no host sync).  ``keep`` (uint8 [n]) restricts the set, e.g. to the output of ``pareto_mask(..., raw=True)``."""
+    if not points.is_cuda or points.dtype != th.float64 or not points.is_contiguous():
+        raise _lib.MorlB200Error("hypervolume: points must be a contiguous float64 CUDA tensor [n, d]")
+    n, d = points.shape
+    ref_point = ref_point.to(device=points.device, dtype=th.float64).contiguous()
+    out = th.empty(1, dtype=th.float64, device=points.device) if out is None else out
+    rc = _lib.load().morl_hypervolume_f64(_ptr(points), _ptr(keep), n, d, _ptr(ref_point), _ptr(out), _stream())
+    _lib.check(rc, "morl_hypervolume_f64")
+    _count()
+    return out
+
+
 class PolyakPlan:
     """Device-side (param, target, size) table for morl_polyak_f32; build once per pair of networks."""
 

@@ -308,12 +308,24 @@ class MOSAC(MOPolicy):
             self._device_update(smp[0], smp[1], smp[2], smp[3], smp[4], with_actor, with_target,
                                 (lambda k: hook((B, act_dim))) if hook is not None else (lambda k: None))
             return
-        # graph path: the host draws the indices (global numpy RNG, as the reference's buffer.sample) into a static device buffer, new
-        # transitions are flushed to the HBM mirror, injected noise (tests) is copied into static tensors, one replay does the rest
+        self._prepare_graph_update()["graph"]()
+
+    def graph_update_ready(self) -> bool:
+        """True when ``update()`` takes the CUDA-graph path (so a population of learners can be replayed as ONE graph, morld.py)."""
+        return bool(self.use_cuda_graph and getattr(self.buffer, "_dev", None) is not None)
+
+    def _prepare_graph_update(self):
+        """Host half of one graph-path update: draw the replay indices (global numpy RNG, as the reference's buffer.sample), stage them and
+        any injected noise into the static device buffers, flush new transitions to the HBM mirror.  Returns the per-(flags) state whose
+        ``step`` closure is the device half (captured by ``st["graph"]`` for this learner alone, or by a PopulationGraph for many)."""
+        with_actor = self.global_step % self.policy_freq == 0
+        with_target = self.global_step % self.target_net_freq == 0
+        B, act_dim = self.batch_size, int(np.prod(self.action_shape))
+        hook = self._noise_hook
         key = (with_actor, with_target, hook is not None, id(self.buffer))
         st = self._graphs.get(key)
         if st is None:
-            st = {"idx_pin": th.zeros(B, dtype=th.int64).pin_memory(), "idx": th.zeros(B, dtype=th.int64, device=self.device),
+            st = {"idx_pin": th.zeros(B, dtype=th.int64).pin_memory(), "idx": th.zeros(B, dtype=th.int64, device=self.device), "key": key,
                   "noise": [th.zeros(B, act_dim, device=self.device) for _ in range(self._n_noise_sites(with_actor))] if hook is not None else None}
 
             def step(st=st, with_actor=with_actor, with_target=with_target):
@@ -322,6 +334,7 @@ class MOSAC(MOPolicy):
                 nz = st["noise"]
                 self._device_update(obs, act, rew, nobs, done, with_actor, with_target, (lambda k: nz[k]) if nz is not None else (lambda k: None))
 
+            st["step"] = step
             st["graph"] = GraphedStep(step, self._mutated_tensors)
             self._graphs[key] = st
         inds = self.buffer._draw(B)
@@ -331,7 +344,7 @@ class MOSAC(MOPolicy):
             for t in st["noise"]:
                 t.copy_(hook((B, act_dim)))
         self.buffer.flush()
-        st["graph"]()
+        return st
 
     def train(self, total_timesteps: int, eval_env=None, start_time=None):
         """Interaction loop (reference mosac_continuous_action.py:509-572)."""

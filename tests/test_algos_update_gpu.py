@@ -150,6 +150,44 @@ def test_morld_population_smoke(cuda):
     assert hypervolume(np.array([-100.0, -100.0]), list(algo.global_front)) > 0
 
 
+def test_morld_population_graph_equals_serial_updates(cuda):
+    """MORL/D ``_update_others`` (reference morld.py:423-433: a strictly serial python loop over the policies): replaying a rank's learners
+    as ONE multi-branch CUDA graph must leave every learner bit-identical to the serial per-policy replays -- same replay-index stream
+    (global numpy RNG consumed in policy order), same injected noise, no cross-learner data flow."""
+    from morl_baselines_b200.multi_policy.morld.morld import MORLD
+
+    def build():
+        th.manual_seed(0)  # (network initialisation draws from the global torch generator)
+        env = FakeEnv(obs_dim=6, continuous_action_dim=2, reward_dim=2, horizon=20)
+        algo = MORLD(env, pop_size=5, exchange_every=60, update_passes=3, log=False, device=cuda, seed=0, weight_init_method="random",
+                     policy_args={"learning_starts": 0, "batch_size": 16, "net_arch": [32, 32], "buffer_size": 256}, neighborhood_size=1)
+        rng = np.random.default_rng(5)
+        for p in algo.population:
+            buf = p.wrapped.get_buffer()
+            for _ in range(64):
+                buf.add(rng.standard_normal(6).astype(np.float32), rng.uniform(-1, 1, 2).astype(np.float32), rng.standard_normal(2).astype(np.float32),
+                        rng.standard_normal(6).astype(np.float32), False)
+            p.wrapped._noise_hook = _Noise(100 + p.id, cuda)
+            p.wrapped.global_step = 4
+        return algo
+
+    a, b = build(), build()
+    b.population_graph = False
+    for algo in (a, b):
+        np.random.seed(3)
+        algo._update_others(algo.population[1])
+    assert len(a._pop_graphs) == 1 and len(b._pop_graphs) == 0
+    for pa, pb in zip(a.population, b.population):
+        for name in ("actor", "qf1", "qf2", "qf1_target", "qf2_target"):
+            for (k, va), (_, vb) in zip(getattr(pa.wrapped, name).state_dict().items(), getattr(pb.wrapped, name).state_dict().items()):
+                assert th.equal(va, vb), (pa.id, name, k)
+        assert th.equal(pa.wrapped.log_alpha, pb.wrapped.log_alpha)
+    # the candidate itself was left alone
+    ref = build().population[1].wrapped.actor.state_dict()
+    for k, v in a.population[1].wrapped.actor.state_dict().items():
+        assert th.equal(v, ref[k])
+
+
 @pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("tag,n_support", [("m5", 5), ("m1", 1)])
 def test_gpipd_continuous_update_matches_reference(cuda, tag, n_support, graph):

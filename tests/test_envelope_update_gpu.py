@@ -15,13 +15,14 @@ from oracle.ref_harness import FakeEnv
 pytestmark = pytest.mark.gpu
 
 
-def _run(cuda, per, tc, graph, lam=0.0, envelope=True, steps=3):
+def _run(cuda, per, tc, graph, lam=0.0, envelope=True, steps=3, W=8, net=(64, 64, 64), param_atol=2e-6):
     from morl_baselines_b200.common.weights import random_weights
     from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
 
-    OBS, A, D, W, B, N = 12, 4, 3, 8, 32, 2048
+    OBS, A, D, B, N = 12, 4, 3, 32, 2048
+    net = list(net)
     th.manual_seed(0)
-    agent = Envelope(FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D), batch_size=B, num_sample_w=W, per=per, buffer_size=N, net_arch=[64, 64, 64],
+    agent = Envelope(FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D), batch_size=B, num_sample_w=W, per=per, buffer_size=N, net_arch=net,
                      log=False, seed=3, device=cuda, use_cuda_graph=graph, use_tensor_cores=tc, initial_homotopy_lambda=lam, envelope=envelope)
     assert agent.use_tensor_cores == tc
     store = synthetic_store(N, OBS, A, D, seed=1)
@@ -32,7 +33,7 @@ def _run(cuda, per, tc, graph, lam=0.0, envelope=True, steps=3):
     if per:
         rb.tree.batch_set(np.arange(N), np.full(N, rb.min_priority))
     sd = {k: v.detach().cpu().clone() for k, v in agent.q_net.state_dict().items()}
-    port = EnvelopeUpdatePort(OBS, A, D, [64, 64, 64], seed=0, state_dict=sd)
+    port = EnvelopeUpdatePort(OBS, A, D, net, seed=0, state_dict=sd)
     rng = np.random.default_rng(3)
     agent.global_step = 1
     losses = []
@@ -55,7 +56,7 @@ def _run(cuda, per, tc, graph, lam=0.0, envelope=True, steps=3):
         losses.append(float(agent._last_loss))
     if envelope:
         for (k, v), (_, v2) in zip(agent.q_net.state_dict().items(), port.q_net.state_dict().items()):
-            np.testing.assert_allclose(v.cpu().numpy(), v2.numpy(), rtol=1e-4, atol=2e-6, err_msg=k)
+            np.testing.assert_allclose(v.cpu().numpy(), v2.numpy(), rtol=1e-4, atol=param_atol, err_msg=k)
     return losses, agent
 
 
@@ -64,6 +65,15 @@ def _run(cuda, per, tc, graph, lam=0.0, envelope=True, steps=3):
 @pytest.mark.parametrize("graph", [False, True])
 def test_envelope_update_matches_reference_port(cuda, per, tc, graph):
     _run(cuda, per, tc, graph)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_envelope_update_single_tile_shape(cuda, graph):
+    """B * |W| = 128 rows: exactly one 128-row tile, the ONE-CTA GEMM kernel (the CTA-pair kernel needs two) with every epilogue flavour
+    of the update -- hidden layers, ReLU mask, fp32 output -- on a 4 x 256 net (the hypervolume-parity training configuration)."""
+    # (4 x 256 net: 140k parameters; Adam's first steps turn the ~1e-8 rounding noise of the smallest gradient elements into ~1e-5 parameter
+    # differences on a handful of them -- tests/test_envelope_update_golden_gpu.py states the full bound)
+    _run(cuda, per=True, tc=True, graph=graph, W=4, net=(256, 256, 256, 256), param_atol=3e-5)
 
 
 def test_envelope_update_homotopy_and_ddqn(cuda):
@@ -117,3 +127,41 @@ def test_envelope_api_surface(cuda):
             assert th.equal(v, before[k])
         agent.update()  # the captured graph is still valid after an in-place load
     assert np.isfinite(float(agent._last_loss))
+
+
+def test_device_per_equals_host_per(cuda):
+    """Device-resident PER (sum tree, sampling, priority power + ratchet + write-back inside the captured step) against the host-tree path
+    of the same engine on the same RNG streams: identical sampled indices and losses every step, identical parameters; priorities equal up
+    to numpy's float32 power (<= 1 ulp)."""
+    from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
+
+    def build(per_dev):
+        th.manual_seed(0)
+        agent = Envelope(FakeEnv(obs_dim=12, n_actions=4, reward_dim=3), batch_size=32, num_sample_w=8, per=True, buffer_size=2048,
+                         net_arch=[64, 64, 64], log=False, seed=3, device=cuda, per_on_device=per_dev)
+        assert agent.replay_buffer.tree_on_device == per_dev
+        store = synthetic_store(2048, 12, 4, 3, seed=1)
+        rb = agent.replay_buffer
+        rb.obs[:], rb.next_obs[:], rb.actions[:], rb.rewards[:], rb.dones[:] = (store[k] for k in ("obs", "next_obs", "actions", "rewards", "dones"))
+        rb.size, rb.ptr = 2048, 0
+        rb.mark_all_dirty()
+        rb.tree.batch_set(np.arange(2048), np.random.default_rng(2).random(2048) + 0.01)
+        agent.global_step = 1
+        return agent
+
+    a, b = build(True), build(False)
+    for step in range(6):
+        rec = []
+        for agent in (a, b):
+            np.random.seed(70 + step)
+            agent.update()
+            rec.append((agent._last_inds.copy(), float(agent._last_loss), np.asarray(agent._last_priority).copy(), agent.replay_buffer.min_priority))
+        (ia, la, pa, ma), (ib, lb, pb, mb) = rec
+        assert np.array_equal(ia, ib), step
+        assert la == lb, (step, la, lb)
+        assert np.all(np.abs(pa.view(np.int32) - pb.view(np.int32)) <= 1), step
+        assert abs(ma - mb) <= 1e-6 * mb
+    for va, vb in zip(a.q_net.state_dict().values(), b.q_net.state_dict().values()):
+        assert th.equal(va, vb)
+    ta, tb = np.concatenate(a.replay_buffer.tree.nodes), np.concatenate(b.replay_buffer.tree.nodes)
+    np.testing.assert_allclose(ta, tb, rtol=1e-6)

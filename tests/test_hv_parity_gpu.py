@@ -64,3 +64,32 @@ def test_envelope_hypervolume_within_one_percent_of_reference(cuda):
     # sanity: neither engine can exceed the hypervolume of the true Pareto front of the deterministic MDP (returns are accumulated
     # from float32 rewards, the true front in float64: allow rounding)
     assert max(hvs) <= gold["true_front_hv"] * (1 + 1e-6)
+
+
+def test_envelope_hypervolume_config2_unsaturated(cuda):
+    """Same protocol at BASELINE configs[1] hyper-parameters (|W| = 32, batch 256, 4 x 256, per=True) on a budget where the REFERENCE has
+    not reached the true front (tests/golden/make_golden_hv_config2.py: 400 environment steps, 300 updates, uniformly random behaviour
+    policy so that both engines learn from identical replay contents) -- unlike the saturated fixture above, a moderate regression of
+    the update path moves this hypervolume."""
+    from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
+
+    path = os.path.join(ROOT, "tests", "golden", "hv_parity_config2.json")
+    gold = json.load(open(path))
+    hp, total = gold["hyper_parameters"], gold["total_timesteps"]
+    assert gold["hv_mean"] < 0.98 * gold["true_front_hv"], "fixture must be unsaturated"
+    hvs, refs = [], []
+    for seed_s, rec in sorted(gold["seeds"].items()):
+        seed, ref = int(seed_s), rec[str(total)]
+        th.manual_seed(seed)
+        np.random.seed(seed)
+        env = TreasureChain(seed=seed)
+        agent = Envelope(env, log=False, seed=seed, device=cuda, **hp)
+        agent.train(total_timesteps=total)
+        front, hv = _evaluate(agent, hp["gamma"], [np.asarray(w, dtype=np.float32) for w in gold["eval_weights"]])
+        hvs.append(hv)
+        refs.append(ref["hv"])
+        print(f"seed {seed}: hv b200 {hv:.4f} vs reference {ref['hv']:.4f} ({100 * ref['hv'] / gold['true_front_hv']:.1f} % of the true front), "
+              f"|front| {len(front)} vs {ref['n_front']}")
+    rel = abs(float(np.mean(hvs)) - float(np.mean(refs))) / float(np.mean(refs))
+    print(f"mean hv b200 {np.mean(hvs):.4f}, reference {np.mean(refs):.4f}, relative difference {rel * 100:.3f} %")
+    assert rel <= 0.01
