@@ -460,6 +460,7 @@ def run_b200(args, rank, local_rank, world):
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
         gemm_traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    gemm_alg_bytes = 2 * gemm_bpe * B * W * NET[0] + gemm_bpe * NET[0] * NET[0]  # A planes read + C planes written + weight planes
     mlp_flops = 5 * B * W * 211712 * 2  # 1.39e11 FLOP/update (2 no-grad fwd + fwd + 2x bwd)
     line = {
         "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
@@ -479,17 +480,18 @@ def run_b200(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        # dominant kernel of the step (profiles/*_launches.txt): one hidden layer of the pair batch on the tensor cores.  Algorithmic flops
-        # (2 M N K, fp32) are executed as 3 fp16 (f16x2) or 6 bf16 (bf16x3) tcgen05 products: `achieved` / `peak` count the MMA
-        # flops actually issued against the measured dense 16-bit peak (the "FP32-accurate peak actually used" of SURVEY 8(d) is peak /
-        # products), `algorithmic_tflops` is the fp32-equivalent rate, `hbm_frac` the same launch against the HBM roofline.
-        "roofline": {"bound": "tensor", "kernel": f"gemm_planes_kernel<pair, {agent.tensor_core_format}> (65536x256x256, {gemm_nprod} fp16/bf16 tcgen05 products per "
-                                                   "fp32 product, CTA pairs)",
-                     "achieved": gemm_flops / t_gemm / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "frac": gemm_flops / t_gemm / 1e12 / bf16_peak,
-                     "algorithmic_flops": gemm_flops // gemm_nprod, "algorithmic_tflops": gemm_flops / gemm_nprod / t_gemm / 1e12,
-                     "fp32_accurate_peak_tflops": bf16_peak / gemm_nprod, "us_per_launch": t_gemm * 1e6, "traffic": gemm_traffic,
-                     "algorithmic_bytes": 2 * gemm_bpe * B * W * NET[0] + gemm_bpe * NET[0] * NET[0], "peak_source": peak_src,
-                     "hbm_frac": (2 * gemm_bpe * B * W * NET[0] + gemm_bpe * NET[0] * NET[0]) / t_gemm / 1e9 / hbm_peak,
+        # dominant kernel of the step (58 % of it, profiles/r02_launches.txt): one hidden layer of the pair batch.  With the f16x2 operand
+        # format its HBM floor (plane bytes in + out) is above its tensor floor, so the binding roofline is HBM: `achieved` = algorithmic
+        # plane bytes / time against the measured bandwidth; the tensor-pipe view (MMA flops actually issued against the measured dense
+        # 16-bit peak; SURVEY 8(d)'s "FP32-accurate peak actually used" = peak / products) is reported under "tensor".
+        "roofline": {"bound": "hbm", "kernel": f"gemm_planes_kernel<pair, {agent.tensor_core_format}> (65536x256x256: one hidden layer of the pair batch, "
+                                                f"{gemm_nprod} 16-bit tcgen05 products per fp32 product, CTA pairs, bias + ReLU + re-split epilogue)",
+                     "achieved": gemm_alg_bytes / t_gemm / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": gemm_alg_bytes / t_gemm / 1e9 / hbm_peak,
+                     "traffic": gemm_traffic, "algorithmic_bytes": gemm_alg_bytes, "us_per_launch": t_gemm * 1e6, "peak_source": peak_src,
+                     "why_hbm": "floors of this launch: HBM 134.5 MB / 6.48 TB/s = 20.7 us, tensor pipe 3 x 8.6 GFLOP / 1687 TFLOP/s = 15.3 us",
+                     "tensor": {"issued_tflops": gemm_flops / t_gemm / 1e12, "peak": bf16_peak, "frac": gemm_flops / t_gemm / 1e12 / bf16_peak,
+                                "algorithmic_flops": gemm_flops // gemm_nprod, "algorithmic_tflops": gemm_flops / gemm_nprod / t_gemm / 1e12,
+                                "fp32_accurate_peak_tflops": bf16_peak / gemm_nprod},
                      "timing": "16 launches on 4 rotating activation sets (4 x 2 x 67 MB > L2) captured in one CUDA graph, 12 replays, CUDA events"},
         # the kernel north_star names: fused envelope-max TD target against the HBM roofline
         "roofline_envelope": {"bound": "hbm", "kernel": "envelope_td_wp_kernel<3,UNFUSED>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

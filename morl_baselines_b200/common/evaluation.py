@@ -58,6 +58,53 @@ def policy_evaluation_mo(agent, env, w: np.ndarray, scalarization=np.dot, rep: i
             np.mean([e[3] for e in evals], axis=0))
 
 
+def policy_evaluation_mo_batched(agent, env, weights: List[np.ndarray], rep: int = 5, seeds: Optional[List[int]] = None):
+    """All ``len(weights) * rep`` evaluation episodes of an evaluation round in LOCKSTEP on copies of ``env``: the
+    reference evaluates one (weight, episode) after the other, one single-row network call per environment step
+    (evaluation.py:118-144 called from a python loop, e.g. envelope.py:545-557: 100 weights x 5 episodes); here every environment step
+    of the whole round is ONE batched ``agent.eval_batch(obs [N, ...], w [N, d])`` call -- one device round trip per step instead of N.
+
+    Returns, per weight, the tuple of ``policy_evaluation_mo``: (scalarised return, scalarised discounted return, vector return,
+    discounted vector return), each averaged over the ``rep`` episodes (scalarisation: np.dot, as the default of the serial routine).
+    Identical to the serial routine for deterministic environments; a stochastic environment's copies share the RNG state of ``env``
+    unless ``seeds`` (one per episode, passed to ``reset``) is given."""
+    from copy import deepcopy
+
+    if not hasattr(agent, "eval_batch"):
+        raise NotImplementedError(f"{type(agent).__name__} has no eval_batch(obs, w): use policy_evaluation_mo")
+    n_w = len(weights)
+    N = n_w * rep
+    envs = [deepcopy(env) for _ in range(N)]
+    w_all = np.repeat(np.asarray(weights, dtype=np.float32), rep, axis=0)  # episode e of weight i sits at row i * rep + e
+    obs = []
+    for k, e in enumerate(envs):
+        o, _ = e.reset(seed=None if seeds is None else seeds[k % rep])
+        obs.append(np.asarray(o))
+    # per-episode accumulators with the serial routine's dtypes and operation order (np.zeros_like(w); python-float discount)
+    vec = [np.zeros_like(w_all[k]) for k in range(N)]
+    disc = [np.zeros_like(w_all[k]) for k in range(N)]
+    gamma = [1.0] * N
+    alive = np.ones(N, dtype=bool)
+    obs = np.stack(obs)
+    while alive.any():
+        idx = np.nonzero(alive)[0]
+        acts = agent.eval_batch(obs[idx], w_all[idx])
+        for a, k in zip(acts, idx):
+            o, r, terminated, truncated, _ = envs[k].step(a)
+            vec[k] += r
+            disc[k] += gamma[k] * r
+            gamma[k] *= agent.gamma
+            obs[k] = o
+            alive[k] = not (terminated or truncated)
+    out = []
+    for i in range(n_w):
+        sl = slice(i * rep, (i + 1) * rep)
+        w = np.asarray(weights[i])
+        out.append((np.mean([np.dot(w, v) for v in vec[sl]]), np.mean([np.dot(w, v) for v in disc[sl]]), np.mean(vec[sl], axis=0),
+                    np.mean(disc[sl], axis=0)))
+    return out
+
+
 def multi_policy_metrics(current_front: List[np.ndarray], hv_ref_point: np.ndarray, reward_dim: int, n_sample_weights: int = 50,
                          ref_front: Optional[List[np.ndarray]] = None) -> dict:
     """The metric values of ``log_all_multi_policy_metrics`` as a dictionary with the reference's wandb key names

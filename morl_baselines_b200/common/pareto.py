@@ -97,19 +97,20 @@ class ParetoArchive:
         self.evaluations: List[np.ndarray] = []
 
     def add(self, candidate, evaluation: np.ndarray):
-        """Append, re-filter the whole archive, rebuild both lists in insertion order with tuple de-duplication."""
-        self.evaluations.append(evaluation)
-        self.individuals.append(deepcopy(candidate))
+        """Append, re-filter the whole archive, rebuild both lists in insertion order with tuple de-duplication (reference pareto.py:149-175).
+        The reference deep-copies the candidate BEFORE the dominance test and throws the copy away when the candidate is dominated or a
+        duplicate; here the copy (a whole learner with its networks in MORL/D) is made only for a candidate that stays -- same archive."""
+        evals_all = self.evaluations + [evaluation]
         if self.convex_hull:
-            nd = {tuple(x) for x in filter_convex_dominated(self.evaluations)}
+            nd = {tuple(x) for x in filter_convex_dominated(evals_all)}
         else:
-            nd = {tuple(x) for x in filter_pareto_dominated(self.evaluations)}
+            nd = {tuple(x) for x in filter_pareto_dominated(evals_all)}
         evals, seen, inds = [], [], []
-        for e, i in zip(self.evaluations, self.individuals):
+        for k, e in enumerate(evals_all):
             te = tuple(e)
             if te in nd and te not in seen:
                 evals.append(e)
                 seen.append(te)
-                inds.append(i)
+                inds.append(self.individuals[k] if k < len(self.individuals) else deepcopy(candidate))
         self.evaluations = evals
         self.individuals = inds

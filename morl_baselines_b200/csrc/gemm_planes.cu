@@ -274,6 +274,7 @@ struct GemmArgs {
     const float* b_scale;
     const float* c_scale;        // scale applied to the output before it is re-split into c_planes; nullptr = 1
     int l2_hint;                 // L2 eviction hints on the operand loads (MORL_GEMM_L2HINT=1, default off): A evict_first, B evict_last
+    int pdl;                     // launched with programmatic stream serialisation: overlap this grid's prologue with the predecessor's tail
     int reverse;                 // walk the row tiles from the last to the first (see morl_gemm_planes_f32: L2 reuse between chained layers)
     unsigned long long* stats;   // diagnostics (MORL_GEMM_STATS=1), else nullptr: [0] MMA wait-on-TMA cycles, [1] MMA wait-on-epilogue,
                                  // [2] MMA loop total, [3] producer wait-on-free-stage, [4] epilogue wait-on-accumulator, [5] epilogue busy
@@ -367,7 +368,6 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) bias_s[t] = (g.bias && t < g.N) ? g.bias[t] : 0.f;
     if (warp == 1) {  // TMEM: 512 columns (two BN-column accumulators); in a pair both CTAs' warp 1 execute the paired allocation
         if (NCTA == 2) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
@@ -377,6 +377,14 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
+    if (g.pdl) {
+        // programmatic dependent launch: this grid may have become resident (barrier init, TMEM allocation above) while the previous kernel
+        // of the stream was still draining its last tiles; let OUR successor do the same, then wait until the predecessor's results are
+        // visible -- nothing above this line reads global memory, everything below may
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) bias_s[t] = (g.bias && t < g.N) ? g.bias[t] : 0.f;
     tc_fence_before();
     __syncthreads();
     if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
@@ -870,6 +878,96 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
 }
 
+// Same reduction, four consecutive columns per thread (128-bit loads of the partial tiles): out[r][c..c+3] = mul * sum_s partial[s][r][c..c+3]
+// for the non-transposed case with cols % 4 == 0 -- the weight-gradient tiles [256 x 256] x 74 splits of every update go through here.
+// blockDim = (32, 8): 128 consecutive output elements per block, the S partials strided over threadIdx.y in the SAME fixed order as
+// reduce_partials_kernel (bit-identical results).  Blocks beyond the matrix reduce the fused column-sum partials (scalar path).
+__global__ void __launch_bounds__(256) reduce_partials_vec4_kernel(const float* __restrict__ partial, int S, int prow, int pcol, int rows, int cols,
+                                                                   float* __restrict__ out, int ld_out, int main_blocks,
+                                                                   const float* __restrict__ vec_partial, float* __restrict__ vec_out,
+                                                                   const float* __restrict__ scale_a, const float* __restrict__ scale_b) {
+    __shared__ float4 red[8][33];
+    if ((int)blockIdx.x >= main_blocks) {  // column-sum tail: one element per thread, as the scalar kernel
+        const float mul = 1.0f / ld_scale(scale_a);
+        const int e = ((int)blockIdx.x - main_blocks) * 32 + threadIdx.x;
+        float acc = 0.f;
+        if (e < rows) {
+            const float* p = vec_partial + e;
+            float a0 = 0.f, a1 = 0.f;
+            int s = threadIdx.y;
+            for (; s + 8 < S; s += 16) {
+                a0 += p[(size_t)s * prow];
+                a1 += p[(size_t)(s + 8) * prow];
+            }
+            if (s < S) a0 += p[(size_t)s * prow];
+            acc = a0 + a1;
+        }
+        red[threadIdx.y][threadIdx.x].x = acc;
+        __syncthreads();
+        if (threadIdx.y == 0 && e < rows) {
+            float t = red[0][threadIdx.x].x;
+#pragma unroll
+            for (int y = 1; y < 8; ++y) t += red[y][threadIdx.x].x;
+            vec_out[e] = t * mul;
+        }
+        return;
+    }
+    const float mul = 1.0f / (ld_scale(scale_a) * ld_scale(scale_b));
+    const int e4 = ((int)blockIdx.x * 32 + threadIdx.x) * 4;  // first of this thread's four output elements (row-major over rows x cols)
+    const int total = rows * cols;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = 0, c = 0;
+    if (e4 < total) {
+        r = e4 / cols;
+        c = e4 - r * cols;
+        const float* p = partial + (size_t)r * pcol + c;
+        const size_t stride = (size_t)prow * pcol;
+        // this thread's partials (s = y, y + 8, ...; at most kRedMax of them) are loaded first -- independent 128-bit loads in flight
+        // together -- and then added in the same alternating a0 / a1 order as the scalar kernel (bit-identical sums)
+        constexpr int kRedMax = 12;
+        float4 a0 = acc, a1 = acc;
+        if (S <= 8 * kRedMax) {
+            float4 v[kRedMax];
+#pragma unroll
+            for (int k = 0; k < kRedMax; ++k) {
+                const int sk = threadIdx.y + 8 * k;
+                v[k] = sk < S ? __ldcg(reinterpret_cast<const float4*>(p + (size_t)sk * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < kRedMax; ++k) {
+                if ((int)threadIdx.y + 8 * k < S) {
+                    if (k & 1) { a1.x += v[k].x; a1.y += v[k].y; a1.z += v[k].z; a1.w += v[k].w; }
+                    else       { a0.x += v[k].x; a0.y += v[k].y; a0.z += v[k].z; a0.w += v[k].w; }
+                }
+            }
+        } else {
+            int s = threadIdx.y;
+            for (; s + 8 < S; s += 16) {
+                const float4 u = *reinterpret_cast<const float4*>(p + (size_t)s * stride);
+                const float4 v = *reinterpret_cast<const float4*>(p + (size_t)(s + 8) * stride);
+                a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+                a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+            }
+            if (s < S) {
+                const float4 u = *reinterpret_cast<const float4*>(p + (size_t)s * stride);
+                a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+            }
+        }
+        acc = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && e4 < total) {
+        float4 t = red[0][threadIdx.x];
+#pragma unroll
+        for (int y = 1; y < 8; ++y) {
+            const float4 q = red[y][threadIdx.x];
+            t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)r * ld_out + c) = make_float4(t.x * mul, t.y * mul, t.z * mul, t.w * mul);
+    }
+}
+
 // column sums of a plane tensor: part[chunk][n] = sum over the chunk's rows and the P planes of G[p][m][n] (still scaled).
 // blockDim = (32, 8): a thread owns 8 consecutive columns (one 16-byte load per plane per row) and every 8th row.
 template <int FMT>
@@ -1324,6 +1422,12 @@ extern "C" int morl_gemm_planes_mn_f32(int fmt, const void* g_planes, long long 
     if (rc) return rc;
     const int total = g_cols * h_cols;
     const int main_blocks = (total + 31) / 32, vec_blocks = colsum_out ? (g_cols + 31) / 32 : 0;
+    if (!transpose_out && h_cols % 4 == 0 && ld_out % 4 == 0 && aligned16(out)) {
+        const int mb4 = (total / 4 + 31) / 32;
+        reduce_partials_vec4_kernel<<<mb4 + vec_blocks, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, out, ld_out, mb4,
+                                                                              g.colsum_partial, colsum_out, g_scale, h_scale);
+        return check_launch("morl_gemm_planes_mn_f32(reduce)");
+    }
     reduce_partials_kernel<<<main_blocks + vec_blocks, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out,
                                                                              main_blocks, g.colsum_partial, colsum_out, g_scale, h_scale);
     return check_launch("morl_gemm_planes_mn_f32(reduce)");
@@ -1505,18 +1609,31 @@ static int launch_gemm_planes(const CUtensorMap& tmA, const CUtensorMap& tmB, co
         cfg.blockDim = dim3(kGemmThreads);
         cfg.dynamicSmemBytes = smem2;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = g.pdl ? 2 : 1;
         cudaLaunchKernelEx(&cfg, gemm_planes_kernel<2, FMT, SPLIT>, tmA, tmB, tmBh, tmC, g);
     } else {
         const int n_tiles = (g.M + kGemmBM - 1) / kGemmBM;
         const int grid = n_tiles < sms ? n_tiles : sms;
-        gemm_planes_kernel<1, FMT, SPLIT><<<grid, kGemmThreads, smem1, st>>>(tmA, tmB, tmBh, tmC, g);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem1;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g.pdl ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, gemm_planes_kernel<1, FMT, SPLIT>, tmA, tmB, tmBh, tmC, g);
     }
     return check_launch("morl_gemm_planes_f32");
 }
@@ -1566,6 +1683,9 @@ extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_p
     g.mask = static_cast<const uint16_t*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
     g.a_scale = a_scale; g.b_scale = b_scale; g.c_scale = c_scale;
     g.reverse = reverse_tiles ? 1 : 0;
+    // programmatic dependent launch between consecutive GEMMs of a chain (MORL_GEMM_PDL=0 disables it: A/B in profiles/r02_pdl_ab.txt)
+    static const bool want_pdl = [] { const char* e = getenv("MORL_GEMM_PDL"); return !(e && e[0] == '0'); }();
+    g.pdl = want_pdl ? 1 : 0;
     // measured on B200 (profiles/r01_s3_l2hint_ab.txt): the hints do not help, so they are opt-in (MORL_GEMM_L2HINT=1)
     static const bool want_hint = [] { const char* e = getenv("MORL_GEMM_L2HINT"); return e && e[0] == '1'; }();
     g.l2_hint = want_hint ? 1 : 0;

@@ -152,12 +152,18 @@ __global__ void __launch_bounds__(256) pair_layer1_grad_kernel(const float* __re
     __threadfence();
     for (int c = grp; c < C; c += 8) {
         if (h0 + hl >= H) continue;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four interleaved chains (fixed order: deterministic)
+        // all kL1Splits partials of this output are loaded FIRST (independent loads in flight together: the sequential version paid one
+        // L2 latency per split), then summed in four interleaved chains in split order (fixed order: deterministic)
+        float v[kL1Splits];
+#pragma unroll
+        for (int ss = 0; ss < kL1Splits; ++ss) v[ss] = __ldcg(partial + ((size_t)ss * H + h0 + hl) * C + c);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
         for (int ss = 0; ss < kL1Splits; ss += 4) {
-            a0 += __ldcg(partial + ((size_t)(ss + 0) * H + h0 + hl) * C + c);
-            a1 += __ldcg(partial + ((size_t)(ss + 1) * H + h0 + hl) * C + c);
-            a2 += __ldcg(partial + ((size_t)(ss + 2) * H + h0 + hl) * C + c);
-            a3 += __ldcg(partial + ((size_t)(ss + 3) * H + h0 + hl) * C + c);
+            a0 += v[ss];
+            a1 += v[ss + 1];
+            a2 += v[ss + 2];
+            a3 += v[ss + 3];
         }
         const float acc = (a0 + a1) + (a2 + a3);
         if (c < F + D)

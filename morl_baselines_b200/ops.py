@@ -403,11 +403,11 @@ def split_planes_multi(jobs, fmt: int = FMT_F16X2) -> None:
 def gemm_planes(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Optional[th.Tensor] = None, relu: bool = False,
                 relu_mask: Optional[th.Tensor] = None, out_f32: bool = True, out_planes: bool = False, c_f32: Optional[th.Tensor] = None,
                 c_planes: Optional[th.Tensor] = None, reverse_tiles: bool = False, a_scale: Optional[th.Tensor] = None,
-                b_scale: Optional[th.Tensor] = None, c_scale: Optional[th.Tensor] = None, split_acc: bool = True):
+                b_scale: Optional[th.Tensor] = None, c_scale: Optional[th.Tensor] = None, split_acc: bool = False):
     """C = act(A . B^T + bias) on the tcgen05 tensor cores with split operands (fp32-accurate).
     a_planes [P, M, K], b_planes [P, N_pad, K]; the scales are device floats the planes were multiplied by (None = 1);
     ``split_acc``: leading and correction products in separate accumulators (the tensor cores truncate their fp32 accumulation; ~2.5x
-    smaller systematic error, a little slower) -- the choice of the accuracy-critical forward passes; False: one double-buffered accumulator.
+    smaller systematic error, ~20 % slower per launch); False (default): one double-buffered accumulator.
     returns (c_f32 [M, n_out] or None, c_planes [P, M, ldp] holding c_scale * C, or None)."""
     fmt = fmt_of(a_planes)
     if fmt_of(b_planes) != fmt or not a_planes.is_cuda:

@@ -77,8 +77,11 @@ class TCPairMlp:
         return len(hidden) == 1 and next(iter(hidden)) % 64 == 0 and n_w <= 64
 
     def __init__(self, net: nn.Sequential, feat_dim: int, n_obs: int, n_w: int, share_weights_with: Optional["TCPairMlp"] = None,
-                 trainable: bool = False, fmt: Optional[int] = None):
+                 trainable: bool = False, fmt: Optional[int] = None, split_acc: bool = False):
         self.net = net
+        # forward GEMMs: one double-buffered accumulator (default) or split leading / correction accumulators (2.5x smaller systematic
+        # error of the truncating tensor-core accumulation, ~20 % slower per layer); the backward dX GEMMs always use one accumulator
+        self.split_acc = bool(split_acc)
         self.lin: List[nn.Linear] = [m for m in net if isinstance(m, nn.Linear)]
         self.feat_dim = feat_dim
         self.B, self.W = n_obs, n_w
@@ -172,10 +175,11 @@ class TCPairMlp:
             l = self.lin[k]
             # alternate the tile order: a layer starts on the rows its producer wrote last (L2-resident)
             _, a = ops.gemm_planes(a, self.wp[k - 1], l.out_features, bias=l.bias, relu=True, out_f32=False, out_planes=True, c_planes=self.h[k],
-                                   reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_act, b_scale=self.s_w[k - 1], c_scale=self.s_act)
+                                   reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_act, b_scale=self.s_w[k - 1], c_scale=self.s_act,
+                                   split_acc=self.split_acc)
         last = self.lin[-1]
         q, _ = ops.gemm_planes(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
-                               reverse_tiles=_SNAKE and bool((n - 1) & 1), a_scale=self.s_act, b_scale=self.s_w[n - 2])
+                               reverse_tiles=_SNAKE and bool((n - 1) & 1), a_scale=self.s_act, b_scale=self.s_w[n - 2], split_acc=self.split_acc)
         return q
 
     @th.no_grad()

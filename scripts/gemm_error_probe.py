@@ -19,7 +19,7 @@ a = th.randn(M, K, device=dev, generator=g).relu_()
 b = th.randn(N, K, device=dev, generator=g) / 16
 ref = a.double() @ b.double().t()
 mag = a.abs().double() @ b.abs().double().t()
-print("accumulators:", "split" if os.environ.get("MORL_GEMM_SPLIT_ACC", "1") != "0" else "single")
+print("accumulators:", "split" if os.environ.get("MORL_GEMM_SPLIT_ACC") == "1" else "single")
 
 
 def stats(name, c):

@@ -31,7 +31,7 @@ sm = ops.sm_count()
 pairs = sm // 2
 mhz = 1965.0
 c = [float(x) for x in buf]
-print(f"format {'bf16x3' if fmt == ops.FMT_BF16X3 else 'f16x2'}, accumulators {'single' if os.environ.get('MORL_GEMM_SPLIT_ACC') == '0' else 'split'}")
+print(f"format {'bf16x3' if fmt == ops.FMT_BF16X3 else 'f16x2'}, accumulators {'split' if os.environ.get('MORL_GEMM_SPLIT_ACC') == '1' else 'single'}")
 print(f"launch {us:.1f} us = {us * mhz:.0f} cycles @ {mhz:.0f} MHz (stats add a little overhead)")
 print(f"MMA thread (per leader, per launch): total {c[2] / pairs / n:.0f} cyc, waiting TMA {c[0] / pairs / n:.0f}, waiting epilogue {c[1] / pairs / n:.0f}")
 print(f"TMA thread (per CTA): waiting for a free stage {c[3] / sm / n:.0f} cyc")

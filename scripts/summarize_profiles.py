@@ -26,17 +26,18 @@ if os.path.exists(lp):
         f.write("# per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
             f.write(f"{t:10.1f} us {n:5d}x  avg {t / n:9.1f} us  {100 * t / tot:5.1f}%  {k}\n")
-        # per-update view: the capture window also holds the roofline micro-benchmarks that bench.py runs after the step loops; the
-        # kernels of ONE gradient update are those launched a whole number of times per td_mse_kernel launch (one per update)
+        # per-update view: the kernels of ONE gradient update are those launched a whole number of times per td_mse_kernel launch (one per
+        # update) inside the capture window -- ALL of them, library kernels included, so that their absence from the captured update is
+        # visible (the window also holds the eval round, the roofline micro-benchmarks and setup kernels, whose counts are not multiples)
         n_upd = next((n for k, (n, t) in agg.items() if "td_mse_kernel" in k), 0)
         if n_upd:
-            # (the window may cut a step: counts per update are rounded)
-            step = [(k, round(n / n_upd), t / n * round(n / n_upd)) for k, (n, t) in agg.items()
-                    if n >= n_upd and "envelope_td" not in k and "distribution_elementwise" not in k and ("morl::" in k or "sgemm" in k or "cublas" in k)]
+            step = [(k, n // n_upd, t / n * (n // n_upd)) for k, (n, t) in agg.items() if n >= n_upd and n % n_upd == 0 and "envelope_td" not in k]
             step += [(k, 1, t / n) for k, (n, t) in agg.items() if "envelope_td" in k][:1]
             tot_s = sum(t for _, _, t in step)
-            f.write(f"\n# one gradient update ({n_upd} captured, window edges rounded): library + morl kernels per update, {tot_s:.0f} us under ncu\n")
-            for k, c, t in sorted(step, key=lambda x: -x[2])[:24]:
+            lib = [k for k, _, _ in step if not ("morl::" in k)]
+            f.write(f"\n# one gradient update ({n_upd} captured): every kernel launched an exact multiple of {n_upd} times, {tot_s:.0f} us under ncu\n")
+            f.write(f"# kernels of the update that are NOT repo kernels (ATen / cuBLAS / cutlass): {lib if lib else 'none'}\n")
+            for k, c, t in sorted(step, key=lambda x: -x[2])[:40]:
                 f.write(f"{t:10.1f} us {c:5d}x per update  {100 * t / tot_s:5.1f}%  {k}\n")
     print("wrote launches summary")
 

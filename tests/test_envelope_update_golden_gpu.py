@@ -105,3 +105,8 @@ def test_homotopy_schedule_update_matches_unmodified_reference(cuda, graph):
 def test_north_star_update_bf16x3_operand_format(cuda):
     """The wide-range operand format (three bf16 planes, six MMAs per product) through the same goldens."""
     _run_case("north_star", cuda, True, True, tensor_core_format="bf16x3")
+
+
+def test_north_star_update_split_accumulators(cuda):
+    """The higher-accuracy accumulator mode of the forward GEMMs (leading / correction products in separate TMEM buffers)."""
+    _run_case("north_star", cuda, True, True, tensor_core_accumulators="split")

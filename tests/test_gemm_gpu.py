@@ -86,10 +86,11 @@ def test_amax_scale(cuda):
             assert np.log2(s) == round(np.log2(s)) and 2.0**8 <= amax * s < 2.0**9, (amax, s)
 
 
+@pytest.mark.parametrize("split", [False, True], ids=["single", "split"])
 @pytest.mark.parametrize("fmt", FMTS)
 @pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1000, 256, 256), (65536, 256, 256), (4096, 24, 256), (777, 256, 64), (513, 64, 64)])
 @pytest.mark.parametrize("relu", [False, True])
-def test_gemm_planes_matches_float64(cuda, fmt, M, N, K, relu):
+def test_gemm_planes_matches_float64(cuda, fmt, M, N, K, relu, split):
     from morl_baselines_b200 import ops
 
     g = th.Generator(device=cuda).manual_seed(M + N + K)
@@ -99,7 +100,8 @@ def test_gemm_planes_matches_float64(cuda, fmt, M, N, K, relu):
     sa, sb, sc = _scale(fmt, 8.0, cuda), _scale(fmt, 4096.0, cuda), _scale(fmt, 16.0, cuda)
     ap = ops.split_planes(a, fmt, scale=sa)
     bp = ops.split_planes(b, fmt, rows_pad=(N + 31) // 32 * 32, scale=sb)
-    c, cp = ops.gemm_planes(ap, bp, N, bias=bias, relu=relu, out_f32=True, out_planes=(N % 32 == 0), a_scale=sa, b_scale=sb, c_scale=sc)
+    c, cp = ops.gemm_planes(ap, bp, N, bias=bias, relu=relu, out_f32=True, out_planes=(N % 32 == 0), a_scale=sa, b_scale=sb, c_scale=sc,
+                            split_acc=split)
     ref = _ref(a, b, bias)
     if relu:
         ref = ref.clamp_min(0)
@@ -253,11 +255,10 @@ def test_pairs_grad_reduce(cuda, fmt):
         np.testing.assert_allclose(dV.cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("env_flags", [{"MORL_GEMM_FORCE_1CTA": "1"}, {"MORL_GEMM_SPLIT_ACC": "0"}, {"MORL_GEMM_FORCE_1CTA": "1", "MORL_GEMM_SPLIT_ACC": "0"}])
+@pytest.mark.parametrize("env_flags", [{"MORL_GEMM_FORCE_1CTA": "1"}, {"MORL_GEMM_SPLIT_ACC": "1"}, {"MORL_GEMM_FORCE_1CTA": "1", "MORL_GEMM_SPLIT_ACC": "1"}])
 def test_gemm_alternative_kernels_still_correct(cuda, env_flags):
-    """Large shapes use the CTA-pair (cta_group::2) kernel with split accumulators; MORL_GEMM_FORCE_1CTA=1 keeps the one-CTA kernel and
-    MORL_GEMM_SPLIT_ACC=0 the single double-buffered accumulator alive as cross-checks.  The switches are read once per process, hence
-    the subprocess."""
+    """Large shapes use the CTA-pair (cta_group::2) kernel; MORL_GEMM_FORCE_1CTA=1 keeps the one-CTA kernel alive and MORL_GEMM_SPLIT_ACC=1
+    forces the split-accumulator mode on every call (cross-checks).  The switches are read once per process, hence the subprocess."""
     import os
     import subprocess
     import sys

@@ -93,3 +93,34 @@ def test_envelope_hypervolume_config2_unsaturated(cuda):
     rel = abs(float(np.mean(hvs)) - float(np.mean(refs))) / float(np.mean(refs))
     print(f"mean hv b200 {np.mean(hvs):.4f}, reference {np.mean(refs):.4f}, relative difference {rel * 100:.3f} %")
     assert rel <= 0.01
+
+
+def test_batched_evaluation_round_equals_serial(cuda):
+    """the lockstep evaluation round (one batched network call per environment step for all weights x episodes) returns
+    exactly what the reference's serial loop of ``policy_eval`` calls returns (deterministic stand-in environment), and the device
+    hypervolume of the resulting front equals the host routine's."""
+    from morl_baselines_b200 import ops
+    from morl_baselines_b200.common.evaluation import policy_evaluation_mo_batched
+    from morl_baselines_b200.common.performance_indicators import hypervolume
+    from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
+
+    th.manual_seed(1)
+    np.random.seed(1)
+    env = TreasureChain(seed=1)
+    agent = Envelope(env, log=False, seed=1, device=cuda, net_arch=[64, 64], batch_size=32, num_sample_w=4, learning_starts=50, buffer_size=1024)
+    agent.train(total_timesteps=300)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "hv_parity.json")))
+    weights = [np.asarray(w, dtype=np.float32) for w in gold["eval_weights"]]
+    serial = [agent.policy_eval(TreasureChain(seed=123), weights=w, num_episodes=3) for w in weights]
+    batched = policy_evaluation_mo_batched(agent, TreasureChain(seed=123), weights, rep=3)
+    for s_, b_ in zip(serial, batched):
+        for x, y in zip(s_, b_):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+    front = np.array([b[3] for b in batched], dtype=np.float64)
+    pts = th.from_numpy(front).to(cuda)
+    keep = ops.pareto_mask(pts, True, raw=True)
+    hv_dev = float(ops.hypervolume(pts, th.from_numpy(HV_REF_POINT), keep=keep))
+    from morl_baselines_b200.common.pareto import filter_pareto_dominated
+
+    hv_host = hypervolume(HV_REF_POINT, list(filter_pareto_dominated(front)))
+    assert abs(hv_dev - hv_host) <= 1e-12 * max(1.0, hv_host)
