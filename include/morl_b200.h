@@ -277,6 +277,12 @@ MORL_API int morl_per_priority_f32(const float* raw, int n, float alpha, double*
  *                     1 / (a_scale * b_scale) before the bias.  Outputs: c_f32 [M, ldc] and/or c_planes [P][M][ldp] holding
  *                     c_scale * C (the operand format of the next layer).  relu != 0 applies max(x, 0); relu_mask_plane0 (plane 0 of
  *                     a forward activation, [M][ld_mask] 16-bit) zeroes the outputs where that activation was <= 0 (ReLU backward).
+ *                     ReLU bit masks (the form the update uses; relu_mask_plane0 stays for callers that only hold planes):
+ *                     relu_bits_out [M][8] uint32 receives bit j of word (c & 1) * 4 + (c >> 1) = (C[m, 32 c + j] > 0) -- 32 bytes per
+ *                     row instead of the 512-byte activation row, words ordered so that the four chunks one epilogue thread owns
+ *                     are one 16-byte load; relu_bits_in (same layout, written by the forward call of the layer or by
+ *                     morl_pairs_relu_split_planes) zeroes the outputs whose bit is clear, i.e. relu'(x) = [x > 0] exactly as
+ *                     torch's ReLU backward (reference networks.py:10-48 under autograd).  Both nullable, 16-byte aligned.
  *                     reverse_tiles != 0 walks the 128-row tiles from the last to the first: alternate it between the layers of
  *                     a chain so that a layer starts on the rows its producer wrote last (still in the 126 MB L2).
  *                     split_accumulators != 0: the leading products A0.B0 and the correction products accumulate in separate TMEM
@@ -304,7 +310,8 @@ MORL_API int morl_split_planes(int fmt, const float* src, int rows, int cols, in
 MORL_API int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* b_planes,
                                   long long b_plane_stride, const float* b_scale, int M, int N, int N_pad, int K, const float* bias,
                                   int relu, const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp,
-                                  long long c_plane_stride, const float* c_scale, int reverse_tiles, int split_accumulators, void* stream);
+                                  long long c_plane_stride, const float* c_scale, int reverse_tiles, int split_accumulators,
+                                  const void* relu_bits_in, void* relu_bits_out, void* stream);
 /* Diagnostics (not part of the reference surface): per-role cycle counters of morl_gemm_planes_f32, summed over CTAs and launches
  * since the last reset; collected only when the environment variable MORL_GEMM_STATS=1 is set before the first GEMM call.
  * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,
@@ -313,7 +320,7 @@ MORL_API int morl_debug_gemm_stats(unsigned long long* out8, int reset);
 /* h[b*W + j, :] = relu(u[b, :] + v[j, :]) written directly as planes [P][B*W][H] of scale * h (separable first layer of the
  * weight-conditioned Q-network: W1 [s || w] + b1 = W1_s s + (W1_w w + b1); reference envelope.py:75 builds the concat). */
 MORL_API int morl_pairs_relu_split_planes(int fmt, const float* u, const float* v, int B, int W, int H, void* dst_planes,
-                                          long long plane_stride, const float* scale, void* stream);
+                                          long long plane_stride, const float* scale, void* relu_bits_out, void* stream);
 
 
 /* Weight-gradient GEMM (reduction over the batch rows), split-K, deterministic:

@@ -24,6 +24,11 @@ class FusedClipAdam(optim.Adam):
         self._cache = {}   # tables referenced by captured CUDA graphs (one per capture)
         self._eager = None  # the single overwritable table of the eager path
 
+    def load_state_dict(self, state_dict):
+        """``optim.Adam.load_state_dict`` replaces the state tensors: the cached pointer tables (which hold their addresses) are dropped."""
+        super().load_state_dict(state_dict)
+        self._tables, self._cache, self._eager = None, {}, None
+
     def _ensure_state(self):
         for group in self.param_groups:
             for p in group["params"]:

@@ -1,4 +1,5 @@
 // api.cu -- version / error plumbing of the C-ABI (include/morl_b200.h).
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -23,6 +24,14 @@ int check_launch(const char* what) {
         return static_cast<int>(e);
     }
     return MORL_OK;
+}
+
+bool pdl_enabled() {
+    // opt-in: measured on the Envelope update (profiles/r02_bench_ab.txt), the attribute on EVERY kernel of the step costs 4.5 % (1,299 ->
+    // 1,242 updates/s): the early-resident CTAs of the small kernels take issue slots and shared memory from the draining grid.  The
+    // GEMM chain keeps its own switch (MORL_GEMM_PDL, on: +3 %), where the prologue that overlaps is long (TMEM allocation, barriers).
+    static const bool on = [] { const char* e = getenv("MORL_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 
 }  // namespace morl

@@ -269,11 +269,16 @@ struct GemmArgs {
     long long plane_stride;      // elements between planes
     const uint16_t* mask;        // plane 0 of the forward activation [M][ld_mask] for the ReLU-backward mask, or nullptr
     int ld_mask;
+    const uint32_t* bits_in;     // ReLU-backward mask as BITS [M][8] words (see morl_b200.h "ReLU bit masks"), or nullptr
+    uint32_t* bits_out;          // forward: bit = (output > 0) per column, same layout, or nullptr
+    int n_stages;                // depth of the TMA ring: as many (A box + B box) stages as fit (3 at N_pad = 256, more for narrow outputs)
+    uint32_t b_stage;            // bytes of one B stage slot (the B box rounded up to 1 KB)
     int relu;
     const float* a_scale;        // device scalars (powers of two) the A / B planes were scaled by; nullptr = 1
     const float* b_scale;
     const float* c_scale;        // scale applied to the output before it is re-split into c_planes; nullptr = 1
     int l2_hint;                 // L2 eviction hints on the operand loads (MORL_GEMM_L2HINT=1, default off): A evict_first, B evict_last
+    int skip_b;                  // TIMING EXPERIMENT ONLY (MORL_GEMM_SKIPB=1, wrong results): B boxes are loaded for the first tile of a CTA only
     int pdl;                     // launched with programmatic stream serialisation: overlap this grid's prologue with the predecessor's tail
     int reverse;                 // walk the row tiles from the last to the first (see morl_gemm_planes_f32: L2 reuse between chained layers)
     unsigned long long* stats;   // diagnostics (MORL_GEMM_STATS=1), else nullptr: [0] MMA wait-on-TMA cycles, [1] MMA wait-on-epilogue,
@@ -286,7 +291,8 @@ __device__ unsigned long long g_gemm_stats[8];
 template <int NCTA, int FMT>
 struct KPlan {
     using F = PlaneFmt<FMT>;
-    static constexpr int kStages = NCTA == 2 ? F::kStages2 : F::kStages1;
+    static constexpr int kStages = NCTA == 2 ? F::kStages2 : F::kStages1;  // ring depth at N_pad = 256
+    static constexpr int kMaxStages = 8;                                          // barrier slots (narrow outputs run a deeper ring)
     static constexpr uint32_t kRowB = F::BK * 2;                                  // bytes per staged row = swizzle span
     static constexpr uint32_t kAStage = F::P * kGemmBM * kRowB;                   // A box bytes
     static constexpr uint32_t kBStage = F::P * (256 / NCTA) * kRowB;              // B box bytes at N_pad = 256
@@ -315,21 +321,22 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     using L = KPlan<NCTA, FMT>;
     constexpr int P = F::P;
     constexpr int BK = F::BK;
-    constexpr int kStages = L::kStages;
+    constexpr int kMaxStages = L::kMaxStages;
     constexpr uint32_t ROWB = L::kRowB;
+    const int kStages = g.n_stages;  // runtime: narrow B boxes leave room for a deeper ring (host: plan_stages)
     extern __shared__ uint8_t gsmem_raw[];
     // 1 KB alignment by pointer arithmetic ON the shared array (not through an integer cast), so that the compiler keeps every derived
     // pointer in the shared address space: through the cast the bias / staging accesses were generic LD.E / ST.E (long-scoreboard stalls)
     uint8_t* gsmem = gsmem_raw + ((1024u - (g_smem_u32(gsmem_raw) & 1023u)) & 1023u);
     const int BN = g.N_pad;
     constexpr uint32_t a_stage_bytes = L::kAStage;
-    constexpr uint32_t b_stage_stride = L::kBStage;
+    const uint32_t b_stage_stride = g.b_stage;
     uint8_t* smA = gsmem;
-    uint8_t* smB = gsmem + L::kOffB;
+    uint8_t* smB = gsmem + (uint32_t)kStages * a_stage_bytes;  // (n_stages * (A + B) <= kOffC, checked on the host)
     uint8_t* stage_c = gsmem + L::kOffC;  // per-epilogue-warp staging tiles for the TMA store of the re-split activations
     uint64_t* full = reinterpret_cast<uint64_t*>(gsmem + L::kOffBar);
-    uint64_t* empty = full + kStages;
-    uint64_t* tfull = empty + kStages;
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tfull = empty + kMaxStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_s = reinterpret_cast<float*>(gsmem + L::kOffBias);  // [256]
@@ -409,10 +416,13 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     g_mbar_wait(&empty[stage], phase ^ 1u);
                     if (g.stats) w_empty += clock64() - c0;
                     if (NCTA == 2) {
+                        const bool load_b = !(g.skip_b && u != unit);
                         // one expect_tx (leader) covers the four boxes of the pair; every box completes on the leader's barrier
-                        if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + (uint32_t)P * (uint32_t)b_rows * ROWB));
+                        if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + (load_b ? (uint32_t)P * (uint32_t)b_rows * ROWB : 0u)));
                         const uint32_t lbar = mapa_rank0(g_smem_u32(&full[stage]));
-                        if (g.l2_hint) {
+                        if (!load_b) {
+                            tma_load_3d_pair(smA + stage * a_stage_bytes, &tmA, lbar, kb * BK, row0, 0);
+                        } else if (g.l2_hint) {
                             tma_load_3d_pair_hint(smA + stage * a_stage_bytes, &tmA, lbar, kb * BK, row0, 0, pol_a);
                             tma_load_3d_pair_hint(smB + stage * b_stage_stride, n_cnt == BN ? &tmB : &tmBh, lbar, kb * BK,
                                                   n_begin + (int)cta_rank * b_rows, 0, pol_b);
@@ -507,13 +517,32 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int t = lane; t < 256; t += 32) bias_s[t] *= fold;
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
         float amax = 0.f;
+        uint4 tile_bits = make_uint4(0u, 0u, 0u, 0u);
         auto process = [&](const uint32_t (&v)[32], int n0, int row, bool row_ok) {
+            // ReLU bit masks: word (c & 1) * 4 + (c >> 1) of the row holds columns [32 c, 32 c + 32); a thread owns the chunks of one parity
+            // (its `half`), so its words of a tile are the four consecutive ones prefetched into tile_bits before the accumulator wait
+            // (both uses are warp-uniform branches: the no-grad forward passes, 8 of the 16 GEMMs of an update, pay nothing for them -- the
+            // epilogue has ~30 % of slack against the MMAs of the next tile and an unconditional version used it up)
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float f = __fmaf_rn(__uint_as_float(v[j]), k_acc, bias_s[n0 + j]);
                 if (g.relu) f = (f < 0.f) ? 0.f : f;  // (NaN stays NaN, like torch.relu: an overflow upstream must reach the loss)
                 x[j] = f;
+            }
+            if (g.bits_in) {
+                const int i4 = n0 >> 6;
+                const uint32_t keep = i4 == 0 ? tile_bits.x : (i4 == 1 ? tile_bits.y : (i4 == 2 ? tile_bits.z : tile_bits.w));
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (!((keep >> j) & 1u)) x[j] = 0.f;
+            }
+            if (g.bits_out) {
+                uint32_t positive = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (x[j] > 0.f) positive |= 1u << j;
+                if (row_ok) g.bits_out[(size_t)row * 8 + ((n0 >> 5) & 1) * 4 + (n0 >> 6)] = positive;
             }
             if (g.mask && row_ok) {
                 const uint4* mrow = reinterpret_cast<const uint4*>(g.mask + (size_t)row * g.ld_mask + n0);
@@ -594,6 +623,10 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int tile, n_begin, n_cnt;
             unit_of(u, tile, n_begin, n_cnt);
             const uint32_t as = SPLIT ? 0u : (it & 1u);
+            if (g.bits_in) {  // independent of the MMAs: in flight while this warp waits for the accumulator
+                const int prow = (tile * NCTA + (int)cta_rank) * kGemmBM + quad * 32 + lane;
+                tile_bits = prow < g.M ? __ldg(reinterpret_cast<const uint4*>(g.bits_in + (size_t)prow * 8 + half * 4)) : make_uint4(0u, 0u, 0u, 0u);
+            }
             const long long c0 = g.stats ? clock64() : 0;
             g_mbar_wait(&tfull[as], SPLIT ? (it & 1u) : ((it >> 1) & 1u));
             const long long c1 = g.stats ? clock64() : 0;
@@ -742,6 +775,7 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();  // (nothing above reads or writes global memory: barriers, the tile of ones and the TMEM allocation overlap the predecessor)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -838,6 +872,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
                                                               int transpose, float* __restrict__ out, int ld_out, int main_blocks,
                                                               const float* __restrict__ vec_partial, float* __restrict__ vec_out,
                                                               const float* __restrict__ scale_a, const float* __restrict__ scale_b) {
+    pdl_enter();
     __shared__ float red[8][33];
     float mul = 1.0f / (ld_scale(scale_a) * ld_scale(scale_b));
     if ((int)blockIdx.x >= main_blocks) {  // uniform per block
@@ -886,6 +921,7 @@ __global__ void __launch_bounds__(256) reduce_partials_vec4_kernel(const float* 
                                                                    float* __restrict__ out, int ld_out, int main_blocks,
                                                                    const float* __restrict__ vec_partial, float* __restrict__ vec_out,
                                                                    const float* __restrict__ scale_a, const float* __restrict__ scale_b) {
+    pdl_enter();
     __shared__ float4 red[8][33];
     if ((int)blockIdx.x >= main_blocks) {  // column-sum tail: one element per thread, as the scalar kernel
         const float mul = 1.0f / ld_scale(scale_a);
@@ -1040,9 +1076,10 @@ __global__ void __launch_bounds__(256) pairs_rowblock_sum_kernel(const uint16_t*
 // transitions of the chunk in registers (its scale is removed by the final reduce_partials_kernel).
 constexpr int kPgrMaxB = 8;
 template <int FMT>
-__global__ void __launch_bounds__(256) pairs_grad_reduce_fused_kernel(const uint16_t* __restrict__ planes, long long plane_stride, int B, int W,
+__global__ void __launch_bounds__(256, 2) pairs_grad_reduce_fused_kernel(const uint16_t* __restrict__ planes, long long plane_stride, int B, int W,
                                                                       int H, int b_per_chunk, float* __restrict__ dU, float* __restrict__ partV,
                                                                       const float* __restrict__ scale) {
+    pdl_enter();
     using F = PlaneFmt<FMT>;
     extern __shared__ float red_dyn[];  // [kPgrMaxB][8][32][9]
     const int h0 = (blockIdx.y * 32 + threadIdx.x) * 8;
@@ -1057,22 +1094,31 @@ __global__ void __launch_bounds__(256) pairs_grad_reduce_fused_kernel(const uint
         float accU[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) accU[c] = 0.f;
-        if (h0 < H) {
+        // four weight rows (x P planes) are loaded before any of them is used: with one row at a time the kernel had 32 bytes in flight per
+        // thread and ran at a third of the HBM bandwidth (latency bound); predicated loads, no branches, same summation order
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int j = threadIdx.y + 8 * k;
-                if (j < W) {
-                    const size_t o = ((size_t)b * W + j) * H + h0;
-                    float v[8];
+        for (int kk = 0; kk < 8; kk += 4) {
+            uint4 ld[4][F::P];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+            for (int q = 0; q < 4; ++q) {
+                const int j = threadIdx.y + 8 * (kk + q);
+                const bool ok = h0 < H && j < W;
+                const size_t o = ok ? ((size_t)b * W + j) * H + h0 : 0;
 #pragma unroll
-                    for (int p = 0; p < F::P; ++p) F::add8(v, __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)));
+                for (int p = 0; p < F::P; ++p)
+                    ld[q][p] = ok ? __ldg(reinterpret_cast<const uint4*>(planes + p * plane_stride + o)) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        accU[c] += v[c];
-                        accV[k][c] += v[c];
-                    }
+            for (int q = 0; q < 4; ++q) {
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = 0.f;
+#pragma unroll
+                for (int p = 0; p < F::P; ++p) F::add8(v, ld[q][p]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    accU[c] += v[c];
+                    accV[kk + q][c] += v[c];
                 }
             }
         }
@@ -1117,6 +1163,7 @@ __device__ __forceinline__ float scale_from_amax(float amax, int target_exp) {
 // ws[0] = running max (bit pattern of a non-negative float), ws[1] = arrival counter; both zero on entry and zero again on exit
 __global__ void __launch_bounds__(256) amax_scale_kernel(const float* __restrict__ src, long long n, int target_exp, float* __restrict__ scale_out,
                                                          unsigned int* __restrict__ ws) {
+    pdl_enter();
     __shared__ float red[8];
     float m = 0.f;
     const long long n4 = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) ? (n >> 2) : 0;
@@ -1172,6 +1219,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256) split_planes_vec8_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
                                                                 uint16_t* __restrict__ dst, int rows_pad, int ldp, long long plane_stride,
                                                                 const float* __restrict__ scale) {
+    pdl_enter();
     using F = PlaneFmt<FMT>;
     const int cpr = ldp >> 3;  // 8-column chunks per row
     const long long total = (long long)rows_pad * cpr;
@@ -1211,6 +1259,7 @@ struct SplitJobs {
     MorlSplitJob job[MORL_SPLIT_MAX_JOBS];
 };
 __global__ void __launch_bounds__(1024) split_amax_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+    pdl_enter();
     __shared__ float red[32];
     const MorlSplitJob& j = jobs.job[blockIdx.x];
     if (!j.auto_scale || !j.scale) return;  // uniform per block
@@ -1241,6 +1290,7 @@ __global__ void __launch_bounds__(1024) split_amax_multi_kernel(const __grid_con
 
 template <int FMT>
 __global__ void __launch_bounds__(256) split_planes_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+    pdl_enter();
     using F = PlaneFmt<FMT>;
     const MorlSplitJob& j = jobs.job[blockIdx.y];
     const float* __restrict__ src = j.src;
@@ -1263,32 +1313,113 @@ __global__ void __launch_bounds__(256) split_planes_multi_kernel(const __grid_co
 // ---- separable first layer: h[b*W + j] = relu(u[b] + v[j]) straight into planes ------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(256) pairs_relu_split_kernel(const float* __restrict__ u, const float* __restrict__ v, int B, int W, int H,
-                                                               uint16_t* __restrict__ dst, long long plane_stride, const float* __restrict__ scale) {
+                                                               uint16_t* __restrict__ dst, long long plane_stride, const float* __restrict__ scale,
+                                                               uint32_t* __restrict__ bits_out) {
+    pdl_enter();
     using F = PlaneFmt<FMT>;
     const int hv = H / 8;  // 8 columns per thread: two float4 loads per operand, one 16-byte store per plane
     const long long total = (long long)B * W * hv;
     const float s = ld_scale(scale);
     float amax = 0.f;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int h8 = (int)(e % hv);
-        const long long row = e / hv;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count (the bit words are assembled with shuffles): e0 = element of lane 0
+    for (long long e0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < total; e0 += (long long)gridDim.x * blockDim.x) {
+        const long long e = e0 + lane;
+        const bool ok = e < total;
+        const long long ee = ok ? e : 0;
+        const int h8 = (int)(ee % hv);
+        const long long row = ee / hv;
         const int b = (int)(row / W), j = (int)(row - (long long)b * W);
         const float4* up = reinterpret_cast<const float4*>(u + (size_t)b * H + 8 * h8);
         const float4* vp = reinterpret_cast<const float4*>(v + (size_t)j * H + 8 * h8);
         const float4 u0 = __ldg(up), u1 = __ldg(up + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
         const float x[8] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w};
         uint32_t o[F::P][4];
+        uint32_t pos = 0;  // bit t = (column 8 h8 + t is positive)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t w[F::P];
             const float r0 = x[2 * q] < 0.f ? 0.f : x[2 * q], r1 = x[2 * q + 1] < 0.f ? 0.f : x[2 * q + 1];  // NaN-propagating ReLU
+            pos |= (r0 > 0.f ? 1u : 0u) << (2 * q) | (r1 > 0.f ? 1u : 0u) << (2 * q + 1);
             F::split2(r0 * s, r1 * s, w, amax);
 #pragma unroll
             for (int p = 0; p < F::P; ++p) o[p][q] = w[p];
         }
-        const long long off = row * H + 8 * h8;
+        if (ok) {
+            const long long off = row * H + 8 * h8;
 #pragma unroll
-        for (int p = 0; p < F::P; ++p) *reinterpret_cast<uint4*>(dst + p * plane_stride + off) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+            for (int p = 0; p < F::P; ++p) *reinterpret_cast<uint4*>(dst + p * plane_stride + off) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+        }
+        if (bits_out) {
+            // four consecutive threads (h8 = 4c .. 4c + 3; H % 32 == 0 keeps them in one aligned lane group) hold one 32-column word
+            uint32_t wbits = pos << (8 * (lane & 3));
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+            if (ok && (lane & 3) == 0) {
+                const int chunk = h8 >> 2;
+                bits_out[(size_t)row * 8 + (chunk & 1) * 4 + (chunk >> 1)] = wbits;
+            }
+        }
+    }
+    if (FMT == MORL_FMT_F16X2) note_overflow(amax);
+}
+
+// H = 256 form (the shape of the update): one warp per (transition b, quarter of the weight set), lane = 8 columns.  u[b] stays in
+// registers for the warp's rows, v[j] comes from L1 / L2 (64 KB in total), four rows are in flight per iteration: half the load traffic of
+// the element-indexed kernel above and no index arithmetic per element -- the kernel is a 67 MB write stream and nothing else.
+template <int FMT>
+__global__ void __launch_bounds__(256) pairs_relu_split_h256_kernel(const float* __restrict__ u, const float* __restrict__ v, int B, int W,
+                                                                    uint16_t* __restrict__ dst, long long plane_stride,
+                                                                    const float* __restrict__ scale, uint32_t* __restrict__ bits_out, int jsplit) {
+    pdl_enter();
+    using F = PlaneFmt<FMT>;
+    constexpr int H = 256;
+    const int lane = threadIdx.x & 31;
+    const long long task = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (task >= (long long)B * jsplit) return;
+    const int b = (int)(task / jsplit), js = (int)(task - (long long)b * jsplit);
+    const int j0 = (int)((long long)W * js / jsplit), j1 = (int)((long long)W * (js + 1) / jsplit);
+    const float s = ld_scale(scale);
+    float amax = 0.f;
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(u + (size_t)b * H + 8 * lane)),
+                 u1 = __ldg(reinterpret_cast<const float4*>(u + (size_t)b * H + 8 * lane) + 1);
+    const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    for (int jb = j0; jb < j1; jb += 4) {
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = min(jb + q, j1 - 1);
+            va[q] = __ldg(reinterpret_cast<const float4*>(v + (size_t)j * H + 8 * lane));
+            vb[q] = __ldg(reinterpret_cast<const float4*>(v + (size_t)j * H + 8 * lane) + 1);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (jb + q >= j1) break;  // (warp-uniform)
+            const float x[8] = {uu[0] + va[q].x, uu[1] + va[q].y, uu[2] + va[q].z, uu[3] + va[q].w,
+                                uu[4] + vb[q].x, uu[5] + vb[q].y, uu[6] + vb[q].z, uu[7] + vb[q].w};
+            uint32_t o[F::P][4];
+            uint32_t pos = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint32_t w[F::P];
+                const float r0 = x[2 * t] < 0.f ? 0.f : x[2 * t], r1 = x[2 * t + 1] < 0.f ? 0.f : x[2 * t + 1];  // NaN-propagating ReLU
+                pos |= (r0 > 0.f ? 1u : 0u) << (2 * t) | (r1 > 0.f ? 1u : 0u) << (2 * t + 1);
+                F::split2(r0 * s, r1 * s, w, amax);
+#pragma unroll
+                for (int p = 0; p < F::P; ++p) o[p][t] = w[p];
+            }
+            const long long row = (long long)b * W + jb + q;
+            const long long off = row * H + 8 * lane;
+#pragma unroll
+            for (int p = 0; p < F::P; ++p) *reinterpret_cast<uint4*>(dst + p * plane_stride + off) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+            if (bits_out) {
+                uint32_t wbits = pos << (8 * (lane & 3));
+                wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+                wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+                const int chunk = lane >> 2;
+                if ((lane & 3) == 0) bits_out[(size_t)row * 8 + (chunk & 1) * 4 + (chunk >> 1)] = wbits;
+            }
+        }
     }
     if (FMT == MORL_FMT_F16X2) note_overflow(amax);
 }
@@ -1368,7 +1499,7 @@ extern "C" int morl_amax_scale_f32(const float* src, long long n, int target_exp
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
-    amax_scale_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, target_exp, scale_out, static_cast<unsigned int*>(workspace));
+    launch_k(amax_scale_kernel, dim3((int)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), src, n, target_exp, scale_out, static_cast<unsigned int*>(workspace));
     return check_launch("morl_amax_scale_f32");
 }
 
@@ -1416,7 +1547,7 @@ extern "C" int morl_gemm_planes_mn_f32(int fmt, const void* g_planes, long long 
             cudaFuncSetAttribute(gemm_planes_mn_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        gemm_planes_mn_kernel<kFmt><<<n_tiles * S, 192, smem, st>>>(tmA, tmB, g);
+        launch_k(gemm_planes_mn_kernel<kFmt>, dim3(n_tiles * S), dim3(192), smem, st, tmA, tmB, g);
     });
     rc = check_launch("morl_gemm_planes_mn_f32");
     if (rc) return rc;
@@ -1424,11 +1555,11 @@ extern "C" int morl_gemm_planes_mn_f32(int fmt, const void* g_planes, long long 
     const int main_blocks = (total + 31) / 32, vec_blocks = colsum_out ? (g_cols + 31) / 32 : 0;
     if (!transpose_out && h_cols % 4 == 0 && ld_out % 4 == 0 && aligned16(out)) {
         const int mb4 = (total / 4 + 31) / 32;
-        reduce_partials_vec4_kernel<<<mb4 + vec_blocks, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, out, ld_out, mb4,
+        launch_k(reduce_partials_vec4_kernel, dim3(mb4 + vec_blocks), dim3(dim3(32, 8)), 0, st, g.partial, S, n_tiles * 128, NB, g_cols, h_cols, out, ld_out, mb4,
                                                                               g.colsum_partial, colsum_out, g_scale, h_scale);
         return check_launch("morl_gemm_planes_mn_f32(reduce)");
     }
-    reduce_partials_kernel<<<main_blocks + vec_blocks, dim3(32, 8), 0, st>>>(g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out,
+    launch_k(reduce_partials_kernel, dim3(main_blocks + vec_blocks), dim3(dim3(32, 8)), 0, st, g.partial, S, n_tiles * 128, NB, g_cols, h_cols, transpose_out, out, ld_out,
                                                                              main_blocks, g.colsum_partial, colsum_out, g_scale, h_scale);
     return check_launch("morl_gemm_planes_mn_f32(reduce)");
 }
@@ -1448,7 +1579,7 @@ extern "C" int morl_colsum_planes(int fmt, const void* planes, long long plane_s
                                static_cast<const uint16_t*>(planes), plane_stride, M, ld, N, rpc, part)));
     int rc = check_launch("morl_colsum_planes");
     if (rc) return rc;
-    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, out, N, 1 << 30, nullptr, nullptr, scale, nullptr);
+    launch_k(reduce_partials_kernel, dim3((N + 31) / 32), dim3(dim3(32, 8)), 0, st, part, nch, 1, N, 1, N, 0, out, N, 1 << 30, nullptr, nullptr, scale, nullptr);
     return check_launch("morl_colsum_planes(reduce)");
 }
 
@@ -1475,12 +1606,12 @@ extern "C" int morl_pairs_grad_reduce_planes(int fmt, const void* planes, long l
                     cudaFuncSetAttribute(pairs_grad_reduce_fused_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf);
                     configured = true;
                 }
-                pairs_grad_reduce_fused_kernel<kFmt><<<dim3((unsigned)nchf, (unsigned)((H + 255) / 256)), dim3(32, 8), smemf, st>>>(pl, plane_stride, B, W,
+                launch_k(pairs_grad_reduce_fused_kernel<kFmt>, dim3(dim3((unsigned)nchf, (unsigned)((H + 255) / 256))), dim3(dim3(32, 8)), smemf, st, pl, plane_stride, B, W,
                                                                                                                                      H, bpc, dU, partf, scale);
             });
             int rcf = check_launch("morl_pairs_grad_reduce_planes(fused)");
             if (rcf) return rcf;
-            reduce_partials_kernel<<<(Nf + 31) / 32, dim3(32, 8), 0, st>>>(partf, nchf, 1, Nf, 1, Nf, 0, dV, Nf, 1 << 30, nullptr, nullptr, scale, nullptr);
+            launch_k(reduce_partials_kernel, dim3((Nf + 31) / 32), dim3(dim3(32, 8)), 0, st, partf, nchf, 1, Nf, 1, Nf, 0, dV, Nf, 1 << 30, nullptr, nullptr, scale, nullptr);
             return check_launch("morl_pairs_grad_reduce_planes(reduce)");
         }
     }
@@ -1499,7 +1630,7 @@ extern "C" int morl_pairs_grad_reduce_planes(int fmt, const void* planes, long l
                                                                                                                                   rpc, part)));
     rc = check_launch("morl_pairs_grad_reduce_planes(dV)");
     if (rc) return rc;
-    reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(part, nch, 1, N, 1, N, 0, dV, N, 1 << 30, nullptr, nullptr, scale, nullptr);
+    launch_k(reduce_partials_kernel, dim3((N + 31) / 32), dim3(dim3(32, 8)), 0, st, part, nch, 1, N, 1, N, 0, dV, N, 1 << 30, nullptr, nullptr, scale, nullptr);
     return check_launch("morl_pairs_grad_reduce_planes(reduce)");
 }
 
@@ -1518,7 +1649,7 @@ extern "C" int morl_split_planes(int fmt, const float* src, int rows, int cols, 
         const long long chunks = total >> 3;
         long long vb = (chunks + 255) / 256;
         if (vb > 148 * 8) vb = 148 * 8;
-        MORL_DISPATCH_FMT(fmt, (split_planes_vec8_kernel<kFmt><<<(int)vb, 256, 0, st>>>(src, rows, cols, ld_src, dst, rows_pad, ldp, plane_stride, scale)));
+        MORL_DISPATCH_FMT(fmt, (launch_k(split_planes_vec8_kernel<kFmt>, dim3((int)vb), dim3(256), 0, st, src, rows, cols, ld_src, dst, rows_pad, ldp, plane_stride, scale)));
         return check_launch("morl_split_planes(vec8)");
     }
     long long blocks = (total + 255) / 256;
@@ -1552,16 +1683,16 @@ extern "C" int morl_split_planes_multi(int fmt, const MorlSplitJob* jobs, int n_
     bool any_auto = false;
     for (int i = 0; i < n_jobs; ++i) any_auto = any_auto || (jobs[i].auto_scale && jobs[i].scale);
     if (any_auto) {
-        split_amax_multi_kernel<<<n_jobs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(sj);
+        launch_k(split_amax_multi_kernel, dim3(n_jobs), dim3(1024), 0, static_cast<cudaStream_t>(stream), sj);
         int rca = check_launch("morl_split_planes_multi(amax)");
         if (rca) return rca;
     }
-    MORL_DISPATCH_FMT(fmt, (split_planes_multi_kernel<kFmt><<<dim3((unsigned)bx, (unsigned)n_jobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(sj)));
+    MORL_DISPATCH_FMT(fmt, (launch_k(split_planes_multi_kernel<kFmt>, dim3(dim3((unsigned)bx, (unsigned)n_jobs)), dim3(256), 0, static_cast<cudaStream_t>(stream), sj)));
     return check_launch("morl_split_planes_multi");
 }
 
 extern "C" int morl_pairs_relu_split_planes(int fmt, const float* u, const float* v, int B, int W, int H, void* dst_planes, long long plane_stride,
-                                            const float* scale, void* stream) {
+                                            const float* scale, void* relu_bits_out, void* stream) {
     using namespace morl;
     MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_pairs_relu_split_planes: unknown plane format %d", fmt);
     MORL_REQUIRE(u && v && dst_planes, MORL_ERR_NULL, "morl_pairs_relu_split_planes: NULL pointer argument");
@@ -1570,8 +1701,18 @@ extern "C" int morl_pairs_relu_split_planes(int fmt, const float* u, const float
     const long long total = (long long)B * W * (H / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    MORL_DISPATCH_FMT(fmt, (pairs_relu_split_kernel<kFmt><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-                               u, v, B, W, H, static_cast<uint16_t*>(dst_planes), plane_stride, scale)));
+    if (relu_bits_out)
+        MORL_REQUIRE(H % 32 == 0 && H <= 256 && aligned16(relu_bits_out), MORL_ERR_SHAPE,
+                     "morl_pairs_relu_split_planes: ReLU bit masks need H %% 32 == 0, H <= 256 (H=%d)", H);
+    if (H == 256) {
+        const int jsplit = W >= 16 ? 4 : 1;
+        const long long tasks = (long long)B * jsplit;
+        MORL_DISPATCH_FMT(fmt, (launch_k(pairs_relu_split_h256_kernel<kFmt>, dim3((unsigned)((tasks + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                         u, v, B, W, static_cast<uint16_t*>(dst_planes), plane_stride, scale, static_cast<uint32_t*>(relu_bits_out), jsplit)));
+        return check_launch("morl_pairs_relu_split_planes(h256)");
+    }
+    MORL_DISPATCH_FMT(fmt, (launch_k(pairs_relu_split_kernel<kFmt>, dim3((int)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+                               u, v, B, W, H, static_cast<uint16_t*>(dst_planes), plane_stride, scale, static_cast<uint32_t*>(relu_bits_out))));
     return check_launch("morl_pairs_relu_split_planes");
 }
 
@@ -1642,7 +1783,8 @@ static int launch_gemm_planes(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* b_planes,
                                     long long b_plane_stride, const float* b_scale, int M, int N, int N_pad, int K, const float* bias, int relu,
                                     const void* relu_mask_plane0, int ld_mask, float* c_f32, int ldc, void* c_planes, int ldp, long long c_plane_stride,
-                                    const float* c_scale, int reverse_tiles, int split_accumulators, void* stream) {
+                                    const float* c_scale, int reverse_tiles, int split_accumulators, const void* relu_bits_in, void* relu_bits_out,
+                                    void* stream) {
     using namespace morl;
     MORL_REQUIRE(fmt_ok(fmt), MORL_ERR_UNSUPPORTED, "morl_gemm_planes_f32: unknown plane format %d", fmt);
     MORL_REQUIRE(a_planes && b_planes && (c_f32 || c_planes), MORL_ERR_NULL, "morl_gemm_planes_f32: NULL pointer argument");
@@ -1651,6 +1793,7 @@ extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_p
     MORL_REQUIRE(K % BK == 0 && N_pad % 32 == 0 && N_pad <= 256, MORL_ERR_UNSUPPORTED,
                  "morl_gemm_planes_f32: need K %% %d == 0, N_pad %% 32 == 0, N_pad <= 256 (K=%d N_pad=%d)", BK, K, N_pad);
     MORL_REQUIRE(aligned16(a_planes) && aligned16(b_planes), MORL_ERR_ALIGN, "morl_gemm_planes_f32: operand planes must be 16-byte aligned");
+    MORL_REQUIRE(aligned16(relu_bits_in) && aligned16(relu_bits_out), MORL_ERR_ALIGN, "morl_gemm_planes_f32: ReLU bit masks must be 16-byte aligned");
     if (c_planes)
         MORL_REQUIRE(ldp % 32 == 0 && ldp >= N && ldp <= N_pad && aligned16(c_planes) && c_plane_stride % 8 == 0, MORL_ERR_SHAPE,
                      "morl_gemm_planes_f32: ldp=%d must be a multiple of 32 with N <= ldp <= N_pad", ldp);
@@ -1681,11 +1824,29 @@ extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_p
     g.bias = bias; g.c_f32 = c_f32; g.ldc = ldc;
     g.c_planes = c_planes; g.ldp = ldp; g.plane_stride = c_plane_stride;
     g.mask = static_cast<const uint16_t*>(relu_mask_plane0); g.ld_mask = ld_mask; g.relu = relu;
+    g.bits_in = static_cast<const uint32_t*>(relu_bits_in); g.bits_out = static_cast<uint32_t*>(relu_bits_out);
+    {
+        // TMA ring: A box + B box per stage; a narrow B box (the output layer: N_pad = 32) leaves room for a deeper ring, which is what
+        // keeps enough bytes in flight per SM when a tile is four A boxes and almost no tensor work
+        const uint32_t rowb = (uint32_t)BK * 2u, P = (uint32_t)fmt_planes(fmt);
+        const uint32_t a_box = P * (uint32_t)kGemmBM * rowb;
+        const uint32_t b_box = (P * (uint32_t)(N_pad / ncta) * rowb + 1023u) & ~1023u;
+        const uint32_t room = fmt == MORL_FMT_F16X2 ? (pair ? KPlan<2, MORL_FMT_F16X2>::kOffC : KPlan<1, MORL_FMT_F16X2>::kOffC)
+                                                    : (pair ? KPlan<2, MORL_FMT_BF16X3>::kOffC : KPlan<1, MORL_FMT_BF16X3>::kOffC);
+        int n_st = (int)(room / (a_box + b_box));
+        if (n_st > 8) n_st = 8;
+        static const int st_env = [] { const char* e = getenv("MORL_GEMM_STAGES"); return e ? atoi(e) : 0; }();
+        if (st_env > 0 && st_env < n_st) n_st = st_env;  // A/B measurements
+        g.n_stages = n_st;
+        g.b_stage = b_box;
+    }
     g.a_scale = a_scale; g.b_scale = b_scale; g.c_scale = c_scale;
     g.reverse = reverse_tiles ? 1 : 0;
     // programmatic dependent launch between consecutive GEMMs of a chain (MORL_GEMM_PDL=0 disables it: A/B in profiles/r02_pdl_ab.txt)
     static const bool want_pdl = [] { const char* e = getenv("MORL_GEMM_PDL"); return !(e && e[0] == '0'); }();
     g.pdl = want_pdl ? 1 : 0;
+    static const bool want_skip_b = [] { const char* e = getenv("MORL_GEMM_SKIPB"); return e && e[0] == '1'; }();
+    g.skip_b = want_skip_b ? 1 : 0;
     // measured on B200 (profiles/r01_s3_l2hint_ab.txt): the hints do not help, so they are opt-in (MORL_GEMM_L2HINT=1)
     static const bool want_hint = [] { const char* e = getenv("MORL_GEMM_L2HINT"); return e && e[0] == '1'; }();
     g.l2_hint = want_hint ? 1 : 0;

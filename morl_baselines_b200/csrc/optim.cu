@@ -11,6 +11,7 @@ namespace morl {
 
 __global__ void __launch_bounds__(256) polyak_kernel(const float* const* __restrict__ params, float* const* __restrict__ targets,
                                                      const int64_t* __restrict__ sizes, float tau, float one_minus_tau) {
+    pdl_enter();
     const int t = blockIdx.y;
     const int64_t n = sizes[t];
     const float* __restrict__ p = params[t];
@@ -38,7 +39,7 @@ extern "C" int morl_polyak_f32(const float* const* params, float* const* targets
     const dim3 grid((unsigned)bx, (unsigned)n_tensors, 1);
     // (1 - tau) is formed in double then rounded, like Python's `1.0 - tau` handed to Tensor.mul_
     const float omt = (float)(1.0 - tau);
-    polyak_kernel<<<grid, 256, 0, st>>>(params, targets, sizes, (float)tau, omt);
+    launch_k(polyak_kernel, dim3(grid), dim3(256), 0, st, params, targets, sizes, (float)tau, omt);
     return check_launch("morl_polyak_f32");
 }
 
@@ -54,6 +55,7 @@ constexpr int kOptBlock = 256;
 
 __global__ void __launch_bounds__(kOptBlock) grad_sqnorm_kernel(const float* const* __restrict__ grads, const int64_t* __restrict__ sizes,
                                                                 float* const* __restrict__ steps, float* __restrict__ partials) {
+    pdl_enter();
     __shared__ float red[kOptBlock / 32];
     const int t = blockIdx.y;
     const int64_t n = sizes[t];
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(kOptBlock) adam_clip_kernel(float* const* __re
                                                               float* const* __restrict__ steps, const int64_t* __restrict__ sizes,
                                                               const float* __restrict__ partials, int n_partials, float max_norm, float lr,
                                                               float beta1, float beta2, float eps) {
+    pdl_enter();
     __shared__ float s_coef;
     __shared__ double s_red[kOptBlock / 32];
     if (max_norm > 0.f) {
@@ -143,10 +146,10 @@ extern "C" int morl_adam_clip_f32(float* const* params, const float* const* grad
     if (bx > 64) bx = 64;
     const dim3 grid((unsigned)bx, (unsigned)n_tensors, 1);
     float* partials = static_cast<float*>(workspace);
-    grad_sqnorm_kernel<<<grid, kOptBlock, 0, st>>>(grads, sizes, steps, partials);
+    launch_k(grad_sqnorm_kernel, dim3(grid), dim3(kOptBlock), 0, st, grads, sizes, steps, partials);
     int rc = check_launch("morl_adam_clip_f32(norm)");
     if (rc) return rc;
-    adam_clip_kernel<<<grid, kOptBlock, 0, st>>>(params, grads, exp_avg, exp_avg_sq, steps, sizes, partials, (int)(bx * n_tensors), max_grad_norm, lr, beta1,
+    launch_k(adam_clip_kernel, dim3(grid), dim3(kOptBlock), 0, st, params, grads, exp_avg, exp_avg_sq, steps, sizes, partials, (int)(bx * n_tensors), max_grad_norm, lr, beta1,
                                                  beta2, eps);
     return check_launch("morl_adam_clip_f32");
 }

@@ -20,6 +20,7 @@ constexpr int kL1Rows = 8;  // rows (transitions or weight vectors) per block of
 __global__ void __launch_bounds__(256) pair_layer1_uv_kernel(const float* __restrict__ feats, const float* __restrict__ wset, const float* __restrict__ W1,
                                                              const float* __restrict__ b1, int B, int W, int F, int D, int H, float* __restrict__ u,
                                                              float* __restrict__ v) {
+    pdl_enter();
     extern __shared__ float xs[];  // [kL1Rows][max(F, D)] input rows of this block
     const int K = F + D;
     const int r0 = blockIdx.x * kL1Rows;
@@ -80,13 +81,14 @@ __global__ void __launch_bounds__(256) pair_layer1_uv_kernel(const float* __rest
 // reduction rows is staged ONCE in shared memory and every thread accumulates all of its columns (c = warp, warp + 8, ...) from it in
 // registers; the partial tiles go to workspace[s][H][F + D + 1] and the LAST block of an h-tile to finish (self-resetting arrival counter)
 // adds the kL1Splits partials in split order: deterministic, no float atomics.
-constexpr int kL1Splits = 32;
+constexpr int kL1Splits = 16;
 constexpr int kL1Chunk = 32;   // reduction rows staged per pass
 constexpr int kL1ColsPerThread = 8;  // columns per thread per column block (8 groups x 8 = 64 columns per block of columns)
 
 __global__ void __launch_bounds__(256) pair_layer1_grad_kernel(const float* __restrict__ dU, const float* __restrict__ dV, const float* __restrict__ feats,
                                                                const float* __restrict__ wset, int B, int W, int F, int D, int H, float* __restrict__ dW1,
                                                                float* __restrict__ db1, float* __restrict__ partial, unsigned int* __restrict__ counters) {
+    pdl_enter();
     __shared__ float gs[kL1Chunk][33];                          // gradient rows (dU or dV) of the chunk, this block's 32 h columns
     __shared__ float xs[kL1Chunk][8 * kL1ColsPerThread + 1];    // input rows of the chunk, the current block of <= 64 columns
     __shared__ unsigned int s_last;
@@ -150,26 +152,36 @@ __global__ void __launch_bounds__(256) pair_layer1_grad_kernel(const float* __re
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int c = grp; c < C; c += 8) {
-        if (h0 + hl >= H) continue;
-        // all kL1Splits partials of this output are loaded FIRST (independent loads in flight together: the sequential version paid one
-        // L2 latency per split), then summed in four interleaved chains in split order (fixed order: deterministic)
-        float v[kL1Splits];
+    if (h0 + hl >= H) return;
+    // every partial of up to kL1TailCols columns of this thread is loaded FIRST (independent loads in flight together: one L2 latency
+    // for the whole tail instead of one per column and split), then summed in four interleaved chains in split order (deterministic)
+    constexpr int kL1TailCols = 5;  // 8 groups x 5 = 40 columns per pass (F + D + 1 = 36 at the north-star shape)
+    for (int cb = grp; cb < C; cb += 8 * kL1TailCols) {
+        float v[kL1TailCols][kL1Splits];
 #pragma unroll
-        for (int ss = 0; ss < kL1Splits; ++ss) v[ss] = __ldcg(partial + ((size_t)ss * H + h0 + hl) * C + c);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int i = 0; i < kL1TailCols; ++i) {
+            const int c = cb + 8 * i;
 #pragma unroll
-        for (int ss = 0; ss < kL1Splits; ss += 4) {
-            a0 += v[ss];
-            a1 += v[ss + 1];
-            a2 += v[ss + 2];
-            a3 += v[ss + 3];
+            for (int ss = 0; ss < kL1Splits; ++ss) v[i][ss] = c < C ? __ldcg(partial + ((size_t)ss * H + h0 + hl) * C + c) : 0.f;
         }
-        const float acc = (a0 + a1) + (a2 + a3);
-        if (c < F + D)
-            dW1[(size_t)(h0 + hl) * (F + D) + c] = acc;
-        else
-            db1[h0 + hl] = acc;
+#pragma unroll
+        for (int i = 0; i < kL1TailCols; ++i) {
+            const int c = cb + 8 * i;
+            if (c >= C) break;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int ss = 0; ss < kL1Splits; ss += 4) {
+                a0 += v[i][ss];
+                a1 += v[i][ss + 1];
+                a2 += v[i][ss + 2];
+                a3 += v[i][ss + 3];
+            }
+            const float acc = (a0 + a1) + (a2 + a3);
+            if (c < F + D)
+                dW1[(size_t)(h0 + hl) * (F + D) + c] = acc;
+            else
+                db1[h0 + hl] = acc;
+        }
     }
 }
 
@@ -184,7 +196,7 @@ extern "C" int morl_pair_layer1_uv_f32(const float* feats, const float* wset, co
     const size_t smem = (size_t)kL1Rows * kmax * sizeof(float);
     MORL_REQUIRE(smem <= 48 * 1024, MORL_ERR_UNSUPPORTED, "morl_pair_layer1_uv_f32: feature dimension %d too large", kmax);
     const int blocks = (B + W + kL1Rows - 1) / kL1Rows;
-    pair_layer1_uv_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(feats, wset, W1, b1, B, W, F, D, H, u, v);
+    launch_k(pair_layer1_uv_kernel, dim3(blocks), dim3(256), smem, static_cast<cudaStream_t>(stream), feats, wset, W1, b1, B, W, F, D, H, u, v);
     return check_launch("morl_pair_layer1_uv_f32");
 }
 
@@ -203,6 +215,6 @@ extern "C" int morl_pair_layer1_grad_f32(const float* dU, const float* dV, const
     float* partial = static_cast<float*>(workspace);
     unsigned int* counters = reinterpret_cast<unsigned int*>(partial + (size_t)kL1Splits * H * (F + D + 1));
     dim3 grid((H + 31) / 32, kL1Splits);
-    pair_layer1_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dU, dV, feats, wset, B, W, F, D, H, dW1, db1, partial, counters);
+    launch_k(pair_layer1_grad_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), dU, dV, feats, wset, B, W, F, D, H, dW1, db1, partial, counters);
     return check_launch("morl_pair_layer1_grad_f32");
 }

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) replay_gather_kernel(const float* __restr
                                                             float* __restrict__ obs_out, float* __restrict__ next_obs_out,
                                                             void* __restrict__ act_out, float* __restrict__ rew_out,
                                                             float* __restrict__ done_out) {
+    pdl_enter();
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     if constexpr (VEC4) {
@@ -81,11 +82,11 @@ extern "C" int morl_replay_gather(const float* obs_store, const float* next_obs_
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (vec4)
-        replay_gather_kernel<true><<<(int)blocks, 256, 0, st>>>(obs_store, next_obs_store, act_store, rew_store, done_store, idx, B, obs_dim,
+        launch_k(replay_gather_kernel<true>, dim3((int)blocks), dim3(256), 0, st, obs_store, next_obs_store, act_store, rew_store, done_store, idx, B, obs_dim,
                                                                 act_dim, rew_dim, act_is_u8, capacity, obs_out, next_obs_out, act_out,
                                                                 rew_out, done_out);
     else
-        replay_gather_kernel<false><<<(int)blocks, 256, 0, st>>>(obs_store, next_obs_store, act_store, rew_store, done_store, idx, B, obs_dim,
+        launch_k(replay_gather_kernel<false>, dim3((int)blocks), dim3(256), 0, st, obs_store, next_obs_store, act_store, rew_store, done_store, idx, B, obs_dim,
                                                                  act_dim, rew_dim, act_is_u8, capacity, obs_out, next_obs_out, act_out,
                                                                  rew_out, done_out);
     return check_launch("morl_replay_gather");

@@ -27,6 +27,7 @@ __device__ __forceinline__ const double* st_level(const double* tree, int l) { r
 
 __global__ void __launch_bounds__(256) sumtree_walk_kernel(const double* __restrict__ tree, int n_levels, const double* __restrict__ u, int n,
                                                            int scale_by_root, long long* __restrict__ out) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double q = scale_by_root ? __dmul_rn(tree[0], u[i]) : u[i];
@@ -46,6 +47,7 @@ constexpr int kStThreads = 1024;
 // one block.  idx [n] leaf indices, prio [n] new priorities (float64), n <= kStMaxBatch.
 __global__ void __launch_bounds__(kStThreads) sumtree_batch_set_kernel(double* __restrict__ tree, int n_levels, const long long* __restrict__ idx,
                                                                        const double* __restrict__ prio, int n, int* __restrict__ err) {
+    pdl_enter();
     __shared__ unsigned long long key[kStMaxBatch];  // (leaf << 13 | position), sorted ascending; position < 2^13
     __shared__ double diff[kStMaxBatch];             // diff of the i-th UNIQUE leaf (compacted)
     __shared__ int leaf[kStMaxBatch];                // the i-th unique leaf
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(32) sumtree_set_kernel(double* __restrict__ tr
 // double) and it becomes a float32 value the first time a priority exceeds it (python max(float, np.float32)).
 __global__ void __launch_bounds__(kStThreads) per_priority_kernel(const float* __restrict__ raw, int n, float alpha, double* __restrict__ min_priority,
                                                                   double* __restrict__ p64, float* __restrict__ p32) {
+    pdl_enter();
     __shared__ float red[kStThreads / 32];
     const double mp64 = *min_priority;
     const float mp = (float)mp64;
@@ -176,7 +179,7 @@ extern "C" int morl_sumtree_walk_f64(const double* tree, int n_levels, const dou
     MORL_REQUIRE(tree && u && out_index, MORL_ERR_NULL, "morl_sumtree_walk_f64: NULL pointer argument");
     MORL_REQUIRE(n_levels >= 1 && n_levels <= 31 && n >= 0, MORL_ERR_SHAPE, "morl_sumtree_walk_f64: bad shape n_levels=%d n=%d", n_levels, n);
     if (n == 0) return MORL_OK;
-    sumtree_walk_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(tree, n_levels, u, n, scale_by_root, out_index);
+    launch_k(sumtree_walk_kernel, dim3((n + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), tree, n_levels, u, n, scale_by_root, out_index);
     return check_launch("morl_sumtree_walk_f64");
 }
 
@@ -187,7 +190,7 @@ extern "C" int morl_sumtree_batch_set_f64(double* tree, int n_levels, const long
     MORL_REQUIRE(n_levels >= 1 && n_levels <= 31 && n >= 0 && n <= kStMaxBatch, MORL_ERR_SHAPE,
                  "morl_sumtree_batch_set_f64: bad shape n_levels=%d n=%d (at most %d indices per call)", n_levels, n, kStMaxBatch);
     if (n == 0) return MORL_OK;
-    sumtree_batch_set_kernel<<<1, kStThreads, 0, static_cast<cudaStream_t>(stream)>>>(tree, n_levels, index, priority, n, err_flag);
+    launch_k(sumtree_batch_set_kernel, dim3(1), dim3(kStThreads), 0, static_cast<cudaStream_t>(stream), tree, n_levels, index, priority, n, err_flag);
     return check_launch("morl_sumtree_batch_set_f64");
 }
 
@@ -204,6 +207,6 @@ extern "C" int morl_per_priority_f32(const float* raw, int n, float alpha, doubl
     using namespace morl;
     MORL_REQUIRE(raw && min_priority && prio64, MORL_ERR_NULL, "morl_per_priority_f32: NULL pointer argument");
     MORL_REQUIRE(n > 0, MORL_ERR_SHAPE, "morl_per_priority_f32: bad n=%d", n);
-    per_priority_kernel<<<1, kStThreads, 0, static_cast<cudaStream_t>(stream)>>>(raw, n, alpha, min_priority, prio64, prio32);
+    launch_k(per_priority_kernel, dim3(1), dim3(kStThreads), 0, static_cast<cudaStream_t>(stream), raw, n, alpha, min_priority, prio64, prio32);
     return check_launch("morl_per_priority_f32");
 }

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kTdThreads) td_mse_kernel(const float* __restr
                                                             float lambda_arg, const float* __restrict__ lambda_dev, int B, int W, int A,
                                                             int row_order, float* __restrict__ grad_q, float* __restrict__ q_taken,
                                                             float* __restrict__ prio_out, float* __restrict__ partials) {
+    pdl_enter();
     __shared__ float red[kTdThreads / 32];
     const float lambda = lambda_dev ? __ldg(lambda_dev) : lambda_arg;  // device-resident schedule value: a captured graph stays valid while it decays
     const long long N = (long long)B * W;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(kTdThreads) td_mse_kernel(const float* __restr
 __global__ void __launch_bounds__(kTdThreads) td_mse_finalize_kernel(const float* __restrict__ partials, int n_blocks, float lambda_arg,
                                                                      const float* __restrict__ lambda_dev, double inv_nd, double inv_n,
                                                                      float* __restrict__ loss_out) {
+    pdl_enter();
     __shared__ double red[2][kTdThreads];
     const float lambda = lambda_dev ? __ldg(lambda_dev) : lambda_arg;
     double a = 0.0, b = 0.0;
@@ -232,12 +234,12 @@ extern "C" int morl_td_mse_priority_f32(const float* q_values, const int32_t* ac
     const long long N = (long long)B * W;
     const int blocks = (int)((N + kTdThreads - 1) / kTdThreads);
     float* partials = static_cast<float*>(workspace);
-    MORL_DISPATCH_D(D, (td_mse_kernel<kD><<<blocks, kTdThreads, 0, st>>>(q_values, action, target_q, wset, homotopy_lambda,
+    MORL_DISPATCH_D(D, (launch_k(td_mse_kernel<kD>, dim3(blocks), dim3(kTdThreads), 0, st, q_values, action, target_q, wset, homotopy_lambda,
                                                                          homotopy_lambda_dev, B, W, A, row_order, grad_q, q_taken, prio_out,
                                                                          partials)));
     int rc = check_launch("morl_td_mse_priority_f32");
     if (rc) return rc;
-    td_mse_finalize_kernel<<<1, kTdThreads, 0, st>>>(partials, blocks, homotopy_lambda, homotopy_lambda_dev, 1.0 / ((double)N * D),
+    launch_k(td_mse_finalize_kernel, dim3(1), dim3(kTdThreads), 0, st, partials, blocks, homotopy_lambda, homotopy_lambda_dev, 1.0 / ((double)N * D),
                                                      1.0 / (double)N, loss_out);
     return check_launch("morl_td_mse_priority_f32(finalize)");
 }

@@ -403,11 +403,15 @@ def split_planes_multi(jobs, fmt: int = FMT_F16X2) -> None:
 def gemm_planes(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Optional[th.Tensor] = None, relu: bool = False,
                 relu_mask: Optional[th.Tensor] = None, out_f32: bool = True, out_planes: bool = False, c_f32: Optional[th.Tensor] = None,
                 c_planes: Optional[th.Tensor] = None, reverse_tiles: bool = False, a_scale: Optional[th.Tensor] = None,
-                b_scale: Optional[th.Tensor] = None, c_scale: Optional[th.Tensor] = None, split_acc: bool = False):
+                b_scale: Optional[th.Tensor] = None, c_scale: Optional[th.Tensor] = None, split_acc: bool = False,
+                relu_bits_in: Optional[th.Tensor] = None, relu_bits_out: Optional[th.Tensor] = None):
     """C = act(A . B^T + bias) on the tcgen05 tensor cores with split operands (fp32-accurate).
     a_planes [P, M, K], b_planes [P, N_pad, K]; the scales are device floats the planes were multiplied by (None = 1);
     ``split_acc``: leading and correction products in separate accumulators (the tensor cores truncate their fp32 accumulation; ~2.5x
     smaller systematic error, ~20 % slower per launch); False (default): one double-buffered accumulator.
+    ``relu_bits_out`` / ``relu_bits_in`` (:func:`empty_relu_bits`): the forward call records [C > 0] as one bit per column, the backward
+    call zeroes the outputs whose bit is clear (ReLU backward from 32 bytes per row instead of the activation planes; ``relu_mask`` is the
+    plane-based form of the same mask).
     returns (c_f32 [M, n_out] or None, c_planes [P, M, ldp] holding c_scale * C, or None)."""
     fmt = fmt_of(a_planes)
     if fmt_of(b_planes) != fmt or not a_planes.is_cuda:
@@ -422,17 +426,36 @@ def gemm_planes(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Opti
     if out_planes and c_planes is None:
         c_planes = empty_planes(fmt, M, _pad(n_out, 32), dev)
     mask0 = None if relu_mask is None else relu_mask[0]
+    for bits in (relu_bits_in, relu_bits_out):
+        if bits is not None and (bits.dtype != th.int32 or tuple(bits.shape) != (M, 8) or not bits.is_contiguous() or bits.device != dev):
+            raise _lib.MorlB200Error(f"gemm_planes: ReLU bit masks must be contiguous int32 [{M}, 8] on {dev}")
     rc = _lib.load().morl_gemm_planes_f32(fmt, _ptr(a_planes), a_planes.stride(0), _ptr(a_scale), _ptr(b_planes), b_planes.stride(0), _ptr(b_scale), M,
                                           n_out, n_pad, K, _ptr(bias), int(relu), _ptr(mask0), 0 if mask0 is None else mask0.stride(0), _ptr(c_f32),
                                           0 if c_f32 is None else c_f32.stride(0), _ptr(c_planes), 0 if c_planes is None else c_planes.shape[2],
-                                          0 if c_planes is None else c_planes.stride(0), _ptr(c_scale), int(reverse_tiles), int(bool(split_acc)), _stream())
+                                          0 if c_planes is None else c_planes.stride(0), _ptr(c_scale), int(reverse_tiles), int(bool(split_acc)),
+                                          _ptr(relu_bits_in), _ptr(relu_bits_out), _stream())
     _lib.check(rc, "morl_gemm_planes_f32")
     _count()
     return c_f32, c_planes
 
 
-def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None, fmt: int = FMT_F16X2, scale: Optional[th.Tensor] = None) -> th.Tensor:
-    """relu(u[b] + v[j]) for every pair, written as planes [P, B*W, H] of scale * h (row b*W + j)."""
+def empty_relu_bits(rows: int, device) -> th.Tensor:
+    """ReLU bit-mask tensor [rows, 8] int32 (layout: include/morl_b200.h, morl_gemm_planes_f32)."""
+    return th.empty((rows, 8), device=device, dtype=th.int32)
+
+
+def unpack_relu_bits(bits: th.Tensor, n_cols: int) -> th.Tensor:
+    """[rows, n_cols] bool from a ReLU bit-mask tensor (tests / diagnostics)."""
+    c = th.arange((n_cols + 31) // 32, device=bits.device)
+    words = bits[:, (c & 1) * 4 + (c >> 1)].to(th.int64) & 0xFFFFFFFF  # [rows, chunks]
+    j = th.arange(32, device=bits.device)
+    return (((words[:, :, None] >> j) & 1) != 0).reshape(bits.shape[0], -1)[:, :n_cols]
+
+
+def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None, fmt: int = FMT_F16X2, scale: Optional[th.Tensor] = None,
+                     relu_bits_out: Optional[th.Tensor] = None) -> th.Tensor:
+    """relu(u[b] + v[j]) for every pair, written as planes [P, B*W, H] of scale * h (row b*W + j); ``relu_bits_out`` [B*W, 8] int32
+    additionally receives [h > 0] as bits (the ReLU-backward mask of :func:`gemm_planes`)."""
     u, v = _dev(u, "u"), _dev(v, "v")
     B, H = u.shape
     W = v.shape[0]
@@ -440,7 +463,7 @@ def pairs_relu_split(u: th.Tensor, v: th.Tensor, out: Optional[th.Tensor] = None
         out = empty_planes(fmt, B * W, H, u.device)
     else:
         fmt = fmt_of(out)
-    rc = _lib.load().morl_pairs_relu_split_planes(fmt, _ptr(u), _ptr(v), B, W, H, _ptr(out), out.stride(0), _ptr(scale), _stream())
+    rc = _lib.load().morl_pairs_relu_split_planes(fmt, _ptr(u), _ptr(v), B, W, H, _ptr(out), out.stride(0), _ptr(scale), _ptr(relu_bits_out), _stream())
     _lib.check(rc, "morl_pairs_relu_split_planes")
     _count()
     return out

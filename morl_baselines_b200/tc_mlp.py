@@ -111,6 +111,8 @@ class TCPairMlp:
             hid = max(l.out_features for l in self.lin[:-1])
             self.g_last = ops.empty_planes(fmt, M, self.ld_last, dev)
             self.g = [ops.empty_planes(fmt, M, hid, dev) for _ in range(2)]
+            # relu'(H_k) as bits (32 B per row), written by the forward pass, read by the dX GEMMs instead of the 512-B activation rows
+            self.hbits = [ops.empty_relu_bits(M, dev) for _ in self.lin[:-1]]
             self.s_g = ops.scale_tensor(1.0, dev) if scaled else None
             self.ws_amax = th.zeros(2, device=dev, dtype=th.int32)
             # transposed weight planes W_l^T [P, in_l, K = padded out_l] for the dX products
@@ -169,14 +171,15 @@ class TCPairMlp:
         if feats.shape[1] != self.feat_dim or first.in_features != self.feat_dim + wset.shape[1]:
             raise ops._lib.MorlB200Error(f"TCPairMlp: feats {tuple(feats.shape)} / wset {tuple(wset.shape)} do not match the first layer ({first.in_features} inputs)")
         u, v = ops.pair_layer1_uv(feats, wset, first.weight.detach(), first.bias.detach())  # one launch (csrc/pair_layer1.cu)
-        a = ops.pairs_relu_split(u, v, out=self.h[0], scale=self.s_act)
+        hb = self.hbits if self.trainable else [None] * len(self.h)
+        a = ops.pairs_relu_split(u, v, out=self.h[0], scale=self.s_act, relu_bits_out=hb[0])
         n = len(self.lin)
         for k in range(1, n - 1):
             l = self.lin[k]
             # alternate the tile order: a layer starts on the rows its producer wrote last (L2-resident)
             _, a = ops.gemm_planes(a, self.wp[k - 1], l.out_features, bias=l.bias, relu=True, out_f32=False, out_planes=True, c_planes=self.h[k],
                                    reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_act, b_scale=self.s_w[k - 1], c_scale=self.s_act,
-                                   split_acc=self.split_acc)
+                                   split_acc=self.split_acc, relu_bits_out=hb[k])
         last = self.lin[-1]
         q, _ = ops.gemm_planes(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
                                reverse_tiles=_SNAKE and bool((n - 1) & 1), a_scale=self.s_act, b_scale=self.s_w[n - 2], split_acc=self.split_acc)
@@ -203,7 +206,7 @@ class TCPairMlp:
             grads[2 * k] = ops.gemm_planes_mn(G, l.out_features, self.h[k - 1], l.in_features, out=grads[2 * k], workspace=self.ws_mn,
                                               colsum=grads[2 * k + 1], g_scale=self.s_g, h_scale=self.s_act)
             # G_{k-1} = (G_k . W_k) masked by relu'(H_{k-1}), kept at the gradient scale
-            _, G = ops.gemm_planes(G, self.wtp[k - 1], l.in_features, relu_mask=self.h[k - 1], out_f32=False, out_planes=True,
+            _, G = ops.gemm_planes(G, self.wtp[k - 1], l.in_features, relu_bits_in=self.hbits[k - 1], out_f32=False, out_planes=True,
                                    c_planes=self.g[k & 1], reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_g, b_scale=self.s_w[k - 1],
                                    c_scale=self.s_g, split_acc=False)  # gradients: Adam is invariant to the ~2e-6 uniform shrinkage
         dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV, scale=self.s_g)

@@ -16,6 +16,12 @@ from morl_baselines_b200 import ops
 
 dev = th.device("cuda:0")
 g = th.Generator(device=dev).manual_seed(0)
+if os.environ.get("SAN_ZERO_PLANES") == "1":
+    # initcheck does not see the writes of TMA bulk tensor STORES (cp.async.bulk.tensor ... global.shared::cta): plane tensors produced
+    # by the GEMM epilogue then look uninitialised to later readers.  Pre-zeroing every plane allocation separates that tool artefact
+    # from a genuine read of memory nobody wrote (profiles/r02_sanitize_initcheck*.txt).
+    _empty = ops.empty_planes
+    ops.empty_planes = lambda *a, **k: _empty(*a, **k).zero_()
 groups = set(sys.argv[1:]) or {"envelope", "td", "gemm", "optim", "pareto", "replay", "layer1"}
 
 
@@ -62,10 +68,18 @@ if "gemm" in groups:
             a, b, bias = rn(M, 128), rn(64, 128, scale=1 / 8), rn(64)
             ap, bp = ops.split_planes(a, fmt, scale=sa), ops.split_planes(b, fmt, scale=sw)
             for split in (True, False):
-                c, cp = ops.gemm_planes(ap, bp, 64, bias=bias, relu=True, out_f32=True, out_planes=True, a_scale=sa, b_scale=sw, c_scale=sa, split_acc=split)
+                bits = ops.empty_relu_bits(M, dev)
+                c, cp = ops.gemm_planes(ap, bp, 64, bias=bias, relu=True, out_f32=True, out_planes=True, a_scale=sa, b_scale=sw, c_scale=sa, split_acc=split,
+                                        relu_bits_out=bits)
                 ops.gemm_planes(ap, bp, 64, relu_mask=cp, out_f32=True, a_scale=sa, b_scale=sw, split_acc=split, reverse_tiles=True)
+                ops.gemm_planes(ap, bp, 64, relu_bits_in=bits, out_f32=True, a_scale=sa, b_scale=sw, split_acc=split)
                 ref = (a.double() @ b.double().t() + bias.double()).clamp_min(0)
                 assert float((c.double() - ref).abs().max()) < 1e-4
+                # the planes the TMA bulk store wrote hold the same values as the fp32 output of the same call: they WERE written, whatever
+                # initcheck reports about later reads of them (it does not track cp.async.bulk.tensor stores)
+                back = sum(cp[i].double() for i in range(cp.shape[0])) / (8.0 if sa is not None else 1.0)
+                assert float((back - c.double()).abs().max()) <= 2.0**-20 * float(c.abs().max())
+                assert bool(th.equal(ops.unpack_relu_bits(bits, 64), c > 0))
         G, H = rn(600, 24, scale=1e-3), rn(600, 128).relu_()
         sg = ops.scale_tensor(2.0**16, dev) if fmt == ops.FMT_F16X2 else None
         Gp, Hp = ops.split_planes(G, fmt, ldp=64, scale=sg), ops.split_planes(H, fmt, scale=sa)
@@ -75,7 +89,7 @@ if "gemm" in groups:
         ops.colsum_planes(Gp, 24, scale=sg)
         ops.pairs_grad_reduce(ops.split_planes(rn(6 * 5, 64), fmt, scale=sa), 6, 5, scale=sa)
         ops.pairs_grad_reduce(ops.split_planes(rn(3 * 70, 64), fmt, scale=sa), 3, 70, scale=sa)
-        ops.pairs_relu_split(rn(6, 64), rn(5, 64), fmt=fmt, scale=sa)
+        ops.pairs_relu_split(rn(6, 64), rn(5, 64), fmt=fmt, scale=sa, relu_bits_out=ops.empty_relu_bits(30, dev))
         w1, w2 = rn(64, 64, scale=0.1), rn(24, 64)
         o = [ops.empty_planes(fmt, 64, 64, dev), ops.empty_planes(fmt, 64, 64, dev), ops.empty_planes(fmt, 32, 64, dev)]
         s1, s2 = ops.scale_tensor(1.0, dev), ops.scale_tensor(1.0, dev)

@@ -165,3 +165,48 @@ def test_device_per_equals_host_per(cuda):
         assert th.equal(va, vb)
     ta, tb = np.concatenate(a.replay_buffer.tree.nodes), np.concatenate(b.replay_buffer.tree.nodes)
     np.testing.assert_allclose(ta, tb, rtol=1e-6)
+
+
+def test_envelope_checkpoint_resume(cuda, tmp_path):
+    """train -> save -> load into a fresh agent -> train must continue exactly like the uninterrupted agent: the loaded replay
+    buffer gets a new HBM mirror (and a new device sum tree), so captured graphs must be re-captured against it, and the optimiser's
+    pointer tables must follow the re-created state tensors."""
+    from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
+
+    def build():
+        th.manual_seed(0)
+        agent = Envelope(FakeEnv(obs_dim=12, n_actions=4, reward_dim=3), batch_size=32, num_sample_w=8, per=True, buffer_size=1024,
+                         net_arch=[64, 64, 64], log=False, seed=3, device=cuda, target_net_update_freq=1)  # (load() sets target := online, as the reference)
+        store = synthetic_store(1024, 12, 4, 3, seed=1)
+        rb = agent.replay_buffer
+        rb.obs[:], rb.next_obs[:], rb.actions[:], rb.rewards[:], rb.dones[:] = (store[k] for k in ("obs", "next_obs", "actions", "rewards", "dones"))
+        rb.size, rb.ptr = 1024, 0
+        rb.mark_all_dirty()
+        rb.tree.batch_set(np.arange(1024), np.random.default_rng(2).random(1024) + 0.01)
+        agent.global_step = 1
+        return agent
+
+    a = build()
+    for step in range(3):
+        np.random.seed(10 + step)
+        a.global_step += 1
+        a.update()
+    a.save(save_dir=str(tmp_path), filename="ckpt")
+    b = build()
+    np.random.seed(99)
+    b.update()  # b has its own captured graph and optimiser state before loading
+    b.load(str(tmp_path / "ckpt.tar"))
+    b.np_random = np.random.default_rng(5)
+    a.np_random = np.random.default_rng(5)
+    b.global_step = a.global_step
+    assert np.array_equal(np.concatenate(a.replay_buffer.tree.nodes), np.concatenate(b.replay_buffer.tree.nodes))
+    for step in range(3):
+        la = []
+        for agent in (a, b):
+            np.random.seed(40 + step)
+            agent.global_step += 1
+            agent.update()
+            la.append((float(agent._last_loss), agent._last_inds.copy()))
+        assert la[0][0] == la[1][0] and np.array_equal(la[0][1], la[1][1]), step
+    for va, vb in zip(a.q_net.state_dict().values(), b.q_net.state_dict().values()):
+        assert th.equal(va, vb)

@@ -146,6 +146,86 @@ def test_gemm_relu_mask_and_chaining(cuda, fmt):
 
 
 @pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("M,H", [(2048, 256), (65536, 256), (777, 128), (100, 64)])
+def test_gemm_relu_bit_masks(cuda, fmt, M, H):
+    """ReLU backward from the bit masks: the forward call records [h > 0] (32 B per row), the backward call masks with it.  The bits must
+    equal the sign pattern of the fp32 output of the same call exactly, and the masked product must equal the plane-masked one bit for bit."""
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(17)
+    x = th.randn(M, H, device=cuda, generator=g)
+    w1 = th.randn(H, H, device=cuda, generator=g) / 8
+    w2 = th.randn(H, H, device=cuda, generator=g) / 8
+    b1 = th.randn(H, device=cuda, generator=g) * 0.1
+    sx, sw, sg = _scale(fmt, 8.0, cuda), _scale(fmt, 1024.0, cuda), _scale(fmt, 64.0, cuda)
+    xp, w1p = ops.split_planes(x, fmt, scale=sx), ops.split_planes(w1, fmt, scale=sw)
+    bits = ops.empty_relu_bits(M, cuda).fill_(-1)
+    h, hp = ops.gemm_planes(xp, w1p, H, bias=b1, relu=True, out_f32=True, out_planes=True, a_scale=sx, b_scale=sw, c_scale=sx, relu_bits_out=bits)
+    got = ops.unpack_relu_bits(bits, H)
+    assert th.equal(got, h > 0)
+    assert 0.2 < float(got.float().mean()) < 0.8
+    # planes-only call (the form the update uses: output scale folded into the epilogue constants) records the same bits
+    bits2 = ops.empty_relu_bits(M, cuda).fill_(0)
+    ops.gemm_planes(xp, w1p, H, bias=b1, relu=True, out_f32=False, out_planes=True, a_scale=sx, b_scale=sw, c_scale=sx, relu_bits_out=bits2)
+    assert th.equal(ops.unpack_relu_bits(bits2, H), got)
+    # backward: G . W2 masked by the bits == masked by the planes == reference
+    gr = th.randn(M, H, device=cuda, generator=g) * 1e-3
+    gp = ops.split_planes(gr, fmt, scale=sg)
+    w2p = ops.split_planes(w2, fmt, scale=sw)
+    d_bits, _ = ops.gemm_planes(gp, w2p, H, relu_bits_in=bits, out_f32=True, a_scale=sg, b_scale=sw)
+    d_planes, _ = ops.gemm_planes(gp, w2p, H, relu_mask=hp, out_f32=True, a_scale=sg, b_scale=sw)
+    tiny = (h > 0) & (hp[0] == 0)  # positive but below the plane format's smallest magnitude: only the bit mask keeps these (as torch does)
+    assert int(tiny.sum()) <= 4
+    assert th.equal(d_bits[~tiny], d_planes[~tiny])
+    ref = _ref(gr, w2, None) * (h > 0)
+    assert bool(((d_bits.double() - ref).abs() <= _bound(gr, w2)).all())
+    # the planes-output form of the backward call (what the update runs) carries the same values
+    _, dpl = ops.gemm_planes(gp, w2p, H, relu_bits_in=bits, out_f32=False, out_planes=True, a_scale=sg, b_scale=sw, c_scale=sg)
+    s = _sum(dpl) / (64.0 if sg is not None else 1.0)
+    assert float((s - d_bits.double()).abs().max()) <= 2.0**-21 * float(d_bits.abs().max())
+    assert ops.plane_overflow_count() == 0
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_pairs_relu_split_bit_masks(cuda, fmt):
+    from morl_baselines_b200 import ops
+
+    g = th.Generator(device=cuda).manual_seed(19)
+    for B, W, H in [(37, 5, 64), (1024, 64, 256), (3, 7, 96), (9, 5, 256), (33, 18, 256)]:  # H = 256: the warp-per-transition kernel
+        u, v = th.randn(B, H, device=cuda, generator=g), th.randn(W, H, device=cuda, generator=g)
+        bits = ops.empty_relu_bits(B * W, cuda).fill_(0)
+        hp = ops.pairs_relu_split(u, v, fmt=fmt, scale=_scale(fmt, 2.0, cuda), relu_bits_out=bits)
+        ref = (u[:, None, :] + v[None, :, :]).reshape(B * W, H)
+        assert th.equal(ops.unpack_relu_bits(bits, H), ref > 0)
+        back = _sum(hp) / (2.0 if fmt == ops.FMT_F16X2 else 1.0)
+        assert float((back - ref.clamp_min(0).double()).abs().max()) <= 2.0**-21 * float(ref.abs().max())
+        assert th.equal(hp, ops.pairs_relu_split(u, v, fmt=fmt, scale=_scale(fmt, 2.0, cuda)))  # planes unchanged by the extra output
+
+
+def test_gemm_ring_depth_does_not_change_results(cuda):
+    """The TMA ring is as deep as the stage boxes allow (3 stages at N_pad = 256, 5 for the 24-wide output layer); MORL_GEMM_STAGES caps it.
+    Depth is a scheduling choice: results are bit-identical."""
+    import os, subprocess, sys
+
+    code = (
+        "import torch as th\n"
+        "from morl_baselines_b200 import ops\n"
+        "g = th.Generator(device='cuda').manual_seed(3)\n"
+        "a = th.randn(5000, 256, device='cuda', generator=g); b = th.randn(24, 256, device='cuda', generator=g) / 16\n"
+        "sa, sb = ops.scale_tensor(8.0, 'cuda'), ops.scale_tensor(1024.0, 'cuda')\n"
+        "c, _ = ops.gemm_planes(ops.split_planes(a, 1, scale=sa), ops.split_planes(b, 1, rows_pad=32, scale=sb), 24, out_f32=True, a_scale=sa, b_scale=sb)\n"
+        "print('SUM', repr(float(c.double().sum())), repr(float(c.double().abs().max())))\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flags in ({}, {"MORL_GEMM_STAGES": "2"}, {"MORL_GEMM_STAGES": "3"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PYTHONPATH=root, **flags), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("SUM")][0])
+    assert outs[0] == outs[1] == outs[2]
+
+
+@pytest.mark.parametrize("fmt", FMTS)
 def test_pairs_relu_split(cuda, fmt):
     from morl_baselines_b200 import ops
 
