@@ -503,7 +503,7 @@ def run_b200(args, rank, local_rank, world):
                 "note": "whole-step time used, so this is a lower bound on the dense-layer rate"},
         "loss": loss_dev, "loss_e2e_last": loss_host,
     }
-    if world == 1:
+    if world == 1 and os.environ.get("MORL_SKIP_CPU_BASELINE", "0") != "1":  # (development runs only: the driver's line always carries it)
         # the reference's CPU update at the SAME config (full batch, full weight set), bounded to ~1 minute of CPU work: 1 warm-up + up to 3
         # timed updates; next to it the de-duplicated CPU restatement (not reference code) for context
         times, kind, threads, info = cpu_reference_arm(max_steps=3, warmup=1, budget_s=float(os.environ.get("MORL_CPU_BASELINE_BUDGET_S", "60")))

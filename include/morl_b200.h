@@ -317,6 +317,35 @@ MORL_API int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_pla
  * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,
  * [3] TMA thread waiting for a free stage, [4] epilogue waiting for an accumulator, [5] epilogue busy; [6], [7] reserved. */
 MORL_API int morl_debug_gemm_stats(unsigned long long* out8, int reset);
+/* GPI-PD Dyna planning: everything between the last layer of the probabilistic ensemble and the imagined transition in ONE
+ * pass (reference common/model_based/probabilistic_ensemble.py:115-154, common/model_based/utils.py:162-170; csrc/dyna.cu).
+ *   out [E, N, 2*O] : raw output of the last EnsembleLayer (mean | logvar);  max_logvar / min_logvar [O]: the soft clamps (:118-119);
+ *   model_idx [N]   : the elite model drawn for every row (np.random.choice(self.elites, N), :143 -- drawn on the host: RNG parity);
+ *   noise [E, N, O] : standard normal draws (th.randn(std.shape), :128) or NULL = deterministic;
+ *   obs [N, O - rew_dim] or NULL: added to the state part of the sample (the model predicts deltas, utils.py:165);
+ *   sample_out / var_out [N, O]: sample and variance of the drawn model;  uncertainty_out [N]: sum_o sqrt(var_ensemble + 1e-12) (:146-149). */
+MORL_API int morl_ensemble_sample_f32(const float* out, const float* max_logvar, const float* min_logvar, const int32_t* model_idx, const float* noise,
+                                      const float* obs, int rew_dim, int E, int N, int O, float* sample_out, float* var_out, float* uncertainty_out,
+                                      void* stream);
+
+/* Output layer of BOTH Q-networks + envelope operator + Bellman line as ONE kernel (csrc/qhead_envelope.cu): replaces, for the two no-grad
+ * passes of Envelope.update (reference envelope.py:420, :429, :422-440, :298),
+ *     morl_gemm_planes_f32 (online, N = A*D) + morl_gemm_planes_f32 (target) + morl_envelope_td_f32
+ * -- the Q tensors live in tensor memory / shared memory only ("envelope operator folded into the last-layer epilogue").
+ *   a_on_planes / a_tg_planes : last hidden activations of the online / target net on s', planes [2][B*W][K] (row b*W + j), f16x2;
+ *   w_on_planes / w_tg_planes : output-layer weight planes [2][32][K] (rows >= A*D zero), scales as in morl_gemm_planes_f32;
+ *   everything from `wset` on  : as morl_envelope_td_f32 (same arithmetic contract, row orders, first-occurrence ties, outputs);
+ *   q_on_out / q_tg_out        : optional fp32 copies of the Q tiles [B*W, A*D] (validation; NULL in the update).
+ * The accumulation order equals morl_gemm_planes_f32's, so targets / indices are bit-identical to the three-launch chain.
+ * morl_qhead_envelope_supported: 1 if the configuration is inside the kernel (f16x2 planes, W <= 64 dividing 128, B*W % 128 == 0,
+ * A*D <= 32, W*A % 16 == 0, W*A*D % 4 == 0, 2 <= D <= 4, K % 64 == 0, K <= 256), else 0 -- callers then use the three-launch chain. */
+MORL_API int morl_qhead_envelope_supported(int fmt, int B, int W, int A, int D, int K);
+MORL_API int morl_qhead_envelope_td_f32(int fmt, const void* a_on_planes, const void* a_tg_planes, long long a_plane_stride,
+                                        const float* a_scale_on, const float* a_scale_tg, const void* w_on_planes, const void* w_tg_planes,
+                                        long long w_plane_stride, const float* w_scale_on, const float* w_scale_tg, const float* bias_on,
+                                        const float* bias_tg, int K, const float* wset, const float* reward, const float* done, float gamma,
+                                        int B, int W, int A, int D, int dot_mode, int row_order, int reverse_tiles, float* target_out,
+                                        int32_t* pref_out, int32_t* act_out, float* q_on_out, float* q_tg_out, void* stream);
 /* h[b*W + j, :] = relu(u[b, :] + v[j, :]) written directly as planes [P][B*W][H] of scale * h (separable first layer of the
  * weight-conditioned Q-network: W1 [s || w] + b1 = W1_s s + (W1_w w + b1); reference envelope.py:75 builds the concat). */
 MORL_API int morl_pairs_relu_split_planes(int fmt, const float* u, const float* v, int B, int W, int H, void* dst_planes,

@@ -96,6 +96,35 @@ class ReplayBuffer:
         self.ptr = (self.ptr + 1) % self.max_size
         self.size = min(self.size + 1, self.max_size)
 
+    def add_batch(self, obs, actions, rewards, next_obs, dones):
+        """Append n transitions at once (arrays or tensors with a leading batch axis): the state afterwards equals n ``add`` calls in
+        row order (ring wrap-around included).  Device tensors are written straight into the HBM mirror as well, so nothing has to be
+        re-sent.  Replaces the row-by-row python loop of the reference's Dyna rollout (gpi_pd.py:394-397)."""
+        n = int(obs.shape[0])
+        if n == 0:
+            return
+        cols = (obs, next_obs, actions, rewards, dones)
+        on_dev = self._dev is not None and all(isinstance(c, th.Tensor) and c.is_cuda for c in cols)
+        if n > self.max_size:  # only the last max_size rows survive n sequential adds
+            skip = n - self.max_size
+            cols = tuple(c[skip:] for c in cols)
+            self.ptr = (self.ptr + skip) % self.max_size
+            n = self.max_size
+        first = min(n, self.max_size - self.ptr)
+        spans = [(self.ptr, 0, first)] + ([(0, first, n - first)] if n > first else [])
+        for h, d, c in zip(self._host_tensors(), self._dev if on_dev else (None,) * 5, cols):
+            c = c if isinstance(c, th.Tensor) else th.as_tensor(np.asarray(c))
+            c = c.reshape((n,) + tuple(h.shape[1:])).to(h.dtype)
+            for dst, src, cnt in spans:
+                if on_dev:
+                    d[dst:dst + cnt].copy_(c[src:src + cnt])
+                h[dst:dst + cnt].copy_(c[src:src + cnt], non_blocking=False)
+        if not on_dev:
+            for dst, _, cnt in spans:
+                self._mark_dirty(dst, dst + cnt)
+        self.ptr = (self.ptr + n) % self.max_size
+        self.size = min(self.size + n, self.max_size)
+
     def _mark_dirty(self, a, b):
         if self._dev is None:
             return

@@ -40,6 +40,9 @@ from ...common.prioritized_buffer import PrioritizedReplayBuffer
 from ...common.utils import linearly_decaying_value
 from ...common.weights import equally_spaced_weights, random_weights
 
+# output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu); MORL_FUSED_HEAD=0 keeps the three-launch chain (A/B runs)
+_FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
+
 
 class QNet(nn.Module):
     """Weight-conditioned vector Q-network; parameter names equal the reference's (envelope.py:33-77)."""
@@ -374,13 +377,29 @@ class Envelope(MOPolicy, MOAgent):
                                                    split_acc=split)
                 # every weight plane this step needs (online, target, transposed-for-backward) in one launch
                 TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
-                q_on = self._tc_on.forward_pairs(nobs, wset).view(B, W, A, D)  # online net selects   (envelope.py:420)
-                q_tg = self._tc_tg.forward_pairs(nobs, wset).view(B, W, A, D)  # target net evaluates (envelope.py:429)
+                fused_head = self.envelope and _FUSED_HEAD and self.tensor_core_accumulators != "split" and self._tc_on.head_operands() is not None \
+                    and ops.qhead_envelope_supported(self._tc_fmt, B, W, A, D, self._tc_on.lin[-1].in_features)
+                if fused_head:
+                    # output layers of both nets + envelope operator + Bellman line in ONE kernel: Q_on / Q_tg (envelope.py:420, :429) exist
+                    # in tensor / shared memory only (csrc/qhead_envelope.cu; bit-identical to the three-launch chain below)
+                    h_on = self._tc_on.forward_hidden(nobs, wset)
+                    h_tg = self._tc_tg.forward_hidden(nobs, wset)
+                    (w_on, sw_on, b_on), (w_tg, sw_tg, b_tg) = self._tc_on.head_operands(), self._tc_tg.head_operands()
+                    target_q, _, _ = ops.qhead_envelope_td(h_on, h_tg, w_on, w_tg, b_on.detach(), b_tg.detach(), wset, rew, done.reshape(-1), self.gamma,
+                                                           B, W, A, D, self.dot_mode, ops.ROWS_BMAJOR, a_scale_on=self._tc_on.s_act,
+                                                           a_scale_tg=self._tc_tg.s_act, w_scale_on=sw_on, w_scale_tg=sw_tg)
+                    q_on = q_tg = None
+                else:
+                    q_on = self._tc_on.forward_pairs(nobs, wset).view(B, W, A, D)  # online net selects   (envelope.py:420)
+                    q_tg = self._tc_tg.forward_pairs(nobs, wset).view(B, W, A, D)  # target net evaluates (envelope.py:429)
             else:
+                fused_head = False
                 q_on = self.q_net.forward_pairs(nobs, wset)
                 q_tg = self.target_q_net.forward_pairs(nobs, wset)
             done1 = done.reshape(-1)
-            if self.envelope:
+            if fused_head:
+                pass
+            elif self.envelope:
                 target_q, _, _ = ops.envelope_td(q_on, q_tg, wset, rew, done1, self.gamma, self.dot_mode, ops.ROWS_BMAJOR, want_indices=False)
             else:
                 target_q, _ = ops.greedy_td(q_on.view(B * W, A, D), q_tg.view(B * W, A, D), wset, rew, done1, self.gamma, self.dot_mode,

@@ -1,6 +1,6 @@
-"""GPI-LS / GPI-PD (discrete actions) on the B200 update engine -- drop-in for the model-free part of reference
-morl_baselines/multi_policy/gpi_pd/gpi_pd.py (same constructor, ``update / gpi_action / eval / max_action /
-_envelope_target / _reset_priorities / set_weight_support / train_iteration / save / load``).
+"""GPI-LS / GPI-PD (discrete actions) on the B200 update engine -- drop-in for reference
+morl_baselines/multi_policy/gpi_pd/gpi_pd.py (same constructor incl. the Dyna arguments, ``update / gpi_action / eval / max_action /
+_envelope_target / _reset_priorities / _rollout_dynamics / _sample_batch_experiences / set_weight_support / train_iteration / save / load``).
 
 Hot-path rows of SURVEY.md section 8 covered here: a7 (``_envelope_target``), a8 (update target + Huber loss + priorities),
 a9 (``gpi_action``), a10 (``_reset_priorities``).  Under the API:
@@ -10,8 +10,11 @@ a9 (``gpi_action``), a10 (``_reset_priorities``).  Under the API:
   * per-net gather + huber + |td| stacks + max + einsum priorities (gpi_pd.py:469-487, 507-520) is ONE kernel
     (morl_td_huber_priority_f32);
   * gpi_action (gpi_pd.py:564-582) = one pairwise forward + ONE kernel.
-Out of scope: the Dyna path (``dyna=True``: probabilistic ensemble, ModelEnv) and the
-LinearSupport weight selector (cvxpy + pycddlib); ``train()`` therefore takes the selector as an argument.
+  * the Dyna path (``dyna=True``, the reference's default): probabilistic ensemble trained from an HBM-resident data set
+    (common/model_based/probabilistic_ensemble.py), model rollouts that never leave the device -- batched GPI action, ONE fused
+    sampling / uncertainty kernel (morl_ensemble_sample_f32), masked bulk insert of the imagined transitions (gpi_pd.py:367-414).
+Out of scope: the LinearSupport weight selector (cvxpy + pycddlib); ``train()`` therefore takes the
+selector as an argument.
 """
 
 from __future__ import annotations
@@ -19,16 +22,19 @@ from __future__ import annotations
 import os
 import random
 from itertools import chain
-from typing import List, Optional, Union
+from typing import Callable, List, Optional, Union
 
 import numpy as np
 import torch as th
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ... import ops
 from ...common.fused_adam import FusedClipAdam
 from ...common.graphed import GraphedStep, optimizer_tensors
 from ...common.buffer import ReplayBuffer
+from ...common.model_based.probabilistic_ensemble import ProbabilisticEnsemble
+from ...common.model_based.utils import ModelEnv
 from ...common.morl_algorithm import MOAgent, MOPolicy
 from ...common.networks import NatureCNN, layer_init, mlp, polyak_update
 from ...common.prioritized_buffer import PrioritizedReplayBuffer
@@ -113,6 +119,18 @@ class GPIPD(MOPolicy, MOAgent):
         min_priority: float = 0.01,
         drop_rate: float = 0.01,
         layer_norm: bool = True,
+        dynamics_normalize_inputs: bool = False,
+        dynamics_uncertainty_threshold: float = 1.5,
+        dynamics_train_freq: Callable = lambda timestep: 250,
+        dynamics_rollout_len: int = 1,
+        dynamics_rollout_starts: int = 5000,
+        dynamics_rollout_freq: int = 250,
+        dynamics_rollout_batch_size: int = 25000,
+        dynamics_buffer_size: int = 100000,
+        dynamics_net_arch: List = [256, 256, 256],
+        dynamics_ensemble_size: int = 5,
+        dynamics_num_elites: int = 2,
+        real_ratio: float = 0.5,
         project_name: str = "MORL-Baselines",
         experiment_name: str = "GPI-PD",
         wandb_entity: Optional[str] = None,
@@ -120,18 +138,11 @@ class GPIPD(MOPolicy, MOAgent):
         seed: Optional[int] = None,
         device: Union[th.device, str] = "auto",
         use_cuda_graph: bool = True,
-        **dyna_kwargs,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
         if self.device.type != "cuda":
             raise ops._lib.MorlB200Error("morl_baselines_b200.GPIPD needs a CUDA device: the update path is CUDA-only (no CPU fallback)")
-        if dyna:
-            # `dyna=True` is the reference's DEFAULT (gpi_pd.py:106): keep the default and fail loudly rather than silently run model-free
-            # under the GPI-PD name.  Pass dyna=False explicitly (or use GPILS) for the model-free algorithm this class accelerates.
-            raise NotImplementedError("GPIPD(dyna=True) -- the reference's default: model-based GPI-PD with a probabilistic ensemble + ModelEnv -- "
-                                      "is outside the accelerated hot path (SURVEY.md section 8(f)3); construct with dyna=False (model-free "
-                                      "GPI-PD / GPI-LS) explicitly")
         ops._lib.load()
         self.learning_rate = learning_rate
         self.initial_epsilon = initial_epsilon
@@ -171,10 +182,28 @@ class GPIPD(MOPolicy, MOAgent):
                                      device=self.device)
         self.min_priority = min_priority
         self.alpha = alpha_per
-        self.dyna = False
+        # model-based part (reference gpi_pd.py:240-268): probabilistic ensemble + imagined-transition buffer
+        self.dyna = dyna
+        self.dynamics_net_arch = dynamics_net_arch
         self.dynamics = None
         self.dynamics_buffer = None
-        self.dynamics_rollout_starts = 0
+        if self.dyna:
+            self.dynamics = ProbabilisticEnsemble(input_dim=self.observation_dim + self.action_dim, output_dim=self.observation_dim + self.reward_dim,
+                                                  arch=self.dynamics_net_arch, normalize_inputs=dynamics_normalize_inputs,
+                                                  ensemble_size=dynamics_ensemble_size, num_elites=dynamics_num_elites, device=self.device)
+            self.dynamics_buffer = ReplayBuffer(self.observation_shape, 1, rew_dim=self.reward_dim, max_size=dynamics_buffer_size, action_dtype=np.uint8,
+                                                device=self.device)
+        self.dynamics_train_freq = dynamics_train_freq
+        self.dynamics_buffer_size = dynamics_buffer_size
+        self.dynamics_normalize_inputs = dynamics_normalize_inputs
+        self.dynamics_num_elites = dynamics_num_elites
+        self.dynamics_ensemble_size = dynamics_ensemble_size
+        self.dynamics_rollout_len = dynamics_rollout_len
+        self.dynamics_rollout_starts = dynamics_rollout_starts if self.dyna else 0
+        self.dynamics_rollout_freq = dynamics_rollout_freq
+        self.dynamics_rollout_batch_size = dynamics_rollout_batch_size
+        self.dynamics_uncertainty_threshold = dynamics_uncertainty_threshold
+        self.real_ratio = real_ratio
         self.weight_support: List[th.Tensor] = []
         self.police_indices = []
         self.dot_mode = ops.DOT_UNFUSED
@@ -192,6 +221,11 @@ class GPIPD(MOPolicy, MOAgent):
             "clip_grand_norm": self.max_grad_norm, "target_net_update_freq": self.target_net_update_freq, "gamma": self.gamma,
             "net_arch": self.net_arch, "gradient_updates": self.gradient_updates, "buffer_size": self.buffer_size,
             "learning_starts": self.learning_starts, "dyna": self.dyna, "drop_rate": self.drop_rate, "layer_norm": self.layer_norm,
+            "dynamics_model_arch": self.dynamics_net_arch, "dynamics_rollout_len": self.dynamics_rollout_len,
+            "dynamics_uncertainty_threshold": self.dynamics_uncertainty_threshold, "dynamics_rollout_starts": self.dynamics_rollout_starts,
+            "dynamics_rollout_freq": self.dynamics_rollout_freq, "dynamics_rollout_batch_size": self.dynamics_rollout_batch_size,
+            "dynamics_buffer_size": self.dynamics_buffer_size, "dynamics_normalize_inputs": self.dynamics_normalize_inputs,
+            "dynamics_ensemble_size": self.dynamics_ensemble_size, "dynamics_num_elites": self.dynamics_num_elites, "real_ratio": self.real_ratio,
             "seed": self.seed,
         }
 
@@ -201,6 +235,8 @@ class GPIPD(MOPolicy, MOAgent):
         params = {f"psi_net_{i}_state_dict": net.state_dict() for i, net in enumerate(self.q_nets)}
         params["psi_nets_optimizer_state_dict"] = self.q_optim.state_dict()
         params["M"] = self.weight_support
+        if self.dyna:
+            params["dynamics_state_dict"] = self.dynamics.state_dict()
         if save_replay_buffer:
             params["replay_buffer"] = self.replay_buffer
         filename = getattr(self, "experiment_name", "GPI-PD") if filename is None else filename
@@ -213,6 +249,8 @@ class GPIPD(MOPolicy, MOAgent):
             tnet.load_state_dict(params[f"psi_net_{i}_state_dict"])
         self.q_optim.load_state_dict(params["psi_nets_optimizer_state_dict"])
         self.weight_support = params["M"]
+        if self.dyna:
+            self.dynamics.load_state_dict(params["dynamics_state_dict"])
         if load_replay_buffer and "replay_buffer" in params:
             self.replay_buffer = params["replay_buffer"]
             if hasattr(self.replay_buffer, "to"):
@@ -220,8 +258,68 @@ class GPIPD(MOPolicy, MOAgent):
         self._graphs, self._support_cache = {}, None  # optimiser state / buffer / support may have been replaced
 
     # ------------------------------------------------------------------------------------------ the update
+    def _uses_model_samples(self) -> bool:
+        return self.dyna and self.global_step >= self.dynamics_rollout_starts and len(self.dynamics_buffer) > 0
+
     def _sample_batch_experiences(self):
-        return self.replay_buffer.sample(self.batch_size, to_tensor=True, device=self.device)
+        """Minibatch of real transitions, or -- once the model is rolled out -- ``real_ratio`` real + the rest imagined ones
+        (reference gpi_pd.py:343-365).  Always returns the 6-tuple; only the real rows carry replay indices."""
+        if not self._uses_model_samples():
+            return self.replay_buffer.sample(self.batch_size, to_tensor=True, device=self.device)
+        num_real = int(self.batch_size * self.real_ratio)
+        s_obs, s_act, s_rew, s_nobs, s_done, idxes = self.replay_buffer.sample(num_real, to_tensor=True, device=self.device)
+        m_obs, m_act, m_rew, m_nobs, m_done, _ = self.dynamics_buffer.sample(self.batch_size - num_real, to_tensor=True, device=self.device)
+        return (th.cat([s_obs, m_obs], dim=0), th.cat([s_act, m_act], dim=0), th.cat([s_rew, m_rew], dim=0), th.cat([s_nobs, m_nobs], dim=0),
+                th.cat([s_done, m_done], dim=0), idxes)
+
+    @th.no_grad()
+    def _rollout_dynamics(self, w: th.Tensor):
+        """Dyna planning (reference gpi_pd.py:367-414): roll the learned model out from replayed states under the GPI policy and keep the
+        imagined transitions whose ensemble uncertainty is below the threshold.  Everything stays on the device: one pairwise forward +
+        one GPI kernel per step for all 10,000 x |M| rows, one batched ensemble forward + one fused sampling kernel
+        (morl_ensemble_sample_f32), a masked BULK insert into the dynamics buffer (the reference appends row by row in python)."""
+        num_times = int(np.ceil(self.dynamics_rollout_batch_size / 10000))
+        batch_size = min(self.dynamics_rollout_batch_size, 10000)
+        num_added_imagined_transitions = 0
+        uncertainties = None
+        model_env = None
+        for _ in range(num_times):
+            obs = self.replay_buffer.sample_obs(batch_size, to_tensor=True, device=self.device)
+            model_env = ModelEnv(self.dynamics, self.env.unwrapped.spec.id, rew_dim=len(w))
+            for _h in range(self.dynamics_rollout_len):
+                M = self._support_matrix()
+                q = self.q_nets[0].forward_pairs(obs, M)  # [N, P, A, D] (module mode as the caller left it: dropout as in the reference)
+                _, _, actions = ops.gpi_envelope(q.unsqueeze(0), w.reshape(1, -1), dot_mode=self.dot_mode)  # argmax_i max_a w . Q(s, a, M_i)
+                actions_one_hot = F.one_hot(actions.long(), num_classes=self.action_dim)
+                next_obs_pred, r_pred, dones, info = model_env.step_device(obs, actions_one_hot, deterministic=False)
+                uncertainties = info["uncertainty"]
+                keep = uncertainties < self.dynamics_uncertainty_threshold
+                n_keep = int(keep.sum())  # (the only host round trip of the step: the bulk insert needs the count)
+                if n_keep:
+                    self.dynamics_buffer.add_batch(obs[keep], actions[keep].to(th.uint8).reshape(-1, 1), r_pred[keep], next_obs_pred[keep],
+                                                   dones[keep].float())
+                    num_added_imagined_transitions += n_keep
+                nonterm_mask = ~dones.squeeze(-1)
+                if int(nonterm_mask.sum()) == 0:
+                    break
+                obs = next_obs_pred[nonterm_mask]
+        if self.log and uncertainties is not None:
+            import wandb
+
+            u = uncertainties.cpu().numpy()
+            wandb.log({"dynamics/uncertainty_mean": u.mean(), "dynamics/uncertainty_max": u.max(), "dynamics/uncertainty_min": u.min(),
+                       "dynamics/model_buffer_size": len(self.dynamics_buffer), "dynamics/imagined_transitions": num_added_imagined_transitions,
+                       "global_step": self.global_step})
+        return num_added_imagined_transitions
+
+    def _train_dynamics(self):
+        """Fit the ensemble on every stored transition: X = [s | one_hot(a)], Y = [r | s' - s] (reference gpi_pd.py:749-754)."""
+        m_obs, m_actions, m_rewards, m_next_obs, _ = self.replay_buffer.get_all_data()
+        one_hot = np.zeros((len(m_obs), self.action_dim))
+        one_hot[np.arange(len(m_obs)), m_actions.astype(int).reshape(len(m_obs))] = 1
+        X = np.hstack((m_obs, one_hot))
+        Y = np.hstack((m_rewards, m_next_obs - m_obs))
+        return self.dynamics.fit(X, Y)
 
     def _support_matrix(self) -> th.Tensor:
         """[P, D] matrix of the support set, cached per support list (captured graphs read it)."""
@@ -278,8 +376,9 @@ class GPIPD(MOPolicy, MOAgent):
         """``gradient_updates`` gradient steps for the given weight vector (reference gpi_pd.py:416-562)."""
         critic_losses = []
         B0, D, rb = self.batch_size, self.reward_dim, self.replay_buffer
-        graphable = self.use_cuda_graph and getattr(rb, "_dev", None) is not None and self.max_grad_norm is None
-        for _ in range(self.gradient_updates):
+        # (mixed real / imagined minibatches come from two stores: they take the eager path)
+        graphable = self.use_cuda_graph and getattr(rb, "_dev", None) is not None and self.max_grad_norm is None and not self._uses_model_samples()
+        for _ in range(self.gradient_updates if self.global_step >= self.dynamics_rollout_starts else 1):
             P = len(self.weight_support)
             want_prio = self.per or self.gpi_pd
             if not graphable:
@@ -444,6 +543,15 @@ class GPIPD(MOPolicy, MOAgent):
             next_obs, vec_reward, terminated, truncated, info = self.env.step(action)
             self.replay_buffer.add(obs, action, vec_reward, next_obs, terminated)
             if self.global_step >= self.learning_starts:
+                if self.dyna:
+                    if self.global_step % self.dynamics_train_freq(self.global_step) == 0:
+                        mean_holdout_loss = self._train_dynamics()
+                        if self.log:
+                            import wandb
+
+                            wandb.log({"dynamics/mean_holdout_loss": mean_holdout_loss, "global_step": self.global_step})
+                    if self.global_step >= self.dynamics_rollout_starts and self.global_step % self.dynamics_rollout_freq == 0:
+                        self._rollout_dynamics(tensor_w)
                 self.update(tensor_w)
             if eval_env is not None and self.log and self.global_step % eval_freq == 0:
                 self.policy_eval(eval_env, weights=weight, log=self.log)

@@ -439,6 +439,75 @@ def gemm_planes(a_planes: th.Tensor, b_planes: th.Tensor, n_out: int, bias: Opti
     return c_f32, c_planes
 
 
+def ensemble_sample(out: th.Tensor, max_logvar: th.Tensor, min_logvar: th.Tensor, model_idx: th.Tensor, noise: Optional[th.Tensor] = None,
+                    obs: Optional[th.Tensor] = None, rew_dim: int = 0):
+    """Probabilistic-ensemble sampling + ensemble uncertainty in one pass (reference probabilistic_ensemble.py:115-154, utils.py:165).
+    out [E, N, 2*O] raw last-layer output, model_idx [N] int32, noise [E, N, O] or None (deterministic), obs [N, O - rew_dim] or None.
+    Returns (sample [N, O], var [N, O], uncertainty [N])."""
+    out = _dev(out, "out")
+    E, N, O2 = out.shape
+    O = O2 // 2
+    max_logvar, min_logvar = _dev(max_logvar, "max_logvar").reshape(-1), _dev(min_logvar, "min_logvar").reshape(-1)
+    model_idx = _dev(model_idx, "model_idx", th.int32)
+    if O2 != 2 * O or max_logvar.numel() != O or min_logvar.numel() != O or model_idx.numel() != N:
+        raise _lib.MorlB200Error(f"ensemble_sample: bad shapes out {tuple(out.shape)}, logvar bounds {max_logvar.numel()}, model_idx {tuple(model_idx.shape)} {model_idx.dtype}")
+    if noise is not None:
+        noise = _dev(noise, "noise")
+        if tuple(noise.shape) != (E, N, O):
+            raise _lib.MorlB200Error(f"ensemble_sample: noise must be [{E}, {N}, {O}]")
+    if obs is not None:
+        obs = _dev(obs, "obs")
+        if tuple(obs.shape) != (N, O - rew_dim):
+            raise _lib.MorlB200Error(f"ensemble_sample: obs must be [{N}, {O - rew_dim}]")
+    sample = th.empty((N, O), device=out.device, dtype=th.float32)
+    var = th.empty((N, O), device=out.device, dtype=th.float32)
+    unc = th.empty(N, device=out.device, dtype=th.float32)
+    rc = _lib.load().morl_ensemble_sample_f32(_ptr(out), _ptr(max_logvar), _ptr(min_logvar), _ptr(model_idx), _ptr(noise), _ptr(obs), int(rew_dim), E, N, O,
+                                              _ptr(sample), _ptr(var), _ptr(unc), _stream())
+    _lib.check(rc, "morl_ensemble_sample_f32")
+    _count()
+    return sample, var, unc
+
+
+def qhead_envelope_supported(fmt: int, B: int, W: int, A: int, D: int, K: int) -> bool:
+    """True if :func:`qhead_envelope_td` covers the configuration (else use gemm_planes x 2 + envelope_td)."""
+    return bool(_lib.load().morl_qhead_envelope_supported(int(fmt), int(B), int(W), int(A), int(D), int(K)))
+
+
+def qhead_envelope_td(a_on: th.Tensor, a_tg: th.Tensor, w_on: th.Tensor, w_tg: th.Tensor, bias_on: th.Tensor, bias_tg: th.Tensor, wset, reward,
+                      done, gamma: float, B: int, W: int, A: int, D: int, dot_mode: int = DOT_UNFUSED, row_order: int = ROWS_REFERENCE,
+                      a_scale_on=None, a_scale_tg=None, w_scale_on=None, w_scale_tg=None, want_indices: bool = False, out=None, pref_out=None,
+                      act_out=None, q_on_out=None, q_tg_out=None, reverse_tiles: bool = False):
+    """Output layer of both Q-networks + envelope operator + Bellman line in ONE kernel (reference envelope.py:420-440, :298): the Q
+    tensors never reach HBM.  a_on / a_tg: last hidden activation planes [2, B*W, K] (row b*W + j) of the online / target net on s';
+    w_on / w_tg: output-layer weight planes [2, 32, K]; the rest as :func:`envelope_td`.  ``q_on_out`` / ``q_tg_out`` ([B*W, A*D] fp32)
+    optionally receive the Q tiles (validation).  Returns (target [W*B, D], pref, act)."""
+    fmt = fmt_of(a_on)
+    if fmt_of(a_tg) != fmt or fmt_of(w_on) != fmt or fmt_of(w_tg) != fmt or not a_on.is_cuda:
+        raise _lib.MorlB200Error("qhead_envelope_td: operands must be CUDA plane tensors of one format")
+    _, M, K = a_on.shape
+    if M != B * W or tuple(a_tg.shape) != tuple(a_on.shape) or a_on.stride(1) != K or a_tg.stride(1) != K or a_tg.stride(0) != a_on.stride(0):
+        raise _lib.MorlB200Error(f"qhead_envelope_td: activation planes must both be [P, {B * W}, K], K-major, equal plane strides")
+    if tuple(w_on.shape) != tuple(w_tg.shape) or w_on.shape[1] != 32 or w_on.shape[2] != K or w_on.stride(1) != K or w_tg.stride(0) != w_on.stride(0):
+        raise _lib.MorlB200Error(f"qhead_envelope_td: weight planes must both be [P, 32, {K}], K-major")
+    wset, reward, done = _dev(wset, "wset"), _dev(reward, "reward"), _dev(done, "done")
+    if wset.shape != (W, D) or reward.shape != (B, D) or done.numel() != B or bias_on.numel() != A * D or bias_tg.numel() != A * D:
+        raise _lib.MorlB200Error(f"bad shapes: wset {tuple(wset.shape)}, reward {tuple(reward.shape)}, done {tuple(done.shape)}, bias {tuple(bias_on.shape)}")
+    dev = a_on.device
+    if out is None:
+        out = th.empty((W * B, D), device=dev, dtype=th.float32)
+    if want_indices:
+        pref_out = th.empty(W * B, device=dev, dtype=th.int32) if pref_out is None else pref_out
+        act_out = th.empty(W * B, device=dev, dtype=th.int32) if act_out is None else act_out
+    rc = _lib.load().morl_qhead_envelope_td_f32(fmt, _ptr(a_on), _ptr(a_tg), a_on.stride(0), _ptr(a_scale_on), _ptr(a_scale_tg), _ptr(w_on), _ptr(w_tg),
+                                                w_on.stride(0), _ptr(w_scale_on), _ptr(w_scale_tg), _ptr(bias_on), _ptr(bias_tg), K, _ptr(wset),
+                                                _ptr(reward), _ptr(done), float(gamma), B, W, A, D, dot_mode, row_order, int(reverse_tiles), _ptr(out),
+                                                _ptr(pref_out), _ptr(act_out), _ptr(q_on_out), _ptr(q_tg_out), _stream())
+    _lib.check(rc, "morl_qhead_envelope_td_f32")
+    _count()
+    return out, pref_out, act_out
+
+
 def empty_relu_bits(rows: int, device) -> th.Tensor:
     """ReLU bit-mask tensor [rows, 8] int32 (layout: include/morl_b200.h, morl_gemm_planes_f32)."""
     return th.empty((rows, 8), device=device, dtype=th.int32)

@@ -170,6 +170,20 @@ class TCPairMlp:
         first = self.lin[0]
         if feats.shape[1] != self.feat_dim or first.in_features != self.feat_dim + wset.shape[1]:
             raise ops._lib.MorlB200Error(f"TCPairMlp: feats {tuple(feats.shape)} / wset {tuple(wset.shape)} do not match the first layer ({first.in_features} inputs)")
+        a = self.forward_hidden(feats, wset, _checked=True)
+        n = len(self.lin)
+        last = self.lin[-1]
+        q, _ = ops.gemm_planes(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
+                               reverse_tiles=_SNAKE and bool((n - 1) & 1), a_scale=self.s_act, b_scale=self.s_w[n - 2], split_acc=self.split_acc)
+        return q
+
+    @th.no_grad()
+    def forward_hidden(self, feats: th.Tensor, wset: th.Tensor, _checked: bool = False) -> th.Tensor:
+        """Layers 1 .. n-1: returns the planes of the LAST hidden activation [P, B*W, H] (the operand of the output layer, which
+        :func:`ops.qhead_envelope_td` consumes together with the other network's)."""
+        first = self.lin[0]
+        if not _checked and (feats.shape[1] != self.feat_dim or first.in_features != self.feat_dim + wset.shape[1]):
+            raise ops._lib.MorlB200Error(f"TCPairMlp: feats {tuple(feats.shape)} / wset {tuple(wset.shape)} do not match the first layer ({first.in_features} inputs)")
         u, v = ops.pair_layer1_uv(feats, wset, first.weight.detach(), first.bias.detach())  # one launch (csrc/pair_layer1.cu)
         hb = self.hbits if self.trainable else [None] * len(self.h)
         a = ops.pairs_relu_split(u, v, out=self.h[0], scale=self.s_act, relu_bits_out=hb[0])
@@ -180,10 +194,15 @@ class TCPairMlp:
             _, a = ops.gemm_planes(a, self.wp[k - 1], l.out_features, bias=l.bias, relu=True, out_f32=False, out_planes=True, c_planes=self.h[k],
                                    reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_act, b_scale=self.s_w[k - 1], c_scale=self.s_act,
                                    split_acc=self.split_acc, relu_bits_out=hb[k])
+        return a
+
+    def head_operands(self):
+        """(weight planes [P, 32, K], weight scale, bias) of the output layer, or None if it is wider than 32 columns."""
         last = self.lin[-1]
-        q, _ = ops.gemm_planes(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
-                               reverse_tiles=_SNAKE and bool((n - 1) & 1), a_scale=self.s_act, b_scale=self.s_w[n - 2], split_acc=self.split_acc)
-        return q
+        wp = self.wp[len(self.lin) - 2]
+        if wp.shape[1] != 32:
+            return None
+        return wp, self.s_w[len(self.lin) - 2], last.bias
 
     @th.no_grad()
     def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor, grads_out: Optional[List[th.Tensor]] = None):
