@@ -160,6 +160,54 @@ def time_envelope_kernel(dev, replays=25):
     return e0.elapsed_time(e1) * 1e-3 / (replays * nsets)
 
 
+def time_qhead_kernel(dev, replays=12):
+    """Average launch duration of morl_qhead_envelope_td_f32 -- output layers of both Q-nets + envelope operator + Bellman line in ONE
+    kernel, the form the update uses -- at the north-star shape: 8 launches on 4 rotating pairs of activation-plane tensors
+    (4 x 2 x 67 MB > L2) captured in one CUDA graph, CUDA events around the replays."""
+    import torch as th
+
+    from morl_baselines_b200 import ops
+
+    fmt, K, M, N = ops.FMT_F16X2, NET[-1], B * W, A * D
+    g = th.Generator(device=dev).manual_seed(3)
+    s_act, s_w = ops.scale_tensor(2.0, dev), ops.scale_tensor(4096.0, dev)
+    nsets = 4
+    a_on = [ops.split_planes(th.randn(M, K, device=dev, generator=g).relu_(), fmt, rows_pad=M, ldp=K, scale=s_act) for _ in range(nsets)]
+    a_tg = [ops.split_planes(th.randn(M, K, device=dev, generator=g).relu_(), fmt, rows_pad=M, ldp=K, scale=s_act) for _ in range(nsets)]
+    p_on = ops.split_planes(th.randn(N, K, device=dev, generator=g) / 16, fmt, rows_pad=32, ldp=K, scale=s_w)
+    p_tg = ops.split_planes(th.randn(N, K, device=dev, generator=g) / 16, fmt, rows_pad=32, ldp=K, scale=s_w)
+    b_on, b_tg = th.randn(N, device=dev, generator=g), th.randn(N, device=dev, generator=g)
+    wset = th.rand(W, D, device=dev, generator=g)
+    wset = wset / wset.sum(1, keepdim=True)
+    rew, done = th.randn(B, D, device=dev, generator=g), (th.rand(B, device=dev, generator=g) < 0.02).float()
+    out = th.empty(W * B, D, device=dev)
+
+    def sweep():
+        for r in range(2):
+            for i in range(nsets):
+                ops.qhead_envelope_td(a_on[i], a_tg[i], p_on, p_tg, b_on, b_tg, wset, rew, done, 0.99, B, W, A, D, ops.DOT_UNFUSED, ops.ROWS_BMAJOR,
+                                      a_scale_on=s_act, a_scale_tg=s_act, w_scale_on=s_w, w_scale_tg=s_w, out=out)
+
+    side = th.cuda.Stream()
+    side.wait_stream(th.cuda.current_stream())
+    with th.cuda.stream(side):
+        sweep()
+    th.cuda.current_stream().wait_stream(side)
+    graph = th.cuda.CUDAGraph()
+    with th.cuda.graph(graph):
+        sweep()
+    for _ in range(3):
+        graph.replay()
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        graph.replay()
+    e1.record()
+    th.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / (replays * 2 * nsets)
+
+
 def time_gemm_kernel(dev, iters=200, fmt=None):
     """Average launch duration of the dominant kernel of the step, morl_gemm_planes_f32 on one hidden layer of the pair batch
     (65,536 x 256 x 256, bias + ReLU + plane re-split epilogue), CUDA events around graph replays, 4 rotating activation sets (> L2).  Returns
@@ -461,6 +509,22 @@ def run_b200(args, rank, local_rank, world):
     if os.path.exists(tpath):
         gemm_traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     gemm_alg_bytes = 2 * gemm_bpe * B * W * NET[0] + gemm_bpe * NET[0] * NET[0]  # A planes read + C planes written + weight planes
+    # fused output layers + envelope + Bellman (the form Envelope.update uses when the shape is inside the kernel): the last hidden
+    # activation planes of both nets are its HBM input (the Q tensors never exist in HBM), plus the small operands and the targets
+    fused = None
+    from morl_baselines_b200 import ops as _ops
+
+    if agent.tensor_core_format == "f16x2" and _ops.qhead_envelope_supported(_ops.FMT_F16X2, B, W, A, D, NET[-1]):
+        t_fused = time_qhead_kernel(dev)
+        fused_bytes = 2 * 4 * B * W * NET[-1] + 2 * 4 * 32 * NET[-1] + W * D * 4 + B * D * 4 + B * 4 + W * B * D * 4
+        tf = os.path.join(ROOT, "profiles", "qhead_envelope_traffic.json")
+        fused = {"bound": "hbm", "kernel": "qhead_envelope_kernel<f16x2, 3, UNFUSED> (output layers of both Q-nets 65536x24x256 on tcgen05 + envelope "
+                                           "operator + Bellman line; Q tiles in tensor / shared memory only)",
+                 "achieved": fused_bytes / t_fused / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": fused_bytes / t_fused / 1e9 / hbm_peak,
+                 "traffic": json.load(open(tf)).get("dram_bytes_per_launch") if os.path.exists(tf) else None, "algorithmic_bytes": fused_bytes,
+                 "us_per_launch": t_fused * 1e6, "peak_source": peak_src, "in_update": bool(getattr(agent, "fused_head_active", False)),
+                 "replaces": "2 x morl_gemm_planes_f32 (N = 24) + morl_envelope_td_f32",
+                 "timing": "8 launches on 4 rotating pairs of activation-plane tensors (4 x 2 x 67 MB > L2) in one CUDA graph, 12 replays, CUDA events"}
     mlp_flops = 5 * B * W * 211712 * 2  # 1.39e11 FLOP/update (2 no-grad fwd + fwd + 2x bwd)
     line = {
         "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
@@ -498,6 +562,7 @@ def run_b200(args, rank, local_rank, world):
                               "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "us_per_launch": t_kernel * 1e6,
                               "peak_source": peak_src,
                               "timing": "16 launches on rotating input sets (214 MB > L2) in one CUDA graph, 25 replays, CUDA events"},
+        "roofline_envelope_fused": fused,
         "mlp": {"flop_per_step": mlp_flops, "fp32_equivalent_tflops": mlp_flops / (ms / K * 1e-3) / 1e12,
                 "path": "layer 1 separable (one fp32 kernel on B + |W| rows), layers 2.. tcgen05 split-operand GEMMs forward and backward",
                 "note": "whole-step time used, so this is a lower bound on the dense-layer rate"},
@@ -612,13 +677,74 @@ def run_morld(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_envelope_dp(args, rank, local_rank, world):
+    """DP-Envelope (reported separately from the replica headline): ONE update stream over `world` GPUs -- the scalarising weight
+    set of every update is sharded over the ranks, ONE gradient all-reduce per update keeps the network identical -- strong scaling:
+    value = updates/s of that single stream (max over ranks of the device time)."""
+    import torch as th
+    import torch.distributed as dist
+
+    from morl_baselines_b200 import ops
+    from morl_baselines_b200.multi_policy.envelope.envelope import Envelope
+    from morl_baselines_b200.testing import FakeEnv, synthetic_store
+
+    dev = th.device("cuda", local_rank)
+    th.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    np.random.seed(1000)  # identical on every rank: the ranks of one learner sample the same minibatches and weight sets
+    th.manual_seed(0)
+    agent = Envelope(FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D), batch_size=B, num_sample_w=W, per=True, buffer_size=STORE, net_arch=NET, log=False, seed=0,
+                     device=dev, replay_on_device=True, dp_group=True if world > 1 else None, per_on_device=(world == 1))
+    _fill_store(agent.replay_buffer, synthetic_store(STORE, OBS, A, D, seed=0))
+    agent.replay_buffer.flush()
+    agent.global_step = 1
+    for _ in range(max(Wm, 3)):
+        agent.update()
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    mon = ClockSampler(local_rank)
+    mon.start()
+    l0 = ops.launch_count
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        agent.update()
+    e1.record()
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = mon.result()
+    t_ms = th.tensor([e0.elapsed_time(e1)], device=dev)
+    psum = th.stack([p.detach().double().sum() for p in agent.q_net.parameters()]).sum().reshape(1)
+    pmin, pmax = psum.clone(), psum.clone()
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t_ms.item())
+        line = {"metric": "envelope_q_dp_updates_per_sec", "value": K / (ms * 1e-3), "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"DP-Envelope: ONE Envelope-Q update stream obs={OBS} |A|={A} d={D} |W|={W} batch={B} net=4x256 per=True over {world} GPU(s)",
+                           "parallelism": f"weight set sharded {W}/{world} per rank for the training pass (targets for all weights recomputed per rank), "
+                                          "ONE all-reduce per update (gradients 851 KB + priorities + loss)" if world > 1 else "single GPU (same code path, no collective)",
+                           "replicas_identical": bool(float(pmin.item()) == float(pmax.item())), "loss": float(agent._last_loss)},
+                "gpu_launches": int(ops.launch_count - l0), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="envelope", choices=["envelope", "morld"])
+    ap.add_argument("--workload", default="envelope", choices=["envelope", "morld", "envelope_dp"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -628,6 +754,8 @@ def main():
         run_reference_arm(args, rank)
     elif args.workload == "morld":
         run_morld(args, rank, local_rank, world)
+    elif args.workload == "envelope_dp":
+        run_envelope_dp(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 

@@ -40,8 +40,9 @@ from ...common.prioritized_buffer import PrioritizedReplayBuffer
 from ...common.utils import linearly_decaying_value
 from ...common.weights import equally_spaced_weights, random_weights
 
-# output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu); MORL_FUSED_HEAD=0 keeps the three-launch chain (A/B runs)
-_FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
+# output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu); MORL_FUSED_HEAD=0 / 1 selects the three-launch chain / the
+# fused kernel (A/B runs).  Default: off until the kernel's first B200 run is in (profiles/r02_qhead_*)
+_FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "0") != "0"
 
 
 class QNet(nn.Module):
@@ -138,12 +139,29 @@ class Envelope(MOPolicy, MOAgent):
         tensor_core_format: Optional[str] = None,
         per_on_device: bool = True,
         tensor_core_accumulators: str = "single",
+        dp_group=None,
     ):
         MOAgent.__init__(self, env, device=device, seed=seed)
         MOPolicy.__init__(self, device=device)
         if self.device.type != "cuda":
             raise ops._lib.MorlB200Error("morl_baselines_b200.Envelope needs a CUDA device: the update path is CUDA-only (no CPU fallback)")
         ops._lib.load()
+        # DP-Envelope: ``dp_group`` (True = the default process group, or a torch.distributed group) shards the scalarising
+        # weight set of every update over the ranks -- each rank evaluates the targets of ALL weights (the envelope maximum needs Q for every
+        # preference row; recomputed, no communication), back-propagates the loss rows of ITS num_sample_w / world weights, and ONE
+        # all-reduce per update (parallel.DPFlat: gradients + the owner's priorities + loss) keeps the conditioned network identical on all
+        # ranks.  Every rank must be constructed and seeded identically and see the same transitions.
+        self._dp = None
+        if dp_group is not None and dp_group is not False:
+            import torch.distributed as dist
+
+            grp = None if dp_group is True else dp_group
+            world = dist.get_world_size(grp) if dist.is_initialized() else 1
+            if world > 1:
+                if num_sample_w % world != 0:
+                    raise ValueError(f"dp_group: num_sample_w ({num_sample_w}) must be a multiple of the group size ({world})")
+                self._dp = {"group": grp, "world": world, "rank": dist.get_rank(grp), "w_loc": num_sample_w // world, "flat": None}
+                per_on_device = False  # the priorities reach every rank through the all-reduce: the tree write-back follows it, on the host
         self.learning_rate = learning_rate
         self.initial_epsilon = initial_epsilon
         self.epsilon = initial_epsilon
@@ -199,6 +217,8 @@ class Envelope(MOPolicy, MOAgent):
         self.tensor_core_accumulators = tensor_core_accumulators
         self.tensor_core_format = fmt_name
         self._tc_fmt = ops.FMT_F16X2 if fmt_name == "f16x2" else ops.FMT_BF16X3
+        if self._dp is not None and not use_tensor_cores:
+            raise ops._lib.MorlB200Error("morl_baselines_b200.Envelope: dp_group needs the tensor-core update path (use_tensor_cores=True)")
         if use_tensor_cores and (self.q_net.feature_extractor is not None
                                  or not TCPairMlp.trainable_supported(self.q_net.net, num_sample_w, self._tc_fmt)):
             raise ops._lib.MorlB200Error(
@@ -373,12 +393,13 @@ class Envelope(MOPolicy, MOAgent):
                     self._tc_on = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W, fmt=self._tc_fmt, split_acc=split)
                     self._tc_tg = TCPairMlp(self.target_q_net.net, self.target_q_net.feat_dim, B, W, fmt=self._tc_fmt, split_acc=split)
                     if TCPairMlp.trainable_supported(self.q_net.net, W, self._tc_fmt):
-                        self._tc_train = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W, share_weights_with=self._tc_on, trainable=True,
-                                                   split_acc=split)
+                        self._tc_train = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W if self._dp is None else self._dp["w_loc"],
+                                                   share_weights_with=self._tc_on, trainable=True, split_acc=split)
                 # every weight plane this step needs (online, target, transposed-for-backward) in one launch
                 TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
                 fused_head = self.envelope and _FUSED_HEAD and self.tensor_core_accumulators != "split" and self._tc_on.head_operands() is not None \
                     and ops.qhead_envelope_supported(self._tc_fmt, B, W, A, D, self._tc_on.lin[-1].in_features)
+                self.fused_head_active = bool(fused_head)
                 if fused_head:
                     # output layers of both nets + envelope operator + Bellman line in ONE kernel: Q_on / Q_tg (envelope.py:420, :429) exist
                     # in tensor / shared memory only (csrc/qhead_envelope.cu; bit-identical to the three-launch chain below)
@@ -404,26 +425,45 @@ class Envelope(MOPolicy, MOAgent):
             else:
                 target_q, _ = ops.greedy_td(q_on.view(B * W, A, D), q_tg.view(B * W, A, D), wset, rew, done1, self.gamma, self.dot_mode,
                                             ops.MAP_TILE, ops.MAP_BLOCK)
+        dp = self._dp
         if self._tc_train is not None and B == self.batch_size and W == self.num_sample_w:
             # training pass on the tensor cores, without autograd: forward, fused loss (emits d loss / d Q, the loss and the priorities),
             # hand-written backward straight into the persistent .grad buffers; weight planes were refreshed above
             with th.no_grad():
-                q_values = self._tc_train.forward_pairs(obs, wset).view(B * W, A, D)
+                Wt, wset_t = W, wset
+                if dp is not None:
+                    # DP-Envelope: this rank's loss rows are those of its own scalarising weights i in [lo, hi) (all transitions); the targets
+                    # above were formed for every i because the envelope maximum runs over all preference rows j
+                    Wt, lo = dp["w_loc"], dp["rank"] * dp["w_loc"]
+                    wset_t = wset[lo : lo + Wt]
+                    target_q = target_q.view(B, W, D)[:, lo : lo + Wt].reshape(B * Wt, D)
+                q_values = self._tc_train.forward_pairs(obs, wset_t).view(B * Wt, A, D)
                 if self._dq is None:
                     self._dq = th.empty_like(q_values)
                     self._grad_bufs = []
-                    for l in self._tc_train.lin:
-                        for p in (l.weight, l.bias):
-                            p.grad = th.zeros_like(p)
-                            self._grad_bufs.append(p.grad)
+                    if dp is not None:
+                        from ...parallel import DPFlat
+
+                        dp["flat"] = DPFlat([p for l in self._tc_train.lin for p in (l.weight, l.bias)], B, dp["group"])
+                        self._grad_bufs = list(dp["flat"].grads)
+                        for prm, gbuf in zip([p for l in self._tc_train.lin for p in (l.weight, l.bias)], self._grad_bufs):
+                            prm.grad = gbuf
+                    else:
+                        for l in self._tc_train.lin:
+                            for p in (l.weight, l.bias):
+                                p.grad = th.zeros_like(p)
+                                self._grad_bufs.append(p.grad)
                 raw = (s["raw_prio"] if device_per else s["prio"]) if self.per else None
-                ops.td_mse_priority(q_values, act.reshape(-1), target_q, wset, 0.0, B, W, ops.ROWS_BMAJOR, want_grad=True, want_prio=self.per,
+                ops.td_mse_priority(q_values, act.reshape(-1), target_q, wset_t, 0.0, B, Wt, ops.ROWS_BMAJOR, want_grad=True, want_prio=self.per,
                                     workspace=s["ws"], loss_out=s["loss1"], grad_out=self._dq, prio_out=raw, lambda_dev=s["lam"])
-                self._ship_results(raw, device_per)
+                if dp is None:
+                    self._ship_results(raw, device_per)
                 for l, (gw, gb) in zip(self._tc_train.lin, zip(self._grad_bufs[0::2], self._grad_bufs[1::2])):
                     if l.weight.grad is not gw or l.bias.grad is not gb:  # (someone called zero_grad(set_to_none=True) in between)
                         l.weight.grad, l.bias.grad = gw, gb
-                self._tc_train.backward(obs, wset, self._dq.view(B * W, A * D), grads_out=self._grad_bufs)
+                self._tc_train.backward(obs, wset_t, self._dq.view(B * Wt, A * D), grads_out=self._grad_bufs)
+            if dp is not None:
+                return  # the collective and the optimiser step follow the captured half (_dp_finish)
         else:
             # explicit validation path (use_tensor_cores=False): torch autograd + library GEMMs around the same fused operators
             q_values = self.q_net.forward_pairs(obs, wset).view(B * W, A, D)
@@ -433,6 +473,18 @@ class Envelope(MOPolicy, MOAgent):
             self.q_optim.zero_grad(set_to_none=True)
             loss.backward()
         self.q_optim.step_fused(self.max_grad_norm)  # clip_grad_norm_ + Adam.step (envelope.py:324-326) in two launches
+
+    def _dp_finish(self):
+        """Second half of a DP-Envelope update, after the (captured) forward / backward half: ONE all-reduce -- mean gradients into the
+        parameters' .grad views, the owner rank's raw priorities and the mean loss into the result record --, then the hand-off of loss and
+        priorities to the host and clip + Adam, identical on every rank."""
+        s, dp = self._static, self._dp
+        prio, loss = dp["flat"].allreduce(s["prio"] if self.per else None, s["loss1"], owns_priorities=(dp["rank"] == 0))
+        if self.per:
+            s["prio"].copy_(prio)
+        s["loss1"].copy_(loss)
+        self._ship_results(s["prio"] if self.per else None, False)
+        self.q_optim.step_fused(self.max_grad_norm)
 
     def _ship_results(self, raw, device_per: bool):
         """Loss and priorities are final (the loss kernel wrote them): ship them to the host before the backward half starts.  With
@@ -574,6 +626,8 @@ class Envelope(MOPolicy, MOAgent):
                 g.replay()
             else:
                 self._step(mode)
+            if self._dp is not None:
+                self._dp_finish()
             # (the static loss scalar is overwritten by the next gradient update: keep a copy when several are averaged)
             critic_losses.append(s["loss"].clone() if self.gradient_updates > 1 else s["loss"])
             self._updates_done += 1

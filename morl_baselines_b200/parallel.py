@@ -148,3 +148,47 @@ def allgather_fronts(local_points: th.Tensor, cap: int = 256, prune: Optional[Ca
     if stats is not None:
         stats.update({"rounds": rounds, "cap": cap, "counts": counts.tolist()})
     return front if extras is None else (front, ex)
+
+
+class DPFlat:
+    """ONE collective per gradient update of a data-parallel Envelope learner ("DP-Envelope": the scalarising weight set
+    of an update is sharded over the ranks, every rank back-propagates the loss rows of its own weights, and the conditioned network stays
+    consistent through a gradient all-reduce).
+
+    Flat float32 buffer ``[ gradients (every parameter, padded to 4 floats) | priorities (B) | loss (1) ]``: the parameters' ``.grad``
+    tensors are VIEWS of the first segment (the backward kernels write into it directly), so the all-reduce needs no packing of the
+    851 KB of gradients.  The priorities of an update come from the loss rows of weight 0 (reference envelope.py:329-331), which only the
+    owner rank holds: it contributes them, the others contribute zeros, and the SUM hands them to everyone -- each rank then applies the
+    same PER write-back and samples the same minibatch next step.  After ``allreduce()``: gradients and loss are the global means
+    (mean over ranks of the local means: equal shard sizes), priorities the owner's."""
+
+    def __init__(self, params, n_prio: int, group=None):
+        params = list(params)
+        dev = params[0].device
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        offs, o = [], 0
+        for p in params:
+            offs.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.n_grad = o
+        self.flat = th.zeros(o + n_prio + 1, dtype=th.float32, device=dev)
+        self.grads = [self.flat[a : a + p.numel()].view_as(p) for a, p in zip(offs, params)]
+        self.prio = self.flat[o : o + n_prio]
+        self.loss = self.flat[o + n_prio : o + n_prio + 1]
+
+    def allreduce(self, prio: Optional[th.Tensor], loss: th.Tensor, owns_priorities: bool):
+        """prio [B] (raw |w . td| of the local weight 0 rows) and loss [1] of the local shard -> in place: global mean gradients in the
+        ``.grad`` views, the owner's priorities in ``self.prio``, the global mean loss in ``self.loss``.  ONE all-reduce."""
+        if prio is not None and owns_priorities:
+            self.prio.copy_(prio.reshape(-1))
+        else:
+            self.prio.zero_()
+        self.loss.copy_(loss.reshape(-1))
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            inv = 1.0 / self.world
+            self.flat[: self.n_grad].mul_(inv)
+            self.loss.mul_(inv)
+        return self.prio, self.loss

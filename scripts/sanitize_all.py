@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python scripts/sanitize_all.py [group ...]
 
-groups: envelope td gemm optim pareto replay layer1 (default: all).  Shapes are small (sanitizer slows kernels 10-100x) but exercise
+groups: envelope td gemm optim pareto replay layer1 qhead dyna (default: all).  Shapes are small (sanitizer slows kernels 10-100x) but exercise
 every code path: all envelope kernel families, both GEMM operand formats x CTA modes x accumulator modes, MN split-K GEMM with the fused
 column sums, every split / reduction helper, the loss kernels, Adam, polyak, Pareto + front records, replay gather."""
 import os
@@ -22,7 +22,7 @@ if os.environ.get("SAN_ZERO_PLANES") == "1":
     # from a genuine read of memory nobody wrote (profiles/r02_sanitize_initcheck*.txt).
     _empty = ops.empty_planes
     ops.empty_planes = lambda *a, **k: _empty(*a, **k).zero_()
-groups = set(sys.argv[1:]) or {"envelope", "td", "gemm", "optim", "pareto", "replay", "layer1"}
+groups = set(sys.argv[1:]) or {"envelope", "td", "gemm", "optim", "pareto", "replay", "layer1", "qhead", "dyna"}
 
 
 def rn(*s, scale=1.0):
@@ -143,4 +143,34 @@ if "replay" in groups:
     ops.replay_gather(obs, nobs, act, rew, done, idx)
     th.cuda.synchronize()
     print("replay ok")
+if "qhead" in groups:
+    # fused output layers + envelope + Bellman (csrc/qhead_envelope.cu): several tiles per CTA are not needed for the protocol (ring and
+    # accumulator phases wrap within 5 tiles of one CTA when the grid is capped) -- MORL has no grid cap switch, so a shape with more tiles
+    # than SMs (B*W/128 = 160) exercises the wrap, and a W = 32 shape the four-transitions-per-tile path with ragged N = 18 rows
+    for (B, W, A, D, K) in [(320, 64, 8, 3, 64), (24, 32, 6, 3, 128)]:
+        M, N = B * W, A * D
+        s_a, s_w = ops.scale_tensor(2.0, dev), ops.scale_tensor(1024.0, dev)
+        a_on = ops.split_planes(rn(M, K).relu_(), ops.FMT_F16X2, rows_pad=M, ldp=K, scale=s_a)
+        a_tg = ops.split_planes(rn(M, K).relu_(), ops.FMT_F16X2, rows_pad=M, ldp=K, scale=s_a)
+        p_on = ops.split_planes(rn(N, K, scale=0.1), ops.FMT_F16X2, rows_pad=32, ldp=K, scale=s_w)
+        p_tg = ops.split_planes(rn(N, K, scale=0.1), ops.FMT_F16X2, rows_pad=32, ldp=K, scale=s_w)
+        b_on, b_tg, wset, rew, done = rn(N), rn(N), th.rand(W, D, device=dev, generator=g), rn(B, D), th.zeros(B, device=dev)
+        q1, _ = ops.gemm_planes(a_on, p_on, N, bias=b_on, a_scale=s_a, b_scale=s_w)
+        q2, _ = ops.gemm_planes(a_tg, p_tg, N, bias=b_tg, a_scale=s_a, b_scale=s_w)
+        ref = ops.envelope_td(q1.view(B, W, A, D), q2.view(B, W, A, D), wset, rew, done, 0.99)
+        qo, qt = th.zeros(M, N, device=dev), th.zeros(M, N, device=dev)
+        out = ops.qhead_envelope_td(a_on, a_tg, p_on, p_tg, b_on, b_tg, wset, rew, done, 0.99, B, W, A, D, a_scale_on=s_a, a_scale_tg=s_a, w_scale_on=s_w,
+                                    w_scale_tg=s_w, want_indices=True, q_on_out=qo, q_tg_out=qt)
+        th.cuda.synchronize()
+        assert th.equal(qo, q1) and th.equal(qt, q2) and all(th.equal(x, y) for x, y in zip(out, ref)), (B, W, A, D, K)
+    print("qhead ok")
+
+if "dyna" in groups:
+    E, N, O = 5, 77, 35
+    raw = rn(E, N, 2 * O, scale=3.0)
+    idx = th.randint(0, E, (N,), device=dev, generator=g, dtype=th.int32)
+    smp, var, unc = ops.ensemble_sample(raw, th.zeros(O, device=dev), th.full((O,), -5.0, device=dev), idx, rn(E, N, O), rn(N, O - 3), 3)
+    th.cuda.synchronize()
+    assert bool(th.isfinite(smp).all()) and bool((var > 0).all()) and bool((unc > 0).all())
+    print("dyna ok")
 print("sanitize run ok")
