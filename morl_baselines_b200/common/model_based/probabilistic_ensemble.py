@@ -158,60 +158,62 @@ class ProbabilisticEnsemble(nn.Module):
         self.inputs_sigma.data = th.tensor(sigma).to(self.device).float()
 
     # ------------------------------------------------------------------------------------------ training
+    _WEIGHT_DECAYS = (0.000025, 0.00005, 0.000075, 0.000075, 0.0001)  # per layer, as the reference (:224)
+
+    def _make_optimizer(self):
+        self.decays = list(self._WEIGHT_DECAYS)
+        groups = [{"params": layer.parameters(), "weight_decay": self.decays[i]} for i, layer in enumerate(self.layers)]
+        groups += [{"params": self.max_logvar}, {"params": self.min_logvar}]
+        self.optim = th.optim.Adam(groups, lr=self.learning_rate)
+
+    def _upload_split(self, X, Y, num_holdout):
+        """Training set and hold-out set as device tensors: ONE upload of X and Y, the split is a device gather by the host permutation
+        (``np.random.permutation``: first draw of the reference's ``fit``)."""
+        order = th.from_numpy(np.random.permutation(X.shape[0])).to(self.device)
+        Xd = th.from_numpy(np.ascontiguousarray(X)).to(self.device).float()
+        Yd = th.from_numpy(np.ascontiguousarray(Y)).to(self.device).float()
+        held, kept = order[:num_holdout], order[num_holdout:]
+        return (Xd[kept], Yd[kept]), (Xd[held], Yd[held])
+
+    def _train_epoch(self, train, table, batch_size):
+        """One pass over the bootstrap table [E, n]: member e of minibatch k sees rows table[e, k*bs:(k+1)*bs] (device gathers)."""
+        xs, ys = train
+        rows = th.from_numpy(table).to(self.device)
+        self.train()
+        for lo in range(0, table.shape[-1], batch_size):
+            pick = rows[:, lo:lo + batch_size]
+            loss = self._compute_loss(xs[pick], ys[pick])
+            self.optim.zero_grad()
+            loss.backward()
+            self.optim.step()
+
     def fit(self, X, Y, batch_size=256, holdout_ratio=0.1, max_holdout_size=5000, max_epochs_no_improvement=5, max_epochs=200):
-        """Maximum-likelihood training with bootstrapped minibatches and hold-out early stopping (reference :197-290); numpy's global
-        RNG is consumed in the reference's order (permutation, bootstrap indices, one uniform table per epoch)."""
+        """Maximum-likelihood training with bootstrapped minibatches and hold-out early stopping (reference :197-290).  numpy's global RNG is
+        consumed in the reference's order: the split permutation, the bootstrap table, one uniform table per epoch (row shuffles)."""
         if self.normalize_inputs:
             self._fit_input_stats(X)
-        self.decays = [0.000025, 0.00005, 0.000075, 0.000075, 0.0001]
-        self.optim = th.optim.Adam(
-            [{"params": self.layers[i].parameters(), "weight_decay": self.decays[i]} for i in range(len(self.layers))]
-            + [{"params": self.max_logvar}, {"params": self.min_logvar}],
-            lr=self.learning_rate,
-        )
+        self._make_optimizer()
         num_holdout = min(int(X.shape[0] * holdout_ratio), max_holdout_size)
-        permutation = np.random.permutation(X.shape[0])
-        dev = self.device
-        # the whole training set goes to HBM once; minibatches are device gathers
-        Xd = th.from_numpy(np.ascontiguousarray(X)).to(dev).float()
-        Yd = th.from_numpy(np.ascontiguousarray(Y)).to(dev).float()
-        perm_d = th.from_numpy(permutation).to(dev)
-        inputs, targets = Xd[perm_d[num_holdout:]], Yd[perm_d[num_holdout:]]
-        holdout_inputs, holdout_targets = Xd[perm_d[:num_holdout]], Yd[perm_d[:num_holdout]]
-        n_train = inputs.shape[0]
-        idxs = np.random.randint(n_train, size=[self.ensemble_size, n_train])
-        num_batches = int(np.ceil(idxs.shape[-1] / batch_size))
-
-        def shuffle_rows(arr):
-            order = np.argsort(np.random.uniform(size=arr.shape), axis=-1)
-            return arr[np.arange(arr.shape[0])[:, None], order]
-
-        num_epochs_no_improvement = 0
-        epoch = 0
-        best_holdout_losses = [float("inf") for _ in range(self.ensemble_size)]
-        holdout_losses = [float("inf")] * self.ensemble_size
-        while num_epochs_no_improvement < max_epochs_no_improvement and epoch < max_epochs:
-            self.train()
-            idxs_d = th.from_numpy(idxs).to(dev)
-            for batch_num in range(num_batches):
-                batch_idxs = idxs_d[:, batch_num * batch_size:(batch_num + 1) * batch_size]
-                loss = self._compute_loss(inputs[batch_idxs], targets[batch_idxs])
-                self.optim.zero_grad()
-                loss.backward()
-                self.optim.step()
-            idxs = shuffle_rows(idxs)
+        train, held = self._upload_split(X, Y, num_holdout)
+        n_train = train[0].shape[0]
+        table = np.random.randint(n_train, size=[self.ensemble_size, n_train])
+        best = [float("inf")] * self.ensemble_size
+        holdout_losses = list(best)
+        stale, epoch = 0, 0
+        while stale < max_epochs_no_improvement and epoch < max_epochs:
+            self._train_epoch(train, table, batch_size)
+            # every member's row is permuted independently for the next epoch (argsort of one uniform table, :243-245)
+            table = np.take_along_axis(table, np.argsort(np.random.uniform(size=table.shape), axis=-1), axis=-1)
             self.eval()
             with th.no_grad():
-                holdout_losses = self._compute_mse_losses(holdout_inputs, holdout_targets).cpu().tolist()  # one copy for the E losses
+                holdout_losses = self._compute_mse_losses(*held).cpu().tolist()  # the E losses in one device-to-host copy
             self.elites = np.argsort(holdout_losses)[: self.num_elites]
+            # a member "improves" when its hold-out loss drops by more than 1 % (always in the first epoch); any improvement resets the counter
             improved = False
-            for i in range(self.ensemble_size):
-                if epoch == 0 or (best_holdout_losses[i] - holdout_losses[i]) / (best_holdout_losses[i]) > 0.01:
-                    best_holdout_losses[i] = holdout_losses[i]
-                    num_epochs_no_improvement = 0
-                    improved = True
-            if not improved:
-                num_epochs_no_improvement += 1
+            for e, cur in enumerate(holdout_losses):
+                if epoch == 0 or (best[e] - cur) / best[e] > 0.01:
+                    best[e], improved = cur, True
+            stale = 0 if improved else stale + 1
             epoch += 1
         print("Epoch:", epoch, "Holdout losses:", ", ".join(["%.4f" % hl for hl in holdout_losses]))
         return np.mean(holdout_losses)

@@ -40,9 +40,11 @@ from ...common.prioritized_buffer import PrioritizedReplayBuffer
 from ...common.utils import linearly_decaying_value
 from ...common.weights import equally_spaced_weights, random_weights
 
-# output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu); MORL_FUSED_HEAD=0 / 1 selects the three-launch chain / the
-# fused kernel (A/B runs).  Default: off until the kernel's first B200 run is in (profiles/r02_qhead_*)
-_FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "0") != "0"
+# output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu: 29.4 us against 57.7 us for the three-launch chain at
+# the north-star shape, bit-identical -- profiles/r02_qhead_time.txt); MORL_FUSED_HEAD=0 keeps the three-launch chain (A/B runs)
+_FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
+# experiment: the online-net and target-net no-grad chains on two streams (MORL_TWO_STREAMS=1; needs the fused head)
+_TWO_STREAMS = os.environ.get("MORL_TWO_STREAMS", "0") == "1"
 
 
 class QNet(nn.Module):
@@ -358,6 +360,7 @@ class Envelope(MOPolicy, MOAgent):
             "prio_ready": th.cuda.Event(external=True),
             "copy_stream": th.cuda.Stream(device=dev),
             "side_stream": th.cuda.Stream(device=dev),
+            "side_stream2": th.cuda.Stream(device=dev),
         }
         # where a caller that stages inputs on the device itself (bench.py's `value` arm) must write them: the staging buffer, not the
         # private copy the graph refreshes from it
@@ -403,8 +406,18 @@ class Envelope(MOPolicy, MOAgent):
                 if fused_head:
                     # output layers of both nets + envelope operator + Bellman line in ONE kernel: Q_on / Q_tg (envelope.py:420, :429) exist
                     # in tensor / shared memory only (csrc/qhead_envelope.cu; bit-identical to the three-launch chain below)
-                    h_on = self._tc_on.forward_hidden(nobs, wset)
-                    h_tg = self._tc_tg.forward_hidden(nobs, wset)
+                    if _TWO_STREAMS:
+                        # the two no-grad chains are independent: fork the target-net chain onto a side stream (a parallel branch of the
+                        # captured graph) so that its kernels fill the launch gaps and tile tails of the online-net chain
+                        main, side = th.cuda.current_stream(), s["side_stream2"]
+                        side.wait_stream(main)
+                        with th.cuda.stream(side):
+                            h_tg = self._tc_tg.forward_hidden(nobs, wset)
+                        h_on = self._tc_on.forward_hidden(nobs, wset)
+                        main.wait_stream(side)
+                    else:
+                        h_on = self._tc_on.forward_hidden(nobs, wset)
+                        h_tg = self._tc_tg.forward_hidden(nobs, wset)
                     (w_on, sw_on, b_on), (w_tg, sw_tg, b_tg) = self._tc_on.head_operands(), self._tc_tg.head_operands()
                     target_q, _, _ = ops.qhead_envelope_td(h_on, h_tg, w_on, w_tg, b_on.detach(), b_tg.detach(), wset, rew, done.reshape(-1), self.gamma,
                                                            B, W, A, D, self.dot_mode, ops.ROWS_BMAJOR, a_scale_on=self._tc_on.s_act,

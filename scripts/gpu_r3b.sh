@@ -14,3 +14,6 @@ PY
 MORL_FUSED_HEAD=0 MORL_SKIP_CPU_BASELINE=1 timeout 600 python bench.py --steps 200 --warmup 5 2>&1 | tail -1 | python -c "
 import json,sys; l=json.loads(sys.stdin.read()); print('MORL_FUSED_HEAD=0', l['value'], l['ms_per_step'], l['e2e']['value'])" | tee gpurun_out/bench_unfused.log
 MORL_FUSED_HEAD=1 timeout 300 python scripts/kernel_timeline.py 8 2>&1 | grep -v Warn | tee gpurun_out/kernel_timeline.log | head -70
+MORL_FUSED_HEAD=1 MORL_TWO_STREAMS=1 MORL_SKIP_CPU_BASELINE=1 timeout 600 python bench.py --steps 200 --warmup 5 2>&1 | tail -1 | python -c "
+import json,sys; l=json.loads(sys.stdin.read()); print('MORL_TWO_STREAMS=1', l['value'], l['ms_per_step'], l['e2e']['value'])" | tee gpurun_out/bench_two_streams.log
+timeout 300 python scripts/gemm_time.py "" MORL_GEMM_SKIPB=1 MORL_GEMM_STAGES=2 "MORL_GEMM_SKIPB=1 MORL_GEMM_STAGES=2" 2>&1 | tee gpurun_out/gemm_time.log

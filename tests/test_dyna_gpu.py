@@ -16,7 +16,7 @@ import torch as th
 
 from morl_baselines_b200.testing import FakeEnv, _Spec
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ENS = dict(OBS=6, A=4, D=3, E=5, ARCH=[64, 64], N=40)
 DYN = dict(OBS=6, A=4, D=3, B=16, N=256, ENV_ID="mo-mountaincar-standin-v0", ROLLOUT_B=64, ROLLOUT_LEN=2, DYN_BUF=40, SEED_ROLLOUT=7, NOISE_SEED=43)

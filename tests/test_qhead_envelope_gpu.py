@@ -17,7 +17,7 @@ import numpy as np
 import pytest
 import torch as th
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
