@@ -696,7 +696,7 @@ def run_envelope_dp(args, rank, local_rank, world):
     np.random.seed(1000)  # identical on every rank: the ranks of one learner sample the same minibatches and weight sets
     th.manual_seed(0)
     agent = Envelope(FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D), batch_size=B, num_sample_w=W, per=True, buffer_size=STORE, net_arch=NET, log=False, seed=0,
-                     device=dev, replay_on_device=True, dp_group=True if world > 1 else None, per_on_device=(world == 1))
+                     device=dev, replay_on_device=True, dp_group=True if world > 1 else None)
     _fill_store(agent.replay_buffer, synthetic_store(STORE, OBS, A, D, seed=0))
     agent.replay_buffer.flush()
     agent.global_step = 1

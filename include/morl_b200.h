@@ -340,6 +340,13 @@ MORL_API int morl_ensemble_sample_f32(const float* out, const float* max_logvar,
  * morl_qhead_envelope_supported: 1 if the configuration is inside the kernel (f16x2 planes, W <= 64 dividing 128, B*W % 128 == 0,
  * A*D <= 32, W*A % 16 == 0, W*A*D % 4 == 0, 2 <= D <= 4, K % 64 == 0, K <= 256), else 0 -- callers then use the three-launch chain. */
 MORL_API int morl_qhead_envelope_supported(int fmt, int B, int W, int A, int D, int K);
+/* The kernel above without its operator half: the output layer of ONE network, q_out [M, N] = A . W^T + bias as fp32 rows (N <= 32: a narrow
+ * morl_gemm_planes_f32 with the weight planes resident in shared memory and a deep activation ring; same accumulation order, bit-identical).
+ * Used for the training pass's output layer (reference envelope.py:300).  M % 128 == 0, f16x2 planes, K % 64 == 0, K <= 256. */
+MORL_API int morl_qhead_gemm_supported(int fmt, int M, int N, int K);
+MORL_API int morl_qhead_gemm_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* w_planes,
+                                 long long w_plane_stride, const float* w_scale, const float* bias, int M, int N, int K, int reverse_tiles,
+                                 float* q_out, void* stream);
 MORL_API int morl_qhead_envelope_td_f32(int fmt, const void* a_on_planes, const void* a_tg_planes, long long a_plane_stride,
                                         const float* a_scale_on, const float* a_scale_tg, const void* w_on_planes, const void* w_tg_planes,
                                         long long w_plane_stride, const float* w_scale_on, const float* w_scale_tg, const float* bias_on,

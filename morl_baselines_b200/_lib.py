@@ -60,6 +60,8 @@ SIGNATURES = {
     "morl_debug_gemm_stats": (_i, [_vp, _i]),
     "morl_ensemble_sample_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "morl_qhead_envelope_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "morl_qhead_gemm_supported": (_i, [_i, _i, _i, _i]),
+    "morl_qhead_gemm_f32": (_i, [_i, _vp, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "morl_qhead_envelope_td_f32": (_i, [_i, _vp, _vp, C.c_longlong, _vp, _vp, _vp, _vp, C.c_longlong, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i,
                                         _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "morl_pairs_relu_split_planes": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp, _vp, _vp]),

@@ -313,6 +313,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
         float amax = 0.f;
         uint4 tile_bits = make_uint4(0u, 0u, 0u, 0u);
+        uint4 out_bits = make_uint4(0u, 0u, 0u, 0u);
         auto process = [&](const uint32_t (&v)[32], int n0, int row, bool row_ok) {
             // ReLU bit masks: word (c & 1) * 4 + (c >> 1) of the row holds columns [32 c, 32 c + 32); a thread owns the chunks of one parity
             // (its `half`), so its words of a tile are the four consecutive ones prefetched into tile_bits before the accumulator wait
@@ -333,11 +334,14 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (!((keep >> j) & 1u)) x[j] = 0.f;
             }
             if (g.bits_out) {
+                // collected per unit and written ONCE after the column loop (one 16-byte store per thread and tile instead of four scattered
+                // 4-byte stores: the forward GEMMs of the training pass ran 37 us against 30 us for the same layer without the mask)
                 uint32_t positive = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (x[j] > 0.f) positive |= 1u << j;
-                if (row_ok) g.bits_out[(size_t)row * 8 + ((n0 >> 5) & 1) * 4 + (n0 >> 6)] = positive;
+                const int i4 = n0 >> 6;
+                if (i4 == 0) out_bits.x = positive; else if (i4 == 1) out_bits.y = positive; else if (i4 == 2) out_bits.z = positive; else out_bits.w = positive;
             }
             if (g.mask && row_ok) {
                 const uint4* mrow = reinterpret_cast<const uint4*>(g.mask + (size_t)row * g.ld_mask + n0);
@@ -467,6 +471,19 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             __syncwarp();
             if (lane == 0) {
                 if (NCTA == 2) mbar_arrive_remote(mapa_rank0(g_smem_u32(&tempty[as]))); else g_mbar_arrive(&tempty[as]);
+            }
+            if (g.bits_out && row_ok) {
+                // this thread's chunks of the unit: output columns n_begin + 32 half + 64 k < n_begin + n_cnt, i.e. words (n_begin >> 6) ...
+                uint32_t* dst = g.bits_out + (size_t)row * 8 + half * 4;
+                const int w0 = n_begin >> 6, w1 = (n_begin + n_cnt - 32 * half + 63) >> 6;  // [w0, w1) of the four words this thread owns
+                if (w0 == 0 && w1 == 4) {
+                    *reinterpret_cast<uint4*>(dst) = out_bits;
+                } else {
+                    const uint32_t wv[4] = {out_bits.x, out_bits.y, out_bits.z, out_bits.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q >= w0 && q < w1) dst[q] = wv[q];
+                }
             }
             if (g.stats) busy += clock64() - c1;
         }

@@ -47,6 +47,7 @@ struct QHeadArgs {
     int32_t* pref_out;            // [W*B] or nullptr
     int32_t* act_out;             // [W*B] or nullptr
     float* q_out[2];              // optional fp32 copies of the Q tiles [B*W, N] (validation against the unfused path), or nullptr
+    int n_nets;                   // 2: the fused operator; 1: output layer of ONE net only, Q written to q_out[0] (morl_qhead_gemm_f32)
 };
 
 // shared-memory plan (host and device agree through this)
@@ -133,14 +134,14 @@ qhead_envelope_kernel(const __grid_constant__ CUtensorMap tmA_on, const __grid_c
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_on) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_tg) : "memory");
-            g_mbar_expect_tx(bfull, 2u * (uint32_t)n_kblk * L::kBChunk);
-            for (int net = 0; net < 2; ++net)
+            g_mbar_expect_tx(bfull, (uint32_t)g.n_nets * (uint32_t)n_kblk * L::kBChunk);
+            for (int net = 0; net < g.n_nets; ++net)
                 for (int kb = 0; kb < n_kblk; ++kb)
                     tma_load_3d(smB + (uint32_t)(net * n_kblk + kb) * L::kBChunk, net ? &tmB_tg : &tmB_on, bfull, kb * BK, 0, 0);
             uint32_t stage = 0, phase = 0;
             for (int u = blockIdx.x; u < g.n_tiles; u += gridDim.x) {
                 const int tile = g.reverse ? g.n_tiles - 1 - u : u;
-                for (int net = 0; net < 2; ++net) {
+                for (int net = 0; net < g.n_nets; ++net) {
                     for (int kb = 0; kb < n_kblk; ++kb) {
                         g_mbar_wait(&empty[stage], phase ^ 1u);
                         g_mbar_expect_tx(&full[stage], L::kAStage);
@@ -166,7 +167,7 @@ qhead_envelope_kernel(const __grid_constant__ CUtensorMap tmA_on, const __grid_c
                 const uint32_t as = it & 1u;
                 g_mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                for (int net = 0; net < 2; ++net) {
+                for (int net = 0; net < g.n_nets; ++net) {
                     const uint32_t d_tmem = tmem_base + as * (2u * kQhBN) + (uint32_t)net * kQhBN;
                     for (int kb = 0; kb < n_kblk; ++kb) {
                         g_mbar_wait(&full[stage], phase);
@@ -201,8 +202,9 @@ qhead_envelope_kernel(const __grid_constant__ CUtensorMap tmA_on, const __grid_c
         const int row = quad * 32 + lane;            // tile row staged by this thread
         const float k_acc = 1.0f / (ld_scale(g.a_scale[grp]) * ld_scale(g.b_scale[grp]));
         const int W = g.W, A = g.A, C = W * A, T = kQhBM / W;
+        const bool fused = g.n_nets == 2;
         wp::Role<D> role;
-        wp::load_role<D>(role, g.wset, W, tid_g);
+        if (fused) wp::load_role<D>(role, g.wset, W, tid_g);
         const int part = tid_g & 1;
         auto sync_g = [&]() { bar_sync_named(2 + grp, 128); };
         uint32_t it = 0;
@@ -220,6 +222,22 @@ qhead_envelope_kernel(const __grid_constant__ CUtensorMap tmA_on, const __grid_c
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = __fmaf_rn(__uint_as_float(v[j]), k_acc, bias_s[grp * kQhBN + j]);
+            if (!fused) {
+                // output layer of one net: the rows go straight to HBM (16-byte stores when the row length allows)
+                if (grp == 0) {
+                    float* orow = g.q_out[0] + ((size_t)tile * kQhBM + row) * N;
+                    if ((N & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < N) *reinterpret_cast<float4*>(orow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < N) orow[j] = x[j];
+                    }
+                }
+                continue;
+            }
             bar_sync_named(1, 256);  // every scan of the previous tile has finished reading the Q tile
             float* qrow = Qst + ((size_t)grp * kQhBM + row) * N;
             if ((N & 3) == 0) {
@@ -233,9 +251,15 @@ qhead_envelope_kernel(const __grid_constant__ CUtensorMap tmA_on, const __grid_c
             }
             if (g.q_out[grp]) {
                 float* orow = g.q_out[grp] + ((size_t)tile * kQhBM + row) * N;
+                if ((N & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < N) orow[j] = x[j];
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < N) *reinterpret_cast<float4*>(orow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < N) orow[j] = x[j];
+                }
             }
             bar_sync_named(1, 256);  // both Q tiles are staged
             for (int t = grp; t < T; t += 2) {
@@ -350,6 +374,7 @@ extern "C" int morl_qhead_envelope_td_f32(int fmt, const void* a_on_planes, cons
     g.row_order = row_order; g.reverse = reverse_tiles ? 1 : 0;
     g.target_out = target_out; g.pref_out = pref_out; g.act_out = act_out;
     g.q_out[0] = q_on_out; g.q_out[1] = q_tg_out;
+    g.n_nets = 2;
     static const bool want_pdl = [] { const char* e = getenv("MORL_GEMM_PDL"); return !(e && e[0] == '0'); }();
     g.pdl = want_pdl ? 1 : 0;
     // activation ring: as many stages as fit beside the resident weight planes, the Q tiles and the scan scratch
@@ -374,4 +399,48 @@ extern "C" int morl_qhead_envelope_td_f32(int fmt, const void* a_on_planes, cons
     }
     MORL_REQUIRE(launched, MORL_ERR_UNSUPPORTED, "morl_qhead_envelope_td_f32: no kernel for D=%d mode=%d", D, dot_mode);
     return ret;
+}
+
+extern "C" int morl_qhead_gemm_supported(int fmt, int M, int N, int K) {
+    using namespace morl;
+    return fmt == MORL_FMT_F16X2 && M > 0 && M % kQhBM == 0 && N > 0 && N <= kQhBN && K > 0 && K % PlaneFmt<MORL_FMT_F16X2>::BK == 0 && K <= 256;
+}
+
+// Output layer of ONE network, Q = A . W^T + b written as fp32 rows: the narrow-N form of morl_gemm_planes_f32 (same accumulation order: bit-identical)
+// with the weight planes resident in shared memory and a deep activation ring -- the kernel above without its operator half.
+extern "C" int morl_qhead_gemm_f32(int fmt, const void* a_planes, long long a_plane_stride, const float* a_scale, const void* w_planes,
+                                   long long w_plane_stride, const float* w_scale, const float* bias, int M, int N, int K, int reverse_tiles, float* q_out,
+                                   void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(a_planes && w_planes && q_out, MORL_ERR_NULL, "morl_qhead_gemm_f32: NULL pointer argument");
+    MORL_REQUIRE(morl_qhead_gemm_supported(fmt, M, N, K), MORL_ERR_UNSUPPORTED,
+                 "morl_qhead_gemm_f32: unsupported configuration fmt=%d M=%d N=%d K=%d (need f16x2 planes, M %% 128 == 0, N <= 32, K %% 64 == 0, K <= 256)", fmt, M,
+                 N, K);
+    MORL_REQUIRE(aligned16(a_planes) && aligned16(w_planes) && aligned16(q_out), MORL_ERR_ALIGN, "morl_qhead_gemm_f32: operands must be 16-byte aligned");
+    constexpr int kFmt = MORL_FMT_F16X2;
+    constexpr int BK = PlaneFmt<kFmt>::BK;
+    CUtensorMap tmA, tmB;
+    int rc = make_plane_map(&tmA, fmt, a_planes, M, K, a_plane_stride, kQhBM, BK);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_qhead_gemm_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
+    rc = make_plane_map(&tmB, fmt, w_planes, kQhBN, K, w_plane_stride, kQhBN, BK);
+    MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_qhead_gemm_f32: cuTensorMapEncodeTiled(W) failed (%d)", rc);
+    QHeadArgs g;
+    memset(&g, 0, sizeof(g));
+    g.B = M / kQhBM; g.W = kQhBM; g.A = 1; g.K = K; g.N = N;  // (B, W, A are not used without the operator half)
+    g.n_tiles = M / kQhBM;
+    g.bias[0] = bias;
+    g.a_scale[0] = a_scale; g.b_scale[0] = w_scale;
+    g.reverse = reverse_tiles ? 1 : 0;
+    g.q_out[0] = q_out;
+    g.n_nets = 1;
+    static const bool want_pdl = [] { const char* e = getenv("MORL_GEMM_PDL"); return !(e && e[0] == '0'); }();
+    g.pdl = want_pdl ? 1 : 0;
+    int n_st = kQhMaxStages;
+    while (n_st > 1 && QhPlan<kFmt>(K, N, n_st).bytes > 227u * 1024u) --n_st;
+    g.n_stages = n_st;
+    const size_t smem = QhPlan<kFmt>(K, N, n_st).bytes;
+    int sms = morl_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int grid = g.n_tiles < sms ? g.n_tiles : sms;
+    return launch_qhead<kFmt, 3, MORL_DOT_UNFUSED>(tmA, tmA, tmB, tmB, g, smem, grid, static_cast<cudaStream_t>(stream));
 }

@@ -43,6 +43,8 @@ from ...common.weights import equally_spaced_weights, random_weights
 # output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu: 29.4 us against 57.7 us for the three-launch chain at
 # the north-star shape, bit-identical -- profiles/r02_qhead_time.txt); MORL_FUSED_HEAD=0 keeps the three-launch chain (A/B runs)
 _FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
+# device PER: fork the priority / sum-tree branch after the backward GEMMs instead of right after the loss (MORL_DEFER_TREE=0: the earlier order)
+_DEFER_TREE = os.environ.get("MORL_DEFER_TREE", "1") != "0"
 # experiment: the online-net and target-net no-grad chains on two streams (MORL_TWO_STREAMS=1; needs the fused head)
 _TWO_STREAMS = os.environ.get("MORL_TWO_STREAMS", "0") == "1"
 
@@ -163,7 +165,6 @@ class Envelope(MOPolicy, MOAgent):
                 if num_sample_w % world != 0:
                     raise ValueError(f"dp_group: num_sample_w ({num_sample_w}) must be a multiple of the group size ({world})")
                 self._dp = {"group": grp, "world": world, "rank": dist.get_rank(grp), "w_loc": num_sample_w // world, "flat": None}
-                per_on_device = False  # the priorities reach every rank through the all-reduce: the tree write-back follows it, on the host
         self.learning_rate = learning_rate
         self.initial_epsilon = initial_epsilon
         self.epsilon = initial_epsilon
@@ -469,12 +470,17 @@ class Envelope(MOPolicy, MOAgent):
                 raw = (s["raw_prio"] if device_per else s["prio"]) if self.per else None
                 ops.td_mse_priority(q_values, act.reshape(-1), target_q, wset_t, 0.0, B, Wt, ops.ROWS_BMAJOR, want_grad=True, want_prio=self.per,
                                     workspace=s["ws"], loss_out=s["loss1"], grad_out=self._dq, prio_out=raw, lambda_dev=s["lam"])
-                if dp is None:
+                # device-resident PER: the priority / sum-tree branch (a 63 us single-block kernel with 45 KB of shared memory) is forked only
+                # AFTER the last persistent GEMM of the backward pass -- forked right here it kept one SM, hence one CTA pair of every GEMM
+                # that overlapped it, waiting (the first dX GEMM ran 46 us instead of 32); the host-tree modes keep the early hand-off
+                defer_ship = dp is None and device_per and _DEFER_TREE
+                if dp is None and not defer_ship:
                     self._ship_results(raw, device_per)
                 for l, (gw, gb) in zip(self._tc_train.lin, zip(self._grad_bufs[0::2], self._grad_bufs[1::2])):
                     if l.weight.grad is not gw or l.bias.grad is not gb:  # (someone called zero_grad(set_to_none=True) in between)
                         l.weight.grad, l.bias.grad = gw, gb
-                self._tc_train.backward(obs, wset_t, self._dq.view(B * Wt, A * D), grads_out=self._grad_bufs)
+                self._tc_train.backward(obs, wset_t, self._dq.view(B * Wt, A * D), grads_out=self._grad_bufs,
+                                        after_gemms=(lambda: self._ship_results(raw, device_per)) if defer_ship else None)
             if dp is not None:
                 return  # the collective and the optimiser step follow the captured half (_dp_finish)
         else:
@@ -492,11 +498,18 @@ class Envelope(MOPolicy, MOAgent):
         parameters' .grad views, the owner rank's raw priorities and the mean loss into the result record --, then the hand-off of loss and
         priorities to the host and clip + Adam, identical on every rank."""
         s, dp = self._static, self._dp
-        prio, loss = dp["flat"].allreduce(s["prio"] if self.per else None, s["loss1"], owns_priorities=(dp["rank"] == 0))
+        device_per = bool(self.per and getattr(self.replay_buffer, "tree_on_device", False) and self.use_cuda_graph)
+        raw = (s["raw_prio"] if device_per else s["prio"]) if self.per else None  # where the captured half left |w . td| of the local rows
+        prio, loss = dp["flat"].allreduce(raw, s["loss1"], owns_priorities=(dp["rank"] == 0))
         if self.per:
-            s["prio"].copy_(prio)
+            raw.copy_(prio)
         s["loss1"].copy_(loss)
-        self._ship_results(s["prio"] if self.per else None, False)
+        # loss + priorities to the host; with the sum tree in HBM the priority power, the ratchet and the tree write-back run here as well
+        # (stream-ordered, no host wait), so every rank's tree is updated with the same values before its next walk
+        self._ship_results(raw, device_per)
+        if self._side_pending:
+            th.cuda.current_stream().wait_stream(s["side_stream"])
+            self._side_pending = False
         self.q_optim.step_fused(self.max_grad_norm)
 
     def _ship_results(self, raw, device_per: bool):

@@ -508,6 +508,27 @@ def qhead_envelope_td(a_on: th.Tensor, a_tg: th.Tensor, w_on: th.Tensor, w_tg: t
     return out, pref_out, act_out
 
 
+def qhead_gemm_supported(fmt: int, M: int, N: int, K: int) -> bool:
+    return bool(_lib.load().morl_qhead_gemm_supported(int(fmt), int(M), int(N), int(K)))
+
+
+def qhead_gemm(a_planes: th.Tensor, w_planes: th.Tensor, n_out: int, bias: th.Tensor, out: Optional[th.Tensor] = None, a_scale=None, w_scale=None,
+               reverse_tiles: bool = False) -> th.Tensor:
+    """Output layer Q = A . W^T + bias (n_out <= 32) as fp32 [M, n_out]: the narrow form of :func:`gemm_planes` (bit-identical) with the weight
+    planes resident in shared memory (csrc/qhead_envelope.cu without its operator half)."""
+    fmt = fmt_of(a_planes)
+    _, M, K = a_planes.shape
+    if fmt_of(w_planes) != fmt or tuple(w_planes.shape[1:]) != (32, K) or a_planes.stride(1) != K or w_planes.stride(1) != K:
+        raise _lib.MorlB200Error(f"qhead_gemm: need K-major planes A [P, M, K] and W [P, 32, K] of one format (got {tuple(a_planes.shape)}, {tuple(w_planes.shape)})")
+    if out is None:
+        out = th.empty((M, n_out), device=a_planes.device, dtype=th.float32)
+    rc = _lib.load().morl_qhead_gemm_f32(fmt, _ptr(a_planes), a_planes.stride(0), _ptr(a_scale), _ptr(w_planes), w_planes.stride(0), _ptr(w_scale), _ptr(bias), M,
+                                         n_out, K, int(reverse_tiles), _ptr(out), _stream())
+    _lib.check(rc, "morl_qhead_gemm_f32")
+    _count()
+    return out
+
+
 def empty_relu_bits(rows: int, device) -> th.Tensor:
     """ReLU bit-mask tensor [rows, 8] int32 (layout: include/morl_b200.h, morl_gemm_planes_f32)."""
     return th.empty((rows, 8), device=device, dtype=th.int32)

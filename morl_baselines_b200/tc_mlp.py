@@ -42,6 +42,7 @@ from torch import nn
 from . import ops
 
 _SNAKE = os.environ.get("MORL_TC_SNAKE", "1") == "1"          # alternate the GEMM tile order between chained layers
+_NARROW_HEAD = os.environ.get("MORL_NARROW_HEAD", "0") == "1"  # output layer through morl_qhead_gemm_f32 (opt-in until its first B200 run)
 _DEFAULT_FMT = ops.FMT_BF16X3 if os.environ.get("MORL_TC_FMT", "f16x2") == "bf16x3" else ops.FMT_F16X2
 
 ACT_SCALE = 2.0        # f16x2 activations: |h| < 32,752 representable
@@ -173,7 +174,12 @@ class TCPairMlp:
         a = self.forward_hidden(feats, wset, _checked=True)
         n = len(self.lin)
         last = self.lin[-1]
-        q, _ = ops.gemm_planes(a, self.wp[n - 2], last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
+        wp_last = self.wp[n - 2]
+        if _NARROW_HEAD and not self.split_acc and wp_last.shape[1] == 32 and ops.qhead_gemm_supported(self.fmt, a.shape[1], last.out_features, a.shape[2]):
+            # narrow output layer: weight planes resident in shared memory, deep activation ring (bit-identical to the general kernel)
+            return ops.qhead_gemm(a, wp_last, last.out_features, last.bias.detach(), out=self.q, a_scale=self.s_act, w_scale=self.s_w[n - 2],
+                                  reverse_tiles=_SNAKE and bool((n - 1) & 1))
+        q, _ = ops.gemm_planes(a, wp_last, last.out_features, bias=last.bias, relu=False, out_f32=True, c_f32=self.q,
                                reverse_tiles=_SNAKE and bool((n - 1) & 1), a_scale=self.s_act, b_scale=self.s_w[n - 2], split_acc=self.split_acc)
         return q
 
@@ -205,9 +211,11 @@ class TCPairMlp:
         return wp, self.s_w[len(self.lin) - 2], last.bias
 
     @th.no_grad()
-    def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor, grads_out: Optional[List[th.Tensor]] = None):
+    def backward(self, feats: th.Tensor, wset: th.Tensor, dq: th.Tensor, grads_out: Optional[List[th.Tensor]] = None, after_gemms=None):
         """Gradients of all Linear parameters given dL/dQ [B*W, out]; uses the activations of the last forward_pairs().
-        ``grads_out`` (weight, bias per Linear, in order) receives them in place -- the persistent ``.grad`` buffers of the update."""
+        ``grads_out`` (weight, bias per Linear, in order) receives them in place -- the persistent ``.grad`` buffers of the update.
+        ``after_gemms`` (callable, optional) is invoked once the last persistent tensor-core GEMM has been enqueued: the place to fork side
+        work that must not take an SM away from those one-CTA-per-SM kernels (the layer-1 reductions that follow are ordinary grids)."""
         n = len(self.lin)
         grads = [None] * (2 * n) if grads_out is None else list(grads_out)
         if getattr(self, "_wt_fresh", False):
@@ -228,6 +236,8 @@ class TCPairMlp:
             _, G = ops.gemm_planes(G, self.wtp[k - 1], l.in_features, relu_bits_in=self.hbits[k - 1], out_f32=False, out_planes=True,
                                    c_planes=self.g[k & 1], reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_g, b_scale=self.s_w[k - 1],
                                    c_scale=self.s_g, split_acc=False)  # gradients: Adam is invariant to the ~2e-6 uniform shrinkage
+        if after_gemms is not None:
+            after_gemms()
         dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV, scale=self.s_g)
         grads[0], grads[1] = ops.pair_layer1_grad(dU, dV, feats, wset, dW1=grads[0], db1=grads[1], workspace=self.ws_l1)
         return grads

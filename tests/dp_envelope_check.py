@@ -16,12 +16,12 @@ from morl_baselines_b200.multi_policy.envelope.envelope import Envelope  # noqa:
 from morl_baselines_b200.testing import FakeEnv, synthetic_store  # noqa: E402
 
 
-def run(dev, dp, graph):
+def run(dev, dp, graph, per_dev=False):
     OBS, A, D, B, W = 12, 4, 3, 64, 8
     th.manual_seed(5)
     np.random.seed(5)
     agent = Envelope(FakeEnv(obs_dim=OBS, n_actions=A, reward_dim=D), batch_size=B, num_sample_w=W, per=True, buffer_size=2048, net_arch=[64, 64, 64], log=False,
-                     seed=5, device=dev, use_cuda_graph=graph, target_net_update_freq=3, dp_group=True if dp else None, per_on_device=False)
+                     seed=5, device=dev, use_cuda_graph=graph, target_net_update_freq=3, dp_group=True if dp else None, per_on_device=per_dev)
     st = synthetic_store(1024, OBS, A, D, seed=2)
     rb = agent.replay_buffer
     rb.obs[:1024], rb.next_obs[:1024], rb.actions[:1024], rb.rewards[:1024], rb.dones[:1024] = st["obs"], st["next_obs"], st["actions"], st["rewards"], st["dones"]
@@ -44,9 +44,9 @@ def main():
     th.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for graph in (False, True):
-        rec1, p1 = run(dev, dp=False, graph=graph)
-        rec2, p2 = run(dev, dp=True, graph=graph)
+    for graph, per_dev in ((False, False), (True, False), (True, True)):  # (device-resident PER needs the captured step)
+        rec1, p1 = run(dev, dp=False, graph=graph, per_dev=per_dev)
+        rec2, p2 = run(dev, dp=True, graph=graph, per_dev=per_dev)
         for (l1, i1, q1), (l2, i2, q2) in zip(rec1, rec2):
             ok &= bool(np.array_equal(i1, i2)) and abs(l1 - l2) <= 1e-5 * abs(l1) and bool(np.allclose(q1, q2, rtol=1e-5, atol=1e-7))
         worst = 0.0
@@ -59,7 +59,7 @@ def main():
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             ok &= float(lo) == float(hi)
         if rank == 0:
-            print(f"graph={graph}: losses single {[round(r[0], 7) for r in rec1]} dp {[round(r[0], 7) for r in rec2]} max |dp - single| over parameters {worst:.2e}")
+            print(f"graph={graph} device_per={per_dev}: losses single {[round(r[0], 7) for r in rec1]} dp {[round(r[0], 7) for r in rec2]} max |dp - single| over parameters {worst:.2e}")
     flag = th.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

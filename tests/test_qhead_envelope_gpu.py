@@ -157,3 +157,24 @@ def test_envelope_update_with_fused_head_equals_update_without(cuda, graph):
         assert np.array_equal(i1, i0) and np.array_equal(x, y)
     for x, y in zip(w1, w0):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("M,N,K", [(65536, 24, 256), (8192, 18, 256), (256, 32, 64), (640, 5, 128)])
+def test_narrow_head_gemm_equals_general_gemm(cuda, M, N, K):
+    """morl_qhead_gemm_f32 (output layer with resident weight planes; the training pass's last layer) == morl_gemm_planes_f32, bit for bit,
+    both tile orders."""
+    from morl_baselines_b200 import ops
+
+    fmt = ops.FMT_F16X2
+    g = th.Generator(device=cuda).manual_seed(M + N)
+    s_a, s_w = ops.scale_tensor(2.0, cuda), ops.scale_tensor(4096.0, cuda)
+    a = ops.split_planes(th.randn(M, K, device=cuda, generator=g).relu_(), fmt, rows_pad=M, ldp=K, scale=s_a)
+    w = ops.split_planes(th.randn(N, K, device=cuda, generator=g) / 16.0, fmt, rows_pad=32, ldp=K, scale=s_w)
+    bias = th.randn(N, device=cuda, generator=g)
+    assert ops.qhead_gemm_supported(fmt, M, N, K)
+    ref, _ = ops.gemm_planes(a, w, N, bias=bias, a_scale=s_a, b_scale=s_w)
+    for rev in (False, True):
+        out = th.full((M, N), float("nan"), device=cuda)
+        ops.qhead_gemm(a, w, N, bias, out=out, a_scale=s_a, w_scale=s_w, reverse_tiles=rev)
+        assert th.equal(out, ref)
+    assert not ops.qhead_gemm_supported(fmt, 100, N, K) and not ops.qhead_gemm_supported(fmt, M, 40, K)
