@@ -508,6 +508,291 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // =================================================================================================================
+// CHAIN kernel: several dense hidden layers of one or two networks in ONE persistent launch (CTA pairs, f16x2 / bf16x3 planes, N = 256 wide
+// layers).  A layer's output rows depend only on the same rows of its input, so a CTA pair can take one of its 256-row tiles through ALL
+// layers: the tile it stores for layer l is the tile it loads for layer l+1 a few units later -- by then still in the 126 MB L2, so only the
+// first layer's input is read from HBM (the per-layer launches re-read every intermediate activation from HBM: 6 x 134 MB for the two
+// no-grad passes of an Envelope update against 6 x 67 MB + 2 x 67 MB here), and the launch prologue / drain is paid once instead of per
+// layer.  Work of a pair: its tiles in groups of `lanes / n_chains`; per group, for every layer, one unit per LANE (lane = (chain, tile
+// of the group)): four lanes keep the dependency distance at four units (unit (l, lane) needs the stores of unit (l-1, lane)), so the
+// producer never waits for the epilogue that has just finished.  Same roles, barriers and arithmetic as gemm_planes_kernel<2, FMT, 0>
+// (bit-identical outputs: tests/test_gemm_gpu.py); additional barrier stored[lane]: the epilogue warps of a CTA arrive once their bulk
+// stores of the unit have COMPLETED, the producer of the same CTA waits for it before loading the next layer of that lane.
+// =================================================================================================================
+constexpr int kChainMaxJobs = 8;   // chains x layers
+constexpr int kChainLanes = 4;
+
+struct alignas(64) ChainMaps {
+    CUtensorMap A[kChainMaxJobs];  // load map of the INPUT of job (chain c, layer l): [P][M][K], box P x 128 x BK
+    CUtensorMap B[kChainMaxJobs];  // weight planes of the job: [P][256][K], box P x 128 x BK (each CTA of the pair stages half of the rows)
+    CUtensorMap C[kChainMaxJobs];  // store map of the OUTPUT of the job: [P][M][256], box P x 32 x 32 (64-byte swizzle)
+};
+
+struct ChainArgs {
+    int M, K;                      // rows, reduction length (= width of the layers: square 256-wide layers, K % BK == 0)
+    int n_chains, n_layers;
+    const float* bias[kChainMaxJobs];
+    const float* b_scale[kChainMaxJobs];
+    uint32_t* bits_out[kChainMaxJobs];  // ReLU bit masks of the job's output, or nullptr
+    const float* a_scale;          // activation scale (input AND output of every layer), device scalar or nullptr
+    int n_stages;
+    int pdl;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
+    using F = PlaneFmt<FMT>;
+    using L = KPlan<2, FMT>;
+    constexpr int P = F::P;
+    constexpr int BK = F::BK;
+    constexpr int BN = 256;
+    constexpr int kMaxStages = L::kMaxStages;
+    constexpr uint32_t ROWB = L::kRowB;
+    const int kStages = g.n_stages;
+    extern __shared__ uint8_t gsmem_raw[];
+    uint8_t* gsmem = gsmem_raw + ((1024u - (g_smem_u32(gsmem_raw) & 1023u)) & 1023u);
+    constexpr uint32_t a_stage_bytes = L::kAStage;
+    constexpr uint32_t b_stage_bytes = L::kBStage;
+    uint8_t* smA = gsmem;
+    uint8_t* smB = gsmem + (uint32_t)kStages * a_stage_bytes;
+    uint8_t* stage_c = gsmem + L::kOffC;
+    uint64_t* full = reinterpret_cast<uint64_t*>(gsmem + L::kOffBar);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tfull = empty + kMaxStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* stored = tempty + 2;  // [kChainLanes]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stored + kChainLanes);
+    float* bias_s = reinterpret_cast<float*>(gsmem + L::kOffBias);  // [256], refilled per unit by the epilogue warps
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const int unit = blockIdx.x / 2, n_units = gridDim.x / 2;
+    const int n_tiles = (g.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+    const int n_kblk = g.K / BK;
+    const int tiles_per_group = kChainLanes / g.n_chains;  // lanes of a group: (tile of the group) x (chain)
+    const int my_tiles = unit < n_tiles ? (n_tiles - unit + n_units - 1) / n_units : 0;
+    const int n_groups = (my_tiles + tiles_per_group - 1) / tiles_per_group;
+    // unit (group gi, layer l, lane ln) -> (job, tile) or tile = -1 (no such tile in the last group)
+    auto unit_of = [&](int gi, int l, int ln, int& job, int& tile) {
+        const int c = ln % g.n_chains, ti = gi * tiles_per_group + ln / g.n_chains;
+        job = c * g.n_layers + l;
+        tile = ti < my_tiles ? unit + ti * n_units : -1;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            g_mbar_init(&full[s], 1);
+            g_mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            g_mbar_init(&tfull[s], 1);
+            g_mbar_init(&tempty[s], 16);  // one arrival per epilogue warp of both CTAs, on the leader's barrier
+        }
+        for (int s = 0; s < kChainLanes; ++s) g_mbar_init(&stored[s], 8);  // the 8 epilogue warps of THIS CTA
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (g.pdl) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            uint32_t done_on_lane[kChainLanes] = {0u, 0u, 0u, 0u};  // units already issued on each lane = completions of stored[lane] to expect
+            for (int gi = 0; gi < n_groups; ++gi)
+                for (int l = 0; l < g.n_layers; ++l)
+                    for (int ln = 0; ln < kChainLanes; ++ln) {
+                        int job, tile;
+                        unit_of(gi, l, ln, job, tile);
+                        if (tile < 0) continue;
+                        if (l > 0) {
+                            // the input tile of this unit is the output tile of the lane's previous unit: wait until THIS CTA's stores of
+                            // it have completed (completion number done_on_lane[ln] of stored[ln])
+                            g_mbar_wait(&stored[ln], (done_on_lane[ln] - 1u) & 1u);
+                            asm volatile("fence.proxy.async.global;" ::: "memory");
+                        }
+                        ++done_on_lane[ln];
+                        const int row0 = (tile * 2 + (int)cta_rank) * kGemmBM;
+                        for (int kb = 0; kb < n_kblk; ++kb) {
+                            g_mbar_wait(&empty[stage], phase ^ 1u);
+                            if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + b_stage_bytes));
+                            const uint32_t lbar = mapa_rank0(g_smem_u32(&full[stage]));
+                            tma_load_3d_pair(smA + stage * a_stage_bytes, &maps.A[job], lbar, kb * BK, row0, 0);
+                            tma_load_3d_pair(smB + stage * b_stage_bytes, &maps.B[job], lbar, kb * BK, (int)cta_rank * (BN / 2), 0);
+                            if (++stage == (uint32_t)kStages) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = (1u << 4) | F::kIdescAB | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((kGemmBM * 2) >> 4) << 24);
+            constexpr uint32_t a_plane = kGemmBM * ROWB;
+            constexpr uint32_t b_plane = (uint32_t)(BN / 2) * ROWB;
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int gi = 0; gi < n_groups; ++gi)
+                for (int l = 0; l < g.n_layers; ++l)
+                    for (int ln = 0; ln < kChainLanes; ++ln) {
+                        int job, tile;
+                        unit_of(gi, l, ln, job, tile);
+                        if (tile < 0) continue;
+                        const uint32_t as = it & 1u;
+                        g_mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + as * 256u;
+                        for (int kb = 0; kb < n_kblk; ++kb) {
+                            g_mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t a0 = g_smem_u32(smA + stage * a_stage_bytes);
+                            const uint32_t b0 = g_smem_u32(smB + stage * b_stage_bytes);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+#pragma unroll
+                                for (int t = 0; t < F::NPROD; ++t) {
+                                    const uint64_t ad = make_desc_k<ROWB>(a0 + F::pa(t) * a_plane + ks * 32);
+                                    const uint64_t bd = make_desc_k<ROWB>(b0 + F::pb(t) * b_plane + ks * 32);
+                                    tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb | ks | t) != 0 ? 1u : 0u);
+                                }
+                            }
+                            tc_commit_pair(&empty[stage]);
+                            if (++stage == (uint32_t)kStages) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                        tc_commit_pair(&tfull[as]);
+                        ++it;
+                    }
+        }
+    } else {
+        // ================= epilogue warps (2..9) =================
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
+        uint8_t* my_stage = stage_c + (warp - 2) * L::kStageC;
+        const float s_act = ld_scale(g.a_scale);
+        float amax = 0.f;
+        uint32_t it = 0;
+        for (int gi = 0; gi < n_groups; ++gi)
+            for (int l = 0; l < g.n_layers; ++l)
+                for (int ln = 0; ln < kChainLanes; ++ln) {
+                    int job, tile;
+                    unit_of(gi, l, ln, job, tile);
+                    if (tile < 0) continue;
+                    const uint32_t as = it & 1u;
+                    // this unit's bias (times the folded output scale) into shared memory: every epilogue warp has left the previous unit
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    bias_s[et] = (g.bias[job] ? __ldg(g.bias[job] + et) : 0.f) * s_act;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    // x * s_act = acc * (s_act / (s_act * sB)) + s_act * bias  (powers of two: exact), as gemm_planes_kernel's folded epilogue
+                    const float k_acc = s_act / (s_act * ld_scale(g.b_scale[job]));
+                    uint32_t* bits_out = g.bits_out[job];
+                    uint4 out_bits = make_uint4(0u, 0u, 0u, 0u);
+                    g_mbar_wait(&tfull[as], (it >> 1) & 1u);
+                    tc_fence_after();
+                    const int row = (tile * 2 + (int)cta_rank) * kGemmBM + quad * 32 + lane;
+                    const bool row_ok = row < g.M;
+                    const uint32_t t_row = tmem_base + as * 256u + ((uint32_t)(quad * 32) << 16);
+                    uint32_t va[32], vb[32];
+                    auto process = [&](const uint32_t (&v)[32], int n0) {
+                        float x[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float f = __fmaf_rn(__uint_as_float(v[j]), k_acc, bias_s[n0 + j]);
+                            x[j] = (f < 0.f) ? 0.f : f;  // ReLU (NaN stays NaN)
+                        }
+                        if (bits_out) {
+                            uint32_t positive = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (x[j] > 0.f) positive |= 1u << j;
+                            const int i4 = n0 >> 6;
+                            if (i4 == 0) out_bits.x = positive; else if (i4 == 1) out_bits.y = positive; else if (i4 == 2) out_bits.z = positive; else out_bits.w = positive;
+                        }
+                        uint32_t pw[P][16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            uint32_t w[P];
+                            F::split2(x[j], x[j + 1], w, amax);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) pw[p][j / 2] = w[p];
+                        }
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        uint8_t* st = my_stage + lane * 64;
+                        const int sw = (lane >> 1) & 3;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int off = ((q ^ sw) << 4);
+#pragma unroll
+                            for (int p = 0; p < P; ++p)
+                                *reinterpret_cast<uint4*>(st + p * 2048 + off) = make_uint4(pw[p][4 * q], pw[p][4 * q + 1], pw[p][4 * q + 2], pw[p][4 * q + 3]);
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.C[job]),
+                                         "r"(g_smem_u32(my_stage)), "r"(n0), "r"(row - lane), "r"(0)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    };
+                    int n0 = 32 * half;
+                    tc_ld32(t_row + (uint32_t)n0, va);
+                    tc_ld_wait();
+                    while (n0 < BN) {
+                        const int n1 = n0 + 64;
+                        if (n1 < BN) tc_ld32(t_row + (uint32_t)n1, vb);
+                        process(va, n0);
+                        tc_ld_wait();
+                        if (n1 >= BN) break;
+                        const int n2 = n1 + 64;
+                        if (n2 < BN) tc_ld32(t_row + (uint32_t)n2, va);
+                        process(vb, n1);
+                        tc_ld_wait();
+                        n0 = n2;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(mapa_rank0(g_smem_u32(&tempty[as])));
+                    if (bits_out && row_ok) *reinterpret_cast<uint4*>(bits_out + (size_t)row * 8 + half * 4) = out_bits;
+                    // the lane's next layer loads what this unit stored: signal once the bulk stores of this warp have completed
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        g_mbar_arrive(&stored[ln]);
+                    }
+                    ++it;
+                }
+        if (FMT == MORL_FMT_F16X2) note_overflow(amax);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// =================================================================================================================
 // MN-major split-K variant: weight gradients  dW[n, k] = sum_m G[m, n] * H[m, k]  (reduction over the 65,536 batch rows).
 // Both operands are the row-major plane tensors the forward/backward GEMMs already produced, read "MN-major" (the MMA's M / N
 // index is the contiguous one), 128-byte swizzle:  A = G^T (M_mma = n, 128 per CTA), B = H^T (N_mma = k <= 256), K_mma = m.
@@ -1645,4 +1930,88 @@ extern "C" int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_p
                          : launch_gemm_planes<MORL_FMT_F16X2, 0>(tmA, tmB, tmBh, tmC, g, pair, sms, st);
     return split_acc ? launch_gemm_planes<MORL_FMT_BF16X3, 1>(tmA, tmB, tmBh, tmC, g, pair, sms, st)
                      : launch_gemm_planes<MORL_FMT_BF16X3, 0>(tmA, tmB, tmBh, tmC, g, pair, sms, st);
+}
+
+
+extern "C" int morl_gemm_chain_supported(int fmt, int M, int K) {
+    using namespace morl;
+    return fmt_ok(fmt) && M >= 2 * kGemmBM && K == 256;
+}
+
+// Several 256-wide hidden layers (Linear + ReLU, planes in / planes out) of one or two networks in ONE persistent launch: job (c, l) computes
+// act[c][l+1] = relu(act[c][l] . W[c][l]^T + bias[c][l]) exactly as morl_gemm_planes_f32 does (bit-identical), but a CTA pair takes its row tiles
+// through all layers, so intermediate activations are re-read from L2 instead of HBM (csrc: gemm_chain_kernel).
+extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const void* const* act_planes, long long act_plane_stride, const float* act_scale,
+                                   const void* const* w_planes, long long w_plane_stride, const float* const* w_scales, const float* const* biases,
+                                   void* const* relu_bits_out, int M, int K, void* stream) {
+    using namespace morl;
+    MORL_REQUIRE(act_planes && w_planes && biases, MORL_ERR_NULL, "morl_gemm_chain_f32: NULL pointer argument");
+    MORL_REQUIRE(n_chains >= 1 && n_chains <= 2 && n_layers >= 1 && n_chains * n_layers <= kChainMaxJobs, MORL_ERR_SHAPE,
+                 "morl_gemm_chain_f32: need 1 <= n_chains <= 2 and n_chains * n_layers <= %d (got %d x %d)", kChainMaxJobs, n_chains, n_layers);
+    MORL_REQUIRE(morl_gemm_chain_supported(fmt, M, K), MORL_ERR_UNSUPPORTED, "morl_gemm_chain_f32: unsupported configuration fmt=%d M=%d K=%d (256-wide layers, M >= 256)",
+                 fmt, M, K);
+    const int BK = fmt == MORL_FMT_F16X2 ? PlaneFmt<MORL_FMT_F16X2>::BK : PlaneFmt<MORL_FMT_BF16X3>::BK;
+    static ChainMaps maps;  // (host staging of the 3 x 8 tensor maps; copied into the kernel parameters by the launch)
+    ChainArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.K = K; g.n_chains = n_chains; g.n_layers = n_layers; g.a_scale = act_scale;
+    for (int c = 0; c < n_chains; ++c)
+        for (int l = 0; l < n_layers; ++l) {
+            const int job = c * n_layers + l;
+            const void* a_in = act_planes[c * (n_layers + 1) + l];
+            const void* a_out = act_planes[c * (n_layers + 1) + l + 1];
+            MORL_REQUIRE(a_in && a_out && w_planes[job] && aligned16(a_in) && aligned16(a_out) && aligned16(w_planes[job]), MORL_ERR_NULL,
+                         "morl_gemm_chain_f32: NULL or misaligned plane pointer (chain %d, layer %d)", c, l);
+            int rc = make_plane_map(&maps.A[job], fmt, a_in, M, K, act_plane_stride, kGemmBM, BK);
+            MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
+            rc = make_plane_map(&maps.B[job], fmt, w_planes[job], 256, K, w_plane_stride, 128, BK);
+            MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+            rc = make_plane_map(&maps.C[job], fmt, a_out, M, 256, act_plane_stride, 32, 32);
+            MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(C) failed (%d)", rc);
+            g.bias[job] = biases[job];
+            g.b_scale[job] = w_scales ? w_scales[job] : nullptr;
+            g.bits_out[job] = relu_bits_out ? static_cast<uint32_t*>(relu_bits_out[job]) : nullptr;
+            MORL_REQUIRE(aligned16(g.bits_out[job]), MORL_ERR_ALIGN, "morl_gemm_chain_f32: ReLU bit masks must be 16-byte aligned");
+        }
+    g.n_stages = fmt == MORL_FMT_F16X2 ? KPlan<2, MORL_FMT_F16X2>::kStages : KPlan<2, MORL_FMT_BF16X3>::kStages;
+    static const bool want_pdl = [] { const char* e = getenv("MORL_GEMM_PDL"); return !(e && e[0] == '0'); }();
+    g.pdl = want_pdl ? 1 : 0;
+    int sms = morl_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int n_tiles = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+    const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g.pdl ? 2 : 1;
+    if (fmt == MORL_FMT_F16X2) {
+        constexpr size_t smem = KPlan<2, MORL_FMT_F16X2>::kBytes;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(gemm_chain_kernel<MORL_FMT_F16X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchKernelEx(&cfg, gemm_chain_kernel<MORL_FMT_F16X2>, maps, g);
+    } else {
+        constexpr size_t smem = KPlan<2, MORL_FMT_BF16X3>::kBytes;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(gemm_chain_kernel<MORL_FMT_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchKernelEx(&cfg, gemm_chain_kernel<MORL_FMT_BF16X3>, maps, g);
+    }
+    return check_launch("morl_gemm_chain_f32");
 }

@@ -45,8 +45,11 @@ from ...common.weights import equally_spaced_weights, random_weights
 _FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
 # device PER: fork the priority / sum-tree branch after the backward GEMMs instead of right after the loss (MORL_DEFER_TREE=0: the earlier order)
 _DEFER_TREE = os.environ.get("MORL_DEFER_TREE", "1") != "0"
-# experiment: the online-net and target-net no-grad chains on two streams (MORL_TWO_STREAMS=1; needs the fused head)
-_TWO_STREAMS = os.environ.get("MORL_TWO_STREAMS", "0") == "1"
+# the online-net and target-net no-grad chains as two branches of the captured graph: one chain's kernels fill the launch gaps and tile
+# tails of the other's (+2 % on the update; MORL_TWO_STREAMS=0: one stream; needs the fused head)
+_TWO_STREAMS = os.environ.get("MORL_TWO_STREAMS", "1") == "1"
+# ... and the training pass's forward as a third branch (+1 %; MORL_THREE_STREAMS=0 disables it)
+_THREE_STREAMS = os.environ.get("MORL_THREE_STREAMS", "1") == "1"
 
 
 class QNet(nn.Module):
@@ -230,6 +233,7 @@ class Envelope(MOPolicy, MOAgent):
                 "pass use_tensor_cores=False to run the (slow) library-GEMM validation path explicitly")
         self.use_tensor_cores = bool(use_tensor_cores)
         self._tc_on = self._tc_tg = self._tc_train = None
+        self._nograd_chain = None
         self._dq = self._grad_bufs = None
         self._last_lazy, self._last_inds_v, self._last_priority_v, self._updates_done = False, None, None, 0
         self._side_pending = False
@@ -362,6 +366,7 @@ class Envelope(MOPolicy, MOAgent):
             "copy_stream": th.cuda.Stream(device=dev),
             "side_stream": th.cuda.Stream(device=dev),
             "side_stream2": th.cuda.Stream(device=dev),
+            "side_stream3": th.cuda.Stream(device=dev),
         }
         # where a caller that stages inputs on the device itself (bench.py's `value` arm) must write them: the staging buffer, not the
         # private copy the graph refreshes from it
@@ -401,13 +406,31 @@ class Envelope(MOPolicy, MOAgent):
                                                    share_weights_with=self._tc_on, trainable=True, split_acc=split)
                 # every weight plane this step needs (online, target, transposed-for-backward) in one launch
                 TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
+                early_q = None
+                if _THREE_STREAMS and self._tc_train is not None:
+                    # the training pass's forward (online net on s) does not depend on the targets: a third branch of the captured graph
+                    main, side3 = th.cuda.current_stream(), s["side_stream3"]
+                    side3.wait_stream(main)
+                    with th.cuda.stream(side3):
+                        dp_ = self._dp
+                        ws_ = wset if dp_ is None else wset[dp_["rank"] * dp_["w_loc"] : (dp_["rank"] + 1) * dp_["w_loc"]]
+                        early_q = self._tc_train.forward_pairs(obs, ws_)
                 fused_head = self.envelope and _FUSED_HEAD and self.tensor_core_accumulators != "split" and self._tc_on.head_operands() is not None \
                     and ops.qhead_envelope_supported(self._tc_fmt, B, W, A, D, self._tc_on.lin[-1].in_features)
                 self.fused_head_active = bool(fused_head)
                 if fused_head:
                     # output layers of both nets + envelope operator + Bellman line in ONE kernel: Q_on / Q_tg (envelope.py:420, :429) exist
                     # in tensor / shared memory only (csrc/qhead_envelope.cu; bit-identical to the three-launch chain below)
-                    if _TWO_STREAMS:
+                    if self._tc_on.chain_supported() and self._tc_tg.chain_supported():
+                        # hidden layers 2.. of BOTH nets in one persistent launch: a CTA pair takes each of its row tiles through all layers of
+                        # both nets, re-reading every intermediate activation from L2 (csrc/gemm_planes.cu: gemm_chain_kernel)
+                        if self._nograd_chain is None:
+                            self._nograd_chain = TCPairMlp.make_chain([self._tc_on, self._tc_tg])
+                        self._tc_on.layer1(nobs, wset)
+                        self._tc_tg.layer1(nobs, wset)
+                        self._nograd_chain()
+                        h_on, h_tg = self._tc_on.h[-1], self._tc_tg.h[-1]
+                    elif _TWO_STREAMS:
                         # the two no-grad chains are independent: fork the target-net chain onto a side stream (a parallel branch of the
                         # captured graph) so that its kernels fill the launch gaps and tile tails of the online-net chain
                         main, side = th.cuda.current_stream(), s["side_stream2"]
@@ -428,7 +451,7 @@ class Envelope(MOPolicy, MOAgent):
                     q_on = self._tc_on.forward_pairs(nobs, wset).view(B, W, A, D)  # online net selects   (envelope.py:420)
                     q_tg = self._tc_tg.forward_pairs(nobs, wset).view(B, W, A, D)  # target net evaluates (envelope.py:429)
             else:
-                fused_head = False
+                fused_head, early_q = False, None
                 q_on = self.q_net.forward_pairs(nobs, wset)
                 q_tg = self.target_q_net.forward_pairs(nobs, wset)
             done1 = done.reshape(-1)
@@ -451,7 +474,11 @@ class Envelope(MOPolicy, MOAgent):
                     Wt, lo = dp["w_loc"], dp["rank"] * dp["w_loc"]
                     wset_t = wset[lo : lo + Wt]
                     target_q = target_q.view(B, W, D)[:, lo : lo + Wt].reshape(B * Wt, D)
-                q_values = self._tc_train.forward_pairs(obs, wset_t).view(B * Wt, A, D)
+                if early_q is not None:
+                    th.cuda.current_stream().wait_stream(s["side_stream3"])
+                    q_values = early_q.view(B * Wt, A, D)
+                else:
+                    q_values = self._tc_train.forward_pairs(obs, wset_t).view(B * Wt, A, D)
                 if self._dq is None:
                     self._dq = th.empty_like(q_values)
                     self._grad_bufs = []

@@ -42,7 +42,8 @@ from torch import nn
 from . import ops
 
 _SNAKE = os.environ.get("MORL_TC_SNAKE", "1") == "1"          # alternate the GEMM tile order between chained layers
-_NARROW_HEAD = os.environ.get("MORL_NARROW_HEAD", "0") == "1"  # output layer through morl_qhead_gemm_f32 (opt-in until its first B200 run)
+_CHAIN = os.environ.get("MORL_GEMM_CHAIN", "0") == "1"        # hidden layers 2.. of a pass as one chained launch (opt-in until validated on a B200)
+_NARROW_HEAD = os.environ.get("MORL_NARROW_HEAD", "1") == "1"  # output layer through morl_qhead_gemm_f32 (19.7 us against 26 us in the update; =0: general kernel)
 _DEFAULT_FMT = ops.FMT_BF16X3 if os.environ.get("MORL_TC_FMT", "f16x2") == "bf16x3" else ops.FMT_F16X2
 
 ACT_SCALE = 2.0        # f16x2 activations: |h| < 32,752 representable
@@ -103,6 +104,7 @@ class TCPairMlp:
             self.wp = [ops.empty_planes(fmt, _pad(l.out_features, 32), l.in_features, dev) for l in self.lin[1:]]
             self.s_w = [ops.scale_tensor(1.0, dev) if scaled else None for _ in self.lin[1:]]
         self.q = th.empty((M, self.lin[-1].out_features), device=dev, dtype=th.float32)
+        self._chain = None
         self.trainable = trainable
         if trainable:
             if n_w > 64:
@@ -194,6 +196,11 @@ class TCPairMlp:
         hb = self.hbits if self.trainable else [None] * len(self.h)
         a = ops.pairs_relu_split(u, v, out=self.h[0], scale=self.s_act, relu_bits_out=hb[0])
         n = len(self.lin)
+        if self.chain_supported():
+            if self._chain is None:
+                self._chain = TCPairMlp.make_chain([self])
+            self._chain()  # hidden layers 2.. in one persistent launch (intermediate activations re-read from L2)
+            return self.h[-1]
         for k in range(1, n - 1):
             l = self.lin[k]
             # alternate the tile order: a layer starts on the rows its producer wrote last (L2-resident)
@@ -201,6 +208,34 @@ class TCPairMlp:
                                    reverse_tiles=_SNAKE and bool(k & 1), a_scale=self.s_act, b_scale=self.s_w[k - 1], c_scale=self.s_act,
                                    split_acc=self.split_acc, relu_bits_out=hb[k])
         return a
+
+    # ------------------------------------------------------------------------------------------------ chained hidden layers
+    def chain_supported(self) -> bool:
+        """Hidden layers 2.. as ONE launch (ops.GemmChain): 256-wide square layers, single accumulator, at least two 128-row tiles."""
+        hid = [l.out_features for l in self.lin[:-1]]
+        return (_CHAIN and not self.split_acc and len(hid) >= 2 and all(h == 256 for h in hid)
+                and ops.gemm_chain_supported(self.fmt, self.B * self.W, 256))
+
+    def layer1(self, feats: th.Tensor, wset: th.Tensor) -> th.Tensor:
+        """Layer 1 only (separable first layer): h1 planes (+ ReLU bits when trainable)."""
+        first = self.lin[0]
+        u, v = ops.pair_layer1_uv(feats, wset, first.weight.detach(), first.bias.detach())
+        hb = self.hbits if self.trainable else [None] * len(self.h)
+        return ops.pairs_relu_split(u, v, out=self.h[0], scale=self.s_act, relu_bits_out=hb[0])
+
+    def chain_spec(self):
+        """(activations, weight planes, biases, weight scales, ReLU bit tensors) of the hidden layers 2.. for ops.GemmChain."""
+        n = len(self.lin)
+        hb = self.hbits if self.trainable else [None] * len(self.h)
+        return (list(self.h), [self.wp[k - 1] for k in range(1, n - 1)], [self.lin[k].bias for k in range(1, n - 1)],
+                [self.s_w[k - 1] for k in range(1, n - 1)], [hb[k] for k in range(1, n - 1)])
+
+    @staticmethod
+    def make_chain(plans):
+        """One chained launch for the hidden layers 2.. of one plan, or of two plans of equal shape (the two no-grad passes)."""
+        specs = [p.chain_spec() for p in plans]
+        return ops.GemmChain([sp[0] for sp in specs], [sp[1] for sp in specs], [sp[2] for sp in specs], [sp[3] for sp in specs],
+                             [sp[4] for sp in specs], act_scale=plans[0].s_act)
 
     def head_operands(self):
         """(weight planes [P, 32, K], weight scale, bias) of the output layer, or None if it is wider than 32 columns."""

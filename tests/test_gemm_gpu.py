@@ -402,3 +402,52 @@ def test_multi_split_auto_scale(cuda):
     rec2 = _sum(outs[2])[:24] / float(s2)
     assert float((rec2 - w2.double()).abs().max()) <= 2.0**-21 * float(w2.abs().max())
     assert ops.plane_overflow_count() == 0
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("n_chains,M,n_layers", [(2, 65536, 3), (1, 65536, 3), (2, 38400, 2), (1, 1280, 3), (2, 1000, 3), (1, 512, 1), (2, 19200, 4)])
+def test_gemm_chain_equals_per_layer_launches(cuda, fmt, n_chains, M, n_layers):
+    """morl_gemm_chain_f32 (hidden layers of one / two networks in ONE persistent launch; intermediate activations re-read from L2) must
+    reproduce the per-layer morl_gemm_planes_f32 launches BIT FOR BIT: every intermediate and final activation plane and every ReLU bit
+    mask.  Shapes: the north-star row count (256 tiles on 74 pairs: groups of 2 + 2 / 2 + 1 tiles), fewer tiles than pairs, a ragged last
+    tile (M = 1000), a single layer, four layers (8 jobs)."""
+    from morl_baselines_b200 import ops
+
+    H = 256
+    g = th.Generator(device=cuda).manual_seed(M + 7 * n_chains + n_layers)
+    sa = _scale(fmt, 2.0, cuda)
+    chains = []
+    for c in range(n_chains):
+        x = th.randn(M, H, device=cuda, generator=g).relu_()
+        a0 = ops.split_planes(x, fmt, rows_pad=M, ldp=H, scale=sa)
+        ws, bs, sws = [], [], []
+        for l in range(n_layers):
+            w = th.randn(H, H, device=cuda, generator=g) / 16.0
+            sw = _scale(fmt, 2048.0 * (1 + l), cuda)
+            ws.append(ops.split_planes(w, fmt, rows_pad=H, ldp=H, scale=sw))
+            sws.append(sw)
+            bs.append(th.randn(H, device=cuda, generator=g) * 0.1)
+        chains.append((a0, ws, bs, sws))
+    # reference: one launch per layer
+    ref_acts, ref_bits = [], []
+    for a0, ws, bs, sws in chains:
+        a, acts, bits = a0, [], []
+        for l in range(n_layers):
+            bt = ops.empty_relu_bits(M, cuda).zero_()
+            _, a = ops.gemm_planes(a, ws[l], H, bias=bs[l], relu=True, out_f32=False, out_planes=True, a_scale=sa, b_scale=sws[l], c_scale=sa, relu_bits_out=bt)
+            acts.append(a)
+            bits.append(bt)
+        ref_acts.append(acts)
+        ref_bits.append(bits)
+    # chained launch into fresh buffers
+    outs = [[ops.empty_planes(fmt, M, H, cuda).zero_() for _ in range(n_layers)] for _ in range(n_chains)]
+    obits = [[ops.empty_relu_bits(M, cuda).zero_() for _ in range(n_layers)] for _ in range(n_chains)]
+    chain = ops.GemmChain([[chains[c][0]] + outs[c] for c in range(n_chains)], [chains[c][1] for c in range(n_chains)], [chains[c][2] for c in range(n_chains)],
+                          None if fmt != ops.FMT_F16X2 else [chains[c][3] for c in range(n_chains)], obits, act_scale=sa)
+    for _ in range(2):  # (twice: the second launch overwrites identical values, a stale-read would not survive the comparison of layer 1 only)
+        chain()
+    th.cuda.synchronize()
+    for c in range(n_chains):
+        for l in range(n_layers):
+            assert th.equal(outs[c][l].view(th.int16), ref_acts[c][l].view(th.int16)), f"planes differ: chain {c} layer {l}"
+            assert th.equal(obits[c][l], ref_bits[c][l]), f"ReLU bits differ: chain {c} layer {l}"
