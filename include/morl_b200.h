@@ -313,18 +313,20 @@ MORL_API int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_pla
                                   long long c_plane_stride, const float* c_scale, int reverse_tiles, int split_accumulators,
                                   const void* relu_bits_in, void* relu_bits_out, void* stream);
 /* Several 256-wide hidden layers (Linear + ReLU) of one or two networks in ONE persistent launch (csrc/gemm_planes.cu: gemm_chain_kernel):
- * job (c, l):  act[c][l+1] = relu(act[c][l] . W[c][l]^T + bias[c][l]),  planes in / planes out at the activation scale `act_scale`,
- * bit-identical to n_chains * n_layers calls of morl_gemm_planes_f32 (relu, c_scale = a_scale) -- but a CTA pair takes each of its 256-row tiles
+ * job (c, l):  act[c][l+1] = f(act[c][l] . W[c][l]^T + bias[c][l]),  planes in / planes out at the scale `act_scale`; f = ReLU (relu != 0:
+ * forward chains, optionally recording the ReLU bit masks) or the ReLU-backward mask relu_bits_in[job] (dX chains of the backward pass:
+ * G_{l-1} = (G_l . W_l) * relu'(H_{l-1}), biases NULL) --
+ * bit-identical to n_chains * n_layers calls of morl_gemm_planes_f32 (c_scale = a_scale) -- but a CTA pair takes each of its 256-row tiles
  * through all layers, so every intermediate activation is re-read from the L2 it was just written to instead of from HBM, and the launch
  * prologue / drain is paid once.  Replaces the per-layer launches behind the reference's hidden nn.Linear + ReLU stack (networks.py:10-48) in the
  * no-grad passes (both networks at once: n_chains = 2) and in the training pass (n_chains = 1, with ReLU bit masks).
  *   act_planes [n_chains * (n_layers + 1)] : plane tensors [P][M][256] (host array of device pointers; index c * (n_layers + 1) + l);
- *   w_planes / w_scales / biases / relu_bits_out [n_chains * n_layers] (index c * n_layers + l; w_scales / relu_bits_out and their entries nullable).
+ *   w_planes / w_scales / biases / relu_bits_in / relu_bits_out [n_chains * n_layers] (index c * n_layers + l; all but w_planes nullable, also per entry).
  * morl_gemm_chain_supported: K == 256 (square 256-wide layers), M >= 256. */
 MORL_API int morl_gemm_chain_supported(int fmt, int M, int K);
 MORL_API int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const void* const* act_planes, long long act_plane_stride, const float* act_scale,
                                  const void* const* w_planes, long long w_plane_stride, const float* const* w_scales, const float* const* biases,
-                                 void* const* relu_bits_out, int M, int K, void* stream);
+                                 int relu, const void* const* relu_bits_in, void* const* relu_bits_out, int M, int K, void* stream);
 /* Diagnostics (not part of the reference surface): per-role cycle counters of morl_gemm_planes_f32, summed over CTAs and launches
  * since the last reset; collected only when the environment variable MORL_GEMM_STATS=1 is set before the first GEMM call.
  * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,

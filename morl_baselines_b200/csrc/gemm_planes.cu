@@ -534,7 +534,9 @@ struct ChainArgs {
     const float* bias[kChainMaxJobs];
     const float* b_scale[kChainMaxJobs];
     uint32_t* bits_out[kChainMaxJobs];  // ReLU bit masks of the job's output, or nullptr
+    const uint32_t* bits_in[kChainMaxJobs];  // ReLU-backward masks applied to the job's output (dX chains), or nullptr
     const float* a_scale;          // activation scale (input AND output of every layer), device scalar or nullptr
+    int relu;                      // max(x, 0) on every job's output (forward chains)
     int n_stages;
     int pdl;
 };
@@ -703,11 +705,14 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     // x * s_act = acc * (s_act / (s_act * sB)) + s_act * bias  (powers of two: exact), as gemm_planes_kernel's folded epilogue
                     const float k_acc = s_act / (s_act * ld_scale(g.b_scale[job]));
                     uint32_t* bits_out = g.bits_out[job];
+                    const uint32_t* bits_in = g.bits_in[job];
                     uint4 out_bits = make_uint4(0u, 0u, 0u, 0u);
-                    g_mbar_wait(&tfull[as], (it >> 1) & 1u);
-                    tc_fence_after();
                     const int row = (tile * 2 + (int)cta_rank) * kGemmBM + quad * 32 + lane;
                     const bool row_ok = row < g.M;
+                    uint4 in_bits = make_uint4(0u, 0u, 0u, 0u);  // (independent of the MMAs: in flight while this warp waits for the accumulator)
+                    if (bits_in && row_ok) in_bits = __ldg(reinterpret_cast<const uint4*>(bits_in + (size_t)row * 8 + half * 4));
+                    g_mbar_wait(&tfull[as], (it >> 1) & 1u);
+                    tc_fence_after();
                     const uint32_t t_row = tmem_base + as * 256u + ((uint32_t)(quad * 32) << 16);
                     uint32_t va[32], vb[32];
                     auto process = [&](const uint32_t (&v)[32], int n0) {
@@ -715,7 +720,15 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float f = __fmaf_rn(__uint_as_float(v[j]), k_acc, bias_s[n0 + j]);
-                            x[j] = (f < 0.f) ? 0.f : f;  // ReLU (NaN stays NaN)
+                            if (g.relu) f = (f < 0.f) ? 0.f : f;  // (NaN stays NaN)
+                            x[j] = f;
+                        }
+                        if (bits_in) {
+                            const int i4 = n0 >> 6;
+                            const uint32_t keep = i4 == 0 ? in_bits.x : (i4 == 1 ? in_bits.y : (i4 == 2 ? in_bits.z : in_bits.w));
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (!((keep >> j) & 1u)) x[j] = 0.f;
                         }
                         if (bits_out) {
                             uint32_t positive = 0;
@@ -1943,9 +1956,9 @@ extern "C" int morl_gemm_chain_supported(int fmt, int M, int K) {
 // through all layers, so intermediate activations are re-read from L2 instead of HBM (csrc: gemm_chain_kernel).
 extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const void* const* act_planes, long long act_plane_stride, const float* act_scale,
                                    const void* const* w_planes, long long w_plane_stride, const float* const* w_scales, const float* const* biases,
-                                   void* const* relu_bits_out, int M, int K, void* stream) {
+                                   int relu, const void* const* relu_bits_in, void* const* relu_bits_out, int M, int K, void* stream) {
     using namespace morl;
-    MORL_REQUIRE(act_planes && w_planes && biases, MORL_ERR_NULL, "morl_gemm_chain_f32: NULL pointer argument");
+    MORL_REQUIRE(act_planes && w_planes, MORL_ERR_NULL, "morl_gemm_chain_f32: NULL pointer argument");
     MORL_REQUIRE(n_chains >= 1 && n_chains <= 2 && n_layers >= 1 && n_chains * n_layers <= kChainMaxJobs, MORL_ERR_SHAPE,
                  "morl_gemm_chain_f32: need 1 <= n_chains <= 2 and n_chains * n_layers <= %d (got %d x %d)", kChainMaxJobs, n_chains, n_layers);
     MORL_REQUIRE(morl_gemm_chain_supported(fmt, M, K), MORL_ERR_UNSUPPORTED, "morl_gemm_chain_f32: unsupported configuration fmt=%d M=%d K=%d (256-wide layers, M >= 256)",
@@ -1954,7 +1967,7 @@ extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const vo
     static ChainMaps maps;  // (host staging of the 3 x 8 tensor maps; copied into the kernel parameters by the launch)
     ChainArgs g;
     memset(&g, 0, sizeof(g));
-    g.M = M; g.K = K; g.n_chains = n_chains; g.n_layers = n_layers; g.a_scale = act_scale;
+    g.M = M; g.K = K; g.n_chains = n_chains; g.n_layers = n_layers; g.a_scale = act_scale; g.relu = relu ? 1 : 0;
     for (int c = 0; c < n_chains; ++c)
         for (int l = 0; l < n_layers; ++l) {
             const int job = c * n_layers + l;
@@ -1968,10 +1981,11 @@ extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const vo
             MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
             rc = make_plane_map(&maps.C[job], fmt, a_out, M, 256, act_plane_stride, 32, 32);
             MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(C) failed (%d)", rc);
-            g.bias[job] = biases[job];
+            g.bias[job] = biases ? biases[job] : nullptr;
             g.b_scale[job] = w_scales ? w_scales[job] : nullptr;
             g.bits_out[job] = relu_bits_out ? static_cast<uint32_t*>(relu_bits_out[job]) : nullptr;
-            MORL_REQUIRE(aligned16(g.bits_out[job]), MORL_ERR_ALIGN, "morl_gemm_chain_f32: ReLU bit masks must be 16-byte aligned");
+            g.bits_in[job] = relu_bits_in ? static_cast<const uint32_t*>(relu_bits_in[job]) : nullptr;
+            MORL_REQUIRE(aligned16(g.bits_out[job]) && aligned16(g.bits_in[job]), MORL_ERR_ALIGN, "morl_gemm_chain_f32: ReLU bit masks must be 16-byte aligned");
         }
     g.n_stages = fmt == MORL_FMT_F16X2 ? KPlan<2, MORL_FMT_F16X2>::kStages : KPlan<2, MORL_FMT_BF16X3>::kStages;
     static const bool want_pdl = [] { const char* e = getenv("MORL_GEMM_PDL"); return !(e && e[0] == '0'); }();

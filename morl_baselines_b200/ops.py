@@ -515,9 +515,10 @@ def gemm_chain_supported(fmt: int, M: int, K: int) -> bool:
 class GemmChain:
     """Static plan of a chained launch (:func:`gemm_chain`): the pointer tables are built once, a call is one launch.
     ``acts[c]``: the n_layers + 1 plane tensors [P, M, 256] of chain c (input, then every layer's output); ``weights[c]`` / ``w_scales[c]`` /
-    ``biases[c]`` / ``bits[c]``: per layer (``bits`` entries / ``w_scales`` may be None)."""
+    ``biases[c]`` / ``bits[c]`` (ReLU masks recorded) / ``bits_in[c]`` (ReLU-backward masks applied): per layer, all optional.  ``relu``: ReLU on every
+    output (forward chains); False for the dX chains of the backward pass."""
 
-    def __init__(self, acts, weights, biases, w_scales=None, bits=None, act_scale=None):
+    def __init__(self, acts, weights, biases=None, w_scales=None, bits=None, act_scale=None, relu: bool = True, bits_in=None):
         import ctypes as C
 
         self.n_chains, self.n_layers = len(acts), len(weights[0])
@@ -526,7 +527,8 @@ class GemmChain:
         _, self.M, self.K = a0.shape
         flat_a = [t for ch in acts for t in ch]
         flat_w = [t for ch in weights for t in ch]
-        flat_b = [t.detach() for ch in biases for t in ch]
+        flat_b = [None] * len(flat_w) if biases is None else [t.detach() for ch in biases for t in ch]
+        flat_i = [None] * len(flat_w) if bits_in is None else [t for ch in bits_in for t in ch]
         flat_s = [None] * len(flat_w) if w_scales is None else [t for ch in w_scales for t in ch]
         flat_m = [None] * len(flat_w) if bits is None else [t for ch in bits for t in ch]
         if len(flat_a) != self.n_chains * (self.n_layers + 1) or any(len(w) != self.n_layers for w in weights):
@@ -537,17 +539,18 @@ class GemmChain:
         for t in flat_w:
             if fmt_of(t) != self.fmt or tuple(t.shape[1:]) != (256, self.K) or t.stride(1) != self.K or t.stride(0) != flat_w[0].stride(0):
                 raise _lib.MorlB200Error("GemmChain: weight planes must be [P, 256, K], K-major")
-        for t in flat_m:
+        for t in flat_m + flat_i:
             if t is not None and (t.dtype != th.int32 or tuple(t.shape) != (self.M, 8) or not t.is_contiguous()):
                 raise _lib.MorlB200Error(f"GemmChain: ReLU bit masks must be contiguous int32 [{self.M}, 8]")
-        self._keep = (flat_a, flat_w, flat_b, flat_s, flat_m, act_scale)
+        self._keep = (flat_a, flat_w, flat_b, flat_s, flat_m, flat_i, act_scale)
+        self.relu = bool(relu)
         arr = lambda ts: (C.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])  # noqa: E731
-        self._pa, self._pw, self._pb, self._ps, self._pm = arr(flat_a), arr(flat_w), arr(flat_b), arr(flat_s), arr(flat_m)
+        self._pa, self._pw, self._pb, self._ps, self._pm, self._pi = arr(flat_a), arr(flat_w), arr(flat_b), arr(flat_s), arr(flat_m), arr(flat_i)
         self._a_stride, self._w_stride, self._act_scale = a0.stride(0), flat_w[0].stride(0), act_scale
 
     def __call__(self):
         rc = _lib.load().morl_gemm_chain_f32(self.fmt, self.n_chains, self.n_layers, self._pa, self._a_stride, _ptr(self._act_scale), self._pw, self._w_stride,
-                                             self._ps, self._pb, self._pm, self.M, self.K, _stream())
+                                             self._ps, self._pb, int(self.relu), self._pi, self._pm, self.M, self.K, _stream())
         _lib.check(rc, "morl_gemm_chain_f32")
         _count()
 

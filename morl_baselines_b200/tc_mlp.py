@@ -42,7 +42,8 @@ from torch import nn
 from . import ops
 
 _SNAKE = os.environ.get("MORL_TC_SNAKE", "1") == "1"          # alternate the GEMM tile order between chained layers
-_CHAIN = os.environ.get("MORL_GEMM_CHAIN", "0") == "1"        # hidden layers 2.. of a pass as one chained launch (opt-in until validated on a B200)
+_CHAIN = os.environ.get("MORL_GEMM_CHAIN", "1") == "1"        # hidden layers 2.. of a pass as ONE chained launch (+10 % on the update; =0: one launch per layer)
+_CHAIN_BWD = os.environ.get("MORL_GEMM_CHAIN_BWD", "0") == "1"  # ... and the 256-wide dX products of the backward pass (opt-in until validated)
 _NARROW_HEAD = os.environ.get("MORL_NARROW_HEAD", "1") == "1"  # output layer through morl_qhead_gemm_f32 (19.7 us against 26 us in the update; =0: general kernel)
 _DEFAULT_FMT = ops.FMT_BF16X3 if os.environ.get("MORL_TC_FMT", "f16x2") == "bf16x3" else ops.FMT_F16X2
 
@@ -104,7 +105,7 @@ class TCPairMlp:
             self.wp = [ops.empty_planes(fmt, _pad(l.out_features, 32), l.in_features, dev) for l in self.lin[1:]]
             self.s_w = [ops.scale_tensor(1.0, dev) if scaled else None for _ in self.lin[1:]]
         self.q = th.empty((M, self.lin[-1].out_features), device=dev, dtype=th.float32)
-        self._chain = None
+        self._chain = self._gchain = self._gbufs = None
         self.trainable = trainable
         if trainable:
             if n_w > 64:
@@ -260,6 +261,8 @@ class TCPairMlp:
         if self.s_g is not None:
             ops.amax_scale(dq, G_TARGET_EXP, self.s_g, self.ws_amax)  # this update's gradient scale
         G = ops.split_planes(dq, self.fmt, rows_pad=dq.shape[0], ldp=self.ld_last, out=self.g_last, scale=self.s_g)
+        if _CHAIN_BWD and self.chain_supported() and n >= 4:
+            return self._backward_chained(feats, wset, G, grads, after_gemms)
         for k in range(n - 1, 0, -1):
             l = self.lin[k]
             # dW_k = G_k^T H_{k-1} and db_k = colsum(G_k) in one pass over the G planes
@@ -276,6 +279,43 @@ class TCPairMlp:
         dU, dV = ops.pairs_grad_reduce(G, self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV, scale=self.s_g)
         grads[0], grads[1] = ops.pair_layer1_grad(dU, dV, feats, wset, dW1=grads[0], db1=grads[1], workspace=self.ws_l1)
         return grads
+
+
+def _backward_chained(self, feats, wset, G, grads, after_gemms):
+    """Backward with the 256-wide dX products as ONE chained launch: G_{n-2} from the (narrow) output layer as before, then
+    G_{k-1} = (G_k . W_k) * relu'(H_{k-1}) for k = n-2 .. 1 in one persistent kernel (each G_k in its own buffer: the weight-gradient
+    products read them afterwards), then the n-1 weight-gradient GEMMs."""
+    n = len(self.lin)
+    dev = G.device
+    if self._gchain is None:
+        M, hid = self.B * self.W, self.lin[1].in_features
+        self._gbufs = [ops.empty_planes(self.fmt, M, hid, dev) for _ in range(n - 1)]  # G_{n-2}, ..., G_0 (G_k = dL/dh_{k+1} ... see below)
+        # chain input = dL/dh_{n-1} (output of the narrow dX product), outputs dL/dh_{n-2}, ..., dL/dh_1
+        ks = list(range(n - 2, 0, -1))  # layers whose dX product is in the chain
+        self._gchain = ops.GemmChain([self._gbufs], [[self.wtp[k - 1] for k in ks]], None, [[self.s_w[k - 1] for k in ks]], None, act_scale=self.s_g,
+                                     relu=False, bits_in=[[self.hbits[k - 1] for k in ks]])
+    last = self.lin[n - 1]
+    if grads[2 * (n - 1) + 1] is None:
+        grads[2 * (n - 1) + 1] = th.empty(last.out_features, device=dev, dtype=th.float32)
+    grads[2 * (n - 1)] = ops.gemm_planes_mn(G, last.out_features, self.h[n - 2], last.in_features, out=grads[2 * (n - 1)], workspace=self.ws_mn,
+                                            colsum=grads[2 * (n - 1) + 1], g_scale=self.s_g, h_scale=self.s_act)
+    ops.gemm_planes(G, self.wtp[n - 2], last.in_features, relu_bits_in=self.hbits[n - 2], out_f32=False, out_planes=True, c_planes=self._gbufs[0],
+                    a_scale=self.s_g, b_scale=self.s_w[n - 2], c_scale=self.s_g, split_acc=False)
+    self._gchain()
+    for i, k in enumerate(range(n - 2, 0, -1)):  # dW_k = (dL/dh_k)^T H_{k-1}: dL/dh_k is _gbufs[i]
+        l = self.lin[k]
+        if grads[2 * k + 1] is None:
+            grads[2 * k + 1] = th.empty(l.out_features, device=dev, dtype=th.float32)
+        grads[2 * k] = ops.gemm_planes_mn(self._gbufs[i], l.out_features, self.h[k - 1], l.in_features, out=grads[2 * k], workspace=self.ws_mn,
+                                          colsum=grads[2 * k + 1], g_scale=self.s_g, h_scale=self.s_act)
+    if after_gemms is not None:
+        after_gemms()
+    dU, dV = ops.pairs_grad_reduce(self._gbufs[n - 2], self.B, self.W, workspace=self.ws_red, dU=self.dU, dV=self.dV, scale=self.s_g)
+    grads[0], grads[1] = ops.pair_layer1_grad(dU, dV, feats, wset, dW1=grads[0], db1=grads[1], workspace=self.ws_l1)
+    return grads
+
+
+TCPairMlp._backward_chained = _backward_chained
 
 
 class TCPairMlpFn(th.autograd.Function):

@@ -178,3 +178,35 @@ def test_narrow_head_gemm_equals_general_gemm(cuda, M, N, K):
         ops.qhead_gemm(a, w, N, bias, out=out, a_scale=s_a, w_scale=s_w, reverse_tiles=rev)
         assert th.equal(out, ref)
     assert not ops.qhead_gemm_supported(fmt, 100, N, K) and not ops.qhead_gemm_supported(fmt, M, 40, K)
+
+
+def test_chained_passes_equal_per_layer_passes(cuda):
+    """TCPairMlp forward / backward with the hidden layers as chained launches (forward chain, dX chain) == the per-layer launches, bit for
+    bit: Q, every gradient tensor."""
+    from torch import nn
+
+    from morl_baselines_b200 import ops, tc_mlp
+
+    th.manual_seed(3)
+    B, W, F, D, H, OUT = 64, 8, 12, 3, 256, 12
+    net = nn.Sequential(nn.Linear(F + D, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, OUT)).to(cuda)
+    feats, wset = th.randn(B, F, device=cuda), th.rand(W, D, device=cuda)
+    dq = th.randn(B * W, OUT, device=cuda) * 1e-3
+    results = []
+    saved = (tc_mlp._CHAIN, tc_mlp._CHAIN_BWD)
+    try:
+        for chain in (False, True):
+            tc_mlp._CHAIN, tc_mlp._CHAIN_BWD = chain, chain
+            plan = tc_mlp.TCPairMlp(net, F, B, W, trainable=True)
+            assert plan.chain_supported() == chain
+            plan.refresh_weights()
+            q = plan.forward_pairs(feats, wset).clone()
+            grads = [g.clone() for g in plan.backward(feats, wset, dq)]
+            th.cuda.synchronize()
+            results.append((q, grads))
+    finally:
+        tc_mlp._CHAIN, tc_mlp._CHAIN_BWD = saved
+    (q0, g0), (q1, g1) = results
+    assert th.equal(q0, q1)
+    for a, b in zip(g0, g1):
+        assert th.equal(a, b)
