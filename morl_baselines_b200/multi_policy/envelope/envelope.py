@@ -43,6 +43,7 @@ from ...common.weights import equally_spaced_weights, random_weights
 # output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu: 29.4 us against 57.7 us for the three-launch chain at
 # the north-star shape, bit-identical -- profiles/r02_qhead_time.txt); MORL_FUSED_HEAD=0 keeps the three-launch chain (A/B runs)
 _FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
+_HEAD_REVERSE = os.environ.get("MORL_HEAD_REVERSE", "0") == "1"  # experiment: fused head walks the tiles from the last one after a chained pass
 # device PER: fork the priority / sum-tree branch after the backward GEMMs instead of right after the loss (MORL_DEFER_TREE=0: the earlier order)
 _DEFER_TREE = os.environ.get("MORL_DEFER_TREE", "1") != "0"
 # the online-net and target-net no-grad chains as two branches of the captured graph: one chain's kernels fill the launch gaps and tile
@@ -418,6 +419,7 @@ class Envelope(MOPolicy, MOAgent):
                 fused_head = self.envelope and _FUSED_HEAD and self.tensor_core_accumulators != "split" and self._tc_on.head_operands() is not None \
                     and ops.qhead_envelope_supported(self._tc_fmt, B, W, A, D, self._tc_on.lin[-1].in_features)
                 self.fused_head_active = bool(fused_head)
+                head_reverse = False
                 if fused_head:
                     # output layers of both nets + envelope operator + Bellman line in ONE kernel: Q_on / Q_tg (envelope.py:420, :429) exist
                     # in tensor / shared memory only (csrc/qhead_envelope.cu; bit-identical to the three-launch chain below)
@@ -430,6 +432,7 @@ class Envelope(MOPolicy, MOAgent):
                         self._tc_tg.layer1(nobs, wset)
                         self._nograd_chain()
                         h_on, h_tg = self._tc_on.h[-1], self._tc_tg.h[-1]
+                        head_reverse = _HEAD_REVERSE  # the chain wrote its highest tiles last: start the head on them (still in L2)
                     elif _TWO_STREAMS:
                         # the two no-grad chains are independent: fork the target-net chain onto a side stream (a parallel branch of the
                         # captured graph) so that its kernels fill the launch gaps and tile tails of the online-net chain
@@ -445,7 +448,7 @@ class Envelope(MOPolicy, MOAgent):
                     (w_on, sw_on, b_on), (w_tg, sw_tg, b_tg) = self._tc_on.head_operands(), self._tc_tg.head_operands()
                     target_q, _, _ = ops.qhead_envelope_td(h_on, h_tg, w_on, w_tg, b_on.detach(), b_tg.detach(), wset, rew, done.reshape(-1), self.gamma,
                                                            B, W, A, D, self.dot_mode, ops.ROWS_BMAJOR, a_scale_on=self._tc_on.s_act,
-                                                           a_scale_tg=self._tc_tg.s_act, w_scale_on=sw_on, w_scale_tg=sw_tg)
+                                                           a_scale_tg=self._tc_tg.s_act, w_scale_on=sw_on, w_scale_tg=sw_tg, reverse_tiles=head_reverse)
                     q_on = q_tg = None
                 else:
                     q_on = self._tc_on.forward_pairs(nobs, wset).view(B, W, A, D)  # online net selects   (envelope.py:420)
