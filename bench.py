@@ -208,6 +208,56 @@ def time_qhead_kernel(dev, replays=12):
     return e0.elapsed_time(e1) * 1e-3 / (replays * 2 * nsets)
 
 
+def time_chain_kernel(dev, replays=10):
+    """Average launch duration of the dominant kernel of the step, morl_gemm_chain_f32 in the form the two no-grad passes use it: hidden layers
+    2..4 of BOTH networks (2 chains x 3 layers of 65,536 x 256 x 256, bias + ReLU + plane re-split epilogue) in ONE persistent launch.  4 launches
+    on 2 rotating sets of activation buffers (2 x 8 x 67 MB, far above L2) captured in one CUDA graph, CUDA events around the replays."""
+    import torch as th
+
+    from morl_baselines_b200 import ops
+
+    fmt, M, H, L = ops.FMT_F16X2, B * W, NET[0], len(NET) - 1
+    g = th.Generator(device=dev).manual_seed(4)
+    sa = ops.scale_tensor(2.0, dev)
+    sets = []
+    for _ in range(2):
+        acts, ws, bs, sws = [], [], [], []
+        for c in range(2):
+            a0 = ops.split_planes(th.randn(M, H, device=dev, generator=g).relu_(), fmt, rows_pad=M, ldp=H, scale=sa)
+            acts.append([a0] + [ops.empty_planes(fmt, M, H, dev) for _ in range(L)])
+            sw = [ops.scale_tensor(2048.0, dev) for _ in range(L)]
+            ws.append([ops.split_planes(th.randn(H, H, device=dev, generator=g) / 16.0, fmt, rows_pad=H, ldp=H, scale=sw[l]) for l in range(L)])
+            bs.append([th.randn(H, device=dev, generator=g) * 0.1 for _ in range(L)])
+            sws.append(sw)
+        sets.append(ops.GemmChain(acts, ws, bs, sws, None, act_scale=sa))
+
+    def sweep():
+        for _ in range(2):
+            for ch in sets:
+                ch()
+
+    side = th.cuda.Stream()
+    side.wait_stream(th.cuda.current_stream())
+    with th.cuda.stream(side):
+        sweep()
+    th.cuda.current_stream().wait_stream(side)
+    graph = th.cuda.CUDAGraph()
+    with th.cuda.graph(graph):
+        sweep()
+    for _ in range(2):
+        graph.replay()
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        graph.replay()
+    e1.record()
+    th.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / (replays * 4)
+    n_prod = 2 * L
+    return t, n_prod, 3 * 2 * M * H * H * n_prod, (2 + n_prod) * 4 * M * H + n_prod * 4 * H * H  # s, layer products, MMA flops issued, algorithmic bytes
+
+
 def time_gemm_kernel(dev, iters=200, fmt=None):
     """Average launch duration of the dominant kernel of the step, morl_gemm_planes_f32 on one hidden layer of the pair batch
     (65,536 x 256 x 256, bias + ReLU + plane re-split epilogue), CUDA events around graph replays, 4 rotating activation sets (> L2).  Returns
@@ -526,6 +576,29 @@ def run_b200(args, rank, local_rank, world):
                  "replaces": "2 x morl_gemm_planes_f32 (N = 24) + morl_envelope_td_f32",
                  "timing": "8 launches on 4 rotating pairs of activation-plane tensors (4 x 2 x 67 MB > L2) in one CUDA graph, 12 replays, CUDA events"}
     mlp_flops = 5 * B * W * 211712 * 2  # 1.39e11 FLOP/update (2 no-grad fwd + fwd + 2x bwd)
+    standalone_env = {"bound": "hbm", "kernel": "envelope_td_wp_kernel<3,UNFUSED> (morl_envelope_td_f32 alone: Q_on / Q_tg read from HBM)", "achieved": achieved,
+                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                      "us_per_launch": t_kernel * 1e6, "peak_source": peak_src,
+                      "timing": "16 launches on rotating input sets (214 MB > L2) in one CUDA graph, 25 replays, CUDA events"}
+    gemm_layer = {"kernel": "gemm_planes_kernel<pair, f16x2> (ONE hidden layer 65536x256x256 per launch: the per-layer form the chained launch replaces)",
+                  "us_per_launch": t_gemm * 1e6, "hbm_frac": gemm_alg_bytes / t_gemm / 1e9 / hbm_peak, "tensor_frac": gemm_flops / t_gemm / 1e12 / bf16_peak}
+    chain_roofline = None
+    if agent.tensor_core_format == "f16x2" and _ops.gemm_chain_supported(_ops.FMT_F16X2, B * W, NET[0]) and os.environ.get("MORL_GEMM_CHAIN", "1") == "1":
+        t_ch, n_prod, ch_flops, ch_bytes = time_chain_kernel(dev)
+        # dominant kernel of the step: the chained hidden layers (3 launches per update, ~45 % of it).  Floors of the 6-product launch: tensor pipe
+        # 6 x 3 x 8.6 GFLOP / 1687 TFLOP/s = 91.6 us, HBM (2 inputs read + 6 outputs written, intermediates re-read from L2) 537 MB / 6.48 TB/s
+        # = 82.9 us -> the binding roofline is the tensor pipe; the HBM view is reported next to it
+        chain_roofline = {"bound": "tensor", "kernel": f"gemm_chain_kernel<f16x2> (hidden layers 2..4 of both Q-networks, {n_prod} products 65536x256x256 in ONE persistent "
+                                                       "launch, 3 fp16 tcgen05 MMAs per fp32 product, CTA pairs, bias + ReLU + re-split epilogue, intermediates re-read from L2)",
+                          "achieved": ch_flops / t_ch / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ch_flops / t_ch / 1e12 / bf16_peak,
+                          "traffic": None, "algorithmic_flops": ch_flops // 3, "algorithmic_tflops": ch_flops / 3 / t_ch / 1e12,
+                          "fp32_accurate_peak_tflops": bf16_peak / 3, "us_per_launch": t_ch * 1e6, "us_per_layer_product": t_ch * 1e6 / n_prod,
+                          "peak_source": peak_src,
+                          "hbm": {"algorithmic_bytes": ch_bytes, "achieved_gbs": ch_bytes / t_ch / 1e9, "peak": hbm_peak, "frac": ch_bytes / t_ch / 1e9 / hbm_peak},
+                          "timing": "4 launches on 2 rotating sets of activation buffers (2 x 8 x 67 MB > L2) captured in one CUDA graph, 10 replays, CUDA events"}
+        tf = os.path.join(ROOT, "profiles", "gemm_chain_traffic.json")
+        if os.path.exists(tf):
+            chain_roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -548,7 +621,7 @@ def run_b200(args, rank, local_rank, world):
         # format its HBM floor (plane bytes in + out) is above its tensor floor, so the binding roofline is HBM: `achieved` = algorithmic
         # plane bytes / time against the measured bandwidth; the tensor-pipe view (MMA flops actually issued against the measured dense
         # 16-bit peak; SURVEY 8(d)'s "FP32-accurate peak actually used" = peak / products) is reported under "tensor".
-        "roofline": {"bound": "hbm", "kernel": f"gemm_planes_kernel<pair, {agent.tensor_core_format}> (65536x256x256: one hidden layer of the pair batch, "
+        "roofline": chain_roofline if chain_roofline is not None else {"bound": "hbm", "kernel": f"gemm_planes_kernel<pair, {agent.tensor_core_format}> (65536x256x256: one hidden layer of the pair batch, "
                                                 f"{gemm_nprod} 16-bit tcgen05 products per fp32 product, CTA pairs, bias + ReLU + re-split epilogue)",
                      "achieved": gemm_alg_bytes / t_gemm / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": gemm_alg_bytes / t_gemm / 1e9 / hbm_peak,
                      "traffic": gemm_traffic, "algorithmic_bytes": gemm_alg_bytes, "us_per_launch": t_gemm * 1e6, "peak_source": peak_src,
@@ -557,12 +630,13 @@ def run_b200(args, rank, local_rank, world):
                                 "algorithmic_flops": gemm_flops // gemm_nprod, "algorithmic_tflops": gemm_flops / gemm_nprod / t_gemm / 1e12,
                                 "fp32_accurate_peak_tflops": bf16_peak / gemm_nprod},
                      "timing": "16 launches on 4 rotating activation sets (4 x 2 x 67 MB > L2) captured in one CUDA graph, 12 replays, CUDA events"},
+        "roofline_gemm_layer": gemm_layer,
         # the kernel north_star names: fused envelope-max TD target against the HBM roofline
-        "roofline_envelope": {"bound": "hbm", "kernel": "envelope_td_wp_kernel<3,UNFUSED>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                              "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "us_per_launch": t_kernel * 1e6,
-                              "peak_source": peak_src,
-                              "timing": "16 launches on rotating input sets (214 MB > L2) in one CUDA graph, 25 replays, CUDA events"},
-        "roofline_envelope_fused": fused,
+        # the kernel north_star names ("the envelope operator ... and the vector-reward Bellman target fused into one kernel"): the form the update
+        # runs -- output layers of both nets + operator + Bellman line in one kernel, Q never in HBM -- when the shape is inside it, else the
+        # standalone operator; the standalone operator (the C-ABI entry morl_envelope_td_f32, issue-bound: DESIGN 4.1) is always reported too
+        "roofline_envelope": fused if (fused is not None and fused["in_update"]) else standalone_env,
+        "roofline_envelope_operator": standalone_env,
         "mlp": {"flop_per_step": mlp_flops, "fp32_equivalent_tflops": mlp_flops / (ms / K * 1e-3) / 1e12,
                 "path": "layer 1 separable (one fp32 kernel on B + |W| rows), layers 2.. tcgen05 split-operand GEMMs forward and backward",
                 "note": "whole-step time used, so this is a lower bound on the dense-layer rate"},

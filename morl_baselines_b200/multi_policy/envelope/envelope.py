@@ -43,6 +43,7 @@ from ...common.weights import equally_spaced_weights, random_weights
 # output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu: 29.4 us against 57.7 us for the three-launch chain at
 # the north-star shape, bit-identical -- profiles/r02_qhead_time.txt); MORL_FUSED_HEAD=0 keeps the three-launch chain (A/B runs)
 _FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
+_PRE_REFRESH = os.environ.get("MORL_PRE_REFRESH", "0") == "1"  # experiment: weight-plane refresh on a side branch, under the tree walk + gather
 _HEAD_REVERSE = os.environ.get("MORL_HEAD_REVERSE", "0") == "1"  # experiment: fused head walks the tiles from the last one after a chained pass
 # device PER: fork the priority / sum-tree branch after the backward GEMMs instead of right after the loss (MORL_DEFER_TREE=0: the earlier order)
 _DEFER_TREE = os.environ.get("MORL_DEFER_TREE", "1") != "0"
@@ -405,8 +406,12 @@ class Envelope(MOPolicy, MOAgent):
                     if TCPairMlp.trainable_supported(self.q_net.net, W, self._tc_fmt):
                         self._tc_train = TCPairMlp(self.q_net.net, self.q_net.feat_dim, B, W if self._dp is None else self._dp["w_loc"],
                                                    share_weights_with=self._tc_on, trainable=True, split_acc=split)
-                # every weight plane this step needs (online, target, transposed-for-backward) in one launch
-                TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
+                # every weight plane this step needs (online, target, transposed-for-backward) in one launch (unless _step already did it on a
+                # side branch)
+                if getattr(self, "_planes_fresh", False):
+                    self._planes_fresh = False
+                else:
+                    TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
                 early_q = None
                 if _THREE_STREAMS and self._tc_train is not None:
                     # the training pass's forward (online net on s) does not depend on the targets: a third branch of the captured graph
@@ -536,10 +541,7 @@ class Envelope(MOPolicy, MOAgent):
         s["loss1"].copy_(loss)
         # loss + priorities to the host; with the sum tree in HBM the priority power, the ratchet and the tree write-back run here as well
         # (stream-ordered, no host wait), so every rank's tree is updated with the same values before its next walk
-        self._ship_results(raw, device_per)
-        if self._side_pending:
-            th.cuda.current_stream().wait_stream(s["side_stream"])
-            self._side_pending = False
+        self._ship_results(raw, device_per)  # (side stream: runs under Adam; joined before the next step's tree walk, in update())
         self.q_optim.step_fused(self.max_grad_norm)
 
     def _ship_results(self, raw, device_per: bool):
@@ -567,6 +569,15 @@ class Envelope(MOPolicy, MOAgent):
         src = s["copy_" + ("device" if mode == "device_per" else mode)][0]  # the segment of the staging buffer this mode's host->device copy fills
         s["work"][src.storage_offset() : src.storage_offset() + src.numel()].copy_(src)
         s["consumed"].record()  # the staging buffer may now be refilled for the next step
+        pre = _PRE_REFRESH and self._tc_on is not None and self.use_tensor_cores
+        if pre:
+            # the weight planes of this step (online, target, transposed) depend only on the parameters: split them on a side branch while the
+            # main branch walks the tree and gathers the minibatch
+            main, side = th.cuda.current_stream(), s["side_stream2"]
+            side.wait_stream(main)
+            with th.cuda.stream(side):
+                TCPairMlp.refresh_many([self._tc_on, self._tc_tg], transposed_of=[self._tc_train] if self._tc_train is not None else [])
+            self._planes_fresh = True
         if mode == "device_per":
             # SumTree.sample on the device (prioritized_buffer.py:30-54): the host only supplied B uniform doubles from the numpy stream
             self.replay_buffer.tree.walk_into(s["u"], s["idx_out"], scale_by_root=True)
@@ -579,6 +590,8 @@ class Envelope(MOPolicy, MOAgent):
         else:
             st = s["stage"]
             obs, act, rew, nobs, done = st["obs"], st["act"], st["rew"], st["nobs"], st["done"]
+        if pre:
+            th.cuda.current_stream().wait_stream(s["side_stream2"])
         self._gradient_step(obs, act, rew, nobs, done, s["wset"], device_per=(mode == "device_per"))
         if self._side_pending:  # join the priority / tree branch
             th.cuda.current_stream().wait_stream(s["side_stream"])
@@ -675,6 +688,9 @@ class Envelope(MOPolicy, MOAgent):
                 dst.copy_(src, non_blocking=True)
                 s["h2d_done"].record()
 
+            if self._dp is not None and self._side_pending:  # the previous update's tree write-back (forked after its all-reduce)
+                th.cuda.current_stream().wait_stream(s["side_stream"])
+                self._side_pending = False
             if self.use_cuda_graph:
                 g = self._graphs.get(mode) or self._capture(mode)
                 if has_mirror:

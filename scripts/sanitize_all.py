@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python scripts/sanitize_all.py [group ...]
 
-groups: envelope td gemm optim pareto replay layer1 qhead dyna (default: all).  Shapes are small (sanitizer slows kernels 10-100x) but exercise
+groups: envelope td gemm optim pareto replay layer1 qhead dyna chain (default: all).  Shapes are small (sanitizer slows kernels 10-100x) but exercise
 every code path: all envelope kernel families, both GEMM operand formats x CTA modes x accumulator modes, MN split-K GEMM with the fused
 column sums, every split / reduction helper, the loss kernels, Adam, polyak, Pareto + front records, replay gather."""
 import os
@@ -22,7 +22,7 @@ if os.environ.get("SAN_ZERO_PLANES") == "1":
     # from a genuine read of memory nobody wrote (profiles/r02_sanitize_initcheck*.txt).
     _empty = ops.empty_planes
     ops.empty_planes = lambda *a, **k: _empty(*a, **k).zero_()
-groups = set(sys.argv[1:]) or {"envelope", "td", "gemm", "optim", "pareto", "replay", "layer1", "qhead", "dyna"}
+groups = set(sys.argv[1:]) or {"envelope", "td", "gemm", "optim", "pareto", "replay", "layer1", "qhead", "dyna", "chain"}
 
 
 def rn(*s, scale=1.0):
@@ -173,4 +173,25 @@ if "dyna" in groups:
     th.cuda.synchronize()
     assert bool(th.isfinite(smp).all()) and bool((var > 0).all()) and bool((unc > 0).all())
     print("dyna ok")
+if "chain" in groups:
+    # chained hidden layers (gemm_chain_kernel): 2 chains x 2 layers on 5 tiles (groups of 2 + a ragged last group), then a 1-chain dX chain with masks
+    M, H = 1200, 256
+    sa, sw = ops.scale_tensor(2.0, dev), ops.scale_tensor(1024.0, dev)
+    acts, ws, bs, sws, bits = [], [], [], [], []
+    for c in range(2):
+        acts.append([ops.split_planes(rn(M, H).relu_(), ops.FMT_F16X2, rows_pad=M, ldp=H, scale=sa)] + [ops.empty_planes(ops.FMT_F16X2, M, H, dev) for _ in range(2)])
+        ws.append([ops.split_planes(rn(H, H, scale=0.06), ops.FMT_F16X2, rows_pad=H, ldp=H, scale=sw) for _ in range(2)])
+        bs.append([rn(H, scale=0.1) for _ in range(2)])
+        sws.append([sw, sw])
+        bits.append([ops.empty_relu_bits(M, dev) for _ in range(2)])
+    ops.GemmChain(acts, ws, bs, sws, bits, act_scale=sa)()
+    for c in range(2):
+        a = acts[c][0]
+        for l in range(2):
+            _, a = ops.gemm_planes(a, ws[c][l], H, bias=bs[c][l], relu=True, out_f32=False, out_planes=True, a_scale=sa, b_scale=sw, c_scale=sa)
+            assert th.equal(a.view(th.int16), acts[c][l + 1].view(th.int16)), (c, l)
+    gb = [acts[0][2]] + [ops.empty_planes(ops.FMT_F16X2, M, H, dev) for _ in range(2)]
+    ops.GemmChain([gb], [ws[0]], None, [sws[0]], None, act_scale=sa, relu=False, bits_in=[bits[0]])()
+    th.cuda.synchronize()
+    print("chain ok")
 print("sanitize run ok")

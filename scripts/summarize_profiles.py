@@ -78,4 +78,12 @@ for rep in glob.glob(os.path.join(OUT, "prof_*.ncu-rep")):
         k = [t for t in traffic if "gemm_planes_kernel" in t[0]] or traffic
         json.dump({"kernel": k[0][0], "dram_bytes_per_launch": k[0][1], "source": f"profiles/{tag}_{name}_ncu.txt"},
                   open(os.path.join(ROOT, "profiles", "gemm_traffic.json"), "w"))
+    if name == "chain" and traffic:
+        k = [t for t in traffic if "gemm_chain_kernel" in t[0]] or traffic
+        json.dump({"kernel": k[0][0], "dram_bytes_per_launch": k[0][1], "source": f"profiles/{tag}_{name}_ncu.txt"},
+                  open(os.path.join(ROOT, "profiles", "gemm_chain_traffic.json"), "w"))
+    if name == "qhead" and traffic:
+        k = [t for t in traffic if "qhead_envelope_kernel" in t[0]] or traffic
+        json.dump({"kernel": k[0][0], "dram_bytes_per_launch": k[0][1], "source": f"profiles/{tag}_{name}_ncu.txt"},
+                  open(os.path.join(ROOT, "profiles", "qhead_envelope_traffic.json"), "w"))
     print("wrote", name)
