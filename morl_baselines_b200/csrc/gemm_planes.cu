@@ -574,13 +574,18 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     const int n_tiles = (g.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
     const int n_kblk = g.K / BK;
     const int tiles_per_group = kChainLanes / g.n_chains;  // lanes of a group: (tile of the group) x (chain)
-    const int my_tiles = unit < n_tiles ? (n_tiles - unit + n_units - 1) / n_units : 0;
-    const int n_groups = (my_tiles + tiles_per_group - 1) / tiles_per_group;
-    // unit (group gi, layer l, lane ln) -> (job, tile) or tile = -1 (no such tile in the last group)
+    // Tile t of chain c goes to pair (t + offset_c) mod n_units with a DIFFERENT rotation per chain: 256 tiles on 74 pairs leave 34 pairs with
+    // four tiles and 40 with three; with both chains on the same pairs the launch lasted 4/3.46 of the balanced time (the 3-tile pairs idled
+    // for a quarter of it), rotated by half the pairs every pair gets 4 + 3 or 3 + 3.
+    const int cu0 = unit, cu1 = (unit + n_units / 2) % n_units;
+    const int mt0 = cu0 < n_tiles ? (n_tiles - cu0 + n_units - 1) / n_units : 0;
+    const int mt1 = g.n_chains > 1 ? (cu1 < n_tiles ? (n_tiles - cu1 + n_units - 1) / n_units : 0) : 0;
+    const int n_groups = ((mt0 > mt1 ? mt0 : mt1) + tiles_per_group - 1) / tiles_per_group;
+    // unit (group gi, layer l, lane ln) -> (job, tile) or tile = -1 (no such tile for this pair)
     auto unit_of = [&](int gi, int l, int ln, int& job, int& tile) {
         const int c = ln % g.n_chains, ti = gi * tiles_per_group + ln / g.n_chains;
         job = c * g.n_layers + l;
-        tile = ti < my_tiles ? unit + ti * n_units : -1;
+        tile = ti < (c ? mt1 : mt0) ? (c ? cu1 : cu0) + ti * n_units : -1;
     };
 
     if (threadIdx.x == 0) {

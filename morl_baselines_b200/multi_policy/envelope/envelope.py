@@ -43,8 +43,8 @@ from ...common.weights import equally_spaced_weights, random_weights
 # output layers + envelope operator + Bellman line as one kernel (csrc/qhead_envelope.cu: 29.4 us against 57.7 us for the three-launch chain at
 # the north-star shape, bit-identical -- profiles/r02_qhead_time.txt); MORL_FUSED_HEAD=0 keeps the three-launch chain (A/B runs)
 _FUSED_HEAD = os.environ.get("MORL_FUSED_HEAD", "1") != "0"
-_PRE_REFRESH = os.environ.get("MORL_PRE_REFRESH", "0") == "1"  # experiment: weight-plane refresh on a side branch, under the tree walk + gather
-_HEAD_REVERSE = os.environ.get("MORL_HEAD_REVERSE", "0") == "1"  # experiment: fused head walks the tiles from the last one after a chained pass
+_PRE_REFRESH = os.environ.get("MORL_PRE_REFRESH", "1") == "1"  # weight-plane refresh on a side branch, under the tree walk + gather (+1.4 %)
+_HEAD_REVERSE = os.environ.get("MORL_HEAD_REVERSE", "1") == "1"  # the fused head walks the tiles from the last one after a chained pass (L2; +1.2 %)
 # device PER: fork the priority / sum-tree branch after the backward GEMMs instead of right after the loss (MORL_DEFER_TREE=0: the earlier order)
 _DEFER_TREE = os.environ.get("MORL_DEFER_TREE", "1") != "0"
 # the online-net and target-net no-grad chains as two branches of the captured graph: one chain's kernels fill the launch gaps and tile
