@@ -25,6 +25,8 @@ for src, dst in (("bench.log", "bench.json"), ("bench_reference.log", "bench_ref
 for src, dst in (("bench_ab.log", "bench_ab.txt"), ("gemm_stats.log", "gemm_stats.txt"), ("golden_diag.log", "golden_diag.txt"),
                  ("sanitize_memcheck.log", "sanitize_memcheck.txt"), ("sanitize_racecheck.log", "sanitize_racecheck.txt"),
                  ("sanitize_synccheck.log", "sanitize_synccheck.txt"), ("sanitize_initcheck.log", "sanitize_initcheck.txt"),
+                 ("sanitize_new_memcheck.log", "sanitize_new_memcheck.txt"), ("sanitize_new_racecheck.log", "sanitize_new_racecheck.txt"),
+                 ("sanitize_new_synccheck.log", "sanitize_new_synccheck.txt"), ("qhead_time.log", "qhead_time.txt"),
                  ("pytest_gpu.log", "pytest_gpu.txt"), ("smoke.log", "smoke.txt")):
     p = os.path.join(OUT, src)
     if os.path.exists(p):
