@@ -20,6 +20,10 @@ from torch import nn as nn
 from torch.nn import functional as F
 
 from ... import ops
+from ..graphed import GraphedStep
+
+# minibatch steps of ``fit`` as CUDA-graph replays (MORL_DYNA_FIT_GRAPH=0: eager steps, the reference's op-by-op form)
+_FIT_GRAPH = os.environ.get("MORL_DYNA_FIT_GRAPH", "1") != "0"
 
 
 class EnsembleLayer(nn.Module):
@@ -129,8 +133,12 @@ class ProbabilisticEnsemble(nn.Module):
         mean, logvar = self.forward(x, deterministic=True, return_dist=True)
         if len(y.shape) < 3:
             y = y.unsqueeze(0).repeat(self.ensemble_size, 1, 1)
-        var = th.exp(logvar)
-        total_losses = F.gaussian_nll_loss(mean, y, var, reduction="none").mean()
+        # F.gaussian_nll_loss(mean, y, exp(logvar), reduction="none") written out with its own arithmetic (eps = 1e-6, full = False): the library
+        # function validates `var >= 0` with a host synchronisation, which is illegal inside a captured step
+        var = th.exp(logvar).clone()
+        with th.no_grad():
+            var.clamp_(min=1e-6)
+        total_losses = (0.5 * (th.log(var) + (mean - y) ** 2 / var)).mean()
         total_losses = total_losses + 0.01 * self.max_logvar.sum() - 0.01 * self.min_logvar.sum()
         return total_losses
 
@@ -160,11 +168,26 @@ class ProbabilisticEnsemble(nn.Module):
     # ------------------------------------------------------------------------------------------ training
     _WEIGHT_DECAYS = (0.000025, 0.00005, 0.000075, 0.000075, 0.0001)  # per layer, as the reference (:224)
 
-    def _make_optimizer(self):
+    def _make_optimizer(self, capturable: bool):
         self.decays = list(self._WEIGHT_DECAYS)
-        groups = [{"params": layer.parameters(), "weight_decay": self.decays[i]} for i, layer in enumerate(self.layers)]
-        groups += [{"params": self.max_logvar}, {"params": self.min_logvar}]
-        self.optim = th.optim.Adam(groups, lr=self.learning_rate)
+        groups = [{"params": list(layer.parameters()), "weight_decay": self.decays[i]} for i, layer in enumerate(self.layers)]
+        groups += [{"params": [self.max_logvar]}, {"params": [self.min_logvar]}]
+        self.optim = th.optim.Adam(groups, lr=self.learning_rate, capturable=capturable)
+        if capturable:
+            # the state a captured step mutates must exist (and be snapshot) before the capture: Adam creates it lazily otherwise
+            for grp in self.optim.param_groups:
+                for prm in grp["params"]:
+                    self.optim.state[prm] = {"step": th.zeros((), dtype=th.float32, device=prm.device), "exp_avg": th.zeros_like(prm),
+                                             "exp_avg_sq": th.zeros_like(prm)}
+                    prm.grad = th.zeros_like(prm)
+
+    def _fit_mutated(self):
+        out = []
+        for grp in self.optim.param_groups:
+            for prm in grp["params"]:
+                st = self.optim.state[prm]
+                out += [prm, prm.grad, st["step"], st["exp_avg"], st["exp_avg_sq"]]
+        return out
 
     def _upload_split(self, X, Y, num_holdout):
         """Training set and hold-out set as device tensors: ONE upload of X and Y, the split is a device gather by the host permutation
@@ -175,24 +198,38 @@ class ProbabilisticEnsemble(nn.Module):
         held, kept = order[:num_holdout], order[num_holdout:]
         return (Xd[kept], Yd[kept]), (Xd[held], Yd[held])
 
-    def _train_epoch(self, train, table, batch_size):
-        """One pass over the bootstrap table [E, n]: member e of minibatch k sees rows table[e, k*bs:(k+1)*bs] (device gathers)."""
+    def _train_step(self, xs, ys, pick):
+        loss = self._compute_loss(xs[pick], ys[pick])
+        self.optim.zero_grad(set_to_none=False)
+        loss.backward()
+        self.optim.step()
+
+    def _train_epoch(self, train, table, batch_size, graph_state):
+        """One pass over the bootstrap table [E, n]: member e of minibatch k sees rows table[e, k*bs:(k+1)*bs] (device gathers).  Full
+        minibatches replay ONE captured step (gather, likelihood, backward, Adam over a static index buffer: ~40 launches -> one graph
+        replay); a ragged last minibatch runs the same step eagerly."""
         xs, ys = train
         rows = th.from_numpy(table).to(self.device)
         self.train()
         for lo in range(0, table.shape[-1], batch_size):
             pick = rows[:, lo:lo + batch_size]
-            loss = self._compute_loss(xs[pick], ys[pick])
-            self.optim.zero_grad()
-            loss.backward()
-            self.optim.step()
+            if graph_state is not None and pick.shape[1] == batch_size:
+                if "step" not in graph_state:
+                    graph_state["idx"] = pick.clone()
+                    graph_state["step"] = GraphedStep(lambda: self._train_step(xs, ys, graph_state["idx"]), self._fit_mutated)
+                graph_state["idx"].copy_(pick)
+                graph_state["step"]()
+            else:
+                self._train_step(xs, ys, pick)
 
     def fit(self, X, Y, batch_size=256, holdout_ratio=0.1, max_holdout_size=5000, max_epochs_no_improvement=5, max_epochs=200):
         """Maximum-likelihood training with bootstrapped minibatches and hold-out early stopping (reference :197-290).  numpy's global RNG is
         consumed in the reference's order: the split permutation, the bootstrap table, one uniform table per epoch (row shuffles)."""
         if self.normalize_inputs:
             self._fit_input_stats(X)
-        self._make_optimizer()
+        use_graph = _FIT_GRAPH
+        self._make_optimizer(capturable=use_graph)
+        graph_state = {} if use_graph else None
         num_holdout = min(int(X.shape[0] * holdout_ratio), max_holdout_size)
         train, held = self._upload_split(X, Y, num_holdout)
         n_train = train[0].shape[0]
@@ -201,7 +238,7 @@ class ProbabilisticEnsemble(nn.Module):
         holdout_losses = list(best)
         stale, epoch = 0, 0
         while stale < max_epochs_no_improvement and epoch < max_epochs:
-            self._train_epoch(train, table, batch_size)
+            self._train_epoch(train, table, batch_size, graph_state)
             # every member's row is permuted independently for the next epoch (argsort of one uniform table, :243-245)
             table = np.take_along_axis(table, np.argsort(np.random.uniform(size=table.shape), axis=-1), axis=-1)
             self.eval()
