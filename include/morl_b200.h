@@ -322,11 +322,13 @@ MORL_API int morl_gemm_planes_f32(int fmt, const void* a_planes, long long a_pla
  * no-grad passes (both networks at once: n_chains = 2) and in the training pass (n_chains = 1, with ReLU bit masks).
  *   act_planes [n_chains * (n_layers + 1)] : plane tensors [P][M][256] (host array of device pointers; index c * (n_layers + 1) + l);
  *   w_planes / w_scales / biases / relu_bits_in / relu_bits_out [n_chains * n_layers] (index c * n_layers + l; all but w_planes nullable, also per entry).
+ *   k_first (0 = K): reduction length of layer 0 -- its input act[c][0] may be a NARROWER dense tensor [P][M][k_first] with weights [P][256][k_first]
+ *   (plane strides M * k_first and 256 * k_first): the dX product of the 24-wide output layer as the first job of the backward chain.
  * morl_gemm_chain_supported: K == 256 (square 256-wide layers), M >= 256. */
 MORL_API int morl_gemm_chain_supported(int fmt, int M, int K);
 MORL_API int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const void* const* act_planes, long long act_plane_stride, const float* act_scale,
                                  const void* const* w_planes, long long w_plane_stride, const float* const* w_scales, const float* const* biases,
-                                 int relu, const void* const* relu_bits_in, void* const* relu_bits_out, int M, int K, void* stream);
+                                 int relu, const void* const* relu_bits_in, void* const* relu_bits_out, int M, int K, int k_first, void* stream);
 /* Diagnostics (not part of the reference surface): per-role cycle counters of morl_gemm_planes_f32, summed over CTAs and launches
  * since the last reset; collected only when the environment variable MORL_GEMM_STATS=1 is set before the first GEMM call.
  * out8: [0] MMA thread waiting for TMA data, [1] waiting for the epilogue to free an accumulator, [2] MMA loop total,

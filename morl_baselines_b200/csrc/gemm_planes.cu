@@ -530,6 +530,7 @@ struct alignas(64) ChainMaps {
 
 struct ChainArgs {
     int M, K;                      // rows, reduction length (= width of the layers: square 256-wide layers, K % BK == 0)
+    int k_first;                   // reduction length of layer 0 of every chain (its INPUT may be narrower: the dX product of the output layer), K % BK == 0
     int n_chains, n_layers;
     const float* bias[kChainMaxJobs];
     const float* b_scale[kChainMaxJobs];
@@ -572,7 +573,7 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     const uint32_t cta_rank = cluster_ctarank();
     const int unit = blockIdx.x / 2, n_units = gridDim.x / 2;
     const int n_tiles = (g.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
-    const int n_kblk = g.K / BK;
+    const int n_kblk_full = g.K / BK, n_kblk_first = g.k_first / BK;
     const int tiles_per_group = kChainLanes / g.n_chains;  // lanes of a group: (tile of the group) x (chain)
     // Tile t of chain c goes to pair (t + offset_c) mod n_units with a DIFFERENT rotation per chain: 256 tiles on 74 pairs leave 34 pairs with
     // four tiles and 40 with three; with both chains on the same pairs the launch lasted 4/3.46 of the balanced time (the 3-tile pairs idled
@@ -633,6 +634,7 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         }
                         ++done_on_lane[ln];
                         const int row0 = (tile * 2 + (int)cta_rank) * kGemmBM;
+                        const int n_kblk = l == 0 ? n_kblk_first : n_kblk_full;
                         for (int kb = 0; kb < n_kblk; ++kb) {
                             g_mbar_wait(&empty[stage], phase ^ 1u);
                             if (cta_rank == 0) g_mbar_expect_tx(&full[stage], 2u * (a_stage_bytes + b_stage_bytes));
@@ -663,6 +665,7 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         g_mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + as * 256u;
+                        const int n_kblk = l == 0 ? n_kblk_first : n_kblk_full;
                         for (int kb = 0; kb < n_kblk; ++kb) {
                             g_mbar_wait(&full[stage], phase);
                             tc_fence_after();
@@ -1961,7 +1964,7 @@ extern "C" int morl_gemm_chain_supported(int fmt, int M, int K) {
 // through all layers, so intermediate activations are re-read from L2 instead of HBM (csrc: gemm_chain_kernel).
 extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const void* const* act_planes, long long act_plane_stride, const float* act_scale,
                                    const void* const* w_planes, long long w_plane_stride, const float* const* w_scales, const float* const* biases,
-                                   int relu, const void* const* relu_bits_in, void* const* relu_bits_out, int M, int K, void* stream) {
+                                   int relu, const void* const* relu_bits_in, void* const* relu_bits_out, int M, int K, int k_first, void* stream) {
     using namespace morl;
     MORL_REQUIRE(act_planes && w_planes, MORL_ERR_NULL, "morl_gemm_chain_f32: NULL pointer argument");
     MORL_REQUIRE(n_chains >= 1 && n_chains <= 2 && n_layers >= 1 && n_chains * n_layers <= kChainMaxJobs, MORL_ERR_SHAPE,
@@ -1969,10 +1972,12 @@ extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const vo
     MORL_REQUIRE(morl_gemm_chain_supported(fmt, M, K), MORL_ERR_UNSUPPORTED, "morl_gemm_chain_f32: unsupported configuration fmt=%d M=%d K=%d (256-wide layers, M >= 256)",
                  fmt, M, K);
     const int BK = fmt == MORL_FMT_F16X2 ? PlaneFmt<MORL_FMT_F16X2>::BK : PlaneFmt<MORL_FMT_BF16X3>::BK;
+    if (k_first <= 0) k_first = K;
+    MORL_REQUIRE(k_first % BK == 0 && k_first <= K, MORL_ERR_SHAPE, "morl_gemm_chain_f32: k_first=%d must be a multiple of %d and <= K", k_first, BK);
     static ChainMaps maps;  // (host staging of the 3 x 8 tensor maps; copied into the kernel parameters by the launch)
     ChainArgs g;
     memset(&g, 0, sizeof(g));
-    g.M = M; g.K = K; g.n_chains = n_chains; g.n_layers = n_layers; g.a_scale = act_scale; g.relu = relu ? 1 : 0;
+    g.M = M; g.K = K; g.k_first = k_first; g.n_chains = n_chains; g.n_layers = n_layers; g.a_scale = act_scale; g.relu = relu ? 1 : 0;
     for (int c = 0; c < n_chains; ++c)
         for (int l = 0; l < n_layers; ++l) {
             const int job = c * n_layers + l;
@@ -1980,9 +1985,13 @@ extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const vo
             const void* a_out = act_planes[c * (n_layers + 1) + l + 1];
             MORL_REQUIRE(a_in && a_out && w_planes[job] && aligned16(a_in) && aligned16(a_out) && aligned16(w_planes[job]), MORL_ERR_NULL,
                          "morl_gemm_chain_f32: NULL or misaligned plane pointer (chain %d, layer %d)", c, l);
-            int rc = make_plane_map(&maps.A[job], fmt, a_in, M, K, act_plane_stride, kGemmBM, BK);
+            // layer 0 may read a narrower input [P][M][k_first] (plane stride M * k_first) through weights [P][256][k_first]
+            const int kj = l == 0 ? k_first : K;
+            const long long a_stride = l == 0 ? (long long)M * k_first : act_plane_stride;
+            const long long w_stride = l == 0 ? (long long)256 * k_first : w_plane_stride;
+            int rc = make_plane_map(&maps.A[job], fmt, a_in, M, kj, a_stride, kGemmBM, BK);
             MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(A) failed (%d)", rc);
-            rc = make_plane_map(&maps.B[job], fmt, w_planes[job], 256, K, w_plane_stride, 128, BK);
+            rc = make_plane_map(&maps.B[job], fmt, w_planes[job], 256, kj, w_stride, 128, BK);
             MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(B) failed (%d)", rc);
             rc = make_plane_map(&maps.C[job], fmt, a_out, M, 256, act_plane_stride, 32, 32);
             MORL_REQUIRE(rc == 0, MORL_ERR_NO_DEVICE, "morl_gemm_chain_f32: cuTensorMapEncodeTiled(C) failed (%d)", rc);

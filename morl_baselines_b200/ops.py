@@ -518,13 +518,14 @@ class GemmChain:
     ``biases[c]`` / ``bits[c]`` (ReLU masks recorded) / ``bits_in[c]`` (ReLU-backward masks applied): per layer, all optional.  ``relu``: ReLU on every
     output (forward chains); False for the dX chains of the backward pass."""
 
-    def __init__(self, acts, weights, biases=None, w_scales=None, bits=None, act_scale=None, relu: bool = True, bits_in=None):
+    def __init__(self, acts, weights, biases=None, w_scales=None, bits=None, act_scale=None, relu: bool = True, bits_in=None, k_first: int = 0):
         import ctypes as C
 
         self.n_chains, self.n_layers = len(acts), len(weights[0])
-        a0 = acts[0][0]
+        a0 = acts[0][1]  # (the first OUTPUT: the chain's input may be narrower, see k_first)
         self.fmt = fmt_of(a0)
         _, self.M, self.K = a0.shape
+        self.k_first = int(k_first) if k_first else self.K
         flat_a = [t for ch in acts for t in ch]
         flat_w = [t for ch in weights for t in ch]
         flat_b = [None] * len(flat_w) if biases is None else [t.detach() for ch in biases for t in ch]
@@ -533,12 +534,14 @@ class GemmChain:
         flat_m = [None] * len(flat_w) if bits is None else [t for ch in bits for t in ch]
         if len(flat_a) != self.n_chains * (self.n_layers + 1) or any(len(w) != self.n_layers for w in weights):
             raise _lib.MorlB200Error("GemmChain: every chain needs n_layers + 1 activation tensors and n_layers weight tensors")
-        for t in flat_a:
-            if fmt_of(t) != self.fmt or tuple(t.shape) != tuple(a0.shape) or t.stride(1) != self.K or t.stride(0) != a0.stride(0) or not t.is_cuda:
-                raise _lib.MorlB200Error("GemmChain: activation planes must be CUDA plane tensors of one shape [P, M, 256], K-major")
-        for t in flat_w:
-            if fmt_of(t) != self.fmt or tuple(t.shape[1:]) != (256, self.K) or t.stride(1) != self.K or t.stride(0) != flat_w[0].stride(0):
-                raise _lib.MorlB200Error("GemmChain: weight planes must be [P, 256, K], K-major")
+        for i, t in enumerate(flat_a):
+            kk = self.k_first if i % (self.n_layers + 1) == 0 else self.K
+            if fmt_of(t) != self.fmt or tuple(t.shape[1:]) != (self.M, kk) or not t.is_contiguous() or not t.is_cuda:
+                raise _lib.MorlB200Error(f"GemmChain: activation planes must be contiguous CUDA plane tensors [P, {self.M}, {kk}] (input {self.k_first} wide, outputs 256)")
+        for i, t in enumerate(flat_w):
+            kk = self.k_first if i % self.n_layers == 0 else self.K
+            if fmt_of(t) != self.fmt or tuple(t.shape[1:]) != (256, kk) or not t.is_contiguous():
+                raise _lib.MorlB200Error(f"GemmChain: weight planes must be contiguous [P, 256, {kk}]")
         for t in flat_m + flat_i:
             if t is not None and (t.dtype != th.int32 or tuple(t.shape) != (self.M, 8) or not t.is_contiguous()):
                 raise _lib.MorlB200Error(f"GemmChain: ReLU bit masks must be contiguous int32 [{self.M}, 8]")
@@ -546,11 +549,11 @@ class GemmChain:
         self.relu = bool(relu)
         arr = lambda ts: (C.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])  # noqa: E731
         self._pa, self._pw, self._pb, self._ps, self._pm, self._pi = arr(flat_a), arr(flat_w), arr(flat_b), arr(flat_s), arr(flat_m), arr(flat_i)
-        self._a_stride, self._w_stride, self._act_scale = a0.stride(0), flat_w[0].stride(0), act_scale
+        self._a_stride, self._w_stride, self._act_scale = a0.stride(0), 256 * self.K, act_scale
 
     def __call__(self):
         rc = _lib.load().morl_gemm_chain_f32(self.fmt, self.n_chains, self.n_layers, self._pa, self._a_stride, _ptr(self._act_scale), self._pw, self._w_stride,
-                                             self._ps, self._pb, int(self.relu), self._pi, self._pm, self.M, self.K, _stream())
+                                             self._ps, self._pb, int(self.relu), self._pi, self._pm, self.M, self.K, self.k_first, _stream())
         _lib.check(rc, "morl_gemm_chain_f32")
         _count()
 

@@ -289,19 +289,17 @@ def _backward_chained(self, feats, wset, G, grads, after_gemms):
     dev = G.device
     if self._gchain is None:
         M, hid = self.B * self.W, self.lin[1].in_features
-        self._gbufs = [ops.empty_planes(self.fmt, M, hid, dev) for _ in range(n - 1)]  # G_{n-2}, ..., G_0 (G_k = dL/dh_{k+1} ... see below)
-        # chain input = dL/dh_{n-1} (output of the narrow dX product), outputs dL/dh_{n-2}, ..., dL/dh_1
-        ks = list(range(n - 2, 0, -1))  # layers whose dX product is in the chain
-        self._gchain = ops.GemmChain([self._gbufs], [[self.wtp[k - 1] for k in ks]], None, [[self.s_w[k - 1] for k in ks]], None, act_scale=self.s_g,
-                                     relu=False, bits_in=[[self.hbits[k - 1] for k in ks]])
+        self._gbufs = [ops.empty_planes(self.fmt, M, hid, dev) for _ in range(n - 1)]  # dL/d(output of lin[n-2]), ..., dL/d(output of lin[0])
+        # chain input = the planes of dL/dQ (ld_last wide: the first job reduces over ld_last columns only), outputs the n - 1 hidden gradients
+        ks = list(range(n - 1, 0, -1))  # layers whose dX product is in the chain: the narrow output layer first
+        self._gchain = ops.GemmChain([[self.g_last] + self._gbufs], [[self.wtp[k - 1] for k in ks]], None, [[self.s_w[k - 1] for k in ks]], None,
+                                     act_scale=self.s_g, relu=False, bits_in=[[self.hbits[k - 1] for k in ks]], k_first=self.ld_last)
     last = self.lin[n - 1]
     if grads[2 * (n - 1) + 1] is None:
         grads[2 * (n - 1) + 1] = th.empty(last.out_features, device=dev, dtype=th.float32)
     grads[2 * (n - 1)] = ops.gemm_planes_mn(G, last.out_features, self.h[n - 2], last.in_features, out=grads[2 * (n - 1)], workspace=self.ws_mn,
                                             colsum=grads[2 * (n - 1) + 1], g_scale=self.s_g, h_scale=self.s_act)
-    ops.gemm_planes(G, self.wtp[n - 2], last.in_features, relu_bits_in=self.hbits[n - 2], out_f32=False, out_planes=True, c_planes=self._gbufs[0],
-                    a_scale=self.s_g, b_scale=self.s_w[n - 2], c_scale=self.s_g, split_acc=False)
-    self._gchain()
+    self._gchain()  # all n - 1 dX products (the narrow one of the output layer included) in one launch
     for i, k in enumerate(range(n - 2, 0, -1)):  # dW_k = (dL/dh_k)^T H_{k-1}: dL/dh_k is _gbufs[i]
         l = self.lin[k]
         if grads[2 * k + 1] is None:
