@@ -843,7 +843,12 @@ struct GemmMnArgs {
     float* colsum_partial;  // [S][n_tiles*128] or nullptr: per-split column sums of G (bias gradient), fused as G^T . ones
 };
 
-template <int FMT>
+// MC = 1 (two column tiles, NB = 256): the two CTAs of a split (column tiles 0 and 1: consecutive blocks) form a CLUSTER; each loads its own
+// 128 G columns and HALF of the H chunks, multicast to both CTAs, so H crosses the L2 -> SM path once per split instead of twice.  The kernel
+// (hypothesis: 67 MB of G + 2 x 67 MB of H per launch through that path at ~6.5 TB/s would explain the 31 us measured.  Built, correct, and
+// measured: no gain, see the launcher -- opt-in.)
+// A stage may be refilled only when BOTH CTAs have consumed it: every MMA commit arrives on the stage's empty barrier of both CTAs.
+template <int FMT, int MC>
 __global__ void __launch_bounds__(192, 1)
 gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmMnArgs g) {
     using F = PlaneFmt<FMT>;
@@ -880,7 +885,7 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             g_mbar_init(&full[s], 1);
-            g_mbar_init(&empty[s], 1);
+            g_mbar_init(&empty[s], MC ? 2 : 1);  // MC: released by the MMA commits of both CTAs of the cluster
         }
         g_mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -891,6 +896,7 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // the peer's barriers exist before any multicast copy / remote arrive targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_enter();  // (nothing above reads or writes global memory: barriers, the tile of ones and the TMEM allocation overlap the predecessor)
@@ -903,7 +909,14 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 g_mbar_expect_tx(&full[stage], (2u + (uint32_t)nb_chunks) * chunk_bytes);
                 const int m0 = m_begin + kb * kMnKT;
                 for (int c = 0; c < 2; ++c) tma_load_3d(smA + stage * a_stage + c * chunk_bytes, &tmA, &full[stage], nt * 128 + c * 64, m0, 0);
-                for (int c = 0; c < nb_chunks; ++c) tma_load_3d(smB + stage * b_stage + c * chunk_bytes, &tmB, &full[stage], c * 64, m0, 0);
+                if (MC) {
+                    // this CTA fetches H chunks 2 nt, 2 nt + 1 for BOTH CTAs (same shared-memory offset and barrier offset in each); the other
+                    // two chunks arrive from the peer's multicast -- every full barrier still counts 2 + 4 chunks
+                    for (int c = 2 * nt; c < 2 * nt + 2; ++c)
+                        tma_load_3d_multicast(smB + stage * b_stage + c * chunk_bytes, &tmB, &full[stage], c * 64, m0, 0, (uint16_t)3);
+                } else {
+                    for (int c = 0; c < nb_chunks; ++c) tma_load_3d(smB + stage * b_stage + c * chunk_bytes, &tmB, &full[stage], c * 64, m0, 0);
+                }
                 if (++stage == kStages) {
                     stage = 0;
                     phase ^= 1u;
@@ -938,7 +951,7 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                         (kb | ks | (P - 1 - pl)) != 0 ? 1u : 0u);
                     }
                 }
-                tc_commit(&empty[stage]);
+                if (MC) tc_commit_mc(&empty[stage]); else tc_commit(&empty[stage]);
                 if (++stage == kStages) {
                     stage = 0;
                     phase ^= 1u;
@@ -975,6 +988,7 @@ gemm_planes_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // no CTA exits while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -1627,12 +1641,38 @@ extern "C" int morl_gemm_planes_mn_f32(int fmt, const void* g_planes, long long 
     MORL_DISPATCH_FMT(fmt, {
         using F = PlaneFmt<kFmt>;
         const size_t smem = (size_t)F::kStagesMn * (6u * F::P * kMnKT * 128u) + 256 + 1024 + 64 + 1024 + 4096;
-        static bool attr_set = false;
+        static bool attr_set = false, attr_set_mc = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(gemm_planes_mn_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(gemm_planes_mn_kernel<kFmt, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        launch_k(gemm_planes_mn_kernel<kFmt>, dim3(n_tiles * S), dim3(192), smem, st, tmA, tmB, g);
+        // measured (profiles/r02_bench_ab_mn_multicast.txt): correct, but the update does not get faster (1,558 vs 1,558 / 1,564 updates/s) -- the
+        // kernel is not bound by the L2 -> SM path of H after all -> opt-in (MORL_MN_MULTICAST=1), the single-CTA form stays the default
+        static const bool mc_env = [] { const char* e = getenv("MORL_MN_MULTICAST"); return e && e[0] == '1'; }();
+        if (mc_env && n_tiles == 2 && NB == 256) {
+            if (!attr_set_mc) {
+                cudaFuncSetAttribute(gemm_planes_mn_kernel<kFmt, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set_mc = true;
+            }
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(n_tiles * S);
+            cfg.blockDim = dim3(192);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = pdl_enabled() ? 2 : 1;
+            cudaLaunchKernelEx(&cfg, gemm_planes_mn_kernel<kFmt, 1>, tmA, tmB, g);
+        } else {
+            launch_k(gemm_planes_mn_kernel<kFmt, 0>, dim3(n_tiles * S), dim3(192), smem, st, tmA, tmB, g);
+        }
     });
     rc = check_launch("morl_gemm_planes_mn_f32");
     if (rc) return rc;
