@@ -2014,7 +2014,8 @@ extern "C" int morl_gemm_chain_f32(int fmt, int n_chains, int n_layers, const vo
     const int BK = fmt == MORL_FMT_F16X2 ? PlaneFmt<MORL_FMT_F16X2>::BK : PlaneFmt<MORL_FMT_BF16X3>::BK;
     if (k_first <= 0) k_first = K;
     MORL_REQUIRE(k_first % BK == 0 && k_first <= K, MORL_ERR_SHAPE, "morl_gemm_chain_f32: k_first=%d must be a multiple of %d and <= K", k_first, BK);
-    static ChainMaps maps;  // (host staging of the 3 x 8 tensor maps; copied into the kernel parameters by the launch)
+    ChainMaps maps;  // (host staging of the 3 x 8 tensor maps on this thread's stack -- the entry point stays re-entrant; copied into the kernel
+                     // parameters by the launch)
     ChainArgs g;
     memset(&g, 0, sizeof(g));
     g.M = M; g.K = K; g.k_first = k_first; g.n_chains = n_chains; g.n_layers = n_layers; g.a_scale = act_scale; g.relu = relu ? 1 : 0;
