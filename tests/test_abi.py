@@ -77,3 +77,29 @@ def test_ops_refuse_cpu_tensors():
         ops.pareto_mask(th.zeros(4, 2))
     with pytest.raises(_lib.MorlB200Error):
         ops.envelope_td(th.zeros(2, 2, 2, 3), th.zeros(2, 2, 2, 3), th.zeros(2, 3), th.zeros(2, 3), th.zeros(2), 0.99)
+
+
+def test_fusion_coverage_predicates_need_no_device():
+    """The `*_supported` predicates that decide between a fused kernel and the launches it replaces are pure host functions: their answers
+    at the BASELINE shapes and just outside them (both sides are CUDA paths; an unsupported shape is refused by the fused entry point)."""
+    from morl_baselines_b200 import _lib
+
+    lib = _lib.load()
+    F16, BF16 = _lib.FMT_F16X2, _lib.FMT_BF16X3
+    # fused output layers + envelope + Bellman: north-star, configs[1] (minecart: |W| 32, |A| 6, d 3), and what falls outside
+    assert lib.morl_qhead_envelope_supported(F16, 1024, 64, 8, 3, 256) == 1
+    assert lib.morl_qhead_envelope_supported(F16, 256, 32, 6, 3, 256) == 1
+    assert lib.morl_qhead_envelope_supported(BF16, 1024, 64, 8, 3, 256) == 0   # f16x2 planes only
+    assert lib.morl_qhead_envelope_supported(F16, 1024, 48, 8, 3, 256) == 0    # |W| must divide 128
+    assert lib.morl_qhead_envelope_supported(F16, 1024, 64, 11, 3, 256) == 0   # |A| d > 32 (and |W||A| not a multiple of 16)
+    assert lib.morl_qhead_envelope_supported(F16, 1024, 64, 8, 5, 256) == 0    # d in 2..4
+    assert lib.morl_qhead_envelope_supported(F16, 1024, 64, 8, 3, 320) == 0    # K <= 256
+    assert lib.morl_qhead_gemm_supported(F16, 65536, 24, 256) == 1 and lib.morl_qhead_gemm_supported(F16, 65536, 40, 256) == 0
+    assert lib.morl_qhead_gemm_supported(F16, 1000, 24, 256) == 0              # M % 128
+    # chained hidden layers: 256-wide layers, at least two 128-row tiles
+    assert lib.morl_gemm_chain_supported(F16, 65536, 256) == 1 and lib.morl_gemm_chain_supported(BF16, 8192, 256) == 1
+    assert lib.morl_gemm_chain_supported(F16, 65536, 128) == 0 and lib.morl_gemm_chain_supported(F16, 128, 256) == 0
+    # refused with an error code and a message, not a crash
+    rc = lib.morl_qhead_envelope_td_f32(F16, 16, 16, 0, None, None, 16, 16, 0, None, None, None, None, 256, 16, 16, 16, 0.99, 1024, 48, 8, 3, 0, 0, 0, 16, None, None, None,
+                                        None, None)
+    assert rc == -4 and b"unsupported configuration" in lib.morl_last_error()
