@@ -5,8 +5,11 @@
 
     layer 1   : u = feats @ W1[:, :F]^T (B rows), v = wset @ W1[:, F:]^T + b1 (W rows)  -- one launch (morl_pair_layer1_uv_f32) --
                  h1[b*W + j] = relu(u[b] + v[j]) written straight into operand planes (morl_pairs_relu_split_planes);
-    layers 2..: morl_gemm_planes_f32 (TMA -> tcgen05.mma -> TMEM -> epilogue) with the activation re-split fused in the
-                 epilogue; the last layer writes fp32 Q-values.
+    layers 2..: the 256-wide hidden layers of a pass as ONE chained launch (morl_gemm_chain_f32: a CTA pair takes its row tiles through
+                 all layers, intermediate activations re-read from L2; both no-grad nets together) -- or, for other widths, one
+                 morl_gemm_planes_f32 launch per layer (TMA -> tcgen05.mma -> TMEM -> epilogue, activation re-split fused in the epilogue);
+                 the last layer writes fp32 Q-values (morl_qhead_gemm_f32 when it is <= 32 wide) or is consumed, together with the other
+                 network's, by the fused head (morl_qhead_envelope_td_f32: Q never reaches HBM).
 
 Operand formats (``fmt``): ``ops.FMT_F16X2`` (default; two fp16 planes of a power-of-two-scaled operand, three MMAs per product, 4 B per
 element) or ``ops.FMT_BF16X3`` (three bf16 planes, six MMAs, 6 B per element, fp32 exponent range).  Scales of the f16x2 format, all
@@ -25,7 +28,7 @@ The weight planes are refreshed with ``refresh_weights()`` after every optimiser
 
 Hand-written backward for the training pass:
     G_L = dL/dQ;  dW_l = G_l^T H_{l-1} (MN-major split-K GEMM);  db_l = colsum(G_l);
-    G_{l-1} = (G_l W_l) * [H_{l-1} > 0] (K-major GEMM with the ReLU mask fused in the epilogue);
+    G_{l-1} = (G_l W_l) * [H_{l-1} > 0] (K-major GEMM with the ReLU mask fused in the epilogue; all layers as one chained launch);
     layer 1: dU = sum_j G_1, dV = sum_b G_1 (morl_pairs_grad_reduce_planes), dW1 = [dU^T feats | dV^T wset], db1 = sum_j dV
              (morl_pair_layer1_grad_f32).
 No library (ATen / cuBLAS) kernel runs anywhere in forward or backward.
