@@ -12,9 +12,12 @@ grad clip -> Adam (+ target sync every 200 steps).
            Envelope.update() with the replay store resident in HBM (per step 9 KB of indices + weights in, 4 KB of priorities + loss out).
   e2e    : updates/s through the same call with a HOST-resident replay buffer: per step the gathered minibatch (pinned, 283 KB) crosses
            host->device and the priorities + loss come back device->host; the loss is read as a python float every update.
-  roofline     : the dominant kernel of the step (bf16x3 tcgen05 GEMM of one hidden layer) against the measured dense bf16 peak.
-  roofline_envelope : the fused envelope-TD kernel (the one north_star names) against the measured HBM bandwidth, timed alone in a
-                 CUDA graph on rotating buffer sets larger than L2.
+  roofline     : the dominant kernel of the step -- the chained hidden-layer launch (layers 2..4 of both Q-networks, 6 f16x2 tcgen05 products in
+                 one persistent kernel) -- against its binding roofline, the measured dense 16-bit tensor peak (HBM view inside);
+                 roofline_gemm_layer: the per-layer kernel it replaces.
+  roofline_envelope : the fused envelope-TD kernel north_star names, in the form the update runs it (output layers of both nets + envelope
+                 operator + Bellman line in one kernel, Q never in HBM), against the measured HBM bandwidth, timed alone in a CUDA graph on
+                 rotating buffer sets larger than L2; roofline_envelope_operator: the standalone operator on Q tensors in HBM.
   cpu_baseline : the reference's CPU implementation (oracle port, or the unmodified reference when mounted) at the SAME full config,
                  a bounded NUMBER of updates (not a bounded batch); cpu_dedup_restatement: the de-duplicated CPU restatement for context.
 N > 1: every rank runs an independent update stream (weak scaling, no data-path collective); the ranks exchange their non-dominated
